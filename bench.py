@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- contact evals/sec (wrench + 6x6 Jacobians, FP64) of the batched
+ContinuousContactModel evaluation, with roofline, CPU baseline and end-to-end numbers.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of synthetic contact states.  Workload at every
+N: BASELINE.json configs[2] -- the sampling-MPC rollout batch, 2 feet x 4096 samples x 100 horizon
+steps = 819 200 states per GPU, wrench + autonomous dynamics + control matrix, uniform foot, SoA
+planes in / SoA wrench+autodyn planes and dense 6x6 out (600 algorithmic bytes per evaluation).
+N > 1 is weak scaling: every rank owns its own 4096 samples (rollouts), no data-path collective in
+the evaluation; the sampling-MPC epilogue (per-rollout cost, arg-min, NCCL all-gather of one
+16-byte pair per rank) is timed separately and reported under "mpc".
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FEET, SAMPLES, HORIZON = 2, 4096, 100
+N_PER_GPU = FEET * SAMPLES * HORIZON          # 819 200
+ROLLOUT_LEN = FEET * HORIZON                  # 200 evaluations per rollout
+BYTES_FULL_UNIFORM = 600                      # 27 live input doubles + 48 output doubles
+METRIC = "contact evals/sec (wrench+6x6 Jacobians, FP64)"
+UNIT = "evals/s"
+WORKLOAD = ("configs[2]: sampling-MPC rollout batch 2 feet x 4096 samples x 100 steps per GPU, "
+            "wrench+autodyn+ctrl, uniform params, SoA")
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the bench runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting",
+               0x100: "display_clock_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int, period: float = 0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples = []
+        self.stop_flag = False
+        self.ok = False
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), clk, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self, t0: float, t1: float) -> dict:
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed"
+        if len(inside) < 3:
+            inside, window = list(self.samples), "warmup+timed (timed region shorter than 3 samples)"
+        clks = sorted(s[1] for s in inside) or [0]
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = [name for bit, name in self.REASONS.items() if bits & bit]
+        return {"sm_mhz": clks[len(clks) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(inside), "window": window}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm (oracle): bench.py may execute oracle/ only here
+# --------------------------------------------------------------------------------------------------
+
+def cpu_reference_pass(st, nthreads: int, min_seconds: float, mask: int = 7):
+    """Time the oracle's faithful per-instance path (threaded) on the given states."""
+    from oracle import ccm_oracle
+    ccm_oracle.build()
+    n = st["twists"].shape[0]
+    best = None
+    spent = 0.0
+    passes = 0
+    while spent < min_seconds or passes < 2:
+        t0 = time.perf_counter()
+        ccm_oracle.eval_batch_states(st, mask=mask, nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        spent += dt
+        passes += 1
+    return n / best, passes, spent
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from bipedal_locomotion_framework_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    sample_n = N_PER_GPU  # one full per-GPU batch per step
+    st = syn.make_states(sample_n, seed=42 + 3)
+    from oracle import ccm_oracle
+    ccm_oracle.build()
+    for _ in range(max(1, min(args.warmup, 3))):
+        ccm_oracle.eval_batch_states(st, mask=7, nthreads=cores)
+    steps = max(1, min(args.steps, 50))  # bounded: each step is one full 819 200-state pass
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ccm_oracle.eval_batch_states(st, mask=7, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = sample_n * steps / dt
+    sample = (f"{steps} passes over one {sample_n}-state batch (configs[2] per-GPU shard), oracle "
+              f"per-instance path, {cores} threads, gcc -O2 -ffp-contract=off")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "evals_per_step": sample_n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference cannot be compiled here (Eigen/iDynTree absent): oracle port timed",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from bipedal_locomotion_framework_b200 import synthetic as syn
+    from bipedal_locomotion_framework_b200.contact_models import FULL, ContinuousContactModelBatch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the contact-model backend has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    n = N_PER_GPU
+    batch = ContinuousContactModelBatch(local)
+    batch.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+
+    # rank r owns samples [r*4096, (r+1)*4096): states r*n .. (r+1)*n of the seeded stream
+    st = syn.make_states(n, seed=42 + 3, start=rank * n)
+    planes_np = syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])
+    NSETS = 3   # rotate distinct input/output buffer sets so no step finds its data in L2
+    planes = [torch.from_numpy(planes_np).to(dev) for _ in range(NSETS)]
+    outs = [batch.alloc_soa_outputs(n, FULL) for _ in range(NSETS)]
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def step(i):
+        batch.evaluate_soa(planes[i % NSETS], None, FULL, out=outs[i % NSETS])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(Wm):
+        step(i)
+    barrier()
+    launches0 = batch.handle.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    t_host0 = time.perf_counter()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for i in range(K):
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    e_end.record()
+    barrier()
+    t_host1 = time.perf_counter()
+    launches = batch.handle.launch_count - launches0
+    total_ms = e_start.elapsed_time(e_end)
+    kern_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n * K / (total_ms * 1e-3)
+    avg_kernel_ms = sum(kern_ms) / len(kern_ms)
+    clocks = sampler.summary(t_host0, t_host1)
+
+    if args.only_main:
+        sampler.stop_flag = True
+        if rank == 0:
+            print(json.dumps({"only_main": True, "value": value, "ms_per_step": total_ms / K,
+                              "avg_launch_ms": avg_kernel_ms, "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- sampling-MPC epilogue: evaluate + per-rollout cost + arg-min (+ NCCL all-gather) --------
+    ref_wrench, weights = [0.0, 0.0, 30.0, 0.0, 0.0, 0.0], [1.0, 10.0]
+    n_roll = n // ROLLOUT_LEN
+    gathered = torch.empty((world, 2), dtype=torch.int64, device=dev)
+
+    def mpc_step(i):
+        _, _, best = batch.rollout_cost_argmin(planes[i % NSETS], ROLLOUT_LEN, ref_wrench, weights,
+                                               mask=FULL, index_base=rank * n_roll,
+                                               out=outs[i % NSETS], want_cost=False)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), best)
+            return batch.argmin_pairs(gathered)
+        return best
+
+    for i in range(Wm):
+        gbest = mpc_step(i)
+    barrier()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Km = min(K, 200)
+    m0.record()
+    for i in range(Km):
+        gbest = mpc_step(i)
+    m1.record()
+    barrier()
+    mpc_ms = m0.elapsed_time(m1)
+    if world > 1:
+        t = torch.tensor([mpc_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mpc_ms = float(t.item())
+    best_cost, best_idx = batch.decode_best(gbest)
+    mpc = {"value": world * n * Km / (mpc_ms * 1e-3), "unit": UNIT, "ms_per_step": mpc_ms / Km,
+           "steps": Km, "rollouts": world * n_roll, "rollout_len": ROLLOUT_LEN,
+           "argmin": {"cost": best_cost, "rollout": best_idx},
+           "collective": "nccl all_gather 16 B/rank + device arg-min" if world > 1 else "none (1 GPU)",
+           "hbm_frac_of_measured": None}
+
+    # ---- end to end through the C ABI with HOST buffers (copies inside the timed region) ---------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_tw, h_po, h_nu = pin(st["twists"]), pin(st["poses"]), pin(st["null_poses"])
+    h_out = {"wrench": torch.empty((n, 6), dtype=torch.float64).pin_memory(),
+             "autodyn": torch.empty((n, 6), dtype=torch.float64).pin_memory(),
+             "ctrl": torch.empty((n, 36), dtype=torch.float64).pin_memory(), "regressor": None}
+    Ke = max(3, min(K, 30))
+    for _ in range(3):
+        batch.evaluate_host(h_tw, h_po, h_nu, None, FULL, out=h_out)
+    barrier()
+    l0 = batch.handle.launch_count
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        batch.evaluate_host(h_tw, h_po, h_nu, None, FULL, out=h_out)
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = batch.handle.launch_count - l0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * n * Ke / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(n * 30 * 8), "d2h_bytes_per_step": int(n * 48 * 8),
+           "ms_per_step": e2e_s / Ke * 1e3, "steps": Ke, "launches_per_step": e2e_launches / Ke,
+           "api": "blf_ccm_eval_batch_host (AoS iDynTree-layout arrays in pinned host memory in/out)"}
+    sampler.stop_flag = True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = _peaks()
+    achieved = BYTES_FULL_UNIFORM * n / (avg_kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": _traffic(),
+                "kernel": "ccm_soa_kernel<WRENCH|AUTODYN|CTRL, uniform, 2 contacts/lane>",
+                "algorithmic_bytes_per_launch": BYTES_FULL_UNIFORM * n,
+                "avg_launch_ms": avg_kernel_ms, "median_launch_ms": kern_ms[len(kern_ms) // 2],
+                "best_launch_ms": kern_ms[0], "peak_source": peak_src}
+    mpc["hbm_frac_of_measured"] = (BYTES_FULL_UNIFORM * n + 8 * n_roll) / (mpc_ms / Km * 1e-3) / 1e9 / peak \
+        if world == 1 else None
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, passes, spent = cpu_reference_pass(st, cores, min_seconds=3.0)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"best of {passes} passes over the same {n}-state batch "
+                                  f"({spent:.1f} s wall x {cores} threads), oracle per-instance path"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "evals_per_step_per_gpu": n, "evals_per_step": world * n,
+                   "layout": "SoA planes in; SoA wrench/autodyn planes + dense row-major 6x6 out",
+                   "parallelism": f"rollout-sharded x{world}, no data-path collective",
+                   "l2": f"{NSETS} rotating input/output buffer sets; one step streams 491.5 MB "
+                         "(> 126 MB L2), no explicit flush"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "mpc": mpc,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only-main", action="store_true",
+                    help="profiling aid: run only the main timed loop (no mpc/e2e/cpu legs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,634 @@
+// ccm_capi.cu -- implementation of include/blf_ccm.h: argument checking, kernel dispatch,
+// persistent-grid sizing, the pipelined host-buffer entry point and the optional NCCL exchange.
+// No CPU evaluation path exists in this library.
+#include "../../include/blf_ccm.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "ccm_kernels.cuh"
+
+using namespace blfccm;
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                    \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(BLF_CCM_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+
+static constexpr int kHostSlots = 3;
+static constexpr int kMaxPartials = 8192;
+
+struct KernelInfo {
+    int blocks_per_sm = 0;
+};
+
+struct blf_ccm_handle {
+    unsigned magic = 0xB1FCC3A1u;
+    int device = -1;
+    int sm_count = 0;
+    bool have_params = false;
+    double length = 0, width = 0, spring = 0, damper = 0;
+    Prm uni{};
+    int last_path = BLF_CCM_PATH_NONE;
+    long long launches = 0;
+    std::map<const void*, KernelInfo> kinfo;
+    // rollout scratch
+    CostIdx* partials = nullptr;
+    unsigned int* counter = nullptr;
+    // host pipeline
+    cudaStream_t hstream[kHostSlots] = {};
+    double* hbuf[kHostSlots] = {};
+    long long hchunk = 0;      // contacts per chunk the slots are sized for
+    size_t hbytes = 0;
+    long long host_chunk_pref = 32768;
+    // tuning overrides (environment, read once at create; 0 = automatic)
+    int tune_cpt = 0;            // BLF_CCM_TUNE_CPT: 1 or 2 contacts per lane in the SoA kernel
+    int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM: cap on resident CTAs/SM; -1 = one tile per warp
+};
+
+static int env_int(const char* name)
+{
+    const char* v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+
+static bool valid(const blf_ccm_handle* h) { return h && h->magic == 0xB1FCC3A1u; }
+
+#define CHECK_HANDLE(h)                                                        \
+    if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle"); \
+    CUDA_TRY(cudaSetDevice((h)->device))
+
+extern "C" const char* blf_ccm_version(void) { return "blf_ccm 0.1.0 (sm_100a)"; }
+extern "C" const char* blf_ccm_last_error(void) { return g_err; }
+
+extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
+{
+    if (!out) return fail(BLF_CCM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(BLF_CCM_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); this backend has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count)
+        return fail(BLF_CCM_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(BLF_CCM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a",
+                    device, prop.major, prop.minor);
+    blf_ccm_handle* h = new (std::nothrow) blf_ccm_handle();
+    if (!h) return fail(BLF_CCM_ERR_INVALID_ARG, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->tune_cpt = env_int("BLF_CCM_TUNE_CPT");
+    h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
+    CUDA_TRY(cudaMalloc(&h->partials, sizeof(CostIdx) * kMaxPartials));
+    CUDA_TRY(cudaMalloc(&h->counter, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(h->counter, 0, sizeof(unsigned int)));
+    *out = h;
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
+{
+    if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
+    cudaSetDevice(h->device);
+    for (int s = 0; s < kHostSlots; ++s) {
+        if (h->hstream[s]) cudaStreamDestroy(h->hstream[s]);
+        if (h->hbuf[s]) cudaFree(h->hbuf[s]);
+    }
+    cudaFree(h->partials);
+    cudaFree(h->counter);
+    h->magic = 0;
+    delete h;
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_set_uniform_params(blf_ccm_handle* h, double length, double width,
+                                          double spring_coeff, double damper_coeff)
+{
+    if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
+    h->length = length;
+    h->width = width;
+    h->spring = spring_coeff;
+    h->damper = damper_coeff;
+    h->uni = make_prm(length, width, spring_coeff, damper_coeff);
+    h->have_params = true;
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_last_path(const blf_ccm_handle* h) { return valid(h) ? h->last_path : BLF_CCM_PATH_NONE; }
+extern "C" int64_t blf_ccm_launch_count(const blf_ccm_handle* h) { return valid(h) ? h->launches : -1; }
+extern "C" int blf_ccm_device(const blf_ccm_handle* h) { return valid(h) ? h->device : -1; }
+extern "C" int blf_ccm_sm_count(const blf_ccm_handle* h) { return valid(h) ? h->sm_count : -1; }
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+
+template <typename K>
+static int persistent_blocks(blf_ccm_handle* h, K kernel, int threads, size_t smem, int* out)
+{
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto it = h->kinfo.find(key);
+    if (it == h->kinfo.end()) {
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+        KernelInfo ki;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, kernel, threads,
+                                                               smem));
+        if (ki.blocks_per_sm < 1)
+            return fail(BLF_CCM_ERR_CUDA, "kernel does not fit on an SM (threads %d, smem %zu)",
+                        threads, smem);
+        it = h->kinfo.emplace(key, ki).first;
+    }
+    int per_sm = it->second.blocks_per_sm;
+    if (h->tune_blocks_per_sm > 0) per_sm = std::min(per_sm, h->tune_blocks_per_sm);
+    *out = h->tune_blocks_per_sm < 0 ? 0x7fffffff : per_sm * h->sm_count;
+    return BLF_CCM_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+// compile-time dispatch over the 15 non-empty output masks
+template <template <unsigned, bool> class F, bool HET, typename... Args>
+static int dispatch_mask(unsigned mask, Args&&... args)
+{
+    switch (mask) {
+#define BLFCCM_CASE(M) \
+    case M:            \
+        return F<M, HET>::run(std::forward<Args>(args)...);
+        BLFCCM_CASE(1) BLFCCM_CASE(2) BLFCCM_CASE(3) BLFCCM_CASE(4) BLFCCM_CASE(5) BLFCCM_CASE(6)
+        BLFCCM_CASE(7) BLFCCM_CASE(8) BLFCCM_CASE(9) BLFCCM_CASE(10) BLFCCM_CASE(11)
+        BLFCCM_CASE(12) BLFCCM_CASE(13) BLFCCM_CASE(14) BLFCCM_CASE(15)
+#undef BLFCCM_CASE
+    default:
+        return fail(BLF_CCM_ERR_INVALID_ARG, "out_mask %u has no valid output bit", mask);
+    }
+}
+
+// ---- SoA -----------------------------------------------------------------------------------------
+
+template <unsigned MASK, bool HET>
+struct SoaLaunch {
+    static int run(blf_ccm_handle* h, const SoaArgs& a, bool vec, cudaStream_t st)
+    {
+        constexpr int threads = 128;
+        if (vec) {
+            constexpr int TILE = 64;
+            const size_t smem = (MASK & M_CTRL) ? size_t(threads / 32) * TILE * 288 : 0;
+            auto k = ccm_soa_kernel<MASK, HET, 2>;
+            int cap = 0;
+            if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
+            const long long tiles = (a.n + TILE - 1) / TILE;
+            const long long want = (tiles + threads / 32 - 1) / (threads / 32);
+            const int grid = static_cast<int>(std::min<long long>(want, cap));
+            k<<<grid, threads, smem, st>>>(a);
+        } else {
+            constexpr int TILE = 32;
+            const size_t smem = (MASK & M_CTRL) ? size_t(threads / 32) * TILE * 288 : 0;
+            auto k = ccm_soa_kernel<MASK, HET, 1>;
+            int cap = 0;
+            if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
+            const long long tiles = (a.n + TILE - 1) / TILE;
+            const long long want = (tiles + threads / 32 - 1) / (threads / 32);
+            const int grid = static_cast<int>(std::min<long long>(want, cap));
+            k<<<grid, threads, smem, st>>>(a);
+        }
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        return BLF_CCM_OK;
+    }
+};
+
+static int fill_soa_args(blf_ccm_handle* h, long long n, const double* const* in_planes,
+                         const double* const* param_planes, unsigned out_mask, unsigned compute_mask,
+                         double* const* wrench_planes, double* const* autodyn_planes, double* ctrl,
+                         double* const* regressor_planes, SoaArgs& a, bool& vec)
+{
+    if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
+    if (!in_planes) return fail(BLF_CCM_ERR_INVALID_ARG, "in_planes is NULL");
+    if (!param_planes && !h->have_params)
+        return fail(BLF_CCM_ERR_NOT_INITIALIZED,
+                    "no parameters: call blf_ccm_set_uniform_params or pass param_planes");
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    a.uni = h->uni;
+    vec = true;
+    const unsigned live = live_planes(compute_mask);
+    for (int i = 0; i < 30; ++i) {
+        if (!(live & (1u << i))) continue;
+        if (!in_planes[i]) return fail(BLF_CCM_ERR_INVALID_ARG, "in_planes[%d] is NULL but live for out_mask %u", i, out_mask);
+        if (!aligned8(in_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "in_planes[%d] not 8-byte aligned", i);
+        a.in[i] = in_planes[i];
+        vec = vec && aligned16(in_planes[i]);
+    }
+    if (param_planes)
+        for (int i = 0; i < 4; ++i) {
+            if (!param_planes[i] || !aligned8(param_planes[i]))
+                return fail(BLF_CCM_ERR_INVALID_ARG, "param_planes[%d] NULL or misaligned", i);
+            a.prm[i] = param_planes[i];
+            vec = vec && aligned16(param_planes[i]);
+        }
+    auto take = [&](double* const* src, double** dst, int cnt, const char* what) -> int {
+        if (!src) return fail(BLF_CCM_ERR_INVALID_ARG, "%s is NULL but requested by out_mask", what);
+        for (int i = 0; i < cnt; ++i) {
+            if (!src[i] || !aligned8(src[i]))
+                return fail(BLF_CCM_ERR_INVALID_ARG, "%s[%d] NULL or misaligned", what, i);
+            dst[i] = src[i];
+            vec = vec && aligned16(src[i]);
+        }
+        return BLF_CCM_OK;
+    };
+    if (out_mask & BLF_CCM_WRENCH)
+        if (int rc = take(wrench_planes, a.wrench, 6, "wrench_planes")) return rc;
+    if (out_mask & BLF_CCM_AUTODYN)
+        if (int rc = take(autodyn_planes, a.autodyn, 6, "autodyn_planes")) return rc;
+    if (out_mask & BLF_CCM_REGRESSOR)
+        if (int rc = take(regressor_planes, a.reg, 12, "regressor_planes")) return rc;
+    if (out_mask & BLF_CCM_CTRL) {
+        if (!ctrl || !aligned8(ctrl)) return fail(BLF_CCM_ERR_INVALID_ARG, "ctrl NULL or misaligned");
+        a.ctrl = ctrl;
+        a.ctrl_bulk = aligned16(ctrl) ? 1 : 0;
+        vec = vec && a.ctrl_bulk;
+    }
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_eval_batch_soa(blf_ccm_handle* h, int64_t n, const double* const* in_planes,
+                                      const double* const* param_planes, unsigned out_mask,
+                                      double* const* wrench_planes, double* const* autodyn_planes,
+                                      double* ctrl, double* const* regressor_planes, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (out_mask == 0 || out_mask > 15u) return fail(BLF_CCM_ERR_INVALID_ARG, "out_mask %u invalid", out_mask);
+    if (n == 0) return BLF_CCM_OK;  // empty batch: nothing to read, nothing to write
+    SoaArgs a;
+    bool vec = false;
+    if (int rc = fill_soa_args(h, n, in_planes, param_planes, out_mask, out_mask, wrench_planes,
+                               autodyn_planes, ctrl, regressor_planes, a, vec))
+        return rc;
+    if (h->tune_cpt == 1) vec = false;
+    h->last_path = vec ? BLF_CCM_PATH_VEC128 : BLF_CCM_PATH_SCALAR64;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (param_planes) return dispatch_mask<SoaLaunch, true>(out_mask, h, a, vec, st);
+    return dispatch_mask<SoaLaunch, false>(out_mask, h, a, vec, st);
+}
+
+// ---- AoS -----------------------------------------------------------------------------------------
+
+template <unsigned MASK, bool HET>
+struct AosLaunch {
+    static int run(blf_ccm_handle* h, const AosArgs& a, bool bulk, cudaStream_t st)
+    {
+        if (bulk) {
+            constexpr int threads = 64;
+            const size_t smem = size_t(threads / 32) * AosSmem<MASK, HET>::bytes;
+            auto k = ccm_aos_kernel<MASK, HET>;
+            int cap = 0;
+            if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
+            const long long tiles = (a.n + 31) / 32;
+            const long long want = (tiles + threads / 32 - 1) / (threads / 32);
+            const int grid = static_cast<int>(std::min<long long>(want, cap));
+            k<<<grid, threads, smem, st>>>(a);
+        } else {
+            constexpr int threads = 128;
+            auto k = ccm_aos_scalar_kernel<MASK, HET>;
+            int cap = 0;
+            if (int rc = persistent_blocks(h, k, threads, 0, &cap)) return rc;
+            const long long want = (a.n + threads - 1) / threads;
+            const int grid = static_cast<int>(std::min<long long>(want, cap));
+            k<<<grid, threads, 0, st>>>(a);
+        }
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        return BLF_CCM_OK;
+    }
+};
+
+static int launch_aos(blf_ccm_handle* h, long long n, const double* twists, const double* poses,
+                      const double* null_poses, const blf_ccm_params* params, unsigned out_mask,
+                      double* wrench, double* autodyn, double* ctrl, double* regressor,
+                      cudaStream_t st)
+{
+    if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
+    if (out_mask == 0 || out_mask > 15u) return fail(BLF_CCM_ERR_INVALID_ARG, "out_mask %u invalid", out_mask);
+    if (n == 0) return BLF_CCM_OK;  // empty batch
+    if (!params && !h->have_params)
+        return fail(BLF_CCM_ERR_NOT_INITIALIZED,
+                    "no parameters: call blf_ccm_set_uniform_params or pass params");
+    const bool need_state = (out_mask & (BLF_CCM_WRENCH | BLF_CCM_AUTODYN | BLF_CCM_REGRESSOR)) != 0;
+    bool bulk = true;
+    auto chk = [&](const void* p, bool needed, const char* what) -> int {
+        if (!needed) return BLF_CCM_OK;
+        if (!p) return fail(BLF_CCM_ERR_INVALID_ARG, "%s is NULL but required by out_mask %u", what, out_mask);
+        if (!aligned8(p)) return fail(BLF_CCM_ERR_INVALID_ARG, "%s not 8-byte aligned", what);
+        bulk = bulk && aligned16(p);
+        return BLF_CCM_OK;
+    };
+    if (int rc = chk(poses, true, "poses")) return rc;
+    if (int rc = chk(twists, need_state, "twists")) return rc;
+    if (int rc = chk(null_poses, need_state, "null_poses")) return rc;
+    if (int rc = chk(params, params != nullptr, "params")) return rc;
+    if (int rc = chk(wrench, out_mask & BLF_CCM_WRENCH, "wrench")) return rc;
+    if (int rc = chk(autodyn, out_mask & BLF_CCM_AUTODYN, "autodyn")) return rc;
+    if (int rc = chk(ctrl, out_mask & BLF_CCM_CTRL, "ctrl")) return rc;
+    if (int rc = chk(regressor, out_mask & BLF_CCM_REGRESSOR, "regressor")) return rc;
+    h->last_path = bulk ? BLF_CCM_PATH_VEC128 : BLF_CCM_PATH_SCALAR64;
+    AosArgs a;
+    memset(&a, 0, sizeof(a));
+    a.twists = twists;
+    a.poses = poses;
+    a.nulls = null_poses;
+    a.prm = reinterpret_cast<const double*>(params);
+    a.wrench = wrench;
+    a.autodyn = autodyn;
+    a.ctrl = ctrl;
+    a.reg = regressor;
+    a.uni = h->uni;
+    a.n = n;
+    if (params) return dispatch_mask<AosLaunch, true>(out_mask, h, a, bulk, st);
+    return dispatch_mask<AosLaunch, false>(out_mask, h, a, bulk, st);
+}
+
+extern "C" int blf_ccm_eval_batch_aos(blf_ccm_handle* h, int64_t n, const double* twists,
+                                      const double* poses, const double* null_poses,
+                                      const blf_ccm_params* params, unsigned out_mask,
+                                      double* wrench, double* autodyn, double* ctrl,
+                                      double* regressor, void* stream)
+{
+    CHECK_HANDLE(h);
+    return launch_aos(h, n, twists, poses, null_poses, params, out_mask, wrench, autodyn, ctrl,
+                      regressor, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host buffers: chunked, three slots, copies and kernels overlapped ---------------------------
+
+extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const double* twists,
+                                       const double* poses, const double* null_poses,
+                                       const blf_ccm_params* params, unsigned out_mask,
+                                       double* wrench, double* autodyn, double* ctrl,
+                                       double* regressor)
+{
+    CHECK_HANDLE(h);
+    if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
+    if (out_mask == 0 || out_mask > 15u) return fail(BLF_CCM_ERR_INVALID_ARG, "out_mask %u invalid", out_mask);
+    if (n == 0) return BLF_CCM_OK;
+    const bool need_state = (out_mask & (BLF_CCM_WRENCH | BLF_CCM_AUTODYN | BLF_CCM_REGRESSOR)) != 0;
+    if (!poses || (need_state && (!twists || !null_poses)))
+        return fail(BLF_CCM_ERR_INVALID_ARG, "an input array required by out_mask %u is NULL", out_mask);
+    if (((out_mask & BLF_CCM_WRENCH) && !wrench) || ((out_mask & BLF_CCM_AUTODYN) && !autodyn) ||
+        ((out_mask & BLF_CCM_CTRL) && !ctrl) || ((out_mask & BLF_CCM_REGRESSOR) && !regressor))
+        return fail(BLF_CCM_ERR_INVALID_ARG, "an output array requested by out_mask %u is NULL", out_mask);
+    if (!params && !h->have_params)
+        return fail(BLF_CCM_ERR_NOT_INITIALIZED,
+                    "no parameters: call blf_ccm_set_uniform_params or pass params");
+
+    // slot layout in doubles per contact (every section starts 16-byte aligned: all even counts)
+    const long long chunk = std::min<long long>(n, h->host_chunk_pref);
+    const size_t per_contact = 6 + 12 + 12 + 4 + 6 + 6 + 36 + 12;
+    const size_t need = size_t(chunk) * per_contact * sizeof(double);
+    if (h->hbytes < need) {
+        for (int s = 0; s < kHostSlots; ++s) {
+            if (h->hbuf[s]) CUDA_TRY(cudaFree(h->hbuf[s]));
+            h->hbuf[s] = nullptr;
+        }
+        for (int s = 0; s < kHostSlots; ++s) CUDA_TRY(cudaMalloc(&h->hbuf[s], need));
+        h->hbytes = need;
+    }
+    h->hchunk = chunk;
+    for (int s = 0; s < kHostSlots; ++s)
+        if (!h->hstream[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream[s], cudaStreamNonBlocking));
+
+    int slot = 0;
+    for (long long off = 0; off < n; off += chunk, slot = (slot + 1) % kHostSlots) {
+        const long long c = std::min<long long>(chunk, n - off);
+        cudaStream_t st = h->hstream[slot];
+        double* b = h->hbuf[slot];
+        double* d_tw = b;
+        double* d_po = d_tw + chunk * 6;
+        double* d_nu = d_po + chunk * 12;
+        double* d_pr = d_nu + chunk * 12;
+        double* d_w = d_pr + chunk * 4;
+        double* d_a = d_w + chunk * 6;
+        double* d_c = d_a + chunk * 6;
+        double* d_r = d_c + chunk * 36;
+        const size_t D = sizeof(double);
+        if (need_state) {
+            CUDA_TRY(cudaMemcpyAsync(d_tw, twists + off * 6, c * 6 * D, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_nu, null_poses + off * 12, c * 12 * D, cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_po, poses + off * 12, c * 12 * D, cudaMemcpyHostToDevice, st));
+        if (params)
+            CUDA_TRY(cudaMemcpyAsync(d_pr, params + off, c * 4 * D, cudaMemcpyHostToDevice, st));
+        if (int rc = launch_aos(h, c, d_tw, d_po, d_nu,
+                                params ? reinterpret_cast<const blf_ccm_params*>(d_pr) : nullptr,
+                                out_mask, d_w, d_a, d_c, d_r, st))
+            return rc;
+        if (out_mask & BLF_CCM_WRENCH)
+            CUDA_TRY(cudaMemcpyAsync(wrench + off * 6, d_w, c * 6 * D, cudaMemcpyDeviceToHost, st));
+        if (out_mask & BLF_CCM_AUTODYN)
+            CUDA_TRY(cudaMemcpyAsync(autodyn + off * 6, d_a, c * 6 * D, cudaMemcpyDeviceToHost, st));
+        if (out_mask & BLF_CCM_CTRL)
+            CUDA_TRY(cudaMemcpyAsync(ctrl + off * 36, d_c, c * 36 * D, cudaMemcpyDeviceToHost, st));
+        if (out_mask & BLF_CCM_REGRESSOR)
+            CUDA_TRY(cudaMemcpyAsync(regressor + off * 12, d_r, c * 12 * D, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kHostSlots; ++s) CUDA_TRY(cudaStreamSynchronize(h->hstream[s]));
+    return BLF_CCM_OK;
+}
+
+// tuning knob for the host pipeline (not part of the reference-facing surface)
+extern "C" int blf_ccm_set_host_chunk(blf_ccm_handle* h, int64_t contacts)
+{
+    if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
+    if (contacts < 32) return fail(BLF_CCM_ERR_INVALID_ARG, "chunk must be >= 32 contacts");
+    h->host_chunk_pref = contacts;
+    return BLF_CCM_OK;
+}
+
+// ---- surface points ------------------------------------------------------------------------------
+
+extern "C" int blf_ccm_eval_surface_points(blf_ccm_handle* h, const double* host_twist,
+                                           const double* host_pose, const double* host_null_pose,
+                                           int64_t m, const double* xy, double* force_out,
+                                           double* torque_out, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!h->have_params) return fail(BLF_CCM_ERR_NOT_INITIALIZED, "call blf_ccm_set_uniform_params first");
+    if (m < 0 || !host_twist || !host_pose || !host_null_pose || (m > 0 && !xy))
+        return fail(BLF_CCM_ERR_INVALID_ARG, "NULL input or m < 0");
+    if (m == 0) return BLF_CCM_OK;
+    PointArgs a;
+    memcpy(a.tw, host_twist, sizeof(a.tw));
+    memcpy(a.pose, host_pose, sizeof(a.pose));
+    memcpy(a.null, host_null_pose, sizeof(a.null));
+    a.length = h->length;
+    a.width = h->width;
+    a.k = h->spring;
+    a.b = h->damper;
+    a.xy = xy;
+    a.force = force_out;
+    a.torque = torque_out;
+    a.m = m;
+    const int threads = 128;
+    const int grid = static_cast<int>(std::min<long long>((m + threads - 1) / threads, 8LL * h->sm_count));
+    ccm_surface_points_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return BLF_CCM_OK;
+}
+
+// ---- rollout cost + arg-min ----------------------------------------------------------------------
+
+template <unsigned OUT, bool HET>
+struct RolloutLaunch {
+    static int run(blf_ccm_handle* h, RolloutArgs& ra, cudaStream_t st)
+    {
+        constexpr int threads = 128;
+        const size_t smem = (OUT & M_CTRL) ? size_t(threads / 32) * 32 * 288 : 0;
+        auto k = ccm_rollout_kernel<OUT, HET>;
+        int cap = 0;
+        if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
+        const long long want = (ra.n_rollouts + threads / 32 - 1) / (threads / 32);
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, std::min(cap, kMaxPartials))));
+        k<<<grid, threads, smem, st>>>(ra);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        return BLF_CCM_OK;
+    }
+};
+
+template <bool HET>
+static int dispatch_rollout(unsigned out, blf_ccm_handle* h, RolloutArgs& ra, cudaStream_t st)
+{
+    switch (out) {  // outputs written besides the cost: any subset of wrench|autodyn|ctrl
+    case 0: return RolloutLaunch<0, HET>::run(h, ra, st);
+    case 1: return RolloutLaunch<1, HET>::run(h, ra, st);
+    case 2: return RolloutLaunch<2, HET>::run(h, ra, st);
+    case 3: return RolloutLaunch<3, HET>::run(h, ra, st);
+    case 4: return RolloutLaunch<4, HET>::run(h, ra, st);
+    case 5: return RolloutLaunch<5, HET>::run(h, ra, st);
+    case 6: return RolloutLaunch<6, HET>::run(h, ra, st);
+    case 7: return RolloutLaunch<7, HET>::run(h, ra, st);
+    default: return fail(BLF_CCM_ERR_INVALID_ARG, "rollout out_mask %u: only wrench|autodyn|ctrl", out);
+    }
+}
+
+extern "C" int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_rollouts,
+                                               int64_t rollout_len, const double* const* in_planes,
+                                               const double* const* param_planes, unsigned out_mask,
+                                               double* const* wrench_planes,
+                                               double* const* autodyn_planes, double* ctrl,
+                                               const double* host_wrench_ref,
+                                               const double* host_weights, int64_t index_base,
+                                               double* cost, void* best, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (n_rollouts < 0 || rollout_len <= 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n_rollouts < 0 or rollout_len <= 0");
+    if (out_mask > 7u) return fail(BLF_CCM_ERR_INVALID_ARG, "rollout out_mask %u: only wrench|autodyn|ctrl", out_mask);
+    if (!host_wrench_ref || !host_weights || !best)
+        return fail(BLF_CCM_ERR_INVALID_ARG, "wrench_ref, weights and best are required");
+    if (!aligned16(best)) return fail(BLF_CCM_ERR_INVALID_ARG, "best must be 16-byte aligned");
+    if (n_rollouts == 0)  // nothing to compare: best = (+inf, -1)
+        return blf_ccm_argmin_pairs(h, 0, best, best, stream);
+    RolloutArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    bool vec = false;
+    if (int rc = fill_soa_args(h, n_rollouts * rollout_len, in_planes, param_planes, out_mask,
+                               out_mask | BLF_CCM_WRENCH, wrench_planes, autodyn_planes, ctrl,
+                               nullptr, ra.soa, vec))
+        return rc;
+    ra.n_rollouts = n_rollouts;
+    ra.rollout_len = rollout_len;
+    ra.index_base = index_base;
+    memcpy(ra.ref, host_wrench_ref, sizeof(ra.ref));
+    ra.wf = host_weights[0];
+    ra.wt = host_weights[1];
+    ra.cost = cost;
+    ra.partials = h->partials;
+    ra.counter = h->counter;
+    ra.best = static_cast<CostIdx*>(best);
+    h->last_path = BLF_CCM_PATH_SCALAR64;  // coalesced 64-bit plane accesses (rollouts start anywhere)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (param_planes) return dispatch_rollout<true>(out_mask, h, ra, st);
+    return dispatch_rollout<false>(out_mask, h, ra, st);
+}
+
+extern "C" int blf_ccm_argmin_pairs(blf_ccm_handle* h, int n_pairs, const void* pairs, void* best,
+                                    void* stream)
+{
+    CHECK_HANDLE(h);
+    if (n_pairs < 0 || !pairs || !best) return fail(BLF_CCM_ERR_INVALID_ARG, "NULL pairs/best or n_pairs < 0");
+    ccm_argmin_pairs_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const CostIdx*>(pairs), n_pairs, static_cast<CostIdx*>(best));
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return BLF_CCM_OK;
+}
+
+// ---- optional NCCL exchange (dlopen: no link-time dependency) ------------------------------------
+
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+
+extern "C" int blf_ccm_argmin_allgather_nccl(blf_ccm_handle* h, void* comm, int nranks,
+                                             const void* best, void* gathered, void* global_best,
+                                             void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!comm || nranks <= 0 || !best || !gathered || !global_best)
+        return fail(BLF_CCM_ERR_INVALID_ARG, "NULL comm/buffers or nranks <= 0");
+    static nccl_allgather_fn allgather = nullptr;
+    static nccl_errstr_fn errstr = nullptr;
+    if (!allgather) {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return fail(BLF_CCM_ERR_NCCL, "libnccl not found: %s", dlerror());
+        allgather = reinterpret_cast<nccl_allgather_fn>(dlsym(lib, "ncclAllGather"));
+        errstr = reinterpret_cast<nccl_errstr_fn>(dlsym(lib, "ncclGetErrorString"));
+        if (!allgather) return fail(BLF_CCM_ERR_NCCL, "ncclAllGather not found in libnccl");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // 16 bytes per rank as ncclInt8 (datatype 0)
+    const int rc = allgather(best, gathered, 16, /*ncclInt8*/ 0, comm, st);
+    if (rc != 0) return fail(BLF_CCM_ERR_NCCL, "ncclAllGather: %s", errstr ? errstr(rc) : "error");
+    return blf_ccm_argmin_pairs(h, nranks, gathered, global_best, stream);
+}

@@ -1,0 +1,91 @@
+// ccm_ptx.cuh -- thin inline-PTX wrappers for sm_100a: mbarrier, 1-D bulk async copies (TMA
+// engine; SASS: UBLKCP), proxy fences.  All shared-memory operands are 32-bit shared-window
+// addresses obtained with __cvta_generic_to_shared.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace blfccm {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+// make the init visible to the async proxy before the first bulk copy signals the barrier
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared::cta bulk copy, completion counted in bytes on an mbarrier.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+// shared::cta -> global bulk copy, tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// all committed groups have finished READING shared memory (buffers reusable)
+__device__ __forceinline__ void bulk_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// all committed groups complete (writes performed)
+__device__ __forceinline__ void bulk_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// order this thread's generic-proxy shared-memory writes before subsequent async-proxy reads
+__device__ __forceinline__ void fence_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+}  // namespace ptx
+}  // namespace blfccm

@@ -1,0 +1,189 @@
+/*
+ * blf_ccm.h -- C ABI of the B200 (sm_100a) backend for ContactModels::ContinuousContactModel.
+ *
+ * This is the drop-in boundary: host code (the C++17 facade in
+ * bipedal_locomotion_framework_b200/cpp, or any FFI) reaches CUDA only through these functions.
+ * Plain pointers and sizes, no C++/torch types.  There is NO CPU fallback behind any of them: with
+ * no CUDA device blf_ccm_create() fails and every other call returns BLF_CCM_ERR_INVALID_HANDLE.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference tree):
+ *   blf_ccm_set_uniform_params   ContinuousContactModel::initializePrivate, the four doubles read
+ *                                from the handler  src/ContactModels/src/ContinuousContactModel.cpp:24-65
+ *   blf_ccm_eval_batch_*         per state: ContactModel::setState (src/ContactModels/src/ContactModel.cpp:35-48),
+ *                                setNullForceTransform (:23-33), getContactWrench (:50-59 ->
+ *                                ContinuousContactModel.cpp:79-108), getAutonomousDynamics (:61-70 ->
+ *                                :110-146), getControlMatrix (:72-81 -> :148-171), getRegressor
+ *                                (:83-92 -> :223-254); the loop over contacts is the caller's, e.g.
+ *                                src/System/src/FloatingBaseSystemDynamics.cpp:199-226
+ *   blf_ccm_eval_surface_points  ContinuousContactModel::getForceAtPoint / getTorqueGeneratedAtPoint
+ *                                ContinuousContactModel.cpp:173-221
+ *   blf_ccm_rollout_*            no reference equivalent (sampling-MPC cost + arg-min)
+ *
+ * Data layouts (all FP64; identical to iDynTree's so arrays of iDynTree objects can be passed):
+ *   twist      6  doubles: linear xyz, angular xyz (mixed representation)  iDynTree::Twist
+ *   pose       12 doubles: position xyz, rotation 3x3 ROW-major           iDynTree::Transform
+ *   wrench     6  doubles: force xyz, torque xyz                           iDynTree::Wrench
+ *   autodyn    6  doubles                                                  iDynTree::Vector6
+ *   ctrl       36 doubles, dense ROW-major 6x6, structural zeros = +0.0    iDynTree::Matrix6x6
+ *   regressor  12 doubles, ROW-major 6x2                                   iDynTree::MatrixDynSize
+ *   SoA input planes, each n doubles, index = BLF_CCM_PLANE_*:
+ *     0-2 v | 3-5 omega | 6-8 p | 9-17 R row-major | 18-20 p0 | 21-29 R0 row-major
+ *     Planes that cannot affect the requested outputs may be NULL: R0's third column (23,26,29)
+ *     always; R02,R12 (11,14) unless AUTODYN is requested.
+ *
+ * Pointers are DEVICE pointers unless the function name says host.  The arrays-of-pointers
+ * themselves (in_planes etc.) are HOST arrays of device pointers.  Alignment: 8 bytes is always
+ * accepted; when every pointer is 16-byte aligned the 128-bit load/store and bulk-copy (TMA) paths
+ * are taken, otherwise a 64-bit path is dispatched (same results; blf_ccm_last_path reports which).
+ *
+ * Threading: a handle is used from one host thread at a time; distinct handles are independent.
+ * Launches are asynchronous on the caller's stream (void* = cudaStream_t, NULL = default stream).
+ * Errors: 0 = ok, negative = blf_ccm_status; text via blf_ccm_last_error(); nothing throws.
+ */
+#ifndef BLF_CCM_H
+#define BLF_CCM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define BLF_CCM_API
+#else
+#define BLF_CCM_API __attribute__((visibility("default")))
+#endif
+
+typedef struct blf_ccm_handle blf_ccm_handle;
+
+typedef enum {
+    BLF_CCM_OK = 0,
+    BLF_CCM_ERR_INVALID_ARG = -1,
+    BLF_CCM_ERR_INVALID_HANDLE = -2,
+    BLF_CCM_ERR_CUDA = -3,
+    BLF_CCM_ERR_NO_DEVICE = -4,
+    BLF_CCM_ERR_NOT_INITIALIZED = -5,
+    BLF_CCM_ERR_NCCL = -6
+} blf_ccm_status;
+
+/* out_mask bits */
+enum {
+    BLF_CCM_WRENCH = 1,    /* getContactWrench      */
+    BLF_CCM_AUTODYN = 2,   /* getAutonomousDynamics */
+    BLF_CCM_CTRL = 4,      /* getControlMatrix      */
+    BLF_CCM_REGRESSOR = 8  /* getRegressor          */
+};
+
+enum { BLF_CCM_NUM_IN_PLANES = 30, BLF_CCM_NUM_PARAM_PLANES = 4 };
+
+/* per-contact parameters for the AoS entry points (keys of initializePrivate, same order as
+ * blf_ccm_set_uniform_params) */
+typedef struct {
+    double length;
+    double width;
+    double spring_coeff;
+    double damper_coeff;
+} blf_ccm_params;
+
+/* code path taken by the last evaluation on a handle */
+enum {
+    BLF_CCM_PATH_NONE = 0,
+    BLF_CCM_PATH_VEC128 = 1, /* 128-bit loads/stores + bulk-copy staging */
+    BLF_CCM_PATH_SCALAR64 = 2 /* 64-bit path for 8-byte-aligned buffers   */
+};
+
+BLF_CCM_API const char* blf_ccm_version(void);
+BLF_CCM_API const char* blf_ccm_last_error(void);
+
+/* Create a handle bound to CUDA device `device`.  Fails with BLF_CCM_ERR_NO_DEVICE when there is
+ * no usable device (there is no CPU path). */
+BLF_CCM_API int blf_ccm_create(int device, blf_ccm_handle** out);
+BLF_CCM_API int blf_ccm_destroy(blf_ccm_handle* h);
+
+/* length, width, spring_coeff, damper_coeff for every contact of subsequent evaluations that pass
+ * no per-contact parameters.  No range validation, as in the reference. */
+BLF_CCM_API int blf_ccm_set_uniform_params(blf_ccm_handle* h, double length, double width,
+                                           double spring_coeff, double damper_coeff);
+
+/* Structure-of-arrays evaluation.  wrench_planes[6], autodyn_planes[6], regressor_planes[12] are
+ * host arrays of device plane pointers (NULL when the bit is not in out_mask); ctrl is one dense
+ * n*36 array.  param_planes = NULL -> uniform parameters, else 4 planes length,width,spring,damper. */
+BLF_CCM_API int blf_ccm_eval_batch_soa(blf_ccm_handle* h, int64_t n,
+                                       const double* const* in_planes,
+                                       const double* const* param_planes, unsigned out_mask,
+                                       double* const* wrench_planes,
+                                       double* const* autodyn_planes, double* ctrl,
+                                       double* const* regressor_planes, void* stream);
+
+/* Array-of-structures evaluation: arrays of iDynTree-layout objects in, arrays of
+ * iDynTree-layout objects out.  twists n*6, poses n*12, null_poses n*12, params NULL or n structs;
+ * wrench n*6, autodyn n*6, ctrl n*36, regressor n*12 (NULL when not in out_mask). */
+BLF_CCM_API int blf_ccm_eval_batch_aos(blf_ccm_handle* h, int64_t n, const double* twists,
+                                       const double* poses, const double* null_poses,
+                                       const blf_ccm_params* params, unsigned out_mask,
+                                       double* wrench, double* autodyn, double* ctrl,
+                                       double* regressor, void* stream);
+
+/* Same as blf_ccm_eval_batch_aos but every pointer is a HOST pointer (pinned memory gives full
+ * PCIe speed; pageable works).  Chunks the batch, and overlaps host->device copies, the kernel and
+ * device->host copies on the handle's own streams; returns after the results are in host memory. */
+BLF_CCM_API int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const double* twists,
+                                        const double* poses, const double* null_poses,
+                                        const blf_ccm_params* params, unsigned out_mask,
+                                        double* wrench, double* autodyn, double* ctrl,
+                                        double* regressor);
+
+/* Contacts per chunk of the blf_ccm_eval_batch_host pipeline (default 32768; tuning knob). */
+BLF_CCM_API int blf_ccm_set_host_chunk(blf_ccm_handle* h, int64_t contacts);
+
+/* Surface-point forces of ONE contact state held in host memory (twist[6], pose[12],
+ * null_pose[12]), for m points xy (device, m*2): force_out / torque_out device m*3 (either may be
+ * NULL).  Zero outside |x| <= length/2, |y| <= width/2.  Uses the uniform parameters. */
+BLF_CCM_API int blf_ccm_eval_surface_points(blf_ccm_handle* h, const double* host_twist,
+                                            const double* host_pose, const double* host_null_pose,
+                                            int64_t m, const double* xy, double* force_out,
+                                            double* torque_out, void* stream);
+
+/*
+ * Sampling-MPC epilogue.  The batch is n_rollouts * rollout_len contact states, rollout-major
+ * (all evaluations of a rollout are contiguous).  One launch evaluates every state (outputs per
+ * out_mask exactly as blf_ccm_eval_batch_soa; out_mask may be 0 to keep only the cost), reduces
+ *   cost[r] = sum_e  weights[0]*|force_e - wrench_ref[0:3]|^2 + weights[1]*|torque_e - wrench_ref[3:6]|^2
+ * per rollout in a fixed order (deterministic), and arg-mins over the local rollouts with
+ * lowest-index tie-break.  cost (device, n_rollouts) may be NULL.  best (device, 2 x 8 bytes):
+ * best[0] = min cost as double, best[1] = rollout index as int64, offset by index_base (the first
+ * global rollout index owned by this rank).
+ */
+BLF_CCM_API int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_rollouts,
+                                                int64_t rollout_len,
+                                                const double* const* in_planes,
+                                                const double* const* param_planes,
+                                                unsigned out_mask, double* const* wrench_planes,
+                                                double* const* autodyn_planes, double* ctrl,
+                                                const double* host_wrench_ref,
+                                                const double* host_weights, int64_t index_base,
+                                                double* cost, void* best, void* stream);
+
+/* Combine per-rank (cost, index) pairs (device, n_pairs x 16 bytes, e.g. the all-gather of every
+ * rank's `best`) into the global arg-min with lowest-index tie-break; result to best (device, 16 B). */
+BLF_CCM_API int blf_ccm_argmin_pairs(blf_ccm_handle* h, int n_pairs, const void* pairs,
+                                     void* best, void* stream);
+
+/* Optional NCCL exchange of the 16-byte (cost,index) pair, for C/C++ hosts that own an
+ * ncclComm_t (void* comm).  libnccl is dlopen()ed on first use; BLF_CCM_ERR_NCCL if absent.
+ * In-place all-gather of `best` into gathered (device, nranks*16 B) then blf_ccm_argmin_pairs. */
+BLF_CCM_API int blf_ccm_argmin_allgather_nccl(blf_ccm_handle* h, void* comm, int nranks,
+                                              const void* best, void* gathered, void* global_best,
+                                              void* stream);
+
+/* Introspection */
+BLF_CCM_API int blf_ccm_last_path(const blf_ccm_handle* h);
+BLF_CCM_API int64_t blf_ccm_launch_count(const blf_ccm_handle* h); /* kernels launched so far */
+BLF_CCM_API int blf_ccm_device(const blf_ccm_handle* h);
+BLF_CCM_API int blf_ccm_sm_count(const blf_ccm_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLF_CCM_H */

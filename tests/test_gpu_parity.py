@@ -1,0 +1,419 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+bits, against the exact-rational golden fixtures, and through size-independent properties at
+BASELINE.json's full sizes.  Tolerance: 1e-12 norm-wise relative per 3-vector block (north_star),
+structural zeros of the control matrix exactly +0.0."""
+import os
+
+import numpy as np
+import pytest
+
+from bipedal_locomotion_framework_b200 import synthetic as syn
+from parity import TOL, assert_ctrl_structure, assert_parity
+
+pytestmark = pytest.mark.gpu
+
+NTHREADS = max(1, (os.cpu_count() or 1))
+W, A, Cc, R = 1, 2, 4, 8
+FULL = W | A | Cc
+KEYS = {W: "wrench", A: "autodyn", Cc: "ctrl", R: "regressor"}
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def batch(torch):
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    b = ContinuousContactModelBatch(0)
+    b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    return b
+
+
+def _dev(torch, a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _soa_inputs(torch, st):
+    planes = _dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+    prm = _dev(torch, st["params"].T) if st["params"] is not None else None
+    return planes, prm
+
+
+def _soa_out_to_aos(out):
+    r = {}
+    for key in ("wrench", "autodyn", "regressor"):
+        r[key] = None if out[key] is None else out[key].cpu().numpy().T.copy()
+    r["ctrl"] = None if out["ctrl"] is None else out["ctrl"].cpu().numpy()
+    return r
+
+
+def _aos_out(out):
+    return {k: (None if v is None else v.cpu().numpy()) for k, v in out.items()}
+
+
+def _check(got, ref, mask, what):
+    worst = 0.0
+    for bit, key in KEYS.items():
+        if mask & bit:
+            e, _ = assert_parity(got[key], ref[key], key, what=what + " ")
+            worst = max(worst, e)
+    if mask & Cc:
+        assert_ctrl_structure(got["ctrl"])
+    return worst
+
+
+# --- golden fixtures -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("layout", ["soa", "aos", "host"])
+def test_golden_vectors(torch, batch, golden, layout):
+    g = golden
+    st = {"twists": g["twists"], "poses": g["poses"], "null_poses": g["null_poses"],
+          "params": g["params"]}
+    mask = FULL | R
+    if layout == "soa":
+        planes, prm = _soa_inputs(torch, st)
+        got = _soa_out_to_aos(batch.evaluate_soa(planes, prm, mask))
+    elif layout == "aos":
+        got = _aos_out(batch.evaluate_aos(_dev(torch, st["twists"]), _dev(torch, st["poses"]),
+                                          _dev(torch, st["null_poses"]), _dev(torch, st["params"]),
+                                          mask))
+    else:
+        got = batch.evaluate_host(st["twists"], st["poses"], st["null_poses"], st["params"], mask)
+    for key in ("wrench", "autodyn", "ctrl"):
+        assert_parity(got[key], g[key], key, what=f"golden/{layout} ")
+    floor = np.full(g["twists"].shape[0], 1e-300)
+    floor[8] = 1e-6  # pose == null pose: the block cancels to exactly 0 (see test_oracle.py)
+    assert_parity(got["regressor"], g["regressor"], "regressor", floor=floor)
+    assert_ctrl_structure(got["ctrl"])
+
+
+# --- BASELINE.json configs ---------------------------------------------------------------------------
+
+def test_config2_one_million_wrench_only_soa(torch, batch, oracle):
+    """configs[1]: 2^20 random states, wrench only, uniform parameters, SoA."""
+    st = syn.make_states(1 << 20, seed=42 + 2)
+    planes, _ = _soa_inputs(torch, st)
+    got = _soa_out_to_aos(batch.evaluate_soa(planes, None, W))
+    assert batch.handle.last_path == 1  # 128-bit path
+    ref = oracle.eval_batch_states(st, mask=W, nthreads=NTHREADS)
+    _check(got, ref, W, "config2")
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_config3_mpc_rollout_batch_full(torch, batch, oracle, layout):
+    """configs[2]: 2 feet x 4096 samples x 100 steps, wrench + autonomous dynamics + control."""
+    n = 2 * 4096 * 100
+    st = syn.make_states(n, seed=42 + 3)
+    ref = oracle.eval_batch_states(st, mask=FULL, nthreads=NTHREADS)
+    if layout == "soa":
+        planes, _ = _soa_inputs(torch, st)
+        got = _soa_out_to_aos(batch.evaluate_soa(planes, None, FULL))
+    else:
+        got = _aos_out(batch.evaluate_aos(_dev(torch, st["twists"]), _dev(torch, st["poses"]),
+                                          _dev(torch, st["null_poses"]), None, FULL))
+    assert batch.handle.last_path == 1
+    _check(got, ref, FULL, f"config3/{layout}")
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_config4_heterogeneous_parameters(torch, batch, oracle, layout):
+    """configs[3] at a size the oracle finishes in seconds: per-contact length/width/spring/damper."""
+    n = (1 << 18) + 37
+    st = syn.make_states(n, seed=42 + 4, heterogeneous=True)
+    ref = oracle.eval_batch_states(st, mask=FULL | R, nthreads=NTHREADS)
+    if layout == "soa":
+        planes, prm = _soa_inputs(torch, st)
+        got = _soa_out_to_aos(batch.evaluate_soa(planes, prm, FULL | R))
+    else:
+        got = _aos_out(batch.evaluate_aos(_dev(torch, st["twists"]), _dev(torch, st["poses"]),
+                                          _dev(torch, st["null_poses"]), _dev(torch, st["params"]),
+                                          FULL | R))
+    _check(got, ref, FULL | R, f"config4/{layout}")
+
+
+def test_host_pipeline_matches_device_path(torch, batch, oracle):
+    """blf_ccm_eval_batch_host (chunked, overlapped copies) over several chunks + a ragged tail."""
+    n = 3 * 32768 + 4321
+    st = syn.make_states(n, seed=11, heterogeneous=True)
+    ref = oracle.eval_batch_states(st, mask=FULL, nthreads=NTHREADS)
+    got = batch.evaluate_host(st["twists"], st["poses"], st["null_poses"], st["params"], FULL)
+    _check(got, ref, FULL, "host")
+    got_u = batch.evaluate_host(st["twists"], st["poses"], st["null_poses"], None, W)
+    ref_u = oracle.eval_batch_aos(st["twists"], st["poses"], st["null_poses"], None,
+                                  syn.REFERENCE_TEST_PARAMS, W, NTHREADS)
+    _check(got_u, ref_u, W, "host/uniform")
+
+
+# --- edge cases ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 1000])
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_ragged_sizes(torch, batch, oracle, n, layout):
+    st = syn.make_states(max(n, 1), seed=5)
+    st = {k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    if layout == "soa":
+        planes = torch.empty((30, n), dtype=torch.float64, device="cuda")
+        if n:
+            planes.copy_(_dev(torch, syn.aos_to_planes(st["twists"], st["poses"],
+                                                       st["null_poses"])))
+        got = _soa_out_to_aos(batch.evaluate_soa(planes, None, FULL | R))
+    else:
+        mk = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        got = _aos_out(batch.evaluate_aos(mk(st["twists"]), mk(st["poses"]), mk(st["null_poses"]),
+                                          None, FULL | R))
+    if n == 0:
+        return
+    ref = oracle.eval_batch_aos(st["twists"], st["poses"], st["null_poses"], None,
+                                syn.REFERENCE_TEST_PARAMS, FULL | R, 1)
+    _check(got, ref, FULL | R, f"n={n}/{layout}")
+
+
+@pytest.mark.parametrize("mask", list(range(1, 16)))
+def test_every_output_mask_and_untouched_outputs(torch, batch, oracle, mask):
+    """Each of the 15 getter combinations; outputs not requested are not written."""
+    n = 777
+    st = syn.make_states(n, seed=9)
+    ref = oracle.eval_batch_states(st, mask=mask, nthreads=1)
+    planes, _ = _soa_inputs(torch, st)
+    sentinel = -123.25
+    out = batch.alloc_soa_outputs(n, 15)
+    for v in out.values():
+        v.fill_(sentinel)
+    call_out = {key: (out[key] if mask & bit else None) for bit, key in KEYS.items()}
+    batch.evaluate_soa(planes, None, mask, out=call_out)
+    got = _soa_out_to_aos(out)
+    _check(got, ref, mask, f"mask={mask}")
+    for bit, key in KEYS.items():
+        if not mask & bit:
+            assert np.all(got[key] == sentinel)
+    # AoS flavour of the same mask
+    aout = batch.evaluate_aos(_dev(torch, st["twists"]), _dev(torch, st["poses"]),
+                              _dev(torch, st["null_poses"]), None, mask)
+    _check(_aos_out(aout), ref, mask, f"mask={mask}/aos")
+
+
+def test_dead_planes_may_be_null(torch, batch, oracle):
+    """Planes that cannot affect the requested outputs are never read (NULL is accepted)."""
+    import ctypes as C
+    from bipedal_locomotion_framework_b200 import _capi
+    n = 4096
+    st = syn.make_states(n, seed=13)
+    planes, _ = _soa_inputs(torch, st)
+    ptrs = [planes[i].data_ptr() for i in range(30)]
+    for dead in (11, 14, 23, 26, 29):   # R02, R12 (autodyn only) and R0's third column
+        ptrs[dead] = None
+    arr = (C.c_void_p * 30)(*ptrs)
+    w = torch.empty((6, n), dtype=torch.float64, device="cuda")
+    c = torch.empty((n, 36), dtype=torch.float64, device="cuda")
+    wp = (C.c_void_p * 6)(*[w[i].data_ptr() for i in range(6)])
+    rc = _capi.lib().blf_ccm_eval_batch_soa(batch.handle.ptr, n, arr, None, W | Cc, wp, None,
+                                            c.data_ptr(), None, None)
+    assert rc == 0, _capi.lib().blf_ccm_last_error()
+    torch.cuda.synchronize()
+    ref = oracle.eval_batch_states(st, mask=W | Cc)
+    assert_parity(w.cpu().numpy().T, ref["wrench"], "wrench")
+    assert_parity(c.cpu().numpy(), ref["ctrl"], "ctrl")
+    # ...but a live plane that is NULL is an argument error, not a crash
+    ptrs[17] = None
+    arr = (C.c_void_p * 30)(*ptrs)
+    rc = _capi.lib().blf_ccm_eval_batch_soa(batch.handle.ptr, n, arr, None, W, wp, None, None,
+                                            None, None)
+    assert rc == _capi.ERR_INVALID_ARG
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_eight_byte_aligned_buffers_take_the_checked_64bit_path(torch, batch, oracle, layout):
+    n = 5000
+    st = syn.make_states(n, seed=21, heterogeneous=True)
+    ref = oracle.eval_batch_states(st, mask=FULL, nthreads=1)
+    if layout == "soa":
+        # shift every plane by one double: rows start 8-byte but not 16-byte aligned
+        big = torch.empty((30, n + 2), dtype=torch.float64, device="cuda")
+        planes = big[:, 1:n + 1]
+        planes.copy_(_dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])))
+        assert planes[0].data_ptr() % 16 == 8
+        prm = _dev(torch, st["params"].T)
+        got = _soa_out_to_aos(batch.evaluate_soa(planes, prm, FULL))
+    else:
+        def shifted(a):
+            buf = torch.empty(a.size + 1, dtype=torch.float64, device="cuda")
+            v = buf[1:].view(a.shape)
+            v.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            assert v.data_ptr() % 16 == 8
+            return v
+        got = _aos_out(batch.evaluate_aos(shifted(st["twists"]), shifted(st["poses"]),
+                                          shifted(st["null_poses"]), _dev(torch, st["params"]),
+                                          FULL))
+    assert batch.handle.last_path == 2  # BLF_CCM_PATH_SCALAR64: dispatched, reported, same results
+    _check(got, ref, FULL, f"unaligned/{layout}")
+
+
+def test_uninitialised_handle_is_an_error(torch):
+    from bipedal_locomotion_framework_b200 import _capi
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    b = ContinuousContactModelBatch(0)
+    planes = torch.zeros((30, 64), dtype=torch.float64, device="cuda")
+    with pytest.raises(_capi.BlfCcmError) as e:
+        b.evaluate_soa(planes, None, W)
+    assert e.value.code == _capi.ERR_NOT_INITIALIZED
+
+
+# --- properties at full size ------------------------------------------------------------------------
+
+def test_full_size_properties(torch, batch):
+    """At configs[2] size without the oracle: (i) AoS and SoA entry points agree, (ii) the wrench
+    is the regressor times [k; b] (ContinousContactModelTest.cpp:107-124), (iii) control-matrix
+    structure, (iv) determinism (two runs bit-identical)."""
+    n = 2 * 4096 * 100
+    st = syn.make_states(n, seed=77)
+    planes, _ = _soa_inputs(torch, st)
+    a = batch.evaluate_soa(planes, None, FULL | R)
+    b2 = batch.evaluate_soa(planes, None, FULL | R)
+    for k in a:
+        assert torch.equal(a[k], b2[k])
+    aos = batch.evaluate_aos(_dev(torch, st["twists"]), _dev(torch, st["poses"]),
+                             _dev(torch, st["null_poses"]), None, FULL | R)
+    soa_as_aos = _soa_out_to_aos(a)
+    aos_np = _aos_out(aos)
+    for bit, key in KEYS.items():
+        assert_parity(aos_np[key], soa_as_aos[key], key, tol=1e-13, what="aos vs soa ")
+    _, _, k, bb = syn.REFERENCE_TEST_PARAMS
+    Y = soa_as_aos["regressor"].reshape(n, 6, 2)
+    via_regressor = Y @ np.array([k, bb])
+    assert_parity(via_regressor, soa_as_aos["wrench"], "wrench", tol=1e-11)
+    assert_ctrl_structure(soa_as_aos["ctrl"])
+    g = soa_as_aos["ctrl"].reshape(n, 6, 6)
+    assert np.array_equal(g[:, 3:, 3:], g[:, 3:, 3:].transpose(0, 2, 1))  # symmetric block
+
+
+# --- per-instance facade: the reference's own test against the GPU ---------------------------------
+
+def _handler(k=2000.0, b=100.0, L=0.12, Wd=0.09):
+    from bipedal_locomotion_framework_b200.contact_models import StdImplementation
+    h = StdImplementation()
+    h.setParameter("spring_coeff", k)
+    h.setParameter("damper_coeff", b)
+    h.setParameter("length", L)
+    h.setParameter("width", Wd)
+    return h
+
+
+def _rodrigues(w):
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+
+
+def test_config1_reference_test_on_the_facade(torch, oracle):
+    """configs[0]: ContinousContactModelTest.cpp:32-214 run against the GPU-backed facade, and
+    every getter compared with the oracle object."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModel
+    rng = np.random.default_rng(42)
+    st = syn.reference_test_state(rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3))
+    tw, pose, null = st["twists"][0], st["poses"][0], st["null_poses"][0]
+    L, Wd, k, b = syn.REFERENCE_TEST_PARAMS
+    model = ContinuousContactModel()
+    assert model.initialize(_handler())
+    model.setState(tw, pose)
+    model.setNullForceTransform(null)
+
+    om = oracle.ContinuousContactModel()
+    om.initialize({"length": L, "width": Wd, "spring_coeff": k, "damper_coeff": b})
+    om.setState(tw, pose)
+    om.setNullForceTransform(null)
+    assert_parity(model.getContactWrench()[None], om.getContactWrench()[None], "wrench")
+    assert_parity(model.getAutonomousDynamics()[None], om.getAutonomousDynamics()[None], "autodyn")
+    assert_parity(model.getControlMatrix().reshape(1, 36), om.getControlMatrix().reshape(1, 36),
+                  "ctrl")
+    assert_parity(model.getRegressor().reshape(1, 12), om.getRegressor().reshape(1, 12),
+                  "regressor")
+    assert_ctrl_structure(model.getControlMatrix())
+
+    # "Test contact wrench" (:60-104): Monte-Carlo surface integral, 1e4 samples, abs 1e-2
+    samples = 10000
+    xs = rng.uniform(-L / 2, L / 2, samples)
+    ys = rng.uniform(-Wd / 2, Wd / 2, samples)
+    f, t = model.surfacePointWrenches(xs, ys)
+    num = np.concatenate([f.sum(0), t.sum(0)]) / samples * (L * Wd) * abs(pose[11])
+    assert np.all(np.abs(num - model.getContactWrench()) <= 1e-2)
+    # single-point getters agree with the oracle's, inside, on the boundary and outside
+    for x, y in ((0.01, -0.02), (L / 2, Wd / 2), (L / 2 + 1e-9, 0.0), (0.0, -Wd)):
+        np.testing.assert_allclose(model.getForceAtPoint(x, y), om.getForceAtPoint(x, y),
+                                   rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(model.getTorqueGeneratedAtPoint(x, y),
+                                   om.getTorqueGeneratedAtPoint(x, y), rtol=1e-12, atol=1e-300)
+
+    # "Test regressor" (:107-124): abs 1e-7
+    assert np.all(np.abs(model.getRegressor() @ np.array([k, b]) - model.getContactWrench()) <= 1e-7)
+
+    # "Test contact dynamics" (:126-213): central difference, step 1e-6, abs 1e-4
+    acc = np.ones(6)
+    dt = 1e-6
+    rate = model.getAutonomousDynamics() + model.getControlMatrix() @ acc
+    Rm = pose[3:].reshape(3, 3)
+    wr = []
+    for sgn in (-1.0, 1.0):
+        p = pose[:3] + sgn * tw[:3] * dt
+        Rn = _rodrigues(sgn * tw[3:] * dt) @ Rm
+        model.setState(tw + sgn * acc * dt, np.concatenate([p, Rn.reshape(9)]))
+        model.setNullForceTransform(null)
+        wr.append(model.getContactWrench().copy())
+    assert np.all(np.abs((wr[1] - wr[0]) / (2 * dt) - rate) <= 1e-4)
+
+
+def test_facade_lazy_flags_and_stale_coefficient_quirk(torch):
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModel
+    st = syn.reference_test_state()
+    m = ContinuousContactModel()
+    assert m.initialize(_handler())
+    m.setState(st["twists"][0], st["poses"][0])
+    w0 = m.getContactWrench().copy()
+    launches = m._handle.launch_count
+    m.getContactWrench()
+    assert m._handle.launch_count == launches          # cached: no second evaluation
+    m.springCoeff = 4000.0                              # does not clear the flags (:256-274)
+    assert np.array_equal(m.getContactWrench(), w0)
+    m.setNullForceTransform(st["null_poses"][0])
+    assert not np.array_equal(m.getContactWrench(), w0)
+
+
+# --- sampling-MPC epilogue ----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("heterogeneous", [False, True])
+@pytest.mark.parametrize("rollout_len,n_rollouts,mask", [(200, 512, 0), (200, 300, FULL),
+                                                         (7, 1000, W), (33, 64, Cc)])
+def test_rollout_cost_argmin(torch, batch, oracle, heterogeneous, rollout_len, n_rollouts, mask):
+    n = rollout_len * n_rollouts
+    st = syn.make_states(n, seed=31, heterogeneous=heterogeneous)
+    planes, prm = _soa_inputs(torch, st)
+    ref_wrench = np.array([1.0, -2.0, 30.0, 0.1, 0.2, -0.3])
+    weights = np.array([1.0, 25.0])
+    out, cost, best = batch.rollout_cost_argmin(planes, rollout_len, ref_wrench, weights, prm,
+                                                mask=mask, index_base=1000)
+    ref = oracle.eval_batch_states(st, mask=mask | W, nthreads=NTHREADS)
+    ref_cost = oracle.rollout_cost(ref["wrench"], rollout_len, ref_wrench, weights)
+    cost = cost.cpu().numpy()
+    np.testing.assert_allclose(cost, ref_cost, rtol=1e-12)
+    bc, bi = batch.decode_best(best)
+    j = int(np.argmin(cost))                    # first minimum = lowest-index tie-break
+    assert bi == 1000 + j and bc == cost[j]
+    assert ref_cost[bi - 1000] <= ref_cost.min() * (1 + 1e-12)
+    if mask:
+        _check(_soa_out_to_aos(out), ref, mask, "rollout outputs")
+    # determinism of the fused reduction
+    _, cost2, best2 = batch.rollout_cost_argmin(planes, rollout_len, ref_wrench, weights, prm,
+                                                mask=0, index_base=1000)
+    assert np.array_equal(cost2.cpu().numpy(), cost) and torch.equal(best, best2)
+
+
+def test_argmin_pairs_tie_break(torch, batch):
+    pairs = torch.tensor([[3.0, 5], [1.5, 9], [1.5, 4], [2.0, 1]], dtype=torch.float64)
+    packed = torch.empty((4, 2), dtype=torch.int64)
+    packed[:, 0] = pairs[:, 0].contiguous().view(torch.int64)
+    packed[:, 1] = pairs[:, 1].to(torch.int64)
+    best = batch.argmin_pairs(packed.cuda())
+    assert batch.decode_best(best) == (1.5, 4)

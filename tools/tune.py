@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""Sweep kernel variants / launch shapes on one GPU and print a table (development aid, not the
+bench).  Each row: GB/s of algorithmic bytes and fraction of the measured HBM peak."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from bipedal_locomotion_framework_b200 import synthetic as syn
+from bipedal_locomotion_framework_b200.contact_models import (FULL, WRENCH,
+                                                               ContinuousContactModelBatch)
+
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+
+
+def timeit(fn, iters=200, warm=10):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def row(name, ms, n, bytes_per):
+    gbs = n * bytes_per / (ms * 1e-3) / 1e9
+    print(f"{name:58s} {ms*1e3:9.1f} us  {n/ms/1e6:8.2f} G evals/s  {gbs:8.1f} GB/s  {gbs/PEAK*100:5.1f} %",
+          flush=True)
+
+
+def make_batch(**env):
+    for k in ("BLF_CCM_TUNE_CPT", "BLF_CCM_TUNE_BLOCKS_PER_SM"):
+        os.environ.pop(k, None)
+    for k, v in env.items():
+        os.environ[k] = str(v)
+    b = ContinuousContactModelBatch(0)
+    b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    return b
+
+
+def main():
+    sizes = {"cfg3 819200": 2 * 4096 * 100, "8M": 1 << 23}
+    NS = 3
+    for label, n in sizes.items():
+        st = syn.make_states(min(n, 1 << 20), seed=45)
+        reps = (n + st["n"] - 1) // st["n"]
+        pl = np.tile(syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]), (1, reps))[:, :n]
+        planes = [torch.from_numpy(np.ascontiguousarray(pl)).cuda() for _ in range(NS)]
+        het = syn.make_states(min(n, 1 << 20), seed=46, heterogeneous=True)
+        prm = torch.from_numpy(np.ascontiguousarray(np.tile(het["params"].T, (1, reps))[:, :n])).cuda()
+        aos = [torch.from_numpy(np.ascontiguousarray(np.tile(st[k], (reps, 1))[:n])).cuda()
+               for k in ("twists", "poses", "null_poses")]
+        prm_aos = prm.T.contiguous()
+        print(f"\n=== n = {n} ({label}); peak {PEAK} GB/s ===")
+        for cpt in (2, 1):
+            for bps in (0, 1, 2, -1):
+                b = make_batch(BLF_CCM_TUNE_CPT=cpt, BLF_CCM_TUNE_BLOCKS_PER_SM=bps)
+                outs = [b.alloc_soa_outputs(n, FULL) for _ in range(NS)]
+                ms = timeit(lambda i: b.evaluate_soa(planes[i % NS], None, FULL, out=outs[i % NS]))
+                row(f"soa full uniform cpt={cpt} blocks/SM={bps or 'occ'}", ms, n, 600)
+                del outs
+        b = make_batch()
+        outs = [b.alloc_soa_outputs(n, FULL) for _ in range(NS)]
+        ms = timeit(lambda i: b.evaluate_soa(planes[i % NS], prm, FULL, out=outs[i % NS]))
+        row("soa full heterogeneous", ms, n, 632)
+        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], 200, [0, 0, 30., 0, 0, 0], [1., 10.],
+                                                    mask=FULL, out=outs[i % NS], want_cost=False))
+        row("rollout(200) full + cost + argmin", ms, n, 600)
+        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], 200, [0, 0, 30., 0, 0, 0], [1., 10.],
+                                                    mask=0, want_cost=True))
+        row("rollout(200) cost only (25 planes in)", ms, n, 200)
+        del outs
+        outs = [b.alloc_soa_outputs(n, WRENCH) for _ in range(NS)]
+        for cpt in (2, 1):
+            b2 = make_batch(BLF_CCM_TUNE_CPT=cpt)
+            ms = timeit(lambda i: b2.evaluate_soa(planes[i % NS], None, WRENCH, out=outs[i % NS]))
+            row(f"soa wrench-only uniform cpt={cpt}", ms, n, 248)
+        del outs
+        for bps in (0, 2, 4, -1):
+            b3 = make_batch(BLF_CCM_TUNE_BLOCKS_PER_SM=bps)
+            outs = [b3.alloc_aos_outputs(n, FULL) for _ in range(2)]
+            ms = timeit(lambda i: b3.evaluate_aos(aos[0], aos[1], aos[2], None, FULL, out=outs[i % 2]))
+            row(f"aos full uniform blocks/SM={bps or 'occ'} (624 B touched)", ms, n, 600)
+            del outs
+        b = make_batch()
+        outs = [b.alloc_aos_outputs(n, FULL) for _ in range(2)]
+        ms = timeit(lambda i: b.evaluate_aos(aos[0], aos[1], aos[2], prm_aos, FULL, out=outs[i % 2]))
+        row("aos full heterogeneous", ms, n, 632)
+        del outs
+        outs = [b.alloc_aos_outputs(n, WRENCH) for _ in range(2)]
+        ms = timeit(lambda i: b.evaluate_aos(aos[0], aos[1], aos[2], None, WRENCH, out=outs[i % 2]))
+        row("aos wrench-only", ms, n, 248)
+        del outs, planes, aos, prm, prm_aos
+        torch.cuda.empty_cache()
+
+    # torch copy reference point (same method as MEASURED_PEAKS)
+    x = torch.empty(1 << 28, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    ms = timeit(lambda i: y.copy_(x), iters=10, warm=3)
+    print(f"\ntorch copy 2 GiB+2 GiB: {2 * x.numel() * 8 / (ms * 1e-3) / 1e9:.1f} GB/s")
+    del x, y
+
+    # host pipeline chunk sweep (config 3, pinned)
+    n = 2 * 4096 * 100
+    st = syn.make_states(n, seed=45)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(st[k]) for k in ("twists", "poses", "null_poses")]
+    ho = {"wrench": torch.empty((n, 6), dtype=torch.float64).pin_memory(),
+          "autodyn": torch.empty((n, 6), dtype=torch.float64).pin_memory(),
+          "ctrl": torch.empty((n, 36), dtype=torch.float64).pin_memory(), "regressor": None}
+    b = make_batch()
+    print("\nhost pipeline (pinned, 240 B in + 384 B out per eval):")
+    for chunk in (8192, 16384, 32768, 65536, 131072, 819200):
+        b.set_host_chunk(chunk)
+        for _ in range(2):
+            b.evaluate_host(h[0], h[1], h[2], None, FULL, out=ho)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            b.evaluate_host(h[0], h[1], h[2], None, FULL, out=ho)
+        dt = (time.perf_counter() - t0) / 5
+        print(f"  chunk {chunk:7d}: {dt*1e3:7.2f} ms  {n/dt/1e6:7.1f} M evals/s  "
+              f"h2d {n*240/dt/1e9:5.1f} GB/s  d2h {n*384/dt/1e9:5.1f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
