@@ -327,7 +327,7 @@ def run_ours(args):
     achieved = BYTES_FULL_UNIFORM * n / (avg_kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": _traffic(),
-                "kernel": "ccm_soa_kernel<WRENCH|AUTODYN|CTRL, uniform, 2 contacts/lane>",
+                "kernel": "ccm_soa_kernel<WRENCH|AUTODYN|CTRL, uniform> (1 contact/lane, 1 tile/warp)",
                 "algorithmic_bytes_per_launch": BYTES_FULL_UNIFORM * n,
                 "avg_launch_ms": avg_kernel_ms, "median_launch_ms": kern_ms[len(kern_ms) // 2],
                 "best_launch_ms": kern_ms[0], "peak_source": peak_src}

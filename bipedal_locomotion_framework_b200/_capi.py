@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libblf_ccm.so")
 
 WRENCH, AUTODYN, CTRL, REGRESSOR = 1, 2, 4, 8
 FULL = WRENCH | AUTODYN | CTRL
-PATH_VEC128, PATH_SCALAR64 = 1, 2
+PATH_BULK, PATH_DIRECT64 = 1, 2
 
 OK, ERR_INVALID_ARG, ERR_INVALID_HANDLE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_INITIALIZED, ERR_NCCL = \
     0, -1, -2, -3, -4, -5, -6
@@ -22,6 +22,8 @@ SYMBOLS = [
     "blf_ccm_eval_batch_host", "blf_ccm_set_host_chunk", "blf_ccm_eval_surface_points",
     "blf_ccm_rollout_cost_argmin_soa", "blf_ccm_argmin_pairs", "blf_ccm_argmin_allgather_nccl",
     "blf_ccm_last_path", "blf_ccm_launch_count", "blf_ccm_device", "blf_ccm_sm_count",
+    "blf_ccm_device_alloc", "blf_ccm_device_free", "blf_ccm_host_alloc", "blf_ccm_host_free",
+    "blf_ccm_copy_h2d", "blf_ccm_copy_d2h", "blf_ccm_stream_synchronize",
 ]
 
 
@@ -58,6 +60,14 @@ def lib():
                                                   i64, vp, vp, vp]
     L.blf_ccm_argmin_pairs.argtypes = [vp, ci, vp, vp, vp]
     L.blf_ccm_argmin_allgather_nccl.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    u64 = C.c_uint64
+    L.blf_ccm_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.blf_ccm_device_free.argtypes = [vp, vp]
+    L.blf_ccm_host_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.blf_ccm_host_free.argtypes = [vp, vp]
+    L.blf_ccm_copy_h2d.argtypes = [vp, vp, vp, u64, vp]
+    L.blf_ccm_copy_d2h.argtypes = [vp, vp, vp, u64, vp]
+    L.blf_ccm_stream_synchronize.argtypes = [vp, vp]
     L.blf_ccm_last_path.argtypes = [vp]
     L.blf_ccm_launch_count.argtypes = [vp]
     L.blf_ccm_launch_count.restype = i64

@@ -1,0 +1,123 @@
+/**
+ * @file StdImplementation.h
+ * std::unordered_map<std::string, std::any> backed parameters handler.
+ *
+ * Same behaviour as the reference's StdImplementation
+ * (src/ParametersHandler/include/BipedalLocomotion/ParametersHandler/StdImplementation.h:27-236,
+ * StdImplementation.tpp:21-105, src/StdImplementation.cpp:14-169): strict std::any_cast typing (an
+ * int stored under a key cannot be read as double), bool + std::cerr errors, groups stored as
+ * shared pointers, getGroup() of a missing name yields an expired weak pointer.
+ */
+#ifndef BIPEDAL_LOCOMOTION_PARAMETERS_HANDLER_STD_IMPLEMENTATION_H
+#define BIPEDAL_LOCOMOTION_PARAMETERS_HANDLER_STD_IMPLEMENTATION_H
+
+#include <any>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <BipedalLocomotion/ParametersHandler/IParametersHandler.h>
+
+namespace BipedalLocomotion
+{
+namespace ParametersHandler
+{
+
+class StdImplementation : public IParametersHandler
+{
+    std::unordered_map<std::string, std::any> m_map;
+
+    template <typename T> bool getParameterPrivate(const std::string& parameterName, T& parameter) const
+    {
+        auto it = m_map.find(parameterName);
+        if (it == m_map.end())
+        {
+            std::cerr << "[StdImplementation::getParameterPrivate] Parameter named " << parameterName
+                      << " not found." << std::endl;
+            return false;
+        }
+        const T* value = std::any_cast<T>(&it->second);
+        if (value == nullptr)
+        {
+            std::cerr << "[StdImplementation::getParameterPrivate] The type of the parameter named "
+                      << parameterName << " is different from the one expected" << std::endl;
+            return false;
+        }
+        parameter = *value;
+        return true;
+    }
+
+public:
+    using unique_ptr = std::unique_ptr<StdImplementation>;
+    using shared_ptr = std::shared_ptr<StdImplementation>;
+    using weak_ptr = std::weak_ptr<StdImplementation>;
+
+    StdImplementation() = default;
+    explicit StdImplementation(const std::unordered_map<std::string, std::any>& map) : m_map(map) {}
+
+    bool getParameter(const std::string& n, int& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, double& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, std::string& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, bool& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, std::vector<bool>& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, std::vector<int>& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, std::vector<double>& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, std::vector<std::string>& p) const final { return getParameterPrivate(n, p); }
+
+    void setParameter(const std::string& n, const int& p) final { m_map[n] = p; }
+    void setParameter(const std::string& n, const double& p) final { m_map[n] = p; }
+    void setParameter(const std::string& n, const std::string& p) final { m_map[n] = p; }
+    void setParameter(const std::string& n, const char* p) final { m_map[n] = std::string(p); }
+    void setParameter(const std::string& n, const bool& p) final { m_map[n] = p; }
+    void setParameter(const std::string& n, const std::vector<bool>& p) final { m_map[n] = p; }
+    void setParameter(const std::string& n, const std::vector<int>& p) final { m_map[n] = p; }
+    void setParameter(const std::string& n, const std::vector<double>& p) final { m_map[n] = p; }
+    void setParameter(const std::string& n, const std::vector<std::string>& p) final { m_map[n] = p; }
+
+    IParametersHandler::weak_ptr getGroup(const std::string& name) const final
+    {
+        auto it = m_map.find(name);
+        if (it == m_map.end()) return std::make_shared<StdImplementation>(); // expires at once
+        const auto* group = std::any_cast<shared_ptr>(&it->second);
+        if (group == nullptr)
+        {
+            std::cerr << "[StdImplementation::getGroup] The element named " << name
+                      << " is not a group" << std::endl;
+            return std::make_shared<StdImplementation>();
+        }
+        return *group;
+    }
+
+    bool setGroup(const std::string& name, IParametersHandler::shared_ptr newGroup) final
+    {
+        auto down = std::dynamic_pointer_cast<StdImplementation>(newGroup);
+        if (down == nullptr)
+        {
+            std::cerr << "[StdImplementation::setGroup] Unable to downcast the pointer to "
+                         "StdImplementation."
+                      << std::endl;
+            return false;
+        }
+        m_map[name] = std::make_any<shared_ptr>(down);
+        return true;
+    }
+
+    void set(const std::unordered_map<std::string, std::any>& object) { m_map = object; }
+
+    std::string toString() const final
+    {
+        std::string keys;
+        for (const auto& kv : m_map) keys += kv.first + " ";
+        return keys;
+    }
+    bool isEmpty() const final { return m_map.empty(); }
+    void clear() final { m_map.clear(); }
+    ~StdImplementation() = default;
+};
+
+} // namespace ParametersHandler
+} // namespace BipedalLocomotion
+
+#endif // BIPEDAL_LOCOMOTION_PARAMETERS_HANDLER_STD_IMPLEMENTATION_H

@@ -63,8 +63,10 @@ struct blf_ccm_handle {
     long long launches = 0;
     std::map<const void*, KernelInfo> kinfo;
     // rollout scratch
-    CostIdx* partials = nullptr;
+    CostIdx* block_best = nullptr;   // kMaxPartials pairs
     unsigned int* counter = nullptr;
+    double* partials = nullptr;      // [n_rollouts][slots] per-(rollout, tile) cost partial sums
+    size_t partials_bytes = 0;
     // host pipeline
     cudaStream_t hstream[kHostSlots] = {};
     double* hbuf[kHostSlots] = {};
@@ -72,8 +74,9 @@ struct blf_ccm_handle {
     size_t hbytes = 0;
     long long host_chunk_pref = 32768;
     // tuning overrides (environment, read once at create; 0 = automatic)
-    int tune_cpt = 0;            // BLF_CCM_TUNE_CPT: 1 or 2 contacts per lane in the SoA kernel
-    int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM: cap on resident CTAs/SM; -1 = one tile per warp
+    int tune_cpt = 0;            // BLF_CCM_TUNE_CPT=2: use the 128-bit two-contacts-per-lane SoA kernel
+    int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM>0: persistent grid with that many CTAs/SM
+                                 // (looping kernels only); default = one tile per warp
 };
 
 static int env_int(const char* name)
@@ -117,7 +120,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->sm_count = prop.multiProcessorCount;
     h->tune_cpt = env_int("BLF_CCM_TUNE_CPT");
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
-    CUDA_TRY(cudaMalloc(&h->partials, sizeof(CostIdx) * kMaxPartials));
+    CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
     CUDA_TRY(cudaMalloc(&h->counter, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(h->counter, 0, sizeof(unsigned int)));
     *out = h;
@@ -132,8 +135,9 @@ extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
         if (h->hstream[s]) cudaStreamDestroy(h->hstream[s]);
         if (h->hbuf[s]) cudaFree(h->hbuf[s]);
     }
-    cudaFree(h->partials);
+    cudaFree(h->block_best);
     cudaFree(h->counter);
+    if (h->partials) cudaFree(h->partials);
     h->magic = 0;
     delete h;
     return BLF_CCM_OK;
@@ -180,7 +184,7 @@ static int persistent_blocks(blf_ccm_handle* h, K kernel, int threads, size_t sm
     }
     int per_sm = it->second.blocks_per_sm;
     if (h->tune_blocks_per_sm > 0) per_sm = std::min(per_sm, h->tune_blocks_per_sm);
-    *out = h->tune_blocks_per_sm < 0 ? 0x7fffffff : per_sm * h->sm_count;
+    *out = h->tune_blocks_per_sm > 0 ? per_sm * h->sm_count : 0x7fffffff;
     return BLF_CCM_OK;
 }
 
@@ -208,13 +212,13 @@ static int dispatch_mask(unsigned mask, Args&&... args)
 
 template <unsigned MASK, bool HET>
 struct SoaLaunch {
-    static int run(blf_ccm_handle* h, const SoaArgs& a, bool vec, cudaStream_t st)
+    static int run(blf_ccm_handle* h, const SoaArgs& a, bool vec2, cudaStream_t st)
     {
         constexpr int threads = 128;
-        if (vec) {
+        if (vec2) {
             constexpr int TILE = 64;
             const size_t smem = (MASK & M_CTRL) ? size_t(threads / 32) * TILE * 288 : 0;
-            auto k = ccm_soa_kernel<MASK, HET, 2>;
+            auto k = ccm_soa_vec2_kernel<MASK, HET>;
             int cap = 0;
             if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
             const long long tiles = (a.n + TILE - 1) / TILE;
@@ -222,15 +226,13 @@ struct SoaLaunch {
             const int grid = static_cast<int>(std::min<long long>(want, cap));
             k<<<grid, threads, smem, st>>>(a);
         } else {
-            constexpr int TILE = 32;
-            const size_t smem = (MASK & M_CTRL) ? size_t(threads / 32) * TILE * 288 : 0;
-            auto k = ccm_soa_kernel<MASK, HET, 1>;
+            const size_t smem = (MASK & M_CTRL) ? size_t(threads / 32) * 32 * 288 : 0;
+            auto k = ccm_soa_kernel<MASK, HET, false>;
             int cap = 0;
-            if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
-            const long long tiles = (a.n + TILE - 1) / TILE;
-            const long long want = (tiles + threads / 32 - 1) / (threads / 32);
-            const int grid = static_cast<int>(std::min<long long>(want, cap));
-            k<<<grid, threads, smem, st>>>(a);
+            if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;  // smem attribute
+            const long long grid = (a.n + threads - 1) / threads;
+            if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");
+            k<<<static_cast<int>(grid), threads, smem, st>>>(a);
         }
         CUDA_TRY(cudaGetLastError());
         h->launches++;
@@ -305,11 +307,12 @@ extern "C" int blf_ccm_eval_batch_soa(blf_ccm_handle* h, int64_t n, const double
     if (int rc = fill_soa_args(h, n, in_planes, param_planes, out_mask, out_mask, wrench_planes,
                                autodyn_planes, ctrl, regressor_planes, a, vec))
         return rc;
-    if (h->tune_cpt == 1) vec = false;
-    h->last_path = vec ? BLF_CCM_PATH_VEC128 : BLF_CCM_PATH_SCALAR64;
+    // planes only need 8-byte alignment; the dense 6x6 leaves by bulk copy when 16-byte aligned
+    h->last_path = ((out_mask & BLF_CCM_CTRL) && !a.ctrl_bulk) ? BLF_CCM_PATH_DIRECT64 : BLF_CCM_PATH_BULK;
+    const bool vec2 = vec && h->tune_cpt == 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (param_planes) return dispatch_mask<SoaLaunch, true>(out_mask, h, a, vec, st);
-    return dispatch_mask<SoaLaunch, false>(out_mask, h, a, vec, st);
+    if (param_planes) return dispatch_mask<SoaLaunch, true>(out_mask, h, a, vec2, st);
+    return dispatch_mask<SoaLaunch, false>(out_mask, h, a, vec2, st);
 }
 
 // ---- AoS -----------------------------------------------------------------------------------------
@@ -371,7 +374,7 @@ static int launch_aos(blf_ccm_handle* h, long long n, const double* twists, cons
     if (int rc = chk(autodyn, out_mask & BLF_CCM_AUTODYN, "autodyn")) return rc;
     if (int rc = chk(ctrl, out_mask & BLF_CCM_CTRL, "ctrl")) return rc;
     if (int rc = chk(regressor, out_mask & BLF_CCM_REGRESSOR, "regressor")) return rc;
-    h->last_path = bulk ? BLF_CCM_PATH_VEC128 : BLF_CCM_PATH_SCALAR64;
+    h->last_path = bulk ? BLF_CCM_PATH_BULK : BLF_CCM_PATH_DIRECT64;
     AosArgs a;
     memset(&a, 0, sizeof(a));
     a.twists = twists;
@@ -519,17 +522,17 @@ extern "C" int blf_ccm_eval_surface_points(blf_ccm_handle* h, const double* host
 // ---- rollout cost + arg-min ----------------------------------------------------------------------
 
 template <unsigned OUT, bool HET>
-struct RolloutLaunch {
-    static int run(blf_ccm_handle* h, RolloutArgs& ra, cudaStream_t st)
+struct CostLaunch {
+    static int run(blf_ccm_handle* h, const SoaArgs& a, cudaStream_t st)
     {
         constexpr int threads = 128;
         const size_t smem = (OUT & M_CTRL) ? size_t(threads / 32) * 32 * 288 : 0;
-        auto k = ccm_rollout_kernel<OUT, HET>;
+        auto k = ccm_soa_kernel<OUT, HET, true>;
         int cap = 0;
         if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
-        const long long want = (ra.n_rollouts + threads / 32 - 1) / (threads / 32);
-        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, std::min(cap, kMaxPartials))));
-        k<<<grid, threads, smem, st>>>(ra);
+        const long long grid = (a.n + threads - 1) / threads;
+        if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");
+        k<<<static_cast<int>(grid), threads, smem, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
         return BLF_CCM_OK;
@@ -537,17 +540,17 @@ struct RolloutLaunch {
 };
 
 template <bool HET>
-static int dispatch_rollout(unsigned out, blf_ccm_handle* h, RolloutArgs& ra, cudaStream_t st)
+static int dispatch_cost(unsigned out, blf_ccm_handle* h, const SoaArgs& a, cudaStream_t st)
 {
     switch (out) {  // outputs written besides the cost: any subset of wrench|autodyn|ctrl
-    case 0: return RolloutLaunch<0, HET>::run(h, ra, st);
-    case 1: return RolloutLaunch<1, HET>::run(h, ra, st);
-    case 2: return RolloutLaunch<2, HET>::run(h, ra, st);
-    case 3: return RolloutLaunch<3, HET>::run(h, ra, st);
-    case 4: return RolloutLaunch<4, HET>::run(h, ra, st);
-    case 5: return RolloutLaunch<5, HET>::run(h, ra, st);
-    case 6: return RolloutLaunch<6, HET>::run(h, ra, st);
-    case 7: return RolloutLaunch<7, HET>::run(h, ra, st);
+    case 0: return CostLaunch<0, HET>::run(h, a, st);
+    case 1: return CostLaunch<1, HET>::run(h, a, st);
+    case 2: return CostLaunch<2, HET>::run(h, a, st);
+    case 3: return CostLaunch<3, HET>::run(h, a, st);
+    case 4: return CostLaunch<4, HET>::run(h, a, st);
+    case 5: return CostLaunch<5, HET>::run(h, a, st);
+    case 6: return CostLaunch<6, HET>::run(h, a, st);
+    case 7: return CostLaunch<7, HET>::run(h, a, st);
     default: return fail(BLF_CCM_ERR_INVALID_ARG, "rollout out_mask %u: only wrench|autodyn|ctrl", out);
     }
 }
@@ -569,27 +572,52 @@ extern "C" int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_roll
     if (!aligned16(best)) return fail(BLF_CCM_ERR_INVALID_ARG, "best must be 16-byte aligned");
     if (n_rollouts == 0)  // nothing to compare: best = (+inf, -1)
         return blf_ccm_argmin_pairs(h, 0, best, best, stream);
-    RolloutArgs ra;
-    memset(&ra, 0, sizeof(ra));
+    SoaArgs a;
     bool vec = false;
     if (int rc = fill_soa_args(h, n_rollouts * rollout_len, in_planes, param_planes, out_mask,
                                out_mask | BLF_CCM_WRENCH, wrench_planes, autodyn_planes, ctrl,
-                               nullptr, ra.soa, vec))
+                               nullptr, a, vec))
         return rc;
+    // per-(rollout, tile) partial sums: a rollout of length L intersects at most (L+62)/32 tiles
+    const int slots = static_cast<int>((rollout_len + 62) / 32);
+    const size_t need = size_t(n_rollouts) * slots * sizeof(double);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->partials_bytes < need) {
+        if (h->partials) {
+            CUDA_TRY(cudaStreamSynchronize(st));  // a previous launch may still read the old buffer
+            CUDA_TRY(cudaFree(h->partials));
+            h->partials = nullptr;
+        }
+        CUDA_TRY(cudaMalloc(&h->partials, need));
+        h->partials_bytes = need;
+    }
+    a.rollout_len = rollout_len;
+    memcpy(a.ref, host_wrench_ref, sizeof(a.ref));
+    a.wf = host_weights[0];
+    a.wt = host_weights[1];
+    a.partials = h->partials;
+    a.slots = slots;
+    h->last_path = ((out_mask & BLF_CCM_CTRL) && !a.ctrl_bulk) ? BLF_CCM_PATH_DIRECT64 : BLF_CCM_PATH_BULK;
+    if (int rc = param_planes ? dispatch_cost<true>(out_mask, h, a, st)
+                              : dispatch_cost<false>(out_mask, h, a, st))
+        return rc;
+
+    ReduceArgs ra;
+    ra.partials = h->partials;
+    ra.slots = slots;
     ra.n_rollouts = n_rollouts;
     ra.rollout_len = rollout_len;
     ra.index_base = index_base;
-    memcpy(ra.ref, host_wrench_ref, sizeof(ra.ref));
-    ra.wf = host_weights[0];
-    ra.wt = host_weights[1];
     ra.cost = cost;
-    ra.partials = h->partials;
+    ra.block_best = h->block_best;
     ra.counter = h->counter;
     ra.best = static_cast<CostIdx*>(best);
-    h->last_path = BLF_CCM_PATH_SCALAR64;  // coalesced 64-bit plane accesses (rollouts start anywhere)
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (param_planes) return dispatch_rollout<true>(out_mask, h, ra, st);
-    return dispatch_rollout<false>(out_mask, h, ra, st);
+    const int threads = 128;
+    const int grid = static_cast<int>(std::min<long long>((n_rollouts + threads - 1) / threads, kMaxPartials));
+    ccm_cost_reduce_kernel<<<grid, threads, 0, st>>>(ra);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return BLF_CCM_OK;
 }
 
 extern "C" int blf_ccm_argmin_pairs(blf_ccm_handle* h, int n_pairs, const void* pairs, void* best,
@@ -601,6 +629,71 @@ extern "C" int blf_ccm_argmin_pairs(blf_ccm_handle* h, int n_pairs, const void* 
         static_cast<const CostIdx*>(pairs), n_pairs, static_cast<CostIdx*>(best));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    return BLF_CCM_OK;
+}
+
+// ---- memory / stream helpers ---------------------------------------------------------------------
+
+extern "C" int blf_ccm_device_alloc(blf_ccm_handle* h, uint64_t bytes, void** out)
+{
+    CHECK_HANDLE(h);
+    if (!out) return fail(BLF_CCM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return BLF_CCM_OK;
+    CUDA_TRY(cudaMalloc(out, bytes));
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_device_free(blf_ccm_handle* h, void* ptr)
+{
+    CHECK_HANDLE(h);
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_host_alloc(blf_ccm_handle* h, uint64_t bytes, void** out)
+{
+    CHECK_HANDLE(h);
+    if (!out) return fail(BLF_CCM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return BLF_CCM_OK;
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_host_free(blf_ccm_handle* h, void* ptr)
+{
+    CHECK_HANDLE(h);
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_copy_h2d(blf_ccm_handle* h, void* dst_device, const void* src_host,
+                                uint64_t bytes, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (bytes && (!dst_device || !src_host)) return fail(BLF_CCM_ERR_INVALID_ARG, "NULL pointer");
+    if (bytes)
+        CUDA_TRY(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_copy_d2h(blf_ccm_handle* h, void* dst_host, const void* src_device,
+                                uint64_t bytes, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (bytes && (!dst_host || !src_device)) return fail(BLF_CCM_ERR_INVALID_ARG, "NULL pointer");
+    if (bytes)
+        CUDA_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost,
+                                 static_cast<cudaStream_t>(stream)));
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_stream_synchronize(blf_ccm_handle* h, void* stream)
+{
+    CHECK_HANDLE(h);
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return BLF_CCM_OK;
 }
 

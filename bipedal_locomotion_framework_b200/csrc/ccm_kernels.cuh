@@ -1,12 +1,15 @@
 // ccm_kernels.cuh -- sm_100a kernels for batched ContinuousContactModel evaluation.
 //
-// Work decomposition (all kernels): a WARP owns a tile of consecutive contacts and never
-// synchronises with other warps; the grid is persistent (a few CTAs per SM) and each warp strides
-// over tiles.  HBM streams are touched exactly once:
-//   SoA planes      128-bit streaming loads / stores (LDG.E.128 / STG.E.128 with evict-first),
-//                   two contacts per lane;
-//   dense 6x6 ctrl  assembled per warp in shared memory (structural zeros written once per
-//                   kernel), then ONE bulk async copy (TMA engine) of tile*288 contiguous bytes;
+// Work decomposition (all kernels): a WARP owns a tile of 32 consecutive contacts and never
+// synchronises with other warps.  Launches are one tile per warp (no persistent loop): measured on
+// B200, the hardware CTA scheduler's natural staggering of loads and stores beats a persistent grid
+// whose warps march in lock-step (profiles/r01_variant_sweep.md).  HBM streams are touched once:
+//   SoA planes      coalesced 64-bit streaming loads / stores, one contact per lane (256 B per warp
+//                   request = two full 128 B lines; LDG.E.EF.64 / STG.E.EF.64).  A 128-bit,
+//                   two-contacts-per-lane variant (ccm_soa_vec2_kernel) is kept selectable: it is
+//                   slower on B200 because its 166 registers cap occupancy at 12 warps/SM;
+//   dense 6x6 ctrl  assembled per warp in shared memory, then ONE bulk async copy (TMA engine,
+//                   SASS UBLKCP) of tile*288 contiguous bytes;
 //   AoS structs     every input array arrives with a bulk async copy per tile signalled on a
 //                   per-warp mbarrier; lanes pick their own struct out of shared memory
 //                   (the AoS->SoA transposition); outputs leave through bulk stores too.
@@ -23,7 +26,7 @@ constexpr int kWarp = 32;
 __device__ __forceinline__ long long min64(long long a, long long b) { return a < b ? a : b; }
 
 // ------------------------------------------------------------------------------------------------
-// SoA kernel
+// SoA kernels
 // ------------------------------------------------------------------------------------------------
 
 struct SoaArgs {
@@ -36,6 +39,12 @@ struct SoaArgs {
     Prm uni;
     long long n;
     int ctrl_bulk;             // ctrl is 16-byte aligned -> bulk store
+    // sampling-MPC cost epilogue (COST kernels only)
+    long long rollout_len;
+    double ref[6];             // reference wrench
+    double wf, wt;             // force / torque weights
+    double* partials;          // [n_rollouts][slots] per-(rollout, tile) partial sums
+    int slots;                 // max tiles one rollout can intersect
 };
 
 template <int CPT>
@@ -117,10 +126,125 @@ __device__ __forceinline__ void flush_ctrl_tile(double* __restrict__ ctrl, const
     }
 }
 
-template <unsigned MASK, bool HET, int CPT>
-__global__ void __launch_bounds__(128, (CPT == 2 ? 3 : 4))
+// first tile (of 32 contacts) a rollout touches, and its slot for tile t
+__device__ __forceinline__ long long rollout_first_tile(long long rid, long long len)
+{
+    return (rid * len) >> 5;
+}
+
+// Primary kernel: one contact per lane, one 32-contact tile per warp, no loop.
+//   OUT   outputs written to HBM (bits of the C-ABI out_mask)
+//   COST  also reduce  wf|F-Fref|^2 + wt|T-Tref|^2  per (rollout, tile) into a.partials
+//         (fixed-order butterfly: deterministic); the wrench is then computed even if not in OUT.
+template <unsigned OUT, bool HET, bool COST>
+__global__ void __launch_bounds__(128, ((OUT & M_CTRL) ? 5 : 6))
 ccm_soa_kernel(const __grid_constant__ SoaArgs a)
 {
+    constexpr unsigned MASK = OUT | (COST ? M_WRENCH : 0u);
+    constexpr unsigned LIVE = live_planes(MASK);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long tile = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    const long long base = tile << 5;
+    if (base >= a.n) return;  // warp-uniform
+    const long long i = base + lane;
+    const bool on = i < a.n;
+    const int cnt = static_cast<int>(min64(kWarp, a.n - base));
+
+    // ---- every live plane in flight before the first use ---------------------------------------
+    double x[30] = {};
+#pragma unroll
+    for (int pl = 0; pl < 30; ++pl)
+        if (LIVE & (1u << pl)) x[pl] = on ? __ldcs(a.in[pl] + i) : 0.0;
+    Prm q = a.uni;
+    if constexpr (HET) {
+        const double l = on ? __ldcs(a.prm[0] + i) : 0.0, w = on ? __ldcs(a.prm[1] + i) : 0.0;
+        const double k = on ? __ldcs(a.prm[2] + i) : 0.0, b = on ? __ldcs(a.prm[3] + i) : 0.0;
+        q = make_prm(l, w, k, b);
+    }
+
+    double* ctile = reinterpret_cast<double*>(smem_raw) + warp * (kWarp * 36);
+    if constexpr ((OUT & M_CTRL) != 0) {
+        // structural zeros of the 32 dense blocks, written while the loads are in flight
+        double2* z = reinterpret_cast<double2*>(ctile);
+#pragma unroll
+        for (int j = 0; j < 18; ++j) z[lane + j * kWarp] = make_double2(0.0, 0.0);
+        __syncwarp();
+    }
+
+    State s;
+    s.v = V3{x[0], x[1], x[2]};
+    s.w = V3{x[3], x[4], x[5]};
+    s.p = V3{x[6], x[7], x[8]};
+    s.e1 = V3{x[9], x[12], x[15]};
+    s.e2 = V3{x[10], x[13], x[16]};
+    s.R02 = x[11];
+    s.R12 = x[14];
+    s.R22 = x[17];
+    s.p0 = V3{x[18], x[19], x[20]};
+    s.n1 = V3{x[21], x[24], x[27]};
+    s.n2 = V3{x[22], x[25], x[28]};
+    Result r;
+    eval_contact<MASK>(s, q, r);
+
+    if (on) {
+        if constexpr ((OUT & M_WRENCH) != 0) {
+            __stcs(a.wrench[0] + i, r.force.x); __stcs(a.wrench[1] + i, r.force.y);
+            __stcs(a.wrench[2] + i, r.force.z); __stcs(a.wrench[3] + i, r.torque.x);
+            __stcs(a.wrench[4] + i, r.torque.y); __stcs(a.wrench[5] + i, r.torque.z);
+        }
+        if constexpr ((OUT & M_AUTODYN) != 0) {
+            __stcs(a.autodyn[0] + i, r.fhead.x); __stcs(a.autodyn[1] + i, r.fhead.y);
+            __stcs(a.autodyn[2] + i, r.fhead.z); __stcs(a.autodyn[3] + i, r.ftail.x);
+            __stcs(a.autodyn[4] + i, r.ftail.y); __stcs(a.autodyn[5] + i, r.ftail.z);
+        }
+        if constexpr ((OUT & M_REGRESSOR) != 0) {
+            // row-major 6x2: plane 2*row + col, col 0 = spring, col 1 = damper
+            __stcs(a.reg[0] + i, r.y_fk.x); __stcs(a.reg[1] + i, r.y_fb.x);
+            __stcs(a.reg[2] + i, r.y_fk.y); __stcs(a.reg[3] + i, r.y_fb.y);
+            __stcs(a.reg[4] + i, r.y_fk.z); __stcs(a.reg[5] + i, r.y_fb.z);
+            __stcs(a.reg[6] + i, r.y_tk.x); __stcs(a.reg[7] + i, r.y_tb.x);
+            __stcs(a.reg[8] + i, r.y_tk.y); __stcs(a.reg[9] + i, r.y_tb.y);
+            __stcs(a.reg[10] + i, r.y_tk.z); __stcs(a.reg[11] + i, r.y_tb.z);
+        }
+        if constexpr ((OUT & M_CTRL) != 0) stage_ctrl(ctile + lane * 36, r);
+    }
+    if constexpr ((OUT & M_CTRL) != 0) flush_ctrl_tile(a.ctrl, ctile, base, cnt, lane, a.ctrl_bulk != 0);
+
+    if constexpr (COST) {
+        double c = 0.0;
+        if (on) {
+            const V3 df = r.force - V3{a.ref[0], a.ref[1], a.ref[2]};
+            const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
+            c = a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
+                a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z);
+        }
+        const long long rid = (on ? i : base + cnt - 1) / a.rollout_len;
+        const long long rid_first = __shfl_sync(0xffffffffu, rid, 0);
+        const long long rid_last = __shfl_sync(0xffffffffu, rid, cnt - 1);
+        for (long long rr = rid_first; rr <= rid_last; ++rr) {
+            double v = (on && rid == rr) ? c : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0)
+                a.partials[rr * a.slots + (tile - rollout_first_tile(rr, a.rollout_len))] = v;
+        }
+    }
+
+    if constexpr ((OUT & M_CTRL) != 0) {
+        // shared memory must stay valid until the bulk engine has read it
+        if (a.ctrl_bulk && lane == 0) ptx::bulk_wait_read_all();
+    }
+}
+
+// 128-bit variant: two contacts per lane, double2 plane accesses, grid-stride over 64-contact tiles.
+template <unsigned MASK, bool HET>
+__global__ void __launch_bounds__(128, 3)
+ccm_soa_vec2_kernel(const __grid_constant__ SoaArgs a)
+{
+    constexpr int CPT = 2;
     constexpr int TILE = kWarp * CPT;
     constexpr unsigned LIVE = live_planes(MASK);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -517,11 +641,9 @@ ccm_surface_points_kernel(const __grid_constant__ PointArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sampling-MPC epilogue: evaluate, reduce a per-rollout cost, arg-min -- one launch.
-// A warp owns whole rollouts (rollout-major batch), so the cost is reduced in a fixed order
-// (lane-strided partial sums, then an xor-butterfly) and is bit-reproducible run to run.  The
-// device-wide arg-min uses the last-block-done pattern: every CTA publishes its (cost,index)
-// pair, the last one to finish combines them.
+// Sampling-MPC epilogue, second (tiny) launch: sum each rollout's per-tile partials in tile order,
+// write cost[r], arg-min with lowest-index tie-break.  Device-wide arg-min by the last-block-done
+// pattern: every CTA publishes its (cost,index) pair, the last one to finish combines them.
 // ------------------------------------------------------------------------------------------------
 
 struct CostIdx {
@@ -533,19 +655,6 @@ __device__ __forceinline__ bool better(double c, long long i, double bc, long lo
 {
     return (c < bc) || (c == bc && i < bi);
 }
-
-struct RolloutArgs {
-    SoaArgs soa;               // planes, outputs, params; soa.n = n_rollouts * rollout_len
-    long long n_rollouts;
-    long long rollout_len;
-    long long index_base;
-    double ref[6];
-    double wf, wt;
-    double* cost;              // n_rollouts or nullptr
-    CostIdx* partials;         // gridDim.x entries (handle scratch)
-    unsigned int* counter;     // zero before launch; reset by the last CTA
-    CostIdx* best;             // result
-};
 
 __device__ __forceinline__ CostIdx warp_best(CostIdx b)
 {
@@ -561,114 +670,51 @@ __device__ __forceinline__ CostIdx warp_best(CostIdx b)
     return b;
 }
 
-// OUT = what is written to HBM; the wrench is always computed (it feeds the cost).
-template <unsigned OUT, bool HET>
-__global__ void __launch_bounds__(128, 4)
-ccm_rollout_kernel(const __grid_constant__ RolloutArgs ra)
+struct ReduceArgs {
+    const double* partials;    // [n_rollouts][slots]
+    int slots;
+    long long n_rollouts;
+    long long rollout_len;
+    long long index_base;
+    double* cost;              // n_rollouts or nullptr
+    CostIdx* block_best;       // gridDim.x entries (handle scratch)
+    unsigned int* counter;     // zero before launch; reset by the last CTA
+    CostIdx* best;             // result
+};
+
+__global__ void __launch_bounds__(128)
+ccm_cost_reduce_kernel(const __grid_constant__ ReduceArgs ra)
 {
-    constexpr unsigned MASK = OUT | M_WRENCH;
-    constexpr unsigned LIVE = live_planes(MASK);
-    constexpr int TILE = kWarp;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ CostIdx s_best[4];
     __shared__ bool s_last;
-
-    const SoaArgs& a = ra.soa;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
-    double* ctile = reinterpret_cast<double*>(smem_raw) + static_cast<size_t>(warp) * TILE * 36;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
-    if constexpr ((OUT & M_CTRL) != 0) {
-        double2* z = reinterpret_cast<double2*>(ctile);
-        for (int i = lane; i < TILE * 18; i += kWarp) z[i] = make_double2(0.0, 0.0);
-        __syncwarp();
-    }
-
-    CostIdx mine{__longlong_as_double(0x7ff0000000000000LL), 0x7fffffffffffffffLL};
-    const long long wstride = static_cast<long long>(gridDim.x) * warps_per_cta;
-    for (long long ro = static_cast<long long>(blockIdx.x) * warps_per_cta + warp;
-         ro < ra.n_rollouts; ro += wstride) {
-        const long long r0 = ro * ra.rollout_len;
+    CostIdx mine{inf, 0x7fffffffffffffffLL};
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long ro = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+         ro < ra.n_rollouts; ro += stride) {
+        const long long t0 = rollout_first_tile(ro, ra.rollout_len);
+        const long long t1 = ((ro + 1) * ra.rollout_len - 1) >> 5;
+        const double* p = ra.partials + ro * ra.slots;
         double acc = 0.0;
-        for (long long off = 0; off < ra.rollout_len; off += TILE) {
-            const long long base = r0 + off;
-            const int cnt = static_cast<int>(min64(TILE, ra.rollout_len - off));
-            const bool on = lane < cnt;
-            const long long i = base + lane;
-
-            Lanes<1> x[30] = {};
-#pragma unroll
-            for (int pl = 0; pl < 30; ++pl)
-                if (LIVE & (1u << pl)) x[pl].v[0] = on ? __ldcs(a.in[pl] + i) : 0.0;
-            Prm q = a.uni;
-            if constexpr (HET) {
-                const double l = on ? __ldcs(a.prm[0] + i) : 0.0, w = on ? __ldcs(a.prm[1] + i) : 0.0;
-                const double k = on ? __ldcs(a.prm[2] + i) : 0.0, b = on ? __ldcs(a.prm[3] + i) : 0.0;
-                q = make_prm(l, w, k, b);
-            }
-            State s;
-            s.v = V3{x[0].v[0], x[1].v[0], x[2].v[0]};
-            s.w = V3{x[3].v[0], x[4].v[0], x[5].v[0]};
-            s.p = V3{x[6].v[0], x[7].v[0], x[8].v[0]};
-            s.e1 = V3{x[9].v[0], x[12].v[0], x[15].v[0]};
-            s.e2 = V3{x[10].v[0], x[13].v[0], x[16].v[0]};
-            s.R02 = x[11].v[0];
-            s.R12 = x[14].v[0];
-            s.R22 = x[17].v[0];
-            s.p0 = V3{x[18].v[0], x[19].v[0], x[20].v[0]};
-            s.n1 = V3{x[21].v[0], x[24].v[0], x[27].v[0]};
-            s.n2 = V3{x[22].v[0], x[25].v[0], x[28].v[0]};
-            Result r;
-            eval_contact<MASK>(s, q, r);
-
-            if (on) {
-                const V3 df = r.force - V3{ra.ref[0], ra.ref[1], ra.ref[2]};
-                const V3 dt = r.torque - V3{ra.ref[3], ra.ref[4], ra.ref[5]};
-                acc += ra.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
-                       ra.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z);
-                if constexpr ((OUT & M_WRENCH) != 0) {
-                    __stcs(a.wrench[0] + i, r.force.x); __stcs(a.wrench[1] + i, r.force.y);
-                    __stcs(a.wrench[2] + i, r.force.z); __stcs(a.wrench[3] + i, r.torque.x);
-                    __stcs(a.wrench[4] + i, r.torque.y); __stcs(a.wrench[5] + i, r.torque.z);
-                }
-                if constexpr ((OUT & M_AUTODYN) != 0) {
-                    __stcs(a.autodyn[0] + i, r.fhead.x); __stcs(a.autodyn[1] + i, r.fhead.y);
-                    __stcs(a.autodyn[2] + i, r.fhead.z); __stcs(a.autodyn[3] + i, r.ftail.x);
-                    __stcs(a.autodyn[4] + i, r.ftail.y); __stcs(a.autodyn[5] + i, r.ftail.z);
-                }
-            }
-            if constexpr ((OUT & M_CTRL) != 0) {
-                if (a.ctrl_bulk) {
-                    if (lane == 0) ptx::bulk_wait_read_all();
-                }
-                __syncwarp();
-                if (on) stage_ctrl(ctile + lane * 36, r);
-                flush_ctrl_tile(a.ctrl, ctile, base, cnt, lane, a.ctrl_bulk != 0);
-            }
-        }
-        // fixed-order reduction over the 32 lane partials
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0 && ra.cost) ra.cost[ro] = acc;
+        for (long long j = 0; j <= t1 - t0; ++j) acc += p[j];
+        if (ra.cost) ra.cost[ro] = acc;
         const long long gi = ra.index_base + ro;
         if (better(acc, gi, mine.cost, mine.idx)) {
             mine.cost = acc;
             mine.idx = gi;
         }
     }
-    if constexpr ((OUT & M_CTRL) != 0) {
-        if (a.ctrl_bulk && lane == 0) ptx::bulk_wait_all();
-    }
-
-    // ---- CTA arg-min, publish, last CTA combines -------------------------------------------
-    if (lane == 0) s_best[warp] = mine;  // all lanes of a warp hold the same pair
+    mine = warp_best(mine);
+    if (lane == 0) s_best[warp] = mine;
     __syncthreads();
     if (threadIdx.x == 0) {
         CostIdx b = s_best[0];
-        for (int w = 1; w < warps_per_cta; ++w)
+        for (int w = 1; w < (blockDim.x >> 5); ++w)
             if (better(s_best[w].cost, s_best[w].idx, b.cost, b.idx)) b = s_best[w];
-        ra.partials[blockIdx.x] = b;
+        ra.block_best[blockIdx.x] = b;
         __threadfence();
         const unsigned int done = atomicAdd(ra.counter, 1u);
         s_last = (done == gridDim.x - 1);
@@ -676,11 +722,11 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs ra)
     __syncthreads();
     if (s_last && warp == 0) {
         __threadfence();
-        CostIdx b{__longlong_as_double(0x7ff0000000000000LL), 0x7fffffffffffffffLL};
+        CostIdx b{inf, 0x7fffffffffffffffLL};
         for (unsigned int j = lane; j < gridDim.x; j += kWarp) {
             CostIdx c;
-            c.cost = *reinterpret_cast<volatile double*>(&ra.partials[j].cost);
-            c.idx = *reinterpret_cast<volatile long long*>(&ra.partials[j].idx);
+            c.cost = *reinterpret_cast<volatile double*>(&ra.block_best[j].cost);
+            c.idx = *reinterpret_cast<volatile long long*>(&ra.block_best[j].idx);
             if (better(c.cost, c.idx, b.cost, b.idx)) b = c;
         }
         b = warp_best(b);

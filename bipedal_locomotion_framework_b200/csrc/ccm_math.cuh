@@ -48,6 +48,15 @@ __device__ __forceinline__ V3 cross(const V3& a, const V3& b)
 {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
+// Cross product with every product rounded on its own (no FMA contraction): a x a is then exactly
+// zero, as in the reference's non-fused arithmetic.  Used for S(e_i) R0.col(i), which cancels
+// exactly when the foot sits at its null-force orientation (R == R0), a common resting state.
+__device__ __forceinline__ V3 cross_exact(const V3& a, const V3& b)
+{
+    return V3{__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)),
+              __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
+              __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x))};
+}
 __device__ __forceinline__ V3 operator+(const V3& a, const V3& b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 __device__ __forceinline__ V3 operator-(const V3& a, const V3& b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 __device__ __forceinline__ V3 operator*(double s, const V3& a) { return V3{s * a.x, s * a.y, s * a.z}; }
@@ -92,8 +101,8 @@ __device__ __forceinline__ void eval_contact(const State& s, const Prm& q, Resul
         t2 = cross(s.e2, s.w);
         u1 = cross(s.e1, t1);    // S(e1)^2 w
         u2 = cross(s.e2, t2);
-        m1 = cross(s.e1, s.n1);  // S(e1) R0.col(0)
-        m2 = cross(s.e2, s.n2);
+        m1 = cross_exact(s.e1, s.n1);  // S(e1) R0.col(0)
+        m2 = cross_exact(s.e2, s.n2);
     }
     if constexpr (kW || kA) {
         sd = q.k * d - q.b * s.v;                       // k (p0 - p) - b v

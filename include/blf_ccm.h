@@ -33,8 +33,10 @@
  *
  * Pointers are DEVICE pointers unless the function name says host.  The arrays-of-pointers
  * themselves (in_planes etc.) are HOST arrays of device pointers.  Alignment: 8 bytes is always
- * accepted; when every pointer is 16-byte aligned the 128-bit load/store and bulk-copy (TMA) paths
- * are taken, otherwise a 64-bit path is dispatched (same results; blf_ccm_last_path reports which).
+ * accepted.  SoA planes are read/written with coalesced 64-bit accesses and need no more.  Buffers
+ * that are staged through shared memory with bulk async copies (the dense ctrl array, and every
+ * array of the AoS entry points) take that path when 16-byte aligned; otherwise a direct 64-bit
+ * path is dispatched -- same results, and blf_ccm_last_path reports which (checked, not silent).
  *
  * Threading: a handle is used from one host thread at a time; distinct handles are independent.
  * Launches are asynchronous on the caller's stream (void* = cudaStream_t, NULL = default stream).
@@ -89,8 +91,8 @@ typedef struct {
 /* code path taken by the last evaluation on a handle */
 enum {
     BLF_CCM_PATH_NONE = 0,
-    BLF_CCM_PATH_VEC128 = 1, /* 128-bit loads/stores + bulk-copy staging */
-    BLF_CCM_PATH_SCALAR64 = 2 /* 64-bit path for 8-byte-aligned buffers   */
+    BLF_CCM_PATH_BULK = 1,    /* bulk-copy (TMA) staging in use: every staged buffer 16-byte aligned */
+    BLF_CCM_PATH_DIRECT64 = 2 /* a staged buffer is only 8-byte aligned: direct 64-bit accesses     */
 };
 
 BLF_CCM_API const char* blf_ccm_version(void);
@@ -147,8 +149,10 @@ BLF_CCM_API int blf_ccm_eval_surface_points(blf_ccm_handle* h, const double* hos
 
 /*
  * Sampling-MPC epilogue.  The batch is n_rollouts * rollout_len contact states, rollout-major
- * (all evaluations of a rollout are contiguous).  One launch evaluates every state (outputs per
- * out_mask exactly as blf_ccm_eval_batch_soa; out_mask may be 0 to keep only the cost), reduces
+ * (all evaluations of a rollout are contiguous).  The evaluation kernel (outputs per out_mask
+ * exactly as blf_ccm_eval_batch_soa; out_mask may be 0 to keep only the cost) also reduces the
+ * cost per (rollout, tile) in its epilogue, so the wrench is never re-read; a second tiny launch
+ * sums each rollout's few partials, i.e.
  *   cost[r] = sum_e  weights[0]*|force_e - wrench_ref[0:3]|^2 + weights[1]*|torque_e - wrench_ref[3:6]|^2
  * per rollout in a fixed order (deterministic), and arg-mins over the local rollouts with
  * lowest-index tie-break.  cost (device, n_rollouts) may be NULL.  best (device, 2 x 8 bytes):
@@ -176,6 +180,21 @@ BLF_CCM_API int blf_ccm_argmin_pairs(blf_ccm_handle* h, int n_pairs, const void*
 BLF_CCM_API int blf_ccm_argmin_allgather_nccl(blf_ccm_handle* h, void* comm, int nranks,
                                               const void* best, void* gathered, void* global_best,
                                               void* stream);
+
+/*
+ * Device / pinned-host memory and stream helpers, so that host code above this ABI (the C++17
+ * facade, the device-side SoA container) needs no CUDA headers.  Device allocations are 256-byte
+ * aligned.  Copies are asynchronous on `stream` when the host side is pinned.
+ */
+BLF_CCM_API int blf_ccm_device_alloc(blf_ccm_handle* h, uint64_t bytes, void** out);
+BLF_CCM_API int blf_ccm_device_free(blf_ccm_handle* h, void* ptr);
+BLF_CCM_API int blf_ccm_host_alloc(blf_ccm_handle* h, uint64_t bytes, void** out); /* pinned */
+BLF_CCM_API int blf_ccm_host_free(blf_ccm_handle* h, void* ptr);
+BLF_CCM_API int blf_ccm_copy_h2d(blf_ccm_handle* h, void* dst_device, const void* src_host,
+                                 uint64_t bytes, void* stream);
+BLF_CCM_API int blf_ccm_copy_d2h(blf_ccm_handle* h, void* dst_host, const void* src_device,
+                                 uint64_t bytes, void* stream);
+BLF_CCM_API int blf_ccm_stream_synchronize(blf_ccm_handle* h, void* stream);
 
 /* Introspection */
 BLF_CCM_API int blf_ccm_last_path(const blf_ccm_handle* h);

@@ -98,7 +98,7 @@ def test_config2_one_million_wrench_only_soa(torch, batch, oracle):
     st = syn.make_states(1 << 20, seed=42 + 2)
     planes, _ = _soa_inputs(torch, st)
     got = _soa_out_to_aos(batch.evaluate_soa(planes, None, W))
-    assert batch.handle.last_path == 1  # 128-bit path
+    assert batch.handle.last_path == 1  # BLF_CCM_PATH_BULK
     ref = oracle.eval_batch_states(st, mask=W, nthreads=NTHREADS)
     _check(got, ref, W, "config2")
 
@@ -237,7 +237,11 @@ def test_eight_byte_aligned_buffers_take_the_checked_64bit_path(torch, batch, or
         planes.copy_(_dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])))
         assert planes[0].data_ptr() % 16 == 8
         prm = _dev(torch, st["params"].T)
-        got = _soa_out_to_aos(batch.evaluate_soa(planes, prm, FULL))
+        out = batch.alloc_soa_outputs(n, FULL)
+        cbuf = torch.empty(n * 36 + 1, dtype=torch.float64, device="cuda")
+        out["ctrl"] = cbuf[1:].view(n, 36)          # dense 6x6 array 8- but not 16-byte aligned
+        assert out["ctrl"].data_ptr() % 16 == 8
+        got = _soa_out_to_aos(batch.evaluate_soa(planes, prm, FULL, out=out))
     else:
         def shifted(a):
             buf = torch.empty(a.size + 1, dtype=torch.float64, device="cuda")
@@ -248,8 +252,33 @@ def test_eight_byte_aligned_buffers_take_the_checked_64bit_path(torch, batch, or
         got = _aos_out(batch.evaluate_aos(shifted(st["twists"]), shifted(st["poses"]),
                                           shifted(st["null_poses"]), _dev(torch, st["params"]),
                                           FULL))
-    assert batch.handle.last_path == 2  # BLF_CCM_PATH_SCALAR64: dispatched, reported, same results
+    assert batch.handle.last_path == 2  # BLF_CCM_PATH_DIRECT64: dispatched, reported, same results
     _check(got, ref, FULL, f"unaligned/{layout}")
+
+
+def test_128bit_two_contacts_per_lane_variant(torch, oracle, monkeypatch):
+    """The selectable 128-bit SoA kernel (BLF_CCM_TUNE_CPT=2), persistent and one-tile-per-warp."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    n = 100000 + 17
+    st = syn.make_states(n + 1, seed=23, heterogeneous=True)
+    st = {k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    ref = oracle.eval_batch_states(st, mask=FULL | R, nthreads=NTHREADS)
+    big = torch.empty((30, n + 1), dtype=torch.float64, device="cuda")  # even pitch: rows 16-B aligned
+    planes = big[:, :n]
+    planes.copy_(_dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])))
+    pbig = torch.empty((4, n + 1), dtype=torch.float64, device="cuda")
+    prm = pbig[:, :n]
+    prm.copy_(_dev(torch, st["params"].T))
+    for blocks in ("0", "2"):
+        monkeypatch.setenv("BLF_CCM_TUNE_CPT", "2")
+        monkeypatch.setenv("BLF_CCM_TUNE_BLOCKS_PER_SM", blocks)
+        b = ContinuousContactModelBatch(0)
+        b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+        out = {k: torch.empty((c, n + 1), dtype=torch.float64, device="cuda")[:, :n]
+               for k, c in (("wrench", 6), ("autodyn", 6), ("regressor", 12))}
+        out["ctrl"] = torch.empty((n, 36), dtype=torch.float64, device="cuda")
+        b.evaluate_soa(planes, prm, FULL | R, out=out)
+        _check(_soa_out_to_aos(out), ref, FULL | R, f"vec2 blocks={blocks}")
 
 
 def test_uninitialised_handle_is_an_error(torch):

@@ -65,35 +65,36 @@ def main():
                for k in ("twists", "poses", "null_poses")]
         prm_aos = prm.T.contiguous()
         print(f"\n=== n = {n} ({label}); peak {PEAK} GB/s ===")
-        for cpt in (2, 1):
-            for bps in (0, 1, 2, -1):
-                b = make_batch(BLF_CCM_TUNE_CPT=cpt, BLF_CCM_TUNE_BLOCKS_PER_SM=bps)
-                outs = [b.alloc_soa_outputs(n, FULL) for _ in range(NS)]
-                ms = timeit(lambda i: b.evaluate_soa(planes[i % NS], None, FULL, out=outs[i % NS]))
-                row(f"soa full uniform cpt={cpt} blocks/SM={bps or 'occ'}", ms, n, 600)
-                del outs
+        for cpt, bps in ((1, 0), (2, 0), (2, 3), (2, 2)):
+            b = make_batch(BLF_CCM_TUNE_CPT=cpt, BLF_CCM_TUNE_BLOCKS_PER_SM=bps)
+            outs = [b.alloc_soa_outputs(n, FULL) for _ in range(NS)]
+            ms = timeit(lambda i: b.evaluate_soa(planes[i % NS], None, FULL, out=outs[i % NS]))
+            row(f"soa full uniform contacts/lane={cpt} {'persistent %d CTA/SM' % bps if bps else 'one tile/warp'}",
+                ms, n, 600)
+            del outs
         b = make_batch()
         outs = [b.alloc_soa_outputs(n, FULL) for _ in range(NS)]
         ms = timeit(lambda i: b.evaluate_soa(planes[i % NS], prm, FULL, out=outs[i % NS]))
         row("soa full heterogeneous", ms, n, 632)
-        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], 200, [0, 0, 30., 0, 0, 0], [1., 10.],
+        rl = 200 if n % 200 == 0 else 256
+        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], rl, [0, 0, 30., 0, 0, 0], [1., 10.],
                                                     mask=FULL, out=outs[i % NS], want_cost=False))
-        row("rollout(200) full + cost + argmin", ms, n, 600)
-        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], 200, [0, 0, 30., 0, 0, 0], [1., 10.],
+        row(f"rollout({rl}) full + cost + argmin (2 launches)", ms, n, 600)
+        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], rl, [0, 0, 30., 0, 0, 0], [1., 10.],
                                                     mask=0, want_cost=True))
-        row("rollout(200) cost only (25 planes in)", ms, n, 200)
+        row(f"rollout({rl}) cost only (25 planes in)", ms, n, 200)
         del outs
         outs = [b.alloc_soa_outputs(n, WRENCH) for _ in range(NS)]
-        for cpt in (2, 1):
+        for cpt in (1, 2):
             b2 = make_batch(BLF_CCM_TUNE_CPT=cpt)
             ms = timeit(lambda i: b2.evaluate_soa(planes[i % NS], None, WRENCH, out=outs[i % NS]))
-            row(f"soa wrench-only uniform cpt={cpt}", ms, n, 248)
+            row(f"soa wrench-only uniform contacts/lane={cpt}", ms, n, 248)
         del outs
-        for bps in (0, 2, 4, -1):
+        for bps in (0, 2):
             b3 = make_batch(BLF_CCM_TUNE_BLOCKS_PER_SM=bps)
             outs = [b3.alloc_aos_outputs(n, FULL) for _ in range(2)]
             ms = timeit(lambda i: b3.evaluate_aos(aos[0], aos[1], aos[2], None, FULL, out=outs[i % 2]))
-            row(f"aos full uniform blocks/SM={bps or 'occ'} (624 B touched)", ms, n, 600)
+            row(f"aos full uniform {'persistent %d CTA/SM' % bps if bps else 'one tile/warp'} (624 B touched)", ms, n, 600)
             del outs
         b = make_batch()
         outs = [b.alloc_aos_outputs(n, FULL) for _ in range(2)]
