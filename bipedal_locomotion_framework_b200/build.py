@@ -57,6 +57,49 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return CUDA_LIB
 
 
+CPP_DIR = os.path.join(_HERE, "cpp")
+CPP_LIB = os.path.join(LIB_DIR, "libblf_contact.so")
+CPP_TESTS = {
+    "ContinuousContactModelUnitTests": "ContinuousContactModelTest.cpp",   # needs a GPU
+    "ParametersHandlerUnitTests": "ParametersHandlerTest.cpp",             # host only
+}
+CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra"]
+
+
+def _cpp_sources() -> list[str]:
+    out = []
+    for root, _, files in os.walk(CPP_DIR):
+        out += [os.path.join(root, f) for f in files if f.endswith((".h", ".cpp", ".txt"))]
+    return out + [os.path.join(ROOT, "include", "blf_ccm.h")]
+
+
+def build_cpp(force: bool = False) -> str:
+    """C++17 host facade (libblf_contact.so, links libblf_ccm.so) and its test executables."""
+    build_cuda()
+    cxx = shutil.which("g++") or "g++"
+    inc = ["-I", os.path.join(CPP_DIR, "include"), "-I", os.path.join(ROOT, "include")]
+    srcs = sorted(os.path.join(CPP_DIR, "src", f) for f in os.listdir(os.path.join(CPP_DIR, "src"))
+                  if f.endswith(".cpp"))
+    deps = _cpp_sources() + [CUDA_LIB]
+
+    def run(cmd):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(" ".join(cmd) + "\n" + r.stdout)
+
+    if force or not _newer(CPP_LIB, deps):
+        run([cxx, *CXX_FLAGS, "-shared", "-o", CPP_LIB, *srcs, *inc, "-L", LIB_DIR, "-lblf_ccm",
+             "-Wl,-rpath,$ORIGIN"])
+    for exe, src in CPP_TESTS.items():
+        target = os.path.join(LIB_DIR, exe)
+        if force or not _newer(target, deps + [CPP_LIB]):
+            run([cxx, *CXX_FLAGS, "-DCATCH_CONFIG_MAIN", "-o", target,
+                 os.path.join(CPP_DIR, "tests", src), *inc, "-I", os.path.join(CPP_DIR, "tests"),
+                 "-L", LIB_DIR, "-lblf_contact", "-lblf_ccm", "-Wl,-rpath,$ORIGIN"])
+    return CPP_LIB
+
+
 if __name__ == "__main__":
     import sys
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cpp(force="--force" in sys.argv))

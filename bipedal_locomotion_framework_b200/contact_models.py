@@ -352,6 +352,70 @@ class ContinuousContactModelBatch:
             self._plane_ptrs(out["regressor"], 12), self._stream()))
         return out
 
+    def prepare_soa(self, planes, param_planes=None, mask: int = FULL, out: dict | None = None):
+        """Bind every argument of blf_ccm_eval_batch_soa once; the returned callable is a single
+        foreign call (a few microseconds of host time), for launch-rate-sensitive loops.
+        Returns (call, out)."""
+        n = planes.shape[1]
+        out = out if out is not None else self.alloc_soa_outputs(n, mask)
+        args = (self._handle.ptr, n, self._plane_ptrs(planes, 30), self._plane_ptrs(param_planes, 4),
+                mask, self._plane_ptrs(out["wrench"], 6), self._plane_ptrs(out["autodyn"], 6),
+                out["ctrl"].data_ptr() if out["ctrl"] is not None else None,
+                self._plane_ptrs(out["regressor"], 12), self._stream())
+        fn = _capi.lib().blf_ccm_eval_batch_soa
+        keep = (planes, param_planes, out)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call, out
+
+    def prepare_aos(self, twists, poses, null_poses, params=None, mask: int = FULL,
+                    out: dict | None = None):
+        n = poses.shape[0]
+        out = out if out is not None else self.alloc_aos_outputs(n, mask)
+        dp = lambda t: t.data_ptr() if t is not None else None
+        args = (self._handle.ptr, n, dp(twists), dp(poses), dp(null_poses), dp(params), mask,
+                dp(out["wrench"]), dp(out["autodyn"]), dp(out["ctrl"]), dp(out["regressor"]),
+                self._stream())
+        fn = _capi.lib().blf_ccm_eval_batch_aos
+        keep = (twists, poses, null_poses, params, out)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call, out
+
+    def prepare_rollout(self, planes, rollout_len: int, wrench_ref, weights, param_planes=None,
+                        mask: int = 0, index_base: int = 0, out: dict | None = None,
+                        want_cost: bool = True):
+        """Prepared form of rollout_cost_argmin.  Returns (call, out, cost, best)."""
+        t = self._torch
+        n = planes.shape[1]
+        assert n % rollout_len == 0
+        n_rollouts = n // rollout_len
+        out = out if out is not None else self.alloc_soa_outputs(n, mask)
+        cost = t.empty(n_rollouts, dtype=t.float64, device=self.device) if want_cost else None
+        best = t.empty(2, dtype=t.int64, device=self.device)
+        ref = np.ascontiguousarray(wrench_ref, dtype=np.float64)
+        wts = np.ascontiguousarray(weights, dtype=np.float64)
+        args = (self._handle.ptr, n_rollouts, rollout_len, self._plane_ptrs(planes, 30),
+                self._plane_ptrs(param_planes, 4), mask, self._plane_ptrs(out["wrench"], 6),
+                self._plane_ptrs(out["autodyn"], 6),
+                out["ctrl"].data_ptr() if out["ctrl"] is not None else None,
+                _np_ptr(ref), _np_ptr(wts), int(index_base),
+                cost.data_ptr() if cost is not None else None, best.data_ptr(), self._stream())
+        fn = _capi.lib().blf_ccm_rollout_cost_argmin_soa
+        keep = (planes, param_planes, out, ref, wts, cost, best)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call, out, cost, best
+
     def evaluate_aos(self, twists, poses, null_poses, params=None, mask: int = FULL,
                      out: dict | None = None):
         n = poses.shape[0]

@@ -82,6 +82,9 @@ public:
 
     explicit ContinuousContactModelBatch(int device = 0);
     explicit ContinuousContactModelBatch(std::shared_ptr<CudaDevice> device);
+    ~ContinuousContactModelBatch();
+    ContinuousContactModelBatch(const ContinuousContactModelBatch&) = delete;
+    ContinuousContactModelBatch& operator=(const ContinuousContactModelBatch&) = delete;
 
     /** Same four required double parameters as ContinuousContactModel; they apply to every contact
      * of evaluations that pass no per-contact parameters. */

