@@ -181,6 +181,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from bipedal_locomotion_framework_b200 import sharding
     from bipedal_locomotion_framework_b200 import synthetic as syn
     from bipedal_locomotion_framework_b200.contact_models import FULL, ContinuousContactModelBatch
 
@@ -201,8 +202,11 @@ def run_ours(args):
     batch = ContinuousContactModelBatch(local)
     batch.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
 
-    # rank r owns samples [r*4096, (r+1)*4096): states r*n .. (r+1)*n of the seeded stream
-    st = syn.make_states(n, seed=42 + 3, start=rank * n)
+    # weak scaling: world*4096 rollouts in total, block-partitioned; rank r owns rollouts
+    # [first, first+count) = states first*200 .. of the seeded stream
+    first_rollout, n_roll = sharding.shard_rollouts(world * SAMPLES, world, rank)
+    assert n_roll * ROLLOUT_LEN == n
+    st = syn.make_states(n, seed=42 + 3, start=first_rollout * ROLLOUT_LEN)
     planes_np = syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])
     NSETS = 3   # rotate distinct input/output buffer sets so no step finds its data in L2
     planes = [torch.from_numpy(planes_np).to(dev) for _ in range(NSETS)]
@@ -259,19 +263,15 @@ def run_ours(args):
 
     # ---- sampling-MPC epilogue: evaluate + per-rollout cost + arg-min (+ NCCL all-gather) --------
     ref_wrench, weights = [0.0, 0.0, 30.0, 0.0, 0.0, 0.0], [1.0, 10.0]
-    n_roll = n // ROLLOUT_LEN
-    gathered = torch.empty((world, 2), dtype=torch.int64, device=dev)
-
     mpc_calls = [batch.prepare_rollout(planes[j], ROLLOUT_LEN, ref_wrench, weights, mask=FULL,
-                                       index_base=rank * n_roll, out=outs[j], want_cost=False)
+                                       index_base=first_rollout, out=outs[j], want_cost=False)
                  for j in range(NSETS)]
 
     def mpc_step(i):
         call, _, _, best = mpc_calls[i % NSETS]
         call()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), best)
-            return batch.argmin_pairs(gathered)
+        if world > 1:   # the only collective of the path: 16 bytes per rank
+            return batch.argmin_pairs(sharding.all_gather_pairs(best, world, dist))
         return best
 
     for i in range(Wm):

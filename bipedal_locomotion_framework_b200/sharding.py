@@ -1,0 +1,41 @@
+"""Multi-GPU host logic of the sampling-MPC path.
+
+One process per GPU.  Rollouts (samples) are block-partitioned across ranks so that every
+evaluation of a rollout lives on one GPU: the contact evaluation itself needs NO collective.  The
+only exchange is the 16-byte (cost, index) pair each rank's arg-min produces: an all-gather over
+NCCL (NVLink 5 / NVSwitch) on the GPU box, gloo in the CPU tests, followed by a lowest-index
+tie-break selection (blf_ccm_argmin_pairs on the device).
+"""
+from __future__ import annotations
+
+import struct
+
+
+def shard_rollouts(n_rollouts: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block partition: returns (first_rollout, count) owned by `rank`."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    first = n_rollouts * rank // world
+    last = n_rollouts * (rank + 1) // world
+    return first, last - first
+
+
+def pack_pair(cost: float, index: int) -> tuple[int, int]:
+    """(cost, index) as the two int64 words the device writes (double bits, index)."""
+    return struct.unpack("<q", struct.pack("<d", cost))[0], int(index)
+
+
+def unpack_pair(word0: int, word1: int) -> tuple[float, int]:
+    return struct.unpack("<d", struct.pack("<q", int(word0)))[0], int(word1)
+
+
+def all_gather_pairs(best, world: int, dist=None):
+    """All-gather every rank's (2,) int64 `best` tensor into a (world, 2) tensor on the same
+    device (16 bytes per rank; pure latency on NVSwitch)."""
+    import torch
+    if world == 1:
+        return best.view(1, 2)
+    dist = dist or torch.distributed
+    gathered = torch.empty((world, 2), dtype=torch.int64, device=best.device)
+    dist.all_gather_into_tensor(gathered.view(-1), best)
+    return gathered
