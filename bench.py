@@ -364,18 +364,155 @@ def run_ours(args):
     return 0
 
 
+# --------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] and configs[4]: strong-scaling workloads (run on request)
+# --------------------------------------------------------------------------------------------------
+
+def run_large(args):
+    import torch
+    import torch.distributed as dist
+
+    from bipedal_locomotion_framework_b200 import sharding
+    from bipedal_locomotion_framework_b200 import synthetic as syn
+    from bipedal_locomotion_framework_b200.contact_models import FULL, ContinuousContactModelBatch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the contact-model backend has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = min(args.steps, 50), max(min(args.warmup, 10), 3)
+
+    batch = ContinuousContactModelBatch(local)
+    batch.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    if args.workload == "config4":
+        total_rollouts = 335544                   # 335 544 x 200 = 67 108 800 ~ 2^26 states
+        first, count = sharding.shard_rollouts(total_rollouts, world, rank)
+        n, het, bytes_per = count * ROLLOUT_LEN, True, 632
+        total = total_rollouts * ROLLOUT_LEN
+        name = ("configs[3]: 64M heterogeneous contact states (per-contact length/width/spring/"
+                "damper), rollouts of 200 sharded by rollout, wrench+autodyn+ctrl + per-rollout "
+                "cost + NCCL arg-min")
+    else:
+        total = 1 << 28
+        first, count = sharding.shard_rollouts(total, world, rank)   # plain block partition
+        n, het, bytes_per = count, False, 600
+        name = "configs[4]: strong scaling, 256M contact states, wrench+autodyn+ctrl, uniform params"
+    planes, prm = syn.make_planes_torch(n, dev, seed=42 + 4 + 1000 * rank, heterogeneous=het)
+    out = batch.alloc_soa_outputs(n, FULL)
+    torch.cuda.synchronize()
+
+    if args.workload == "config4":
+        call, _, _, best = batch.prepare_rollout(planes, ROLLOUT_LEN, [0.0, 0.0, 30.0, 0.0, 0.0, 0.0],
+                                                 [1.0, 10.0], param_planes=prm, mask=FULL,
+                                                 index_base=first, out=out, want_cost=False)
+
+        def step():
+            call()
+            if world > 1:
+                return batch.argmin_pairs(sharding.all_gather_pairs(best, world, dist))
+            return best
+    else:
+        call, _ = batch.prepare_soa(planes, None, FULL, out=out)
+
+        def step():
+            call()
+            return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(Wm):
+        res = step()
+    barrier()
+    l0 = batch.handle.launch_count
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        res = step()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    launches = batch.handle.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.summary(t0, t1)
+    sampler.stop_flag = True
+
+    # parity on a sample of the same device bits (every 4099th state of this rank's shard)
+    parity = None
+    if rank == 0:
+        from oracle import ccm_oracle
+        idx = torch.arange(0, n, 4099, device=dev)
+        st = syn.sample_states_from_planes(planes, prm, idx)
+        ref = ccm_oracle.eval_batch_states(st, mask=7, nthreads=os.cpu_count() or 1)
+        worst = 0.0
+        got = {"wrench": torch.stack([p[idx] for p in out["wrench"]], 1).cpu().numpy(),
+               "autodyn": torch.stack([p[idx] for p in out["autodyn"]], 1).cpu().numpy(),
+               "ctrl": out["ctrl"][idx].cpu().numpy()}
+        for key, blocks in (("wrench", [slice(0, 3), slice(3, 6)]), ("autodyn", [slice(0, 3), slice(3, 6)]),
+                            ("ctrl", [slice(6 * q + 3 * (q // 3), 6 * q + 3 * (q // 3) + 3) for q in range(6)])):
+            for sl in blocks:
+                num = np.abs(got[key][:, sl] - ref[key][:, sl]).max(axis=1)
+                den = np.maximum(np.abs(ref[key][:, sl]).max(axis=1), 1e-300)
+                worst = max(worst, float(np.where(num == 0, 0, num / den).max()))
+        parity = {"sampled_states": int(idx.numel()), "worst_block_rel_err": worst, "tol": 1e-12,
+                  "ok": bool(worst <= 1e-12)}
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        per_gpu_gbs = bytes_per * n / (ms / K * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (device-generated)",
+            "config": {"workload": name, "evals_per_step": total, "evals_per_step_per_gpu": n,
+                       "parallelism": f"sharded x{world}" + (", NCCL all_gather 16 B/rank" if args.workload == "config4" and world > 1 else ""),
+                       "l2": "per-GPU working set >> 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": per_gpu_gbs / peak, "traffic": None,
+                         "note": "whole step (kernel + epilogue launches) on rank 0's shard", "peak_source": peak_src},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+            "parity": parity,
+        }
+        if res is not None:
+            c, i = batch.decode_best(res)
+            line["argmin"] = {"cost": c, "rollout": i}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"],
+                    help="config3 (default, the headline): MPC batch, weak scaling; config4: 64M "
+                         "heterogeneous states + NCCL arg-min, strong; config5: 256M states, strong")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--only-main", action="store_true",
                     help="profiling aid: run only the main timed loop (no mpc/e2e/cpu legs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "config3":
+        return run_large(args)
     return run_ours(args)
 
 

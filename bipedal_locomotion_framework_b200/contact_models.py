@@ -334,14 +334,25 @@ class ContinuousContactModelBatch:
 
     @staticmethod
     def _plane_ptrs(t, count):
+        """2-D (count, n) tensor with unit inner stride, or a list of 1-D tensors / None."""
         if t is None:
             return None
+        if isinstance(t, (list, tuple)):
+            assert len(t) == count
+            return _ptr_array([None if p is None else p.data_ptr() for p in t])
         assert t.shape[0] == count and t.stride(1) == 1
         return _ptr_array([t[i].data_ptr() for i in range(count)])
 
+    @staticmethod
+    def _num_contacts(planes):
+        if isinstance(planes, (list, tuple)):
+            return next(p for p in planes if p is not None).shape[0]
+        return planes.shape[1]
+
     def evaluate_soa(self, planes, param_planes=None, mask: int = FULL, out: dict | None = None):
-        """planes: (30, n) float64 CUDA tensor (rows may be views with their own alignment)."""
-        n = planes.shape[1]
+        """planes: (30, n) float64 CUDA tensor (rows may be views with their own alignment), or a
+        list of 30 1-D tensors where dead planes may be None."""
+        n = self._num_contacts(planes)
         out = out if out is not None else self.alloc_soa_outputs(n, mask)
         inp = self._plane_ptrs(planes, 30)
         prm = self._plane_ptrs(param_planes, 4)
@@ -356,7 +367,7 @@ class ContinuousContactModelBatch:
         """Bind every argument of blf_ccm_eval_batch_soa once; the returned callable is a single
         foreign call (a few microseconds of host time), for launch-rate-sensitive loops.
         Returns (call, out)."""
-        n = planes.shape[1]
+        n = self._num_contacts(planes)
         out = out if out is not None else self.alloc_soa_outputs(n, mask)
         args = (self._handle.ptr, n, self._plane_ptrs(planes, 30), self._plane_ptrs(param_planes, 4),
                 mask, self._plane_ptrs(out["wrench"], 6), self._plane_ptrs(out["autodyn"], 6),
@@ -393,7 +404,7 @@ class ContinuousContactModelBatch:
                         want_cost: bool = True):
         """Prepared form of rollout_cost_argmin.  Returns (call, out, cost, best)."""
         t = self._torch
-        n = planes.shape[1]
+        n = self._num_contacts(planes)
         assert n % rollout_len == 0
         n_rollouts = n // rollout_len
         out = out if out is not None else self.alloc_soa_outputs(n, mask)
@@ -461,7 +472,7 @@ class ContinuousContactModelBatch:
         Returns (out, cost tensor or None, best) with best a (2,) int64-viewable tensor:
         best.view(float64)[0] = cost, best[1] = index."""
         t = self._torch
-        n = planes.shape[1]
+        n = self._num_contacts(planes)
         assert n % rollout_len == 0
         n_rollouts = n // rollout_len
         out = out if out is not None else self.alloc_soa_outputs(n, mask)

@@ -152,3 +152,89 @@ def reference_test_state(v=(0.3, -0.7, 0.2), w=(-0.5, 0.4, 0.9)) -> dict:
         "params": None,
         "uniform": REFERENCE_TEST_PARAMS,
     }
+
+
+# --------------------------------------------------------------------------------------------------
+# Device-side generation for the configurations that do not fit host memory comfortably
+# (BASELINE.json configs[3] = 64M heterogeneous, configs[4] = 256M).  Same distributions as
+# make_states, drawn with torch's generator (plumbing), chunked so temporaries stay small.  The
+# bits differ from the numpy stream; parity at these sizes is checked by copying a sample of the
+# SAME device bits back to the host and running the oracle on it.
+# --------------------------------------------------------------------------------------------------
+
+def make_planes_torch(n: int, device, seed: int = 42, heterogeneous: bool = False,
+                      live_only: bool = True, chunk: int = 1 << 22):
+    """Returns (planes, param_planes): lists of 30 (and 4) 1-D float64 CUDA tensors of n doubles;
+    planes that cannot affect any output (R0's third column) are None when live_only."""
+    import math
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    dead = {23, 26, 29} if live_only else set()
+    planes = [None if i in dead else torch.empty(n, dtype=torch.float64, device=device)
+              for i in range(30)]
+    prm = [torch.empty(n, dtype=torch.float64, device=device) for _ in range(4)] \
+        if heterogeneous else None
+
+    def U(m, lo, hi):
+        return lo + (hi - lo) * torch.rand(m, dtype=torch.float64, device=device, generator=g)
+
+    def rpy(r, p, y):
+        cr, sr, cp, sp, cy, sy = r.cos(), r.sin(), p.cos(), p.sin(), y.cos(), y.sin()
+        return [cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                -sp, cp * sr, cp * cr]
+
+    for a in range(0, n, chunk):
+        m = min(chunk, n - a)
+        sl = slice(a, a + m)
+        for c in range(3):
+            planes[c][sl] = U(m, -1.0, 1.0)           # v
+            planes[3 + c][sl] = U(m, -1.0, 1.0)       # w
+            p = U(m, -0.05, 0.05)
+            planes[6 + c][sl] = p
+            planes[18 + c][sl] = p + U(m, -0.01, 0.01)
+        sel = U(m, 0.0, 1.0)
+        yaw = U(m, -math.pi, math.pi)
+        R = rpy(U(m, -0.3, 0.3), U(m, -0.3, 0.3), yaw)
+        # uniform SO(3) from a normalised Gaussian quaternion
+        q = torch.randn((4, m), dtype=torch.float64, device=device, generator=g)
+        q = q / q.norm(dim=0, keepdim=True).clamp_min(1e-300)
+        qw, qx, qy, qz = q
+        Rq = [1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+              2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+              2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]
+        full = (sel >= 0.85) & (sel < 0.95)
+        nonortho = sel >= 0.95
+        for e in range(9):
+            r = torch.where(full, Rq[e], R[e])
+            r = torch.where(nonortho, r * (1.0 + 1e-3 * U(m, -1.0, 1.0)), r)
+            planes[9 + e][sl] = r
+        R0 = rpy(U(m, -0.05, 0.05), U(m, -0.05, 0.05), yaw + U(m, -0.1, 0.1))
+        for e in range(9):
+            if planes[21 + e] is not None:
+                planes[21 + e][sl] = R0[e]
+        if heterogeneous:
+            prm[0][sl] = U(m, 0.08, 0.30)
+            prm[1][sl] = U(m, 0.04, 0.15)
+            prm[2][sl] = torch.exp(U(m, math.log(1e3), math.log(1e6)))
+            prm[3][sl] = torch.exp(U(m, math.log(10.0), math.log(1e4)))
+        del R, Rq, R0, q, sel, yaw, full, nonortho
+    return planes, prm
+
+
+def sample_states_from_planes(planes, prm, idx) -> dict:
+    """Copy the states at device indices `idx` (1-D int64 tensor) back to host AoS arrays, for the
+    oracle.  Dead planes read as 0."""
+    import torch
+    cols = []
+    for p in planes:
+        cols.append(torch.zeros(idx.numel(), dtype=torch.float64) if p is None else p[idx].cpu())
+    a = torch.stack(cols, dim=1).numpy()
+    out = {"n": int(idx.numel()), "twists": np.ascontiguousarray(a[:, 0:6]),
+           "poses": np.ascontiguousarray(a[:, 6:18]), "null_poses": np.ascontiguousarray(a[:, 18:30]),
+           "params": None, "uniform": REFERENCE_TEST_PARAMS}
+    if prm is not None:
+        out["params"] = np.ascontiguousarray(torch.stack([q[idx].cpu() for q in prm], dim=1).numpy())
+    return out

@@ -446,3 +446,46 @@ def test_argmin_pairs_tie_break(torch, batch):
     packed[:, 1] = pairs[:, 1].to(torch.int64)
     best = batch.argmin_pairs(packed.cuda())
     assert batch.decode_best(best) == (1.5, 4)
+
+
+def test_config4_full_size_64m_heterogeneous_properties(torch, batch, oracle):
+    """configs[3] at its full size (335 544 rollouts x 200 = 67 108 800 heterogeneous states) on one
+    GPU: oracle parity on a strided sample of the same device bits, per-rollout cost on sampled
+    rollouts, arg-min consistency, control-matrix structure over the whole batch."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of free device memory")
+    n_rollouts, rl = 335544, 200
+    n = n_rollouts * rl
+    planes, prm = syn.make_planes_torch(n, torch.device("cuda", 0), seed=46, heterogeneous=True)
+    ref_wrench, weights = [0.0, 0.0, 30.0, 0.0, 0.0, 0.0], [1.0, 10.0]
+    out, cost, best = batch.rollout_cost_argmin(planes, rl, ref_wrench, weights, prm, mask=FULL)
+    torch.cuda.synchronize()
+    # (i) oracle parity on every 4099th state
+    idx = torch.arange(0, n, 4099, device="cuda")
+    st = syn.sample_states_from_planes(planes, prm, idx)
+    ref = oracle.eval_batch_states(st, mask=FULL, nthreads=NTHREADS)
+    got = {"wrench": out["wrench"][:, idx].T.cpu().numpy(), "autodyn": out["autodyn"][:, idx].T.cpu().numpy(),
+           "ctrl": out["ctrl"][idx].cpu().numpy()}
+    _check(got, ref, FULL, "config4 full size")
+    # (ii) cost of sampled rollouts against the oracle on those rollouts' 200 states
+    for r in (0, 1, 777, 200000, n_rollouts - 1):
+        ridx = torch.arange(r * rl, (r + 1) * rl, device="cuda")
+        rs = syn.sample_states_from_planes(planes, prm, ridx)
+        rw = oracle.eval_batch_states(rs, mask=W)["wrench"]
+        rc = oracle.rollout_cost(rw, rl, ref_wrench, weights)[0]
+        assert abs(float(cost[r]) - rc) <= 1e-12 * abs(rc)
+    # (iii) arg-min is the first minimum of the device's own cost vector
+    bc, bi = batch.decode_best(best)
+    j = int(torch.argmin(cost))
+    cmin = float(cost[j])
+    first = int(torch.nonzero(cost == cmin)[0])
+    assert bi == first and bc == cmin
+    # (iv) structural zeros over all 67M dense blocks, on the device
+    c = out["ctrl"].view(n, 6, 6)
+    assert not bool(c[:, :3, 3:].any()) and not bool(c[:, 3:, :3].any())
+    offdiag = c[:, :3, :3].clone()
+    offdiag.diagonal(dim1=1, dim2=2).zero_()
+    assert not bool(offdiag.any())
+    del offdiag
+    assert bool(torch.isfinite(out["wrench"]).all()) and bool(torch.isfinite(out["autodyn"]).all())

@@ -9,7 +9,7 @@ for n in $(echo $N | tr ',' ' '); do
   if [ "$n" = "1" ]; then
     python bench.py --gpus 1 --steps 1000 --warmup 10 > $O/bench_n1.json 2> $O/bench_n1.err
   else
-    NCCL_DEBUG=WARN python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus $n --steps 1000 --warmup 10 > $O/bench_n$n.json 2> $O/bench_n$n.err
   fi
   echo "N=$n exit $?"; tail -c 1200 $O/bench_n$n.json; echo; tail -3 $O/bench_n$n.err
