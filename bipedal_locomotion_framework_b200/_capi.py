@@ -24,6 +24,7 @@ SYMBOLS = [
     "blf_ccm_last_path", "blf_ccm_launch_count", "blf_ccm_device", "blf_ccm_sm_count",
     "blf_ccm_device_alloc", "blf_ccm_device_free", "blf_ccm_host_alloc", "blf_ccm_host_free",
     "blf_ccm_copy_h2d", "blf_ccm_copy_d2h", "blf_ccm_stream_synchronize",
+    "blf_rls_advance_batch", "blf_rls_advance_host", "blf_ccm_rls_advance_contacts",
 ]
 
 
@@ -68,6 +69,9 @@ def lib():
     L.blf_ccm_copy_h2d.argtypes = [vp, vp, vp, u64, vp]
     L.blf_ccm_copy_d2h.argtypes = [vp, vp, vp, u64, vp]
     L.blf_ccm_stream_synchronize.argtypes = [vp, vp]
+    L.blf_rls_advance_batch.argtypes = [vp, i64, ci, ci, vp, vp, vp, dbl, vp, vp, vp]
+    L.blf_rls_advance_host.argtypes = [vp, i64, ci, ci, vp, vp, vp, dbl, vp, vp]
+    L.blf_ccm_rls_advance_contacts.argtypes = [vp, i64, vp, vp, vp, vp, dbl, vp, vp, vp]
     L.blf_ccm_last_path.argtypes = [vp]
     L.blf_ccm_launch_count.argtypes = [vp]
     L.blf_ccm_launch_count.restype = i64

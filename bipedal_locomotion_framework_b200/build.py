@@ -62,6 +62,7 @@ CPP_LIB = os.path.join(LIB_DIR, "libblf_contact.so")
 CPP_TESTS = {
     "ContinuousContactModelUnitTests": "ContinuousContactModelTest.cpp",   # needs a GPU
     "ParametersHandlerUnitTests": "ParametersHandlerTest.cpp",             # host only
+    "RecursiveLeastSquareUnitTests": "RecursiveLeastSquareTest.cpp",       # needs a GPU
 }
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra"]
 

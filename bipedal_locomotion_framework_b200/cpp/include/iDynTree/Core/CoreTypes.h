@@ -182,6 +182,24 @@ class SpatialAcc : public SpatialVector6
 {
 };
 
+class VectorDynSize
+{
+    std::vector<double> m_data;
+
+public:
+    VectorDynSize() = default;
+    explicit VectorDynSize(std::size_t n) : m_data(n, 0.0) {}
+    void resize(std::size_t n) { m_data.resize(n, 0.0); }
+    void zero() { m_data.assign(m_data.size(), 0.0); }
+    double& operator()(std::size_t i) { return m_data[i]; }
+    const double& operator()(std::size_t i) const { return m_data[i]; }
+    double& operator[](std::size_t i) { return m_data[i]; }
+    const double& operator[](std::size_t i) const { return m_data[i]; }
+    double* data() { return m_data.data(); }
+    const double* data() const { return m_data.data(); }
+    std::size_t size() const { return m_data.size(); }
+};
+
 class MatrixDynSize
 {
     std::vector<double> m_data; // row-major

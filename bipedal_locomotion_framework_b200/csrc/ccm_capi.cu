@@ -15,6 +15,7 @@
 #include <new>
 
 #include "ccm_kernels.cuh"
+#include "rls_kernels.cuh"
 
 using namespace blfccm;
 
@@ -627,6 +628,197 @@ extern "C" int blf_ccm_argmin_pairs(blf_ccm_handle* h, int n_pairs, const void* 
     if (n_pairs < 0 || !pairs || !best) return fail(BLF_CCM_ERR_INVALID_ARG, "NULL pairs/best or n_pairs < 0");
     ccm_argmin_pairs_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const CostIdx*>(pairs), n_pairs, static_cast<CostIdx*>(best));
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return BLF_CCM_OK;
+}
+
+// ---- batched recursive least squares -------------------------------------------------------------
+
+template <int P, int M, bool AOS>
+static int rls_launch(blf_ccm_handle* h, const RlsArgs& a, cudaStream_t st)
+{
+    const int threads = 128;
+    const long long grid = (a.n + threads - 1) / threads;
+    if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");
+    rls_advance_kernel<P, M, AOS><<<static_cast<int>(grid), threads, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return BLF_CCM_OK;
+}
+
+template <int P, bool AOS>
+static int rls_dispatch_m(int m, blf_ccm_handle* h, const RlsArgs& a, cudaStream_t st)
+{
+    switch (m) {
+    case 1: return rls_launch<P, 1, AOS>(h, a, st);
+    case 2: return rls_launch<P, 2, AOS>(h, a, st);
+    case 3: return rls_launch<P, 3, AOS>(h, a, st);
+    case 4: return rls_launch<P, 4, AOS>(h, a, st);
+    case 5: return rls_launch<P, 5, AOS>(h, a, st);
+    case 6: return rls_launch<P, 6, AOS>(h, a, st);
+    default: return fail(BLF_CCM_ERR_INVALID_ARG, "m = %d unsupported (1..6)", m);
+    }
+}
+
+template <bool AOS>
+static int rls_dispatch(int p, int m, blf_ccm_handle* h, const RlsArgs& a, cudaStream_t st)
+{
+    switch (p) {
+    case 1: return rls_dispatch_m<1, AOS>(m, h, a, st);
+    case 2: return rls_dispatch_m<2, AOS>(m, h, a, st);
+    case 3: return rls_dispatch_m<3, AOS>(m, h, a, st);
+    case 4: return rls_dispatch_m<4, AOS>(m, h, a, st);
+    default: return fail(BLF_CCM_ERR_INVALID_ARG, "p = %d unsupported (1..4)", p);
+    }
+}
+
+static int rls_check_sizes(int p, int m, double lambda, const double* cov)
+{
+    if (p < 1 || p > kRlsMaxP) return fail(BLF_CCM_ERR_INVALID_ARG, "p = %d unsupported (1..4)", p);
+    if (m < 1 || m > kRlsMaxM) return fail(BLF_CCM_ERR_INVALID_ARG, "m = %d unsupported (1..6)", m);
+    if (!cov) return fail(BLF_CCM_ERR_INVALID_ARG, "measurement covariance is NULL");
+    if (!(lambda != 0.0)) return fail(BLF_CCM_ERR_INVALID_ARG, "lambda must be non-zero");
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_rls_advance_batch(blf_ccm_handle* h, int64_t n, int p, int m,
+                                     const double* const* regressor_planes,
+                                     const double* const* measurement_planes,
+                                     const double* host_measurement_cov, double lambda,
+                                     double* const* state_planes, double* const* cov_planes,
+                                     void* stream)
+{
+    CHECK_HANDLE(h);
+    if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
+    if (int rc = rls_check_sizes(p, m, lambda, host_measurement_cov)) return rc;
+    if (n == 0) return BLF_CCM_OK;
+    if (!regressor_planes || !measurement_planes || !state_planes || !cov_planes)
+        return fail(BLF_CCM_ERR_INVALID_ARG, "a plane-pointer array is NULL");
+    RlsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    a.lambda = lambda;
+    for (int i = 0; i < m; ++i) a.r[i] = host_measurement_cov[i];
+    auto bad = [](const void* q) { return !q || !aligned8(q); };
+    for (int i = 0; i < m * p; ++i) {
+        if (bad(regressor_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "regressor_planes[%d] NULL or misaligned", i);
+        a.Y[i] = regressor_planes[i];
+    }
+    for (int i = 0; i < m; ++i) {
+        if (bad(measurement_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "measurement_planes[%d] NULL or misaligned", i);
+        a.z[i] = measurement_planes[i];
+    }
+    for (int i = 0; i < p; ++i) {
+        if (bad(state_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "state_planes[%d] NULL or misaligned", i);
+        a.theta[i] = state_planes[i];
+    }
+    for (int i = 0; i < p * p; ++i) {
+        if (bad(cov_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "cov_planes[%d] NULL or misaligned", i);
+        a.cov[i] = cov_planes[i];
+    }
+    return rls_dispatch<false>(p, m, h, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int blf_rls_advance_host(blf_ccm_handle* h, int64_t n, int p, int m, const double* Y,
+                                    const double* z, const double* host_measurement_cov,
+                                    double lambda, double* theta, double* P)
+{
+    CHECK_HANDLE(h);
+    if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
+    if (int rc = rls_check_sizes(p, m, lambda, host_measurement_cov)) return rc;
+    if (n == 0) return BLF_CCM_OK;
+    if (!Y || !z || !theta || !P) return fail(BLF_CCM_ERR_INVALID_ARG, "NULL array");
+    const size_t per = size_t(m * p + m + p + p * p);
+    const size_t need = size_t(n) * per * sizeof(double);
+    if (h->hbytes < need) {
+        for (int s = 0; s < kHostSlots; ++s) {
+            if (h->hbuf[s]) CUDA_TRY(cudaFree(h->hbuf[s]));
+            h->hbuf[s] = nullptr;
+        }
+        for (int s = 0; s < kHostSlots; ++s) CUDA_TRY(cudaMalloc(&h->hbuf[s], need));
+        h->hbytes = need;
+    }
+    if (!h->hstream[0]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream[0], cudaStreamNonBlocking));
+    cudaStream_t st = h->hstream[0];
+    double* dY = h->hbuf[0];
+    double* dz = dY + size_t(n) * m * p;
+    double* dth = dz + size_t(n) * m;
+    double* dP = dth + size_t(n) * p;
+    const size_t D = sizeof(double);
+    CUDA_TRY(cudaMemcpyAsync(dY, Y, size_t(n) * m * p * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dz, z, size_t(n) * m * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dth, theta, size_t(n) * p * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dP, P, size_t(n) * p * p * D, cudaMemcpyHostToDevice, st));
+    RlsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    a.lambda = lambda;
+    for (int i = 0; i < m; ++i) a.r[i] = host_measurement_cov[i];
+    a.Y[0] = dY;
+    a.z[0] = dz;
+    a.theta[0] = dth;
+    a.cov[0] = dP;
+    if (int rc = rls_dispatch<true>(p, m, h, a, st)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(theta, dth, size_t(n) * p * D, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(P, dP, size_t(n) * p * p * D, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_rls_advance_contacts(blf_ccm_handle* h, int64_t n,
+                                            const double* const* in_planes,
+                                            const double* const* geometry_planes,
+                                            const double* const* measured_wrench_planes,
+                                            const double* host_measurement_cov, double lambda,
+                                            double* const* state_planes, double* const* cov_planes,
+                                            void* stream)
+{
+    CHECK_HANDLE(h);
+    if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
+    if (int rc = rls_check_sizes(2, 6, lambda, host_measurement_cov)) return rc;
+    if (n == 0) return BLF_CCM_OK;
+    if (!geometry_planes && !h->have_params)
+        return fail(BLF_CCM_ERR_NOT_INITIALIZED,
+                    "no geometry: call blf_ccm_set_uniform_params or pass geometry_planes");
+    if (!in_planes || !measured_wrench_planes || !state_planes || !cov_planes)
+        return fail(BLF_CCM_ERR_INVALID_ARG, "a plane-pointer array is NULL");
+    CcmRlsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    a.lambda = lambda;
+    a.length = h->length;
+    a.width = h->width;
+    auto bad = [](const void* q) { return !q || !aligned8(q); };
+    const unsigned live = live_planes(M_REGRESSOR);
+    for (int i = 0; i < 30; ++i) {
+        if (!(live & (1u << i))) continue;
+        if (bad(in_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "in_planes[%d] NULL or misaligned", i);
+        a.in[i] = in_planes[i];
+    }
+    for (int i = 0; i < 6; ++i) {
+        if (bad(measured_wrench_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "measured_wrench_planes[%d] NULL or misaligned", i);
+        a.z[i] = measured_wrench_planes[i];
+        a.r[i] = host_measurement_cov[i];
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (bad(state_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "state_planes[%d] NULL or misaligned", i);
+        a.theta[i] = state_planes[i];
+        if (geometry_planes) {
+            if (bad(geometry_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "geometry_planes[%d] NULL or misaligned", i);
+            a.geom[i] = geometry_planes[i];
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (bad(cov_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "cov_planes[%d] NULL or misaligned", i);
+        a.cov[i] = cov_planes[i];
+    }
+    const int threads = 128;
+    const long long grid = (n + threads - 1) / threads;
+    if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (geometry_planes) ccm_rls_kernel<true><<<static_cast<int>(grid), threads, 0, st>>>(a);
+    else ccm_rls_kernel<false><<<static_cast<int>(grid), threads, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return BLF_CCM_OK;

@@ -1,0 +1,217 @@
+// rls_kernels.cuh -- batched Estimators::RecursiveLeastSquare::advance on sm_100a
+// (reference: src/Estimators/src/RecursiveLeastSquare.cpp:96-133).
+//
+// One independent estimator per thread, everything in registers (P <= 4 parameters, M <= 6
+// measurements; the contact model has P = 2 [spring, damper], M = 6 [wrench]):
+//   K     = P Y^T (lambda R + Y P Y^T)^-1
+//   theta = theta + K (z - Y theta)
+//   P     = (P - K Y P) / lambda
+// The M x M system is solved by Gaussian elimination in registers (the matrix is symmetric
+// positive definite up to rounding: lambda R > 0 plus a Gram term), the same direct form the
+// reference uses -- NOT the information form with a P x P inverse, whose conditioning follows
+// cond(P) and breaks 1e-12 agreement once spring and damper scales drift apart.
+// HBM-bound: (M*P + M + P + P*P) doubles in, (P + P*P) out per estimator and step; the fused
+// contact variant computes Y from the contact state in registers so the regressor never exists
+// in HBM.
+#pragma once
+
+#include "ccm_math.cuh"
+
+namespace blfccm {
+
+template <int P, int M>
+__device__ __forceinline__ void rls_advance(const double (&Y)[M][P], const double (&z)[M],
+                                            const double (&r)[M], double lambda, double (&th)[P],
+                                            double (&C)[P][P])
+{
+    // A = Y C (M x P),  B = Y C^T (M x P)
+    double A[M][P], B[M][P];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                a += Y[i][k] * C[k][c];
+                b += Y[i][k] * C[c][k];
+            }
+            A[i][c] = a;
+            B[i][c] = b;
+        }
+    // St = (lambda R + A Y^T)^T ; solve St X = B, X = K^T (M x P)
+    double St[M][M];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            double s = (i == j) ? lambda * r[i] : 0.0;
+#pragma unroll
+            for (int k = 0; k < P; ++k) s += A[j][k] * Y[i][k];
+            St[i][j] = s;
+        }
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < M; ++i) {
+            const double f = St[i][k] / St[k][k];
+#pragma unroll
+            for (int j = k + 1; j < M; ++j) St[i][j] -= f * St[k][j];
+#pragma unroll
+            for (int c = 0; c < P; ++c) B[i][c] -= f * B[k][c];
+        }
+    }
+#pragma unroll
+    for (int ii = 0; ii < M; ++ii) {
+        const int i = M - 1 - ii;   // counted upwards so the loop fully unrolls (registers only)
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+            double acc = B[i][c];
+#pragma unroll
+            for (int j = i + 1; j < M; ++j) acc -= St[i][j] * B[j][c];
+            B[i][c] = acc / St[i][i];   // B now holds X = K^T
+        }
+    }
+    // theta += K (z - Y theta)
+    double innov[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc += Y[i][k] * th[k];
+        innov[i] = z[i] - acc;
+    }
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc += B[i][c] * innov[i];
+        th[c] += acc;
+    }
+    // C = (C - K A) / lambda
+    double Cn[P][P];
+#pragma unroll
+    for (int rr = 0; rr < P; ++rr)
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) acc += B[i][rr] * A[i][c];
+            Cn[rr][c] = (C[rr][c] - acc) / lambda;
+        }
+#pragma unroll
+    for (int rr = 0; rr < P; ++rr)
+#pragma unroll
+        for (int c = 0; c < P; ++c) C[rr][c] = Cn[rr][c];
+}
+
+constexpr int kRlsMaxP = 4, kRlsMaxM = 6;
+
+struct RlsArgs {
+    // SoA: plane pointers; AoS: element [0] of each array is the base pointer
+    const double* Y[kRlsMaxM * kRlsMaxP];
+    const double* z[kRlsMaxM];
+    double* theta[kRlsMaxP];
+    double* cov[kRlsMaxP * kRlsMaxP];
+    double r[kRlsMaxM];
+    double lambda;
+    long long n;
+};
+
+template <int P, int M, bool AOS>
+__global__ void __launch_bounds__(128)
+rls_advance_kernel(const __grid_constant__ RlsArgs a)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double Y[M][P], z[M], r[M], th[P], C[P][P];
+#pragma unroll
+    for (int q = 0; q < M; ++q) {
+        r[q] = a.r[q];
+        z[q] = AOS ? a.z[0][i * M + q] : __ldcs(a.z[q] + i);
+#pragma unroll
+        for (int c = 0; c < P; ++c)
+            Y[q][c] = AOS ? a.Y[0][i * (M * P) + q * P + c] : __ldcs(a.Y[q * P + c] + i);
+    }
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+        th[c] = AOS ? a.theta[0][i * P + c] : __ldcs(a.theta[c] + i);
+#pragma unroll
+        for (int d = 0; d < P; ++d)
+            C[c][d] = AOS ? a.cov[0][i * (P * P) + c * P + d] : __ldcs(a.cov[c * P + d] + i);
+    }
+    rls_advance<P, M>(Y, z, r, a.lambda, th, C);
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+        if (AOS) a.theta[0][i * P + c] = th[c];
+        else __stcs(a.theta[c] + i, th[c]);
+#pragma unroll
+        for (int d = 0; d < P; ++d) {
+            if (AOS) a.cov[0][i * (P * P) + c * P + d] = C[c][d];
+            else __stcs(a.cov[c * P + d] + i, C[c][d]);
+        }
+    }
+}
+
+// Fused: contact state -> regressor (registers) -> RLS update of (spring, damper) per contact.
+struct CcmRlsArgs {
+    const double* in[30];
+    const double* geom[2];     // length, width planes (HETG) else uniform
+    const double* z[6];        // measured wrench planes
+    double* theta[2];          // spring, damper estimates (in/out)
+    double* cov[4];            // 2x2 covariance, row-major planes (in/out)
+    double r[6];
+    double lambda;
+    double length, width;
+    long long n;
+};
+
+template <bool HETG>
+__global__ void __launch_bounds__(128)
+ccm_rls_kernel(const __grid_constant__ CcmRlsArgs a)
+{
+    constexpr unsigned LIVE = live_planes(M_REGRESSOR);
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double x[30] = {};
+#pragma unroll
+    for (int pl = 0; pl < 30; ++pl)
+        if (LIVE & (1u << pl)) x[pl] = __ldcs(a.in[pl] + i);
+    double z[6], r[6], th[2], C[2][2];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        z[q] = __ldcs(a.z[q] + i);
+        r[q] = a.r[q];
+    }
+    th[0] = __ldcs(a.theta[0] + i);
+    th[1] = __ldcs(a.theta[1] + i);
+    C[0][0] = __ldcs(a.cov[0] + i); C[0][1] = __ldcs(a.cov[1] + i);
+    C[1][0] = __ldcs(a.cov[2] + i); C[1][1] = __ldcs(a.cov[3] + i);
+    double L = a.length, W = a.width;
+    if constexpr (HETG) {
+        L = __ldcs(a.geom[0] + i);
+        W = __ldcs(a.geom[1] + i);
+    }
+    State s;
+    s.v = V3{x[0], x[1], x[2]};
+    s.w = V3{x[3], x[4], x[5]};
+    s.p = V3{x[6], x[7], x[8]};
+    s.e1 = V3{x[9], x[12], x[15]};
+    s.e2 = V3{x[10], x[13], x[16]};
+    s.R02 = 0.0; s.R12 = 0.0;
+    s.R22 = x[17];
+    s.p0 = V3{x[18], x[19], x[20]};
+    s.n1 = V3{x[21], x[24], x[27]};
+    s.n2 = V3{x[22], x[25], x[28]};
+    Result res;
+    eval_contact<M_REGRESSOR>(s, make_prm(L, W, 0.0, 0.0), res);
+    const double Y[6][2] = {{res.y_fk.x, res.y_fb.x}, {res.y_fk.y, res.y_fb.y}, {res.y_fk.z, res.y_fb.z},
+                            {res.y_tk.x, res.y_tb.x}, {res.y_tk.y, res.y_tb.y}, {res.y_tk.z, res.y_tb.z}};
+    rls_advance<2, 6>(Y, z, r, a.lambda, th, C);
+    __stcs(a.theta[0] + i, th[0]);
+    __stcs(a.theta[1] + i, th[1]);
+    __stcs(a.cov[0] + i, C[0][0]); __stcs(a.cov[1] + i, C[0][1]);
+    __stcs(a.cov[2] + i, C[1][0]); __stcs(a.cov[3] + i, C[1][1]);
+}
+
+}  // namespace blfccm

@@ -182,6 +182,45 @@ BLF_CCM_API int blf_ccm_argmin_allgather_nccl(blf_ccm_handle* h, void* comm, int
                                               void* stream);
 
 /*
+ * Batched Estimators::RecursiveLeastSquare::advance (reference:
+ * src/Estimators/src/RecursiveLeastSquare.cpp:96-133), n independent estimators, one step each:
+ *   K = P Y^T (lambda R + Y P Y^T)^-1 ; theta += K (z - Y theta) ; P = (P - K Y P) / lambda
+ * p parameters (1..4), m measurements (1..6).  SoA device planes of n doubles:
+ * regressor_planes[m*p] (row-major m x p index), measurement_planes[m], state_planes[p] (in/out),
+ * cov_planes[p*p] (row-major, in/out).  host_measurement_cov[m] is the diagonal of R (the reference
+ * assumes uncorrelated measurements, RecursiveLeastSquare.cpp:38-50).
+ */
+BLF_CCM_API int blf_rls_advance_batch(blf_ccm_handle* h, int64_t n, int p, int m,
+                                      const double* const* regressor_planes,
+                                      const double* const* measurement_planes,
+                                      const double* host_measurement_cov, double lambda,
+                                      double* const* state_planes, double* const* cov_planes,
+                                      void* stream);
+
+/* Same update for n estimators held in HOST arrays (array-of-structures: Y n*(m*p) row-major per
+ * estimator, z n*m, theta n*p in/out, P n*(p*p) in/out); what the per-instance
+ * RecursiveLeastSquare facade calls with n = 1.  Synchronous. */
+BLF_CCM_API int blf_rls_advance_host(blf_ccm_handle* h, int64_t n, int p, int m, const double* Y,
+                                     const double* z, const double* host_measurement_cov,
+                                     double lambda, double* theta, double* P);
+
+/*
+ * Fused identification step for the contact model: per contact, the 6x2 regressor
+ * (ContinuousContactModel.cpp:223-254) is computed from the contact state in registers and used at
+ * once for one RLS step on theta = [spring_coeff; damper_coeff] with the measured wrench -- the
+ * regressor never goes to HBM.  in_planes as in blf_ccm_eval_batch_soa (the 25 planes live for the
+ * regressor); geometry_planes = {length, width} planes or NULL for the handle's uniform geometry;
+ * measured_wrench_planes[6]; state_planes[2] = spring, damper estimates (in/out); cov_planes[4].
+ */
+BLF_CCM_API int blf_ccm_rls_advance_contacts(blf_ccm_handle* h, int64_t n,
+                                             const double* const* in_planes,
+                                             const double* const* geometry_planes,
+                                             const double* const* measured_wrench_planes,
+                                             const double* host_measurement_cov, double lambda,
+                                             double* const* state_planes,
+                                             double* const* cov_planes, void* stream);
+
+/*
  * Device / pinned-host memory and stream helpers, so that host code above this ABI (the C++17
  * facade, the device-side SoA container) needs no CUDA headers.  Device allocations are 256-byte
  * aligned.  Copies are asynchronous on `stream` when the host side is pinned.

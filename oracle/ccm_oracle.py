@@ -20,7 +20,8 @@ WRENCH, AUTODYN, CTRL, REGRESSOR = 1, 2, 4, 8
 
 def build(force: bool = False) -> str:
     """Compile the C oracle with oracle/Makefile (gcc -O2 -ffp-contract=off)."""
-    src = [os.path.join(_HERE, f) for f in ("ccm_oracle.c", "ccm_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ccm_oracle.c", "ccm_oracle.h", "rls_oracle.c",
+                                            "rls_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)
              or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in src))
     if force or stale:
@@ -66,6 +67,8 @@ def lib():
         L.ccmo_eval_batch_soa.argtypes = [C.c_size_t] + [C.c_void_p] * 3 + [C.c_uint] + \
             [C.c_void_p] * 4 + [C.c_int]
         L.ccmo_rollout_cost.argtypes = [C.c_size_t, C.c_size_t] + [C.c_void_p] * 4
+        L.rlso_advance_batch.argtypes = [C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -183,3 +186,64 @@ def rollout_cost(wrench, rollout_len, wrench_ref, weights):
 
 def now() -> float:
     return lib().ccmo_now()
+
+
+# --------------------------------------------------------------------------------------------------
+# Estimators::RecursiveLeastSquare oracle (rls_oracle.c)
+# --------------------------------------------------------------------------------------------------
+
+def rls_advance_batch(Y, z, measurement_cov, lam, theta, P):
+    """One advance() of n independent estimators.  Y (n,m,p), z (n,m), theta (n,p), P (n,p,p);
+    returns new (theta, P) copies."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    n, m, p = Y.shape
+    z = np.ascontiguousarray(z, dtype=np.float64).reshape(n, m)
+    r = np.ascontiguousarray(measurement_cov, dtype=np.float64).reshape(m)
+    theta = np.array(theta, dtype=np.float64).reshape(n, p).copy()
+    P = np.array(P, dtype=np.float64).reshape(n, p, p).copy()
+    lib().rlso_advance_batch(n, p, m, _ptr(Y), _ptr(z), _ptr(r), float(lam), _ptr(theta), _ptr(P))
+    return theta, P
+
+
+class RecursiveLeastSquare:
+    """Per-instance oracle with the reference's method names
+    (src/Estimators/include/BipedalLocomotion/Estimators/RecursiveLeastSquare.h:28-111)."""
+
+    def __init__(self):
+        self._ready = False
+        self._regressor = None
+
+    def initialize(self, params: dict) -> bool:
+        if self._ready:
+            return False  # "already initialized"
+        try:
+            self._r = np.array(params["measurement_covariance"], dtype=np.float64)
+            self._lam = float(params["lambda"])
+            self._theta = np.array(params["state"], dtype=np.float64)
+            self._P = np.diag(np.array(params["state_covariance"], dtype=np.float64))
+        except KeyError:
+            return False
+        self._z = np.zeros(self._r.size)
+        self._ready = True
+        return True
+
+    def setRegressorFunction(self, fn):
+        self._regressor = fn
+
+    def setMeasurements(self, z):
+        self._z = np.array(z, dtype=np.float64)
+
+    def advance(self) -> bool:
+        if self._regressor is None or not self._ready:
+            return False
+        Y = np.array(self._regressor(), dtype=np.float64)
+        th, P = rls_advance_batch(Y[None], self._z[None], self._r, self._lam, self._theta[None],
+                                  self._P[None])
+        self._theta, self._P = th[0], P[0]
+        return True
+
+    def parametersExpectedValue(self):
+        return self._theta
+
+    def parametersCovarianceMatrix(self):
+        return self._P

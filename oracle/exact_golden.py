@@ -134,6 +134,72 @@ def _edge_states():
     return out
 
 
+def exact_rls_advance(Y, z, r, lam, theta, P):
+    """One RecursiveLeastSquare::advance (src/Estimators/src/RecursiveLeastSquare.cpp:120-130) in
+    exact rational arithmetic.  Y m x p, z m, r m (diag of R), theta p, P p x p -> (theta, P)."""
+    m, p = len(Y), len(Y[0])
+    Y = [[F(float(v)) for v in row] for row in Y]
+    z = [F(float(v)) for v in z]
+    r = [F(float(v)) for v in r]
+    lam = F(float(lam))
+    th = [F(float(v)) for v in theta]
+    Pm = [[F(float(v)) for v in row] for row in P]
+    mul = lambda A, B: [[sum(A[i][k] * B[k][j] for k in range(len(B))) for j in range(len(B[0]))]
+                        for i in range(len(A))]
+    T = lambda A: [list(c) for c in zip(*A)]
+    S = mul(mul(Y, Pm), T(Y))
+    for i in range(m):
+        S[i][i] += lam * r[i]
+    # exact inverse by Gauss-Jordan on rationals
+    n = m
+    aug = [S[i] + [F(int(i == j)) for j in range(n)] for i in range(n)]
+    for c in range(n):
+        piv = next(i for i in range(c, n) if aug[i][c] != 0)
+        aug[c], aug[piv] = aug[piv], aug[c]
+        d = aug[c][c]
+        aug[c] = [v / d for v in aug[c]]
+        for i in range(n):
+            if i != c and aug[i][c] != 0:
+                f = aug[i][c]
+                aug[i] = [a - f * b for a, b in zip(aug[i], aug[c])]
+    Sinv = [row[n:] for row in aug]
+    K = mul(mul(Pm, T(Y)), Sinv)
+    innov = [z[i] - sum(Y[i][k] * th[k] for k in range(p)) for i in range(m)]
+    th_new = [th[c] + sum(K[c][i] * innov[i] for i in range(m)) for c in range(p)]
+    KYP = mul(mul(K, Y), Pm)
+    P_new = [[(Pm[a][b] - KYP[a][b]) / lam for b in range(p)] for a in range(p)]
+    return ([float(v) for v in th_new], [[float(v) for v in row] for row in P_new])
+
+
+def write_rls_golden(n: int = 48, steps: int = 3, seed: int = 42):
+    """Contact-model identification: p = 2 (spring, damper), m = 6, regressors from exact_eval of
+    synthetic contact states, a few consecutive steps per estimator (exact all the way)."""
+    sys.path.insert(0, _ROOT)
+    from bipedal_locomotion_framework_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    st = syn.make_states(n * steps, seed=seed + 9, heterogeneous=True)
+    r = np.array([0.5, 0.5, 0.5, 0.05, 0.05, 0.05])
+    lam = 0.98
+    Ys = np.empty((n, steps, 6, 2)); zs = np.empty((n, steps, 6))
+    th = np.empty((n, steps + 1, 2)); Ps = np.empty((n, steps + 1, 2, 2))
+    for e in range(n):
+        true = np.array([rng.uniform(1e3, 1e5), rng.uniform(10, 1e3)])
+        theta = [0.5 * true[0], 2.0 * true[1]]
+        P = [[1e8, 0.0], [0.0, 1e4]]
+        th[e, 0] = theta; Ps[e, 0] = P
+        for t in range(steps):
+            i = e * steps + t
+            prm = st["params"][i].copy()
+            ex = exact_eval(st["twists"][i], st["poses"][i], st["null_poses"][i], prm)
+            Y = np.array([float(v) for v in ex["regressor"]]).reshape(6, 2)
+            z = Y @ true + rng.normal(0, 0.1, 6)
+            theta, P = exact_rls_advance(Y.tolist(), z.tolist(), r.tolist(), lam, theta, P)
+            Ys[e, t] = Y; zs[e, t] = z; th[e, t + 1] = theta; Ps[e, t + 1] = P
+    np.savez_compressed(os.path.join(_ROOT, "tests", "golden", "rls_exact_golden.npz"),
+                        Y=Ys, z=zs, theta=th, P=Ps, r=r, lam=np.array(lam))
+    return n
+
+
 def write_golden(n_random: int = 96, seed: int = 42):
     sys.path.insert(0, _ROOT)
     from bipedal_locomotion_framework_b200 import synthetic as syn
@@ -182,3 +248,4 @@ def write_golden(n_random: int = 96, seed: int = 42):
 
 if __name__ == "__main__":
     print("wrote", write_golden(), "golden states")
+    print("wrote", write_rls_golden(), "golden RLS estimators")

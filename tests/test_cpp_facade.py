@@ -47,3 +47,12 @@ def test_reference_catch2_sections_on_the_gpu_facade(cpp):
     r = _run("ContinuousContactModelUnitTests")
     assert r.returncode == 0, r.stdout + r.stderr
     assert "3 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_rls_test_on_the_gpu_estimator(cpp):
+    """src/Estimators/tests/RecursiveLeastSquareTest.cpp:91-142 restated in
+    cpp/tests/RecursiveLeastSquareTest.cpp against the GPU-backed estimator."""
+    r = _run("RecursiveLeastSquareUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "2 test case(s)" in r.stdout and "0 failure(s)" in r.stdout

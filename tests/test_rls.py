@@ -1,0 +1,200 @@
+"""Estimators::RecursiveLeastSquare: oracle pinned on CPU, CUDA path
+checked against it on the GPU.  Reference: src/Estimators/src/RecursiveLeastSquare.cpp:96-133,
+test src/Estimators/tests/RecursiveLeastSquareTest.cpp:91-142.
+Tolerance 1e-12 relative (norm-wise per quantity: theta as one block, P as one block)."""
+import os
+
+import numpy as np
+import pytest
+
+from bipedal_locomotion_framework_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-12
+
+
+def _rel(got, ref):
+    got, ref = np.asarray(got), np.asarray(ref)
+    n = ref.shape[0]
+    num = np.abs(got - ref).reshape(n, -1).max(axis=1)
+    den = np.maximum(np.abs(ref).reshape(n, -1).max(axis=1), 1e-300)
+    return float((num / den).max())
+
+
+@pytest.fixture(scope="module")
+def rls_golden():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "rls_exact_golden.npz")))
+
+
+def _reference_test_model(rng):
+    """y = [[x, x^2], [sin x, cos x]] p + noise, RecursiveLeastSquareTest.cpp:35-89."""
+    params = np.array([43.2, 12.2])
+    x = [0.0]
+    reg = lambda: np.array([[x[0], x[0] ** 2], [np.sin(x[0]), np.cos(x[0])]])
+    out = lambda: reg() @ params + rng.normal(0.0, 0.5, 2)
+    return params, x, reg, out
+
+
+# --- CPU: the oracle is pinned -----------------------------------------------------------------
+
+def test_rls_oracle_matches_exact_golden(oracle, rls_golden):
+    g = rls_golden
+    steps = g["z"].shape[1]
+    for t in range(steps):  # every step from the golden's own (exactly rounded) previous state
+        th, P = oracle.rls_advance_batch(g["Y"][:, t], g["z"][:, t], g["r"], float(g["lam"]),
+                                         g["theta"][:, t], g["P"][:, t])
+        assert _rel(th, g["theta"][:, t + 1]) <= 1e-13
+        assert _rel(P, g["P"][:, t + 1]) <= 1e-13
+
+
+def test_rls_oracle_reference_convergence_property(oracle):
+    """10 000 steps recover (43.2, 12.2) within 0.1 % (RecursiveLeastSquareTest.cpp:122-141);
+    configuration of src/Estimators/tests/config.ini."""
+    rng = np.random.default_rng(42)
+    params, x, reg, out = _reference_test_model(rng)
+    est = oracle.RecursiveLeastSquare()
+    cfg = {"lambda": 1.0, "measurement_covariance": [0.5, 0.5], "state": [0.0, 0.0],
+           "state_covariance": [10.0, 10.0]}
+    assert est.initialize(cfg)
+    assert not est.initialize(cfg)            # "already initialized"
+    est.setRegressorFunction(reg)
+    for i in range(10000):
+        x[0] = np.cos(i / 10.0)
+        est.setMeasurements(out())
+        assert est.advance()
+    assert np.all(np.abs(est.parametersExpectedValue() - params) / params < 1e-3)
+
+
+# --- GPU -----------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def batch(torch):
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    b = ContinuousContactModelBatch(0)
+    b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    return b
+
+
+def _handler(**kw):
+    from bipedal_locomotion_framework_b200.contact_models import StdImplementation
+    h = StdImplementation()
+    for k, v in kw.items():
+        h.setParameter(k if k != "lam" else "lambda", v)
+    return h
+
+
+@pytest.mark.gpu
+def test_reference_rls_test_on_the_gpu_facade(torch):
+    from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquare
+    rng = np.random.default_rng(42)
+    params, x, reg, out = _reference_test_model(rng)
+    est = RecursiveLeastSquare()
+    assert not est.advance()                                       # not initialised, no regressor
+    assert not est.initialize(_handler(lam=1.0, state=[0.0, 0.0], state_covariance=[10.0, 10.0]))
+    h = _handler(lam=1.0, measurement_covariance=[0.5, 0.5], state=[0.0, 0.0],
+                 state_covariance=[10.0, 10.0])
+    assert est.initialize(h)
+    assert not est.initialize(h)                                   # already initialised
+    est.setRegressorFunction(reg)
+    for i in range(10000):
+        x[0] = np.cos(i / 10.0)
+        est.setMeasurements(out())
+        assert est.advance()
+    assert np.all(np.abs(est.parametersExpectedValue() - params) / params < 1e-3)
+    P = est.parametersCovarianceMatrix()
+    assert P.shape == (2, 2) and np.all(np.diag(P) > 0) and np.all(np.diag(P) < 10.0)
+
+
+@pytest.mark.gpu
+def test_rls_exact_golden_on_gpu(torch, batch, rls_golden):
+    from bipedal_locomotion_framework_b200 import _capi
+    from bipedal_locomotion_framework_b200.contact_models import _np_ptr
+    g = rls_golden
+    n, steps = g["z"].shape[:2]
+    for t in range(steps):
+        th = np.ascontiguousarray(g["theta"][:, t]).copy()
+        P = np.ascontiguousarray(g["P"][:, t]).copy()
+        Y = np.ascontiguousarray(g["Y"][:, t])
+        z = np.ascontiguousarray(g["z"][:, t])
+        r = np.ascontiguousarray(g["r"])
+        _capi.check(_capi.lib().blf_rls_advance_host(batch.handle.ptr, n, 2, 6, _np_ptr(Y), _np_ptr(z),
+                                                     _np_ptr(r), float(g["lam"]), _np_ptr(th),
+                                                     _np_ptr(P)))
+        assert _rel(th, g["theta"][:, t + 1]) <= TOL
+        assert _rel(P, g["P"][:, t + 1]) <= TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,m", [(1, 1), (2, 2), (2, 6), (3, 4), (4, 6), (1, 6), (4, 1)])
+def test_rls_batch_sizes_against_oracle(torch, batch, oracle, p, m):
+    from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquareBatch
+    rng = np.random.default_rng(100 * p + m)
+    n = 4097
+    r = rng.uniform(0.1, 1.0, m)
+    lam = 0.97
+    rls = RecursiveLeastSquareBatch(batch, r, lam)
+    theta = rng.normal(0, 1, (n, p))
+    A = rng.normal(0, 1, (n, p, p))
+    P = A @ A.transpose(0, 2, 1) + 0.5 * np.eye(p)                 # SPD covariances
+    d_theta = torch.from_numpy(np.ascontiguousarray(theta.T)).cuda()
+    d_P = torch.from_numpy(np.ascontiguousarray(P.reshape(n, p * p).T)).cuda()
+    for step in range(5):
+        Y = rng.normal(0, 1, (n, m, p))
+        z = rng.normal(0, 1, (n, m))
+        theta, P = oracle.rls_advance_batch(Y, z, r, lam, theta, P)
+        rls.advance(torch.from_numpy(np.ascontiguousarray(Y.reshape(n, m * p).T)).cuda(),
+                    torch.from_numpy(np.ascontiguousarray(z.T)).cuda(), d_theta, d_P)
+        assert _rel(d_theta.cpu().numpy().T, theta) <= TOL, f"theta step {step}"
+        assert _rel(d_P.cpu().numpy().T.reshape(n, p, p), P) <= TOL, f"P step {step}"
+        # continue both chains from identical bits
+        d_theta.copy_(torch.from_numpy(np.ascontiguousarray(theta.T)))
+        d_P.copy_(torch.from_numpy(np.ascontiguousarray(P.reshape(n, p * p).T)))
+
+
+@pytest.mark.gpu
+def test_fused_contact_identification(torch, batch, oracle):
+    """blf_ccm_rls_advance_contacts == regressor kernel + blf_rls_advance_batch (bit for bit), and
+    agrees with the oracle chain regressor -> advance; over many steps it recovers each contact's
+    own (spring, damper) from noisy wrenches."""
+    from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquareBatch
+    n, steps = 20000, 60
+    rng = np.random.default_rng(5)
+    true_k = rng.uniform(1e3, 1e5, n)
+    true_b = rng.uniform(10.0, 1e3, n)
+    geom = np.stack([rng.uniform(0.08, 0.3, n), rng.uniform(0.04, 0.15, n)], axis=0)
+    r = np.array([1.0, 1.0, 1.0, 1e-2, 1e-2, 1e-2])
+    lam = 1.0
+    rls = RecursiveLeastSquareBatch(batch, r, lam)
+    mk = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    th_f, th_u = mk(np.stack([0.5 * true_k, 2.0 * true_b])), None
+    P_f = mk(np.stack([np.full(n, 1e10), np.zeros(n), np.zeros(n), np.full(n, 1e6)]))
+    th_u, P_u = th_f.clone(), P_f.clone()
+    th_o = th_f.cpu().numpy().T.copy()
+    P_o = P_f.cpu().numpy().T.reshape(n, 2, 2).copy()
+    d_geom = mk(geom)
+    for t in range(steps):
+        st = syn.make_states(n, seed=900 + t)
+        st["params"] = np.ascontiguousarray(np.stack([geom[0], geom[1], true_k, true_b], axis=1))
+        ref = oracle.eval_batch_states(st, mask=1 | 8, nthreads=os.cpu_count() or 1)
+        z = ref["wrench"] + rng.normal(0, 1.0, (n, 6)) * np.sqrt(r)
+        planes = mk(syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+        d_z = mk(z.T)
+        rls.advance_contacts(planes, d_z, th_f, P_f, geometry_planes=d_geom)
+        if t < 3:
+            # unfused: regressor through HBM, then the generic batch update
+            prm = mk(np.stack([geom[0], geom[1], np.zeros(n), np.zeros(n)]))
+            out = batch.evaluate_soa(planes, prm, 8)
+            rls.advance(out["regressor"], d_z, th_u, P_u)
+            assert torch.equal(th_f, th_u) and torch.equal(P_f, P_u)
+            th_o, P_o = oracle.rls_advance_batch(ref["regressor"].reshape(n, 6, 2), z, r, lam, th_o, P_o)
+            assert _rel(th_f.cpu().numpy().T, th_o) <= 1e-11
+            assert _rel(P_f.cpu().numpy().T.reshape(n, 2, 2), P_o) <= 1e-11
+    est = th_f.cpu().numpy()
+    assert np.median(np.abs(est[0] - true_k) / true_k) < 0.05
+    assert np.median(np.abs(est[1] - true_b) / true_b) < 0.05
