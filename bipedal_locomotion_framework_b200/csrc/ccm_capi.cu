@@ -679,6 +679,9 @@ static int rls_check_sizes(int p, int m, double lambda, const double* cov)
     if (m < 1 || m > kRlsMaxM) return fail(BLF_CCM_ERR_INVALID_ARG, "m = %d unsupported (1..6)", m);
     if (!cov) return fail(BLF_CCM_ERR_INVALID_ARG, "measurement covariance is NULL");
     if (!(lambda != 0.0)) return fail(BLF_CCM_ERR_INVALID_ARG, "lambda must be non-zero");
+    for (int i = 0; i < m; ++i)
+        if (!(cov[i] != 0.0))
+            return fail(BLF_CCM_ERR_INVALID_ARG, "measurement covariance %d is zero (singular R)", i);
     return BLF_CCM_OK;
 }
 
@@ -699,7 +702,7 @@ extern "C" int blf_rls_advance_batch(blf_ccm_handle* h, int64_t n, int p, int m,
     memset(&a, 0, sizeof(a));
     a.n = n;
     a.lambda = lambda;
-    for (int i = 0; i < m; ++i) a.r[i] = host_measurement_cov[i];
+    for (int i = 0; i < m; ++i) a.w[i] = lambda * host_measurement_cov[i];
     auto bad = [](const void* q) { return !q || !aligned8(q); };
     for (int i = 0; i < m * p; ++i) {
         if (bad(regressor_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "regressor_planes[%d] NULL or misaligned", i);
@@ -754,7 +757,7 @@ extern "C" int blf_rls_advance_host(blf_ccm_handle* h, int64_t n, int p, int m, 
     memset(&a, 0, sizeof(a));
     a.n = n;
     a.lambda = lambda;
-    for (int i = 0; i < m; ++i) a.r[i] = host_measurement_cov[i];
+    for (int i = 0; i < m; ++i) a.w[i] = lambda * host_measurement_cov[i];
     a.Y[0] = dY;
     a.z[0] = dz;
     a.theta[0] = dth;
@@ -799,7 +802,7 @@ extern "C" int blf_ccm_rls_advance_contacts(blf_ccm_handle* h, int64_t n,
     for (int i = 0; i < 6; ++i) {
         if (bad(measured_wrench_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "measured_wrench_planes[%d] NULL or misaligned", i);
         a.z[i] = measured_wrench_planes[i];
-        a.r[i] = host_measurement_cov[i];
+        a.w[i] = lambda * host_measurement_cov[i];
     }
     for (int i = 0; i < 2; ++i) {
         if (bad(state_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "state_planes[%d] NULL or misaligned", i);

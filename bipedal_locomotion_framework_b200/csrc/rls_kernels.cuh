@@ -6,22 +6,28 @@
 //   K     = P Y^T (lambda R + Y P Y^T)^-1
 //   theta = theta + K (z - Y theta)
 //   P     = (P - K Y P) / lambda
-// The M x M system is solved by Gaussian elimination in registers (the matrix is symmetric
-// positive definite up to rounding: lambda R > 0 plus a Gram term), the same direct form the
-// reference uses -- NOT the information form with a P x P inverse, whose conditioning follows
-// cond(P) and breaks 1e-12 agreement once spring and damper scales drift apart.
-// HBM-bound: (M*P + M + P + P*P) doubles in, (P + P*P) out per estimator and step; the fused
-// contact variant computes Y from the contact state in registers so the regressor never exists
-// in HBM.
+// Same structure as the reference: the M x M matrix S = lambda R + Y P Y^T is factorised and
+// K^T = S^-1 (Y P^T).  S is symmetric positive definite (lambda R > 0 plus a Gram term), so the
+// factorisation is an in-register LDL^T on the lower triangle with M reciprocals -- about 350 FP64
+// instructions for the contact model, which keeps the kernel HBM-bound (a first version with a full
+// Gaussian elimination and 27 true divisions was FP64-bound at 24 % of the HBM roofline).  The
+// error is governed by cond(S), as for the reference's LU.  Shortcuts through a P x P system
+// (information form, push-through identity) were rejected: their conditioning picks up cond(P),
+// which grows by decades when spring and damper variances drift apart (tests caught 2e-12 misses).
+// theta and P are updated with the reference's own expressions (including the cancellation-prone
+// P - K Y P), so rounding behaves like the reference's.
+// HBM: (M*P + M + P + P*P) doubles in, (P + P*P) out per estimator and step; the fused contact
+// variant computes Y from the contact state in registers so the regressor never exists in HBM.
 #pragma once
 
 #include "ccm_math.cuh"
 
 namespace blfccm {
 
+// lr[i] = lambda * r[i] (diagonal of lambda R), precomputed on the host: uniform over the batch.
 template <int P, int M>
 __device__ __forceinline__ void rls_advance(const double (&Y)[M][P], const double (&z)[M],
-                                            const double (&r)[M], double lambda, double (&th)[P],
+                                            const double (&lr)[M], double lambda, double (&th)[P],
                                             double (&C)[P][P])
 {
     // A = Y C (M x P),  B = Y C^T (M x P)
@@ -39,37 +45,44 @@ __device__ __forceinline__ void rls_advance(const double (&Y)[M][P], const doubl
             A[i][c] = a;
             B[i][c] = b;
         }
-    // St = (lambda R + A Y^T)^T ; solve St X = B, X = K^T (M x P)
-    double St[M][M];
+    // lower triangle of S = lambda R + A Y^T
+    double S[M][M];
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-            double s = (i == j) ? lambda * r[i] : 0.0;
+        for (int j = 0; j <= i; ++j) {
+            double v = (i == j) ? lr[i] : 0.0;
 #pragma unroll
-            for (int k = 0; k < P; ++k) s += A[j][k] * Y[i][k];
-            St[i][j] = s;
+            for (int k = 0; k < P; ++k) v += A[i][k] * Y[j][k];
+            S[i][j] = v;
         }
+    // LDL^T: afterwards S[i][k] (i > k) holds l_ik, inv[k] = 1 / d_k; B is forward-substituted
+    double inv[M];
 #pragma unroll
     for (int k = 0; k < M; ++k) {
+        inv[k] = 1.0 / S[k][k];
+        double l[M];                         // l_ik for this column; S[.][k] stays unscaled (l d)
+#pragma unroll
+        for (int i = k + 1; i < M; ++i) l[i] = S[i][k] * inv[k];
 #pragma unroll
         for (int i = k + 1; i < M; ++i) {
-            const double f = St[i][k] / St[k][k];
 #pragma unroll
-            for (int j = k + 1; j < M; ++j) St[i][j] -= f * St[k][j];
+            for (int j = k + 1; j <= i; ++j) S[i][j] -= l[i] * S[j][k];
 #pragma unroll
-            for (int c = 0; c < P; ++c) B[i][c] -= f * B[k][c];
+            for (int c = 0; c < P; ++c) B[i][c] -= l[i] * B[k][c];
         }
+#pragma unroll
+        for (int i = k + 1; i < M; ++i) S[i][k] = l[i];
     }
 #pragma unroll
-    for (int ii = 0; ii < M; ++ii) {
-        const int i = M - 1 - ii;   // counted upwards so the loop fully unrolls (registers only)
+    for (int kk = 0; kk < M; ++kk) {        // D^-1 then L^T back substitution (counted upwards)
+        const int k = M - 1 - kk;
 #pragma unroll
         for (int c = 0; c < P; ++c) {
-            double acc = B[i][c];
+            double acc = B[k][c] * inv[k];
 #pragma unroll
-            for (int j = i + 1; j < M; ++j) acc -= St[i][j] * B[j][c];
-            B[i][c] = acc / St[i][i];   // B now holds X = K^T
+            for (int i = k + 1; i < M; ++i) acc -= S[i][k] * B[i][c];
+            B[k][c] = acc;                  // B now holds K^T
         }
     }
     // theta += K (z - Y theta)
@@ -88,21 +101,21 @@ __device__ __forceinline__ void rls_advance(const double (&Y)[M][P], const doubl
         for (int i = 0; i < M; ++i) acc += B[i][c] * innov[i];
         th[c] += acc;
     }
-    // C = (C - K A) / lambda
+    // C = (C - K A) / lambda     (the reference's expression)
     double Cn[P][P];
 #pragma unroll
-    for (int rr = 0; rr < P; ++rr)
+    for (int a = 0; a < P; ++a)
 #pragma unroll
         for (int c = 0; c < P; ++c) {
             double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < M; ++i) acc += B[i][rr] * A[i][c];
-            Cn[rr][c] = (C[rr][c] - acc) / lambda;
+            for (int i = 0; i < M; ++i) acc += B[i][a] * A[i][c];
+            Cn[a][c] = (C[a][c] - acc) / lambda;
         }
 #pragma unroll
-    for (int rr = 0; rr < P; ++rr)
+    for (int a = 0; a < P; ++a)
 #pragma unroll
-        for (int c = 0; c < P; ++c) C[rr][c] = Cn[rr][c];
+        for (int c = 0; c < P; ++c) C[a][c] = Cn[a][c];
 }
 
 constexpr int kRlsMaxP = 4, kRlsMaxM = 6;
@@ -113,7 +126,7 @@ struct RlsArgs {
     const double* z[kRlsMaxM];
     double* theta[kRlsMaxP];
     double* cov[kRlsMaxP * kRlsMaxP];
-    double r[kRlsMaxM];
+    double w[kRlsMaxM];        // lambda * r[i]
     double lambda;
     long long n;
 };
@@ -127,7 +140,7 @@ rls_advance_kernel(const __grid_constant__ RlsArgs a)
     double Y[M][P], z[M], r[M], th[P], C[P][P];
 #pragma unroll
     for (int q = 0; q < M; ++q) {
-        r[q] = a.r[q];
+        r[q] = a.w[q];
         z[q] = AOS ? a.z[0][i * M + q] : __ldcs(a.z[q] + i);
 #pragma unroll
         for (int c = 0; c < P; ++c)
@@ -160,7 +173,7 @@ struct CcmRlsArgs {
     const double* z[6];        // measured wrench planes
     double* theta[2];          // spring, damper estimates (in/out)
     double* cov[4];            // 2x2 covariance, row-major planes (in/out)
-    double r[6];
+    double w[6];               // lambda * r[i]
     double lambda;
     double length, width;
     long long n;
@@ -181,7 +194,7 @@ ccm_rls_kernel(const __grid_constant__ CcmRlsArgs a)
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
         z[q] = __ldcs(a.z[q] + i);
-        r[q] = a.r[q];
+        r[q] = a.w[q];
     }
     th[0] = __ldcs(a.theta[0] + i);
     th[1] = __ldcs(a.theta[1] + i);

@@ -51,7 +51,34 @@ def make_batch(**env):
     return b
 
 
+def rls_only():
+    from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquareBatch
+    b = make_batch()
+    for n in (2 * 4096 * 100, 1 << 23):
+        st = syn.make_states(min(n, 1 << 20), seed=45)
+        reps = (n + st["n"] - 1) // st["n"]
+        pl = np.tile(syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]), (1, reps))[:, :n]
+        planes = torch.from_numpy(np.ascontiguousarray(pl)).cuda()
+        rls = RecursiveLeastSquareBatch(b, [1.0, 1.0, 1.0, 0.01, 0.01, 0.01], 0.99)
+        th = torch.rand((2, n), dtype=torch.float64, device="cuda") * 1e3 + 10
+        P = torch.zeros((4, n), dtype=torch.float64, device="cuda"); P[0] = 1e6; P[3] = 1e4
+        zz = torch.randn((6, n), dtype=torch.float64, device="cuda")
+        Yp = torch.randn((12, n), dtype=torch.float64, device="cuda") * 1e-2
+        print(f"=== n = {n} ===")
+        ms = timeit(lambda i: rls.advance(Yp, zz, th, P), iters=100)
+        row("rls advance p=2 m=6 (regressor planes in)", ms, n, 240)
+        P.zero_(); P[0] = 1e6; P[3] = 1e4
+        ms = timeit(lambda i: rls.advance_contacts(planes, zz, th, P), iters=100)
+        row("rls fused contact identification (state planes in)", ms, n, 344)
+        out = b.alloc_soa_outputs(n, 8)
+        ms = timeit(lambda i: b.evaluate_soa(planes, None, 8, out=out), iters=100)
+        row("regressor-only kernel (25 planes in, 12 out)", ms, n, 296)
+        del planes, th, P, zz, Yp, out
+
+
 def main():
+    if "--rls-only" in sys.argv:
+        return rls_only()
     sizes = {"cfg3 819200": 2 * 4096 * 100, "8M": 1 << 23}
     NS = 3
     for label, n in sizes.items():
@@ -108,6 +135,19 @@ def main():
         outs = [b.alloc_aos_outputs(n, WRENCH) for _ in range(2)]
         ms = timeit(lambda i: b.evaluate_aos(aos[0], aos[1], aos[2], None, WRENCH, out=outs[i % 2]))
         row("aos wrench-only", ms, n, 248)
+        # recursive least squares (section 8f row 1)
+        from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquareBatch
+        rls = RecursiveLeastSquareBatch(b, [1.0, 1.0, 1.0, 0.01, 0.01, 0.01], 0.99)
+        th = torch.rand((2, n), dtype=torch.float64, device="cuda") * 1e3 + 10
+        P = torch.zeros((4, n), dtype=torch.float64, device="cuda"); P[0] = 1e6; P[3] = 1e4
+        zz = torch.randn((6, n), dtype=torch.float64, device="cuda")
+        Yp = torch.randn((12, n), dtype=torch.float64, device="cuda") * 1e-2
+        ms = timeit(lambda i: rls.advance(Yp, zz, th, P), iters=100)
+        row("rls advance p=2 m=6 (regressor planes in)", ms, n, 240)
+        P.zero_(); P[0] = 1e6; P[3] = 1e4
+        ms = timeit(lambda i: rls.advance_contacts(planes[i % NS], zz, th, P), iters=100)
+        row("rls fused contact identification (state planes in)", ms, n, 344)
+        del th, P, zz, Yp
         del outs, planes, aos, prm, prm_aos
         torch.cuda.empty_cache()
 
