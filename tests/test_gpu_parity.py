@@ -489,3 +489,84 @@ def test_config4_full_size_64m_heterogeneous_properties(torch, batch, oracle):
     assert not bool(offdiag.any())
     del offdiag
     assert bool(torch.isfinite(out["wrench"]).all()) and bool(torch.isfinite(out["autodyn"]).all())
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 65, 129, 4097])
+def test_no_out_of_bounds_writes_canaries(torch, batch, n):
+    """compute-sanitizer is closed on this pool: every output lives between sentinel-filled guard
+    bands (and inputs are followed by NaN guards, so an over-read would poison a result)."""
+    guard, sentinel = 64, -7.25
+    st = syn.make_states(n, seed=3, heterogeneous=True)
+
+    def guarded(rows, cols, fill=sentinel):
+        """(rows, cols) view with `guard` doubles of sentinel before and after every row."""
+        buf = torch.full((rows, cols + 2 * guard), fill, dtype=torch.float64, device="cuda")
+        return buf, buf[:, guard:guard + cols]
+
+    def check(buf, cols, what):
+        assert bool((buf[:, :guard] == sentinel).all()) and \
+            bool((buf[:, guard + cols:] == sentinel).all()), f"{what}: guard band overwritten (n={n})"
+
+    # SoA: planes with NaN guards after each row, outputs with sentinel guards
+    pbuf = torch.full((30, n + 2 * guard), float("nan"), dtype=torch.float64, device="cuda")
+    planes = pbuf[:, guard:guard + n]
+    planes.copy_(_dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])))
+    qbuf = torch.full((4, n + 2 * guard), float("nan"), dtype=torch.float64, device="cuda")
+    prm = qbuf[:, guard:guard + n]
+    prm.copy_(_dev(torch, st["params"].T))
+    wb, w = guarded(6, n)
+    ab, a = guarded(6, n)
+    rb, r = guarded(12, n)
+    cb, c = guarded(1, n * 36)
+    out = {"wrench": w, "autodyn": a, "regressor": r, "ctrl": c.view(n, 36)}
+    batch.evaluate_soa(planes, prm, FULL | R, out=out)
+    torch.cuda.synchronize()
+    for b_, cols, what in ((wb, n, "wrench"), (ab, n, "autodyn"), (rb, n, "regressor"),
+                           (cb, n * 36, "ctrl")):
+        check(b_, cols, "soa " + what)
+    assert bool(torch.isfinite(w).all()) and bool(torch.isfinite(c).all())   # no NaN guard was read
+
+    # rollout epilogue on the same guarded buffers (rollout_len 1 and n)
+    for rl in (1, n):
+        costb, cost = guarded(1, n // rl)
+        for b_ in (wb, ab, cb):
+            b_[:, guard:-guard].fill_(0.0)
+        import ctypes as C
+        from bipedal_locomotion_framework_b200 import _capi
+        best = torch.empty(2, dtype=torch.int64, device="cuda")
+        ref = np.zeros(6)
+        wts = np.ones(2)
+        pp = batch._plane_ptrs
+        rc = _capi.lib().blf_ccm_rollout_cost_argmin_soa(
+            batch.handle.ptr, n // rl, rl, pp(planes, 30), pp(prm, 4), FULL, pp(w, 6), pp(a, 6),
+            c.data_ptr(), ref.ctypes.data_as(C.c_void_p), wts.ctypes.data_as(C.c_void_p), 0,
+            cost.data_ptr(), best.data_ptr(), None)
+        assert rc == 0, _capi.lib().blf_ccm_last_error()
+        torch.cuda.synchronize()
+        check(costb, n // rl, f"rollout cost rl={rl}")
+        for b_, cols, what in ((wb, n, "wrench"), (ab, n, "autodyn"), (cb, n * 36, "ctrl")):
+            check(b_, cols, f"rollout {what} rl={rl}")
+        assert bool(torch.isfinite(cost).all())
+
+    # AoS: each array inside guards (16-byte aligned: guard is even)
+    def guarded_aos(arr, fill):
+        flat = torch.full((arr.size + 2 * guard,), fill, dtype=torch.float64, device="cuda")
+        v = flat[guard:guard + arr.size].view(arr.shape)
+        v.copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+        return flat, v
+
+    _, tw = guarded_aos(st["twists"], float("nan"))
+    _, po = guarded_aos(st["poses"], float("nan"))
+    _, nu = guarded_aos(st["null_poses"], float("nan"))
+    _, pr = guarded_aos(st["params"], float("nan"))
+    outs = {}
+    flats = {}
+    for key, width in (("wrench", 6), ("autodyn", 6), ("ctrl", 36), ("regressor", 12)):
+        flats[key], outs[key] = guarded_aos(np.zeros((n, width)), sentinel)
+    batch.evaluate_aos(tw, po, nu, pr, FULL | R, out=outs)
+    torch.cuda.synchronize()
+    for key, width in (("wrench", 6), ("autodyn", 6), ("ctrl", 36), ("regressor", 12)):
+        f = flats[key]
+        assert bool((f[:guard] == sentinel).all()) and bool((f[guard + n * width:] == sentinel).all()), \
+            f"aos {key}: guard band overwritten (n={n})"
+        assert bool(torch.isfinite(outs[key]).all())
