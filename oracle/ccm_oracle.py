@@ -21,7 +21,8 @@ WRENCH, AUTODYN, CTRL, REGRESSOR = 1, 2, 4, 8
 def build(force: bool = False) -> str:
     """Compile the C oracle with oracle/Makefile (gcc -O2 -ffp-contract=off)."""
     src = [os.path.join(_HERE, f) for f in ("ccm_oracle.c", "ccm_oracle.h", "rls_oracle.c",
-                                            "rls_oracle.h", "Makefile")]
+                                            "rls_oracle.h", "sys_oracle.c", "sys_oracle.h",
+                                            "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)
              or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in src))
     if force or stale:

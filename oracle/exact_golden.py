@@ -45,11 +45,12 @@ def exact_eval(twist, pose, null_pose, params):
     Returns dict wrench[6], autodyn[6], ctrl[36] row-major, regressor[12] row-major 6x2.
     """
     fr = lambda xs: [F(float(x)) for x in xs]
-    v, w = fr(twist[0:3]), fr(twist[3:6])
-    p, R = fr(pose[0:3]), fr(pose[3:12])
-    p0, R0 = fr(null_pose[0:3]), fr(null_pose[3:12])
-    L, W, k, b = fr(params)
+    return closed_form(fr(twist[0:3]), fr(twist[3:6]), fr(pose[0:3]), fr(pose[3:12]),
+                       fr(null_pose[0:3]), fr(null_pose[3:12]), *fr(params), zero=F(0))
 
+
+def closed_form(v, w, p, R, p0, R0, L, W, k, b, zero):
+    """The closed form on any exact / high-precision number type (Fraction, mpmath.mpf)."""
     A = L * W
     A12 = A / 12
     c = R[8]
@@ -83,23 +84,23 @@ def exact_eval(twist, pose, null_pose, params):
     # M = L^2 S(e1)^2 + W^2 S(e2)^2,  S(e)^2 = e e^T - |e|^2 I
     def s2(e):
         n2_ = e[0] * e[0] + e[1] * e[1] + e[2] * e[2]
-        return [[e[i] * e[j] - (n2_ if i == j else 0) for j in range(3)] for i in range(3)]
+        return [[e[i] * e[j] - (n2_ if i == j else zero) for j in range(3)] for i in range(3)]
 
     S1, S2 = s2(e1), s2(e2)
     M = [[L2 * S1[i][j] + W2 * S2[i][j] for j in range(3)] for i in range(3)]
-    ctrl = [F(0)] * 36
+    ctrl = [zero] * 36
     for i in range(3):
         ctrl[6 * i + i] = -A * b * c
         for j in range(3):
             ctrl[6 * (3 + i) + 3 + j] = A12 * c * b * M[i][j]
 
-    reg = [F(0)] * 12
+    reg = [zero] * 12
     bl = _add(_scale(L2, _cross(e1, n1)), _scale(W2, _cross(e2, n2)))
     for i in range(3):
         reg[2 * i] = absc * A * d[i]
         reg[2 * i + 1] = -absc * A * v[i]
         reg[2 * (3 + i)] = A12 * absc * bl[i]
-        reg[2 * (3 + i) + 1] = A12 * absc * sum(M[i][j] * w[j] for j in range(3))
+        reg[2 * (3 + i) + 1] = A12 * absc * sum((M[i][j] * w[j] for j in range(3)), zero)
 
     return {"wrench": force + torque, "autodyn": head + tail, "ctrl": ctrl, "regressor": reg}
 
