@@ -16,6 +16,7 @@
 
 #include "ccm_kernels.cuh"
 #include "rls_kernels.cuh"
+#include "sys_kernels.cuh"
 
 using namespace blfccm;
 
@@ -606,6 +607,7 @@ extern "C" int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_roll
     ReduceArgs ra;
     ra.partials = h->partials;
     ra.slots = slots;
+    ra.fixed_count = 0;
     ra.n_rollouts = n_rollouts;
     ra.rollout_len = rollout_len;
     ra.index_base = index_base;
@@ -920,3 +922,6 @@ extern "C" int blf_ccm_argmin_allgather_nccl(blf_ccm_handle* h, void* comm, int 
     if (rc != 0) return fail(BLF_CCM_ERR_NCCL, "ncclAllGather: %s", errstr ? errstr(rc) : "error");
     return blf_ccm_argmin_pairs(h, nranks, gathered, global_best, stream);
 }
+
+// ---- System component (rows 2 and 3 of SURVEY.md section 8(f)) -----------------------------------
+#include "sys_capi.inc"

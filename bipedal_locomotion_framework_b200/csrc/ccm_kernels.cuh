@@ -673,6 +673,7 @@ __device__ __forceinline__ CostIdx warp_best(CostIdx b)
 struct ReduceArgs {
     const double* partials;    // [n_rollouts][slots]
     int slots;
+    int fixed_count;           // > 0: every rollout has exactly this many partials (slots == it)
     long long n_rollouts;
     long long rollout_len;
     long long index_base;
@@ -695,11 +696,15 @@ ccm_cost_reduce_kernel(const __grid_constant__ ReduceArgs ra)
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long ro = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
          ro < ra.n_rollouts; ro += stride) {
-        const long long t0 = rollout_first_tile(ro, ra.rollout_len);
-        const long long t1 = ((ro + 1) * ra.rollout_len - 1) >> 5;
+        long long cntp = ra.fixed_count;
+        if (cntp <= 0) {
+            const long long t0 = rollout_first_tile(ro, ra.rollout_len);
+            const long long t1 = ((ro + 1) * ra.rollout_len - 1) >> 5;
+            cntp = t1 - t0 + 1;
+        }
         const double* p = ra.partials + ro * ra.slots;
         double acc = 0.0;
-        for (long long j = 0; j <= t1 - t0; ++j) acc += p[j];
+        for (long long j = 0; j < cntp; ++j) acc += p[j];
         if (ra.cost) ra.cost[ro] = acc;
         const long long gi = ra.index_base + ro;
         if (better(acc, gi, mine.cost, mine.idx)) {

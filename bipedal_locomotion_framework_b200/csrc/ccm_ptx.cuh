@@ -87,5 +87,23 @@ __device__ __forceinline__ void fence_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- per-thread async copies (LDGSTS): 8 bytes global -> shared, tracked by commit groups ------
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// at most N of this thread's committed groups still pending
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 }  // namespace ptx
 }  // namespace blfccm

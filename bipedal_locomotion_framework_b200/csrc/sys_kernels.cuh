@@ -1,0 +1,478 @@
+// sys_kernels.cuh -- the steps either side of the contact model.
+//
+//   kin_euler_step            FloatingBaseSystemKinematics::dynamics (base part) + one ForwardEuler
+//                             step   src/System/src/FloatingBaseSystemKinematics.cpp:36-73,
+//                             src/System/include/BipedalLocomotion/System/ForwardEuler.h:45-53
+//   sys_kin_euler_kernel      that step for n independent systems, SoA planes (HBM-bound, 240 B)
+//   sys_kin_aos_kernel        derivative / multi-step integrate for the per-instance facade
+//   ccm_rollout_kernel        fused sampling-MPC rollout: one lane owns one (rollout, foot) chain,
+//                             pose and null pose stay in registers for the whole horizon; per step
+//                             only the 48-byte twist comes from HBM (cp.async ring, 8 steps ahead)
+//                             -> contact model -> cost -> Euler step.  The 216 input bytes per
+//                             evaluation of the unfused path never touch HBM; cost-only rollouts
+//                             are FP64-pipe bound instead of HBM bound.
+//   ccm_genforce_kernel       out[s] = base[s] + sum_c J_c^T wrench_c
+//                             (src/System/src/FloatingBaseSystemDynamics.cpp:199-226): wrench in
+//                             registers (never written to HBM unless asked), Jacobians streamed by
+//                             TMA bulk copies through a per-warp ring, lanes own columns.
+//
+// Derivation differs from the oracle on purpose: Rdot's columns are w x c_j (not -(c_j x w) through
+// a matrix), R R^T is accumulated as a sum of column outer products, and its inverse uses the
+// symmetric adjugate (6 cofactors) instead of Eigen's general 3x3 formula.
+#pragma once
+
+#include "ccm_kernels.cuh"
+
+namespace blfccm {
+
+// ------------------------------------------------------------------------------------------------
+// kinematics
+// ------------------------------------------------------------------------------------------------
+
+struct Pose {
+    V3 p;           // position
+    V3 c0, c1, c2;  // columns of R
+};
+
+template <bool BAUM>
+__device__ __forceinline__ void kin_rates(const Pose& s, const V3& w, double half_rho, V3& d0,
+                                          V3& d1, V3& d2)
+{
+    d0 = cross(w, s.c0);
+    d1 = cross(w, s.c1);
+    d2 = cross(w, s.c2);
+    if constexpr (BAUM) {
+        // G = R R^T = sum_j c_j c_j^T
+        const double gxx = s.c0.x * s.c0.x + s.c1.x * s.c1.x + s.c2.x * s.c2.x;
+        const double gxy = s.c0.x * s.c0.y + s.c1.x * s.c1.y + s.c2.x * s.c2.y;
+        const double gxz = s.c0.x * s.c0.z + s.c1.x * s.c1.z + s.c2.x * s.c2.z;
+        const double gyy = s.c0.y * s.c0.y + s.c1.y * s.c1.y + s.c2.y * s.c2.y;
+        const double gyz = s.c0.y * s.c0.z + s.c1.y * s.c1.z + s.c2.y * s.c2.z;
+        const double gzz = s.c0.z * s.c0.z + s.c1.z * s.c1.z + s.c2.z * s.c2.z;
+        // symmetric adjugate
+        const double axx = gyy * gzz - gyz * gyz;
+        const double axy = gxz * gyz - gxy * gzz;
+        const double axz = gxy * gyz - gxz * gyy;
+        const double ayy = gxx * gzz - gxz * gxz;
+        const double ayz = gxy * gxz - gxx * gyz;
+        const double azz = gxx * gyy - gxy * gxy;
+        const double inv = 1.0 / (gxx * axx + gxy * axy + gxz * axz);
+        // M = rho/2 (G^-1 - I)
+        const double mxx = half_rho * (axx * inv - 1.0), mxy = half_rho * (axy * inv);
+        const double mxz = half_rho * (axz * inv), myy = half_rho * (ayy * inv - 1.0);
+        const double myz = half_rho * (ayz * inv), mzz = half_rho * (azz * inv - 1.0);
+        auto mul = [&](const V3& c) {
+            return V3{mxx * c.x + mxy * c.y + mxz * c.z, mxy * c.x + myy * c.y + myz * c.z,
+                      mxz * c.x + myz * c.y + mzz * c.z};
+        };
+        d0 = d0 + mul(s.c0);
+        d1 = d1 + mul(s.c1);
+        d2 = d2 + mul(s.c2);
+    }
+}
+
+// x += dx * dT  (ForwardEuler.h:50)
+template <bool BAUM>
+__device__ __forceinline__ void kin_euler_step(Pose& s, const V3& v, const V3& w, double half_rho,
+                                               double dT)
+{
+    V3 d0, d1, d2;
+    kin_rates<BAUM>(s, w, half_rho, d0, d1, d2);
+    s.p = s.p + dT * v;
+    s.c0 = s.c0 + dT * d0;
+    s.c1 = s.c1 + dT * d1;
+    s.c2 = s.c2 + dT * d2;
+}
+
+struct KinArgs {
+    const double* tw[6];
+    double* pos[3];   // in/out
+    double* rot[9];   // in/out, row-major index
+    double half_rho, dT;
+    long long n;
+};
+
+template <bool BAUM>
+__global__ void __launch_bounds__(256)
+sys_kin_euler_kernel(const __grid_constant__ KinArgs a)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double t[6], x[12];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) t[j] = __ldcs(a.tw[j] + i);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) x[j] = __ldcs(a.pos[j] + i);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) x[3 + j] = __ldcs(a.rot[j] + i);
+    Pose s{V3{x[0], x[1], x[2]}, V3{x[3], x[6], x[9]}, V3{x[4], x[7], x[10]}, V3{x[5], x[8], x[11]}};
+    kin_euler_step<BAUM>(s, V3{t[0], t[1], t[2]}, V3{t[3], t[4], t[5]}, a.half_rho, a.dT);
+    __stcs(a.pos[0] + i, s.p.x); __stcs(a.pos[1] + i, s.p.y); __stcs(a.pos[2] + i, s.p.z);
+    __stcs(a.rot[0] + i, s.c0.x); __stcs(a.rot[1] + i, s.c1.x); __stcs(a.rot[2] + i, s.c2.x);
+    __stcs(a.rot[3] + i, s.c0.y); __stcs(a.rot[4] + i, s.c1.y); __stcs(a.rot[5] + i, s.c2.y);
+    __stcs(a.rot[6] + i, s.c0.z); __stcs(a.rot[7] + i, s.c1.z); __stcs(a.rot[8] + i, s.c2.z);
+}
+
+// Per-instance facade kernel (array-of-structures, n is tiny): mode 0 = derivative only
+// (pos_dot n*3, rot_dot n*9), mode 1 = `steps` Euler steps with a constant twist, the first
+// steps-1 of size step_dT and the last of size last_dT (FixedStepIntegrator::integrate's schedule).
+struct KinAosArgs {
+    const double* twists;   // n*6
+    double* pos;            // n*3   (mode 0: pos_dot out; mode 1: in/out)
+    double* rot;            // n*9   (mode 1: in/out)
+    const double* rot_in;   // mode 0: rotation in
+    double* rot_dot;        // mode 0: out
+    double half_rho, step_dT, last_dT;
+    long long n;
+    int steps;
+    int mode;
+};
+
+template <bool BAUM>
+__global__ void __launch_bounds__(128)
+sys_kin_aos_kernel(const __grid_constant__ KinAosArgs a)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const double* T = a.twists + 6 * i;
+    const V3 v{T[0], T[1], T[2]}, w{T[3], T[4], T[5]};
+    const double* R = (a.mode == 0 ? a.rot_in : a.rot) + 9 * i;
+    Pose s{V3{0.0, 0.0, 0.0}, V3{R[0], R[3], R[6]}, V3{R[1], R[4], R[7]}, V3{R[2], R[5], R[8]}};
+    if (a.mode == 0) {
+        V3 d0, d1, d2;
+        kin_rates<BAUM>(s, w, a.half_rho, d0, d1, d2);
+        double* o = a.rot_dot + 9 * i;
+        o[0] = d0.x; o[1] = d1.x; o[2] = d2.x;
+        o[3] = d0.y; o[4] = d1.y; o[5] = d2.y;
+        o[6] = d0.z; o[7] = d1.z; o[8] = d2.z;
+        a.pos[3 * i] = v.x; a.pos[3 * i + 1] = v.y; a.pos[3 * i + 2] = v.z;
+        return;
+    }
+    s.p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
+    for (int k = 0; k < a.steps - 1; ++k) kin_euler_step<BAUM>(s, v, w, a.half_rho, a.step_dT);
+    kin_euler_step<BAUM>(s, v, w, a.half_rho, a.last_dT);
+    a.pos[3 * i] = s.p.x; a.pos[3 * i + 1] = s.p.y; a.pos[3 * i + 2] = s.p.z;
+    double* o = a.rot + 9 * i;
+    o[0] = s.c0.x; o[1] = s.c1.x; o[2] = s.c2.x;
+    o[3] = s.c0.y; o[4] = s.c1.y; o[5] = s.c2.y;
+    o[6] = s.c0.z; o[7] = s.c1.z; o[8] = s.c2.z;
+}
+
+// joint positions: x += v * dT per step (elementwise, layout-agnostic)
+__global__ void __launch_bounds__(256)
+sys_axpy_steps_kernel(double* __restrict__ x, const double* __restrict__ v, long long n, int steps,
+                      double step_dT, double last_dT)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double xi = x[i];
+    const double vi = v[i];
+    for (int k = 0; k < steps - 1; ++k) xi = xi + vi * step_dT;
+    xi = xi + vi * last_dT;
+    x[i] = xi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused rollout
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kRolloutDepth = 8;                               // twist prefetch distance (steps)
+constexpr int kRolloutRingBytes = kRolloutDepth * 6 * 32 * 8;  // per warp
+
+struct RolloutArgs {
+    const double* tw[6];     // [horizon*chains], index t*chains + chain
+    const double* pos0[3];   // [chains]
+    const double* rot0[9];
+    const double* nul[12];   // null-force pose per chain: pos 0-2, rot row-major 3-11
+    const double* prm[4];    // per-chain parameters (HET)
+    double* pos_out[3];      // final pose (all NULL when not wanted; may alias pos0/rot0)
+    double* rot_out[9];
+    double* wrench[6];       // [horizon*chains]
+    double* autodyn[6];
+    double* ctrl;            // [horizon*chains][36]
+    double* chain_cost;      // [chains]
+    Prm uni;
+    double ref[6];
+    double wf, wt;
+    double half_rho, dT;
+    long long chains;
+    int horizon;
+    int ctrl_bulk;
+    int write_final;
+};
+
+template <unsigned OUT, bool HET, bool BAUM>
+__global__ void __launch_bounds__(128)
+ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
+{
+    constexpr unsigned MASK = OUT | M_WRENCH;   // the cost needs the wrench
+    constexpr int D = kRolloutDepth;
+    constexpr int kPerWarp = kRolloutRingBytes + ((OUT & M_CTRL) ? kWarp * 288 : 0);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wbase =
+        (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp) * kWarp;
+    if (wbase >= a.chains) return;  // warp-uniform
+    const long long c = wbase + lane;
+    const bool on = c < a.chains;
+    const int cnt = static_cast<int>(min64(kWarp, a.chains - wbase));
+    const int H = a.horizon;
+
+    double* ring = reinterpret_cast<double*>(smem_raw + static_cast<size_t>(warp) * kPerWarp);
+    double* ctile = ring + D * 6 * kWarp;
+    const uint32_t ring_s = ptx::smem_addr(ring) + static_cast<uint32_t>(lane) * 8u;
+
+    // every lane stages its own six twist components of step t; nobody else reads them
+    auto issue = [&](int t) {
+        if (on && t < H) {
+            const uint32_t dst = ring_s + static_cast<uint32_t>((t & (D - 1)) * 6 * kWarp * 8);
+            const long long src = static_cast<long long>(t) * a.chains + c;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, a.tw[j] + src);
+        }
+        ptx::cp_async_commit();
+    };
+#pragma unroll
+    for (int t = 0; t < D; ++t) issue(t);
+
+    // chain constants
+    Pose s{};
+    V3 p0{}, n1{}, n2{};
+    Prm q = a.uni;
+    if (on) {
+        s.p = V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)};
+        s.c0 = V3{__ldg(a.rot0[0] + c), __ldg(a.rot0[3] + c), __ldg(a.rot0[6] + c)};
+        s.c1 = V3{__ldg(a.rot0[1] + c), __ldg(a.rot0[4] + c), __ldg(a.rot0[7] + c)};
+        s.c2 = V3{__ldg(a.rot0[2] + c), __ldg(a.rot0[5] + c), __ldg(a.rot0[8] + c)};
+        p0 = V3{__ldg(a.nul[0] + c), __ldg(a.nul[1] + c), __ldg(a.nul[2] + c)};
+        n1 = V3{__ldg(a.nul[3] + c), __ldg(a.nul[6] + c), __ldg(a.nul[9] + c)};
+        n2 = V3{__ldg(a.nul[4] + c), __ldg(a.nul[7] + c), __ldg(a.nul[10] + c)};
+        if constexpr (HET)
+            q = make_prm(__ldg(a.prm[0] + c), __ldg(a.prm[1] + c), __ldg(a.prm[2] + c),
+                         __ldg(a.prm[3] + c));
+    }
+    if constexpr ((OUT & M_CTRL) != 0) {
+        double2* z = reinterpret_cast<double2*>(ctile);
+#pragma unroll
+        for (int j = 0; j < 18; ++j) z[lane + j * kWarp] = make_double2(0.0, 0.0);
+        __syncwarp();
+    }
+
+    double acc = 0.0;
+    for (int t = 0; t < H; ++t) {
+        ptx::cp_async_wait<D - 1>();
+        V3 v{}, w{};
+        if (on) {
+            const double* r = ring + (t & (D - 1)) * 6 * kWarp + lane;
+            v = V3{r[0], r[kWarp], r[2 * kWarp]};
+            w = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
+        }
+        State st;
+        st.v = v; st.w = w; st.p = s.p; st.p0 = p0;
+        st.e1 = s.c0; st.e2 = s.c1;
+        st.R02 = s.c2.x; st.R12 = s.c2.y; st.R22 = s.c2.z;
+        st.n1 = n1; st.n2 = n2;
+        Result r;
+        eval_contact<MASK>(st, q, r);
+
+        const long long i = static_cast<long long>(t) * a.chains + c;
+        if constexpr ((OUT & M_CTRL) != 0) {
+            // previous step's tile must have left shared memory before it is overwritten
+            if (t > 0 && a.ctrl_bulk && lane == 0) ptx::bulk_wait_read_all();
+            __syncwarp();
+        }
+        if (on) {
+            if constexpr ((OUT & M_WRENCH) != 0) {
+                __stcs(a.wrench[0] + i, r.force.x); __stcs(a.wrench[1] + i, r.force.y);
+                __stcs(a.wrench[2] + i, r.force.z); __stcs(a.wrench[3] + i, r.torque.x);
+                __stcs(a.wrench[4] + i, r.torque.y); __stcs(a.wrench[5] + i, r.torque.z);
+            }
+            if constexpr ((OUT & M_AUTODYN) != 0) {
+                __stcs(a.autodyn[0] + i, r.fhead.x); __stcs(a.autodyn[1] + i, r.fhead.y);
+                __stcs(a.autodyn[2] + i, r.fhead.z); __stcs(a.autodyn[3] + i, r.ftail.x);
+                __stcs(a.autodyn[4] + i, r.ftail.y); __stcs(a.autodyn[5] + i, r.ftail.z);
+            }
+            if constexpr ((OUT & M_CTRL) != 0) stage_ctrl(ctile + lane * 36, r);
+            const V3 df = r.force - V3{a.ref[0], a.ref[1], a.ref[2]};
+            const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
+            acc = acc + (a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
+                         a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
+        }
+        if constexpr ((OUT & M_CTRL) != 0)
+            flush_ctrl_tile(a.ctrl, ctile, static_cast<long long>(t) * a.chains + wbase, cnt, lane,
+                            a.ctrl_bulk != 0);
+
+        kin_euler_step<BAUM>(s, v, w, a.half_rho, a.dT);
+        issue(t + D);   // the slot just consumed
+    }
+
+    if (on) {
+        a.chain_cost[c] = acc;
+        if (a.write_final) {
+            a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
+            a.rot_out[0][c] = s.c0.x; a.rot_out[1][c] = s.c1.x; a.rot_out[2][c] = s.c2.x;
+            a.rot_out[3][c] = s.c0.y; a.rot_out[4][c] = s.c1.y; a.rot_out[5][c] = s.c2.y;
+            a.rot_out[6][c] = s.c0.z; a.rot_out[7][c] = s.c1.z; a.rot_out[8][c] = s.c2.z;
+        }
+    }
+    ptx::cp_async_wait<0>();
+    if constexpr ((OUT & M_CTRL) != 0) {
+        if (a.ctrl_bulk && lane == 0) ptx::bulk_wait_read_all();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// J^T * wrench accumulation
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kGfStages = 4;    // Jacobian blocks in flight per warp
+constexpr int kGfMaxChunks = 4; // ncols <= 128
+
+struct GenForceArgs {
+    const double* in[30];
+    const double* prm[4];
+    Prm uni;
+    const double* jac;     // [n_contacts][6][ncols] row-major
+    const double* base;    // [n_systems][ncols] or nullptr
+    double* out;           // [n_systems][ncols]
+    double* wrench[6];     // optional planes (all nullptr when not wanted)
+    long long n_systems;
+    int cps;               // contacts per system (1..32)
+    int ncols;
+    int sys_per_warp;      // 32 / cps
+    int jac_bulk;          // jac 16-byte aligned -> TMA ring; else direct loads
+    int want_wrench;
+    int stage_bytes;       // per-stage shared-memory bytes (48*ncols rounded up to 128)
+};
+
+template <bool HET>
+__global__ void __launch_bounds__(128)
+ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
+{
+    constexpr unsigned LIVE = live_planes(M_WRENCH);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    const long long sys0 = wid * a.sys_per_warp;
+    if (sys0 >= a.n_systems) return;  // warp-uniform
+    const int nsys = static_cast<int>(min64(a.sys_per_warp, a.n_systems - sys0));
+    const int ncont = nsys * a.cps;
+    const long long c0 = sys0 * a.cps;   // first contact of this warp
+    const int jbytes = 48 * a.ncols;     // one contact's Jacobian
+
+    unsigned char* ws = smem_raw + static_cast<size_t>(warp) * (kGfStages * a.stage_bytes + 128);
+    const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * a.stage_bytes);
+    if (a.jac_bulk) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+            ptx::fence_mbar_init();
+#pragma unroll
+            for (int s = 0; s < kGfStages; ++s)
+                if (s < ncont) {
+                    ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
+                    ptx::bulk_g2s(ptx::smem_addr(ws + s * a.stage_bytes),
+                                  a.jac + (c0 + s) * 6 * a.ncols, jbytes, bar0 + 8 * s);
+                }
+        }
+        __syncwarp();
+    }
+
+    // ---- wrench of this lane's contact --------------------------------------------------------
+    const bool on = lane < ncont;
+    const long long i = c0 + lane;
+    double x[30] = {};
+#pragma unroll
+    for (int pl = 0; pl < 30; ++pl)
+        if (LIVE & (1u << pl)) x[pl] = on ? __ldcs(a.in[pl] + i) : 0.0;
+    Prm q = a.uni;
+    if constexpr (HET) {
+        const double l = on ? __ldcs(a.prm[0] + i) : 0.0, w = on ? __ldcs(a.prm[1] + i) : 0.0;
+        const double k = on ? __ldcs(a.prm[2] + i) : 0.0, b = on ? __ldcs(a.prm[3] + i) : 0.0;
+        q = make_prm(l, w, k, b);
+    }
+    State st;
+    st.v = V3{x[0], x[1], x[2]};
+    st.w = V3{x[3], x[4], x[5]};
+    st.p = V3{x[6], x[7], x[8]};
+    st.e1 = V3{x[9], x[12], x[15]};
+    st.e2 = V3{x[10], x[13], x[16]};
+    st.R02 = 0.0; st.R12 = 0.0;
+    st.R22 = x[17];
+    st.p0 = V3{x[18], x[19], x[20]};
+    st.n1 = V3{x[21], x[24], x[27]};
+    st.n2 = V3{x[22], x[25], x[28]};
+    Result r;
+    eval_contact<M_WRENCH>(st, q, r);
+    if (a.want_wrench && on) {
+        __stcs(a.wrench[0] + i, r.force.x); __stcs(a.wrench[1] + i, r.force.y);
+        __stcs(a.wrench[2] + i, r.force.z); __stcs(a.wrench[3] + i, r.torque.x);
+        __stcs(a.wrench[4] + i, r.torque.y); __stcs(a.wrench[5] + i, r.torque.z);
+    }
+
+    // ---- lanes own columns; contacts are visited in order -------------------------------------
+    const int nch = (a.ncols + kWarp - 1) / kWarp;
+    double acc[kGfMaxChunks];
+    uint32_t phase = 0;   // bit s = parity of stage s
+    for (int k = 0; k < ncont; ++k) {
+        const int sys = k / a.cps;
+        const bool first = (k - sys * a.cps) == 0, last = (k - sys * a.cps) == a.cps - 1;
+        const long long row = (sys0 + sys) * a.ncols;
+        if (first) {
+#pragma unroll
+            for (int ch = 0; ch < kGfMaxChunks; ++ch) {
+                const int col = ch * kWarp + lane;
+                acc[ch] = (ch < nch && col < a.ncols && a.base) ? __ldcs(a.base + row + col) : 0.0;
+            }
+        }
+        const double w0 = __shfl_sync(0xffffffffu, r.force.x, k);
+        const double w1 = __shfl_sync(0xffffffffu, r.force.y, k);
+        const double w2 = __shfl_sync(0xffffffffu, r.force.z, k);
+        const double w3 = __shfl_sync(0xffffffffu, r.torque.x, k);
+        const double w4 = __shfl_sync(0xffffffffu, r.torque.y, k);
+        const double w5 = __shfl_sync(0xffffffffu, r.torque.z, k);
+        const int s = k % kGfStages;
+        const double* J;
+        if (a.jac_bulk) {
+            ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
+            phase ^= 1u << s;
+            J = reinterpret_cast<const double*>(ws + s * a.stage_bytes);
+        } else {
+            J = a.jac + (c0 + k) * 6 * a.ncols;
+        }
+#pragma unroll
+        for (int ch = 0; ch < kGfMaxChunks; ++ch) {
+            const int col = ch * kWarp + lane;
+            if (ch < nch && col < a.ncols) {
+                // (J^T w)[col], rows in order; then known += product  (:224-225)
+                double t = J[col] * w0;
+                t += J[a.ncols + col] * w1;
+                t += J[2 * a.ncols + col] * w2;
+                t += J[3 * a.ncols + col] * w3;
+                t += J[4 * a.ncols + col] * w4;
+                t += J[5 * a.ncols + col] * w5;
+                acc[ch] = acc[ch] + t;
+            }
+        }
+        if (a.jac_bulk) {
+            __syncwarp();   // every lane is done with stage s
+            if (lane == 0 && k + kGfStages < ncont) {
+                ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
+                ptx::bulk_g2s(ptx::smem_addr(ws + s * a.stage_bytes),
+                              a.jac + (c0 + k + kGfStages) * 6 * a.ncols, jbytes, bar0 + 8 * s);
+            }
+        }
+        if (last) {
+#pragma unroll
+            for (int ch = 0; ch < kGfMaxChunks; ++ch) {
+                const int col = ch * kWarp + lane;
+                if (ch < nch && col < a.ncols) __stcs(a.out + row + col, acc[ch]);
+            }
+        }
+    }
+}
+
+}  // namespace blfccm

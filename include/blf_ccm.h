@@ -221,6 +221,91 @@ BLF_CCM_API int blf_ccm_rls_advance_contacts(blf_ccm_handle* h, int64_t n,
                                              double* const* cov_planes, void* stream);
 
 /*
+ * ---- System component: the steps either side of the contact model ------------------------------
+ *
+ * blf_sys_kinematics_*: System::FloatingBaseSystemKinematics::dynamics (base position + rotation;
+ * src/System/src/FloatingBaseSystemKinematics.cpp:36-73)
+ *   pos_dot = twist.head<3>();  rot_dot = -R.colwise().cross(w) + rho/2 ((R R^T)^-1 - I) R
+ * advanced by System::ForwardEuler (x += dx*dT, src/System/include/BipedalLocomotion/System/
+ * ForwardEuler.h:45-53, ForwardEuler.tpp:19-49).  rho is the Baumgarte parameter ("rho" key of
+ * FloatingBaseSystemKinematics::initalize, :13-34).  With rho == 0 the inverse is skipped (the
+ * reference would turn a singular R into NaN there; this backend leaves it finite).
+ */
+
+/* One ForwardEuler step for n independent systems, SoA device planes of n doubles:
+ * twist_planes[6] (linear xyz, angular xyz), pos_planes[3] and rot_planes[9] (row-major index)
+ * updated in place. */
+BLF_CCM_API int blf_sys_kinematics_euler_step_soa(blf_ccm_handle* h, int64_t n, double rho,
+                                                  double dT, const double* const* twist_planes,
+                                                  double* const* pos_planes,
+                                                  double* const* rot_planes, void* stream);
+
+/* dynamics() for n systems held in HOST arrays (what the per-instance facade calls with n = 1):
+ * twists n*6, rotations n*9 row-major -> pos_dot n*3, rot_dot n*9.  Synchronous. */
+BLF_CCM_API int blf_sys_kinematics_dynamics_host(blf_ccm_handle* h, int64_t n, double rho,
+                                                 const double* twists, const double* rotations,
+                                                 double* pos_dot, double* rot_dot);
+
+/* FixedStepIntegrator::integrate on HOST arrays with a constant control input: n_steps Euler
+ * steps, the first n_steps-1 of size step_dT and the last of size last_dT (the caller computes
+ * the reference's schedule, FixedStepIntegrator.tpp:48-64).  positions n*3, rotations n*9 in/out;
+ * joint_pos (n_joint_values doubles, any layout) += joint_vel * dT per step, NULL/0 for none. */
+BLF_CCM_API int blf_sys_kinematics_integrate_host(blf_ccm_handle* h, int64_t n, double rho,
+                                                  double step_dT, double last_dT, int n_steps,
+                                                  const double* twists, double* positions,
+                                                  double* rotations, int64_t n_joint_values,
+                                                  const double* joint_vel, double* joint_pos);
+
+/*
+ * Fused sampling-MPC rollout: integrate -> contact model -> cost, the pose never leaves registers.
+ * chains = n_rollouts * feet, chain c = rollout*feet + foot.  For t = 0..horizon-1 and every chain:
+ * the contact model is evaluated at (twist[t][c], pose_c) exactly as blf_ccm_eval_batch_soa would
+ * (outputs per out_mask at index t*chains + c: TIME-major), the cost term is accumulated, then
+ * pose_c advances by one ForwardEuler step of FloatingBaseSystemKinematics with that twist -- the
+ * order in which FloatingBaseDynamicalSystem::dynamics + ForwardEuler visit them.
+ *   twist_planes[6]            each horizon*chains doubles, index t*chains + c
+ *   pos_planes[3], rot_planes[9]   initial pose per chain (chains doubles each), not modified
+ *   null_planes[12]            null-force pose per chain: pos 0-2, rot row-major 3-11; the third
+ *                              rotation column (5, 8, 11) may be NULL
+ *   param_planes[4]            per-chain length,width,spring,damper, or NULL -> uniform parameters
+ *   out_mask                   subset of WRENCH|AUTODYN|CTRL to write as trajectories (0 = none);
+ *                              wrench_planes[6], autodyn_planes[6]: horizon*chains; ctrl dense
+ *                              horizon*chains*36
+ *   final_pos_planes[3], final_rot_planes[9]   pose after the last step, or both NULL
+ *   cost[r] = sum_foot ( sum_t  w0|F-Fref|^2 + w1|T-Tref|^2 )  (t inner, in order; then feet in
+ *   order: deterministic); cost may be NULL.  best as in blf_ccm_rollout_cost_argmin_soa.
+ * Per step only the 48-byte twist (and the requested outputs) cross HBM.
+ */
+BLF_CCM_API int blf_ccm_rollout_integrate_cost(
+    blf_ccm_handle* h, int64_t n_rollouts, int feet, int horizon, double dT, double rho,
+    const double* const* twist_planes, const double* const* pos_planes,
+    const double* const* rot_planes, const double* const* null_planes,
+    const double* const* param_planes, unsigned out_mask, double* const* wrench_planes,
+    double* const* autodyn_planes, double* ctrl, double* const* final_pos_planes,
+    double* const* final_rot_planes, const double* host_wrench_ref, const double* host_weights,
+    int64_t index_base, double* cost, void* best, void* stream);
+
+/*
+ * Contact part of FloatingBaseDynamicalSystem::dynamics
+ * (src/System/src/FloatingBaseSystemDynamics.cpp:199-226): per system s
+ *   out[s] = base[s] + sum_{c < contacts_per_system, in order}  J_c^T * wrench_c
+ * wrench_c = getContactWrench() of contact s*contacts_per_system + c, evaluated from the SoA state
+ * planes in registers (in_planes / param_planes as blf_ccm_eval_batch_soa with out_mask WRENCH);
+ * J_c = 6 x ncols row-major frame Jacobian (iDynTree::MatrixDynSize), jacobians =
+ * n_systems*contacts_per_system*6*ncols doubles; base (NULL = zeros; the reference starts from the
+ * negated bias forces, :191-196) and out are n_systems*ncols; base may alias out.
+ * wrench_planes[6] optional (NULL): also write the wrenches.  contacts_per_system 1..32,
+ * ncols 1..128.  jacobians 16-byte aligned -> TMA ring, else direct loads (blf_ccm_last_path).
+ */
+BLF_CCM_API int blf_ccm_generalized_force_soa(blf_ccm_handle* h, int64_t n_systems,
+                                              int contacts_per_system, int ncols,
+                                              const double* const* in_planes,
+                                              const double* const* param_planes,
+                                              const double* jacobians, const double* base,
+                                              double* out, double* const* wrench_planes,
+                                              void* stream);
+
+/*
  * Device / pinned-host memory and stream helpers, so that host code above this ABI (the C++17
  * facade, the device-side SoA container) needs no CUDA headers.  Device allocations are 256-byte
  * aligned.  Copies are asynchronous on `stream` when the host side is pinned.

@@ -22,7 +22,7 @@ def lib():
 
 def test_library_exports_every_declared_symbol(lib):
     header = open(os.path.join(ROOT, "include", "blf_ccm.h")).read()
-    declared = set(re.findall(r"BLF_CCM_API\s+[\w\s\*]+?\b(blf_(?:ccm|rls)_\w+)\s*\(", header))
+    declared = set(re.findall(r"BLF_CCM_API\s+[\w\s\*]+?\b(blf_(?:ccm|rls|sys)_\w+)\s*\(", header))
     assert declared, "no declarations parsed from include/blf_ccm.h"
     assert declared == set(_capi.SYMBOLS)
     for name in declared:

@@ -1,0 +1,333 @@
+"""GPU parity tests for the steps either side of the contact model (SURVEY.md section 8(f) rows 2
+and 3): FloatingBaseSystemKinematics + ForwardEuler, the fused integrate -> contact -> cost
+rollout, and the J^T * wrench accumulation -- the CUDA path through the C ABI against the CPU
+oracle on the same bits and against the exact / 80-digit golden fixtures.
+Tolerance 1e-12 norm-wise relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from bipedal_locomotion_framework_b200 import synthetic as syn
+from parity import TOL, assert_ctrl_structure, assert_parity
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NTHREADS = max(1, (os.cpu_count() or 1))
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def batch(torch):
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    b = ContinuousContactModelBatch(0)
+    b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    return b
+
+
+@pytest.fixture(scope="module")
+def so(oracle):
+    from oracle import sys_oracle
+    return sys_oracle
+
+
+@pytest.fixture(scope="module")
+def g():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "sys_exact_golden.npz")))
+
+
+def _dev(torch, a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(got, ref, axis=-1, floor=1e-300):
+    num = np.abs(np.asarray(got) - ref).max(axis=axis)
+    den = np.maximum(np.abs(ref).max(axis=axis), floor)
+    return np.where(num == 0, 0.0, num / den)
+
+
+# --- kinematics ------------------------------------------------------------------------------------
+
+def test_euler_step_matches_exact_rationals(torch, batch, g):
+    from bipedal_locomotion_framework_b200.system import KinematicsBatch
+    kb = KinematicsBatch(0, batch.handle)
+    n = g["step_twists"].shape[0]
+    # rho and dT are per launch: run each golden state through its own launch group
+    for i in range(n):
+        tw = _dev(torch, g["step_twists"][i:i + 1].T)
+        p = _dev(torch, g["step_pos"][i:i + 1].T)
+        r = _dev(torch, g["step_rot"][i:i + 1].T)
+        kb.euler_step(g["step_rho"][i], g["step_dT"][i], tw, p, r)
+        assert rel(p.cpu().numpy()[:, 0], g["step_pos_new"][i]) <= TOL
+        assert rel(r.cpu().numpy()[:, 0], g["step_rot_new"][i]) <= TOL
+
+
+@pytest.mark.parametrize("rho", [0.0, 7.5])
+def test_euler_step_batch_vs_oracle(torch, batch, so, rho):
+    from bipedal_locomotion_framework_b200.system import KinematicsBatch
+    kb = KinematicsBatch(0, batch.handle)
+    n = 100_003                                        # ragged
+    st = syn.make_states(n, seed=91)
+    tw = np.ascontiguousarray(st["twists"].T)
+    p0 = np.ascontiguousarray(st["poses"][:, :3].T)
+    r0 = np.ascontiguousarray(st["poses"][:, 3:].T)
+    p_ref, r_ref = so.euler_step_batch_soa(rho, 2e-3, tw, p0, r0, nthreads=NTHREADS)
+    p, r = _dev(torch, p0), _dev(torch, r0)
+    kb.euler_step(rho, 2e-3, _dev(torch, tw), p, r)
+    assert rel(p.cpu().numpy().T, p_ref.T).max() <= TOL
+    assert rel(r.cpu().numpy().T, r_ref.T).max() <= TOL
+
+
+def test_per_instance_facade_reference_property(torch):
+    """IntegratorTest.cpp:80-126 through the Python mirror of the facade (every step on the GPU):
+    identity start, constant twist; 200 integrate(0, dT) calls, then the closed form."""
+    from bipedal_locomotion_framework_b200.contact_models import StdImplementation
+    from bipedal_locomotion_framework_b200.system import FloatingBaseSystemKinematics, ForwardEuler
+    rng = np.random.default_rng(5)
+    twist, jv = rng.uniform(-1, 1, 6), rng.uniform(-1, 1, 20)
+    sysm = FloatingBaseSystemKinematics(0)
+    assert sysm.initalize(None) is False
+    h = StdImplementation()
+    assert sysm.initalize(h) is False                      # "rho" missing
+    h.setParameter("rho", 0.0)
+    assert sysm.initalize(h)
+    sysm.setControlInput((twist, jv))
+    sysm.setState((np.zeros(3), np.eye(3), np.zeros(20)))
+    ok, (pd, rd, sd) = sysm.dynamics()
+    assert ok and np.array_equal(pd, twist[:3]) and np.array_equal(sd, jv)
+    w = twist[3:]
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    assert np.allclose(rd, K, atol=1e-15)                  # Rdot = S(w) R at R = I
+    integ = ForwardEuler(1e-4)
+    assert integ.setDynamicalSystem(sysm) and not integ.setDynamicalSystem(sysm)
+    for _ in range(200):
+        assert integ.integrate(0, 1e-4)
+    t = 200 * 1e-4
+    p, R, s = integ.getSolution()
+    th = np.linalg.norm(w)
+    k = K / th
+    Rex = np.eye(3) + np.sin(th * t) * k + (1 - np.cos(th * t)) * k @ k
+    assert np.linalg.norm(R - Rex) <= 1e-3 * np.linalg.norm(Rex)
+    assert np.allclose(p, t * twist[:3], rtol=1e-12) and np.allclose(s, t * jv, rtol=1e-12)
+    # schedule quirk: integrate(0, 1.0) with dT 0.25 covers 1.25 s (FixedStepIntegrator.tpp:48-64)
+    sysm.setState((np.zeros(3), np.eye(3), np.zeros(20)))
+    integ2 = ForwardEuler(0.25)
+    integ2.setDynamicalSystem(sysm)
+    assert integ2.integrate(0.0, 1.0)
+    assert np.allclose(integ2.getSolution()[0], 1.25 * twist[:3], rtol=1e-14)
+    assert not integ2.integrate(1.0, 0.5) and not integ2.integrate(1.0, 1.0)
+
+
+def test_per_instance_integrate_vs_oracle(torch, so):
+    from bipedal_locomotion_framework_b200.contact_models import StdImplementation
+    from bipedal_locomotion_framework_b200.system import FloatingBaseSystemKinematics, ForwardEuler
+    rng = np.random.default_rng(6)
+    st = syn.make_states(4, seed=77)
+    for i in range(4):
+        twist, jv = st["twists"][i], rng.uniform(-1, 1, 7)
+        R0 = st["poses"][i, 3:].reshape(3, 3)
+        p0, s0 = st["poses"][i, :3], rng.uniform(-1, 1, 7)
+        rho = [0.0, 3.0, 20.0, 0.5][i]
+        sysm = FloatingBaseSystemKinematics(0)
+        h = StdImplementation()
+        h.setParameter("rho", rho)
+        assert sysm.initalize(h)
+        sysm.setControlInput((twist, jv))
+        sysm.setState((p0, R0, s0))
+        integ = ForwardEuler(0.003)
+        integ.setDynamicalSystem(sysm)
+        assert integ.integrate(0.1, 0.2)
+        n, p_ref, R_ref, s_ref = so.integrate(rho, 0.003, 0.1, 0.2, twist, p0, R0, jv, s0)
+        assert n == 34
+        p, R, s = integ.getSolution()
+        assert rel(p, p_ref) <= TOL and rel(R.reshape(9), R_ref.reshape(9)) <= TOL
+        assert rel(s, s_ref) <= TOL
+
+
+# --- fused rollout ---------------------------------------------------------------------------------
+
+def _check_traj(out, ref, mask, what):
+    if mask & 1:
+        assert_parity(out["wrench"].cpu().numpy().T, ref["wrench"].T, "wrench", what=what + " ")
+    if mask & 2:
+        assert_parity(out["autodyn"].cpu().numpy().T, ref["autodyn"].T, "autodyn", what=what + " ")
+    if mask & 4:
+        c = out["ctrl"].cpu().numpy()
+        assert_parity(c, ref["ctrl"], "ctrl", what=what + " ")
+        assert_ctrl_structure(c)
+
+
+def test_rollout_matches_80_digit_golden(torch, batch, g):
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    rb = RolloutBatch(batch)
+    nr, feet, H = (int(x) for x in g["ro_shape"])
+    out = rb.run(nr, feet, H, float(g["ro_dT"]), float(g["ro_rho"]), _dev(torch, g["ro_twists"]),
+                 _dev(torch, g["ro_pos0"]), _dev(torch, g["ro_rot0"]), _dev(torch, g["ro_null"]),
+                 g["ro_ref"], g["ro_weights"], param_planes=_dev(torch, g["ro_params"]), mask=7,
+                 want_final=True)
+    ref = {k[3:]: v for k, v in g.items() if k.startswith("ro_")}
+    _check_traj(out, ref, 7, "rollout/golden")
+    assert rel(out["final_pos"].cpu().numpy().T, ref["pos"].T).max() <= TOL
+    assert rel(out["final_rot"].cpu().numpy().T, ref["rot"].T).max() <= TOL
+    assert rel(out["cost"].cpu().numpy(), ref["cost"], axis=None) <= TOL
+    cost, idx = batch.decode_best(out["best"])
+    assert idx == int(np.argmin(ref["cost"])) and abs(cost - ref["cost"].min()) <= TOL * ref["cost"].min()
+
+
+@pytest.mark.parametrize("het,rho,mask,nr,feet,H", [
+    (False, 0.0, 0, 4096, 2, 100),     # configs[2] shape, cost only
+    (False, 0.0, 7, 512, 2, 50),
+    (True, 4.0, 7, 333, 3, 37),        # ragged: 999 chains, odd horizon, Baumgarte on
+    (True, 4.0, 1, 1000, 1, 9),        # horizon shorter than... the prefetch ring + 1
+    (False, 1.0, 5, 70, 2, 3),         # horizon < prefetch depth
+])
+def test_rollout_vs_oracle(torch, batch, so, het, rho, mask, nr, feet, H):
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    rb = RolloutBatch(batch)
+    chains = nr * feet
+    st = syn.make_states(chains, seed=123, heterogeneous=het)
+    tw = np.ascontiguousarray(syn.make_states(H * chains, seed=124)["twists"].T)
+    pos0 = np.ascontiguousarray(st["poses"][:, :3].T)
+    rot0 = np.ascontiguousarray(st["poses"][:, 3:].T)
+    null = np.ascontiguousarray(st["null_poses"].T)
+    prm = np.ascontiguousarray(st["params"].T) if het else None
+    ref_w, wts = np.array([0.0, 0.0, 30.0, 0.1, -0.1, 0.0]), np.array([1.0, 25.0])
+    dT = 0.01
+    ref = so.rollout(nr, feet, H, dT, rho, tw, pos0, rot0, null, param_planes=prm,
+                     uniform=syn.REFERENCE_TEST_PARAMS, mask=mask, wrench_ref=ref_w, weights=wts,
+                     nthreads=NTHREADS)
+    # the dead third column of the null rotation may be absent
+    null_list = [None if i in (5, 8, 11) else _dev(torch, null[i]) for i in range(12)]
+    out = rb.run(nr, feet, H, dT, rho, _dev(torch, tw), _dev(torch, pos0), _dev(torch, rot0),
+                 null_list, ref_w, wts, param_planes=_dev(torch, prm), mask=mask, want_final=True)
+    _check_traj(out, ref, mask, f"rollout het={het}")
+    assert rel(out["final_pos"].cpu().numpy().T, ref["pos"].T).max() <= TOL
+    assert rel(out["final_rot"].cpu().numpy().T, ref["rot"].T).max() <= TOL
+    cost = out["cost"].cpu().numpy()
+    assert np.all(rel(cost[:, None], ref["cost"][:, None]) <= TOL)
+    c, idx = batch.decode_best(out["best"])
+    assert c == cost.min() and idx == int(np.argmin(cost))
+    # deterministic run to run
+    out2 = rb.run(nr, feet, H, dT, rho, _dev(torch, tw), _dev(torch, pos0), _dev(torch, rot0),
+                  null_list, ref_w, wts, param_planes=_dev(torch, prm), mask=0)
+    assert np.array_equal(out2["cost"].cpu().numpy(), cost)
+
+
+def test_rollout_equals_unfused_pipeline(torch, batch):
+    """Size-independent property at configs[2] size: the fused rollout's wrench trajectory equals
+    stepping KinematicsBatch + evaluate_soa one horizon step at a time (same arithmetic; the
+    compiler may contract differently per kernel, so compared at the parity tolerance)."""
+    from bipedal_locomotion_framework_b200.system import KinematicsBatch, RolloutBatch
+    rb, kb = RolloutBatch(batch), KinematicsBatch(0, batch.handle)
+    nr, feet, H = 4096, 2, 100
+    chains = nr * feet
+    st = syn.make_states(chains, seed=321)
+    tw = _dev(torch, syn.make_states(H * chains, seed=322)["twists"].T)
+    pos = _dev(torch, st["poses"][:, :3].T)
+    rot = _dev(torch, st["poses"][:, 3:].T)
+    null = _dev(torch, st["null_poses"].T)
+    ref_w, wts = np.zeros(6), np.array([1.0, 1.0])
+    out = rb.run(nr, feet, H, 0.005, 2.0, tw, pos, rot, null, ref_w, wts, mask=1, want_final=True)
+    p, r = pos.clone(), rot.clone()
+    for t in range(H):
+        twt = tw[:, t * chains:(t + 1) * chains]
+        planes = [twt[i] for i in range(6)] + [p[i] for i in range(3)] + [r[i] for i in range(9)] + \
+                 [null[i] for i in range(12)]
+        w = batch.evaluate_soa(planes, None, 1)["wrench"]
+        assert_parity(out["wrench"][:, t * chains:(t + 1) * chains].cpu().numpy().T,
+                      w.cpu().numpy().T, "wrench", what=f"step {t} ")
+        kb.euler_step(2.0, 0.005, twt, p, r)
+    assert rel(out["final_pos"].cpu().numpy().T, p.cpu().numpy().T).max() <= TOL
+    assert rel(out["final_rot"].cpu().numpy().T, r.cpu().numpy().T).max() <= TOL
+
+
+def test_rollout_argument_errors(torch, batch):
+    from bipedal_locomotion_framework_b200 import _capi
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    rb = RolloutBatch(batch)
+    z = lambda *s: torch.zeros(s, dtype=torch.float64, device="cuda")
+    with pytest.raises(_capi.BlfCcmError):
+        rb.run(4, 0, 5, 0.01, 0.0, z(6, 20), z(3, 4), z(9, 4), z(12, 4), np.zeros(6), np.ones(2))
+    with pytest.raises(_capi.BlfCcmError):
+        rb.run(4, 1, 5, 0.01, 0.0, z(6, 20), z(3, 4), z(9, 4), z(12, 4), np.zeros(6), np.ones(2),
+               mask=8)
+    out = rb.run(0, 2, 5, 0.01, 0.0, z(6, 0), z(3, 0), z(9, 0), z(12, 0), np.zeros(6), np.ones(2))
+    assert batch.decode_best(out["best"])[1] == -1
+
+
+# --- J^T wrench ------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["gfa", "gfb"])
+def test_generalized_force_matches_exact(torch, batch, g, tag):
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    gf = GeneralizedForceBatch(batch)
+    ns, cps, ncols = (int(x) for x in g[tag + "_shape"])
+    planes = _dev(torch, syn.aos_to_planes(g[tag + "_twists"], g[tag + "_poses"],
+                                           g[tag + "_null_poses"]))
+    out, wr = gf.run(cps, ncols, planes, _dev(torch, g[tag + "_J"]), _dev(torch, g[tag + "_base"]),
+                     param_planes=_dev(torch, g[tag + "_params"].T), want_wrench=True)
+    J = g[tag + "_J"].reshape(ns, cps, 6, ncols)
+    Wm = g[tag + "_wrench"].reshape(ns, cps, 6)
+    mag = np.abs(g[tag + "_base"]) + np.einsum("scrq,scr->sq", np.abs(J), np.abs(Wm))
+    assert (np.abs(out.cpu().numpy() - g[tag + "_out"]).max(axis=1) <= TOL * mag.max(axis=1)).all()
+    assert_parity(wr.cpu().numpy().T, g[tag + "_wrench"], "wrench")
+
+
+@pytest.mark.parametrize("cps,ncols,ns,het,aligned,with_base", [
+    (2, 29, 50_001, False, True, True),     # iCub-sized: 6 + 23 DoF, two feet; ragged system count
+    (2, 29, 4_099, True, False, True),      # Jacobians only 8-byte aligned: direct path
+    (1, 6, 10_000, False, True, False),     # base-only Jacobian, no bias
+    (3, 38, 3_000, True, True, True),       # 32 % 3 != 0, two column chunks
+    (32, 128, 65, False, True, True),       # maxima
+    (5, 1, 777, False, True, True),         # single column
+])
+def test_generalized_force_vs_oracle(torch, batch, so, cps, ncols, ns, het, aligned, with_base):
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    gf = GeneralizedForceBatch(batch)
+    n = ns * cps
+    st = syn.make_states(n, seed=55 + cps, heterogeneous=het)
+    rng = np.random.default_rng(cps * 1000 + ncols)
+    J = rng.uniform(-1.0, 1.0, (n, 6, ncols))
+    base = rng.uniform(-50.0, 50.0, (ns, ncols)) if with_base else None
+    planes_h = syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])
+    prm_h = np.ascontiguousarray(st["params"].T) if het else None
+    ref, wref = so.generalized_force(cps, ncols, planes_h, J, base, param_planes=prm_h,
+                                     uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True,
+                                     nthreads=NTHREADS)
+    if aligned:
+        Jd = _dev(torch, J)
+    else:
+        buf = torch.empty(J.size + 1, dtype=torch.float64, device="cuda")
+        Jd = buf[1:].view(n, 6, ncols)
+        Jd.copy_(torch.from_numpy(J))
+    out, wr = gf.run(cps, ncols, _dev(torch, planes_h), Jd, _dev(torch, base),
+                     param_planes=_dev(torch, prm_h), want_wrench=True)
+    assert batch.handle.last_path == (1 if aligned else 2)
+    Wm = np.abs(wref.T.reshape(ns, cps, 6))
+    mag = (np.abs(base) if with_base else 0.0) + \
+        np.einsum("scrq,scr->sq", np.abs(J.reshape(ns, cps, 6, ncols)), Wm)
+    err = np.abs(out.cpu().numpy() - ref).max(axis=1) / np.maximum(mag.max(axis=1), 1e-300)
+    assert err.max() <= TOL, (int(np.argmax(err)), err.max())
+    assert_parity(wr.cpu().numpy().T, wref.T, "wrench")
+    if with_base:   # in place: base aliases out
+        b = _dev(torch, base)
+        gf.run(cps, ncols, _dev(torch, planes_h), Jd, b, param_planes=_dev(torch, prm_h), out=b)
+        assert torch.equal(b, out)
+
+
+def test_generalized_force_argument_errors(torch, batch):
+    from bipedal_locomotion_framework_b200 import _capi
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    gf = GeneralizedForceBatch(batch)
+    z = lambda *s: torch.zeros(s, dtype=torch.float64, device="cuda")
+    with pytest.raises(_capi.BlfCcmError):
+        gf.run(33, 4, z(30, 33), z(33, 6, 4))
+    with pytest.raises(_capi.BlfCcmError):
+        gf.run(1, 129, z(30, 2), z(2, 6, 129))

@@ -76,9 +76,67 @@ def rls_only():
         del planes, th, P, zz, Yp, out
 
 
+def sys_only():
+    """Rows 2 and 3 of SURVEY.md section 8(f): Euler step, fused rollout, J^T wrench."""
+    from bipedal_locomotion_framework_b200.system import (GeneralizedForceBatch, KinematicsBatch,
+                                                          RolloutBatch)
+    b = make_batch()
+    kb, rb, gf = KinematicsBatch(0, b.handle), RolloutBatch(b), GeneralizedForceBatch(b)
+    rnd = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda") * 2 - 1
+    print(f"peak {PEAK} GB/s")
+    # --- Euler step --------------------------------------------------------------------------------
+    for n in (819200, 1 << 23):
+        st = syn.make_states(min(n, 1 << 18), seed=47)
+        reps = (n + st["n"] - 1) // st["n"]
+        rot = torch.from_numpy(np.ascontiguousarray(np.tile(st["poses"][:, 3:].T, (1, reps))[:, :n])).cuda()
+        sets = [(rnd(6, n), rnd(3, n), rot.clone()) for _ in range(3)]
+        for rho in (0.0, 2.0):
+            cl = [kb.prepare_euler_step(rho, 1e-4, *s_) for s_ in sets]
+            ms = timeit(lambda i: cl[i % 3](), iters=100)
+            row(f"kinematics euler step n={n} rho={rho}", ms, n, 240)
+        del sets, rot
+    # --- fused rollout -----------------------------------------------------------------------------
+    for nr, feet, H in ((4096, 2, 100), (65536, 2, 100), (335544, 1, 200)):
+        chains, n = nr * feet, nr * feet * H
+        st = syn.make_states(min(chains, 1 << 18), seed=48)
+        reps = (chains + st["n"] - 1) // st["n"]
+        tile = lambda a: torch.from_numpy(np.ascontiguousarray(np.tile(a.T, (1, reps))[:, :chains])).cuda()
+        pos, rot, null = tile(st["poses"][:, :3]), tile(st["poses"][:, 3:]), tile(st["null_poses"])
+        tws = [rnd(6, n) for _ in range(2)]
+        print(f"=== rollout {nr} x {feet} x {H} = {n} evals ===")
+        for rho in (0.0, 2.0):
+            for mask, bytes_per in ((0, 48), (1, 96), (7, 432)):
+                cls = [rb.prepare(nr, feet, H, 0.01, rho, tw, pos, rot, null, [0, 0, 30., 0, 0, 0],
+                                  [1., 10.], mask=mask)[0] for tw in tws]
+                ms = timeit(lambda i: cls[i % 2](), iters=20, warm=3)
+                row(f"fused rollout rho={rho} out_mask={mask} ({bytes_per} B/eval)", ms, n, bytes_per)
+                del cls
+                torch.cuda.empty_cache()
+        del tws, pos, rot, null
+        torch.cuda.empty_cache()
+    # --- J^T wrench --------------------------------------------------------------------------------
+    for ns, cps, ncols in ((409600, 2, 29), (1 << 21, 2, 29), (1 << 20, 4, 38), (1 << 21, 1, 6)):
+        n = ns * cps
+        st = syn.make_states(min(n, 1 << 18), seed=49)
+        reps = (n + st["n"] - 1) // st["n"]
+        pl = torch.from_numpy(np.ascontiguousarray(np.tile(
+            syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]), (1, reps))[:, :n])).cuda()
+        Js = [rnd(n, 6, ncols) for _ in range(2)]
+        base = rnd(ns, ncols)
+        outs = [torch.empty_like(base) for _ in range(2)]
+        cls = [gf.prepare(cps, ncols, pl, Js[j], base, out=outs[j])[0] for j in range(2)]
+        ms = timeit(lambda i: cls[i % 2](), iters=50, warm=5)
+        per_contact = 200 + 48 * ncols + 16 * ncols / cps
+        row(f"J^T wrench systems={ns} contacts/system={cps} ncols={ncols}", ms, n, per_contact)
+        del Js, base, outs, cls, pl
+        torch.cuda.empty_cache()
+
+
 def main():
     if "--rls-only" in sys.argv:
         return rls_only()
+    if "--sys-only" in sys.argv:
+        return sys_only()
     sizes = {"cfg3 819200": 2 * 4096 * 100, "8M": 1 << 23}
     NS = 3
     for label, n in sizes.items():
