@@ -340,7 +340,7 @@ class ContinuousContactModelBatch:
         if isinstance(t, (list, tuple)):
             assert len(t) == count
             return _ptr_array([None if p is None else p.data_ptr() for p in t])
-        assert t.shape[0] == count and t.stride(1) == 1
+        assert t.shape[0] == count and (t.shape[1] <= 1 or t.stride(1) == 1)
         return _ptr_array([t[i].data_ptr() for i in range(count)])
 
     @staticmethod

@@ -93,7 +93,7 @@ struct KinArgs {
 };
 
 template <bool BAUM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 5)
 sys_kin_euler_kernel(const __grid_constant__ KinArgs a)
 {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

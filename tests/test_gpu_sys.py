@@ -214,10 +214,14 @@ def test_rollout_vs_oracle(torch, batch, so, het, rho, mask, nr, feet, H):
     assert np.all(rel(cost[:, None], ref["cost"][:, None]) <= TOL)
     c, idx = batch.decode_best(out["best"])
     assert c == cost.min() and idx == int(np.argmin(cost))
-    # deterministic run to run
+    # deterministic run to run (same kernel, same bits) ...
     out2 = rb.run(nr, feet, H, dT, rho, _dev(torch, tw), _dev(torch, pos0), _dev(torch, rot0),
-                  null_list, ref_w, wts, param_planes=_dev(torch, prm), mask=0)
+                  null_list, ref_w, wts, param_planes=_dev(torch, prm), mask=mask)
     assert np.array_equal(out2["cost"].cpu().numpy(), cost)
+    # ... and the cost-only variant (another template instance, other FMA contraction) agrees
+    out3 = rb.run(nr, feet, H, dT, rho, _dev(torch, tw), _dev(torch, pos0), _dev(torch, rot0),
+                  null_list, ref_w, wts, param_planes=_dev(torch, prm), mask=0)
+    assert np.all(rel(out3["cost"].cpu().numpy()[:, None], ref["cost"][:, None]) <= TOL)
 
 
 def test_rollout_equals_unfused_pipeline(torch, batch):
