@@ -63,6 +63,7 @@ CPP_TESTS = {
     "ContinuousContactModelUnitTests": "ContinuousContactModelTest.cpp",   # needs a GPU
     "ParametersHandlerUnitTests": "ParametersHandlerTest.cpp",             # host only
     "RecursiveLeastSquareUnitTests": "RecursiveLeastSquareTest.cpp",       # needs a GPU
+    "IntegratorUnitTests": "IntegratorTest.cpp",                           # host section + GPU
 }
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra"]
 

@@ -1,0 +1,88 @@
+/**
+ * @file ContactRolloutBatch.h
+ * Batched forms of the steps either side of the contact model (no reference equivalent as a
+ * class; the per-system semantics are those of FloatingBaseSystemKinematics + ForwardEuler and of
+ * the contact loop of FloatingBaseDynamicalSystem::dynamics,
+ * src/System/src/FloatingBaseSystemDynamics.cpp:199-226).  Host code is C++17 and reaches the GPU
+ * only through the C ABI (include/blf_ccm.h).
+ */
+#ifndef BIPEDAL_LOCOMOTION_SYSTEM_CONTACT_ROLLOUT_BATCH_H
+#define BIPEDAL_LOCOMOTION_SYSTEM_CONTACT_ROLLOUT_BATCH_H
+
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+
+#include <BipedalLocomotion/ContactModels/ContinuousContactModelBatch.h>
+#include <BipedalLocomotion/GenericContainer/DeviceSoA.h>
+
+namespace BipedalLocomotion
+{
+namespace System
+{
+
+class ContactRolloutBatch
+{
+public:
+    struct Result
+    {
+        double cost;
+        std::int64_t index; /**< -1 when there is nothing to compare */
+    };
+
+    /** Shares the device handle (and the uniform contact parameters) of `model`. */
+    explicit ContactRolloutBatch(std::shared_ptr<ContactModels::CudaDevice> device);
+    ~ContactRolloutBatch();
+    ContactRolloutBatch(const ContactRolloutBatch&) = delete;
+    ContactRolloutBatch& operator=(const ContactRolloutBatch&) = delete;
+
+    /** One ForwardEuler step of FloatingBaseSystemKinematics for every system:
+     * twists 6 planes, positions 3 planes and rotations 9 planes (row-major) updated in place. */
+    bool eulerStep(double rho, double dT, const GenericContainer::DeviceSoA& twists,
+                   GenericContainer::DeviceSoA& positions, GenericContainer::DeviceSoA& rotations,
+                   void* stream = nullptr);
+
+    /**
+     * Fused sampling-MPC rollout (integrate -> contact model -> cost); layouts in
+     * include/blf_ccm.h, blf_ccm_rollout_integrate_cost.  twists: 6 planes of horizon*chains
+     * (time-major), positions/rotations/nullPoses: 3/9/12 planes of chains = nRollouts*feet.
+     * Optional trajectories per `outputs` (ContinuousContactModelBatch::Output bits 1|2|4),
+     * optional final pose; costs (device, nRollouts) may be nullptr; best = 16 device bytes.
+     */
+    bool rollout(std::size_t nRollouts, int feet, int horizon, double dT, double rho,
+                 const GenericContainer::DeviceSoA& twists, const GenericContainer::DeviceSoA& positions,
+                 const GenericContainer::DeviceSoA& rotations, const GenericContainer::DeviceSoA& nullPoses,
+                 const GenericContainer::DeviceSoA* parameters, unsigned outputs,
+                 GenericContainer::DeviceSoA* wrench, GenericContainer::DeviceSoA* autonomousDynamics,
+                 double* controlMatrix, GenericContainer::DeviceSoA* finalPositions,
+                 GenericContainer::DeviceSoA* finalRotations, const iDynTree::Wrench& referenceWrench,
+                 double forceWeight, double torqueWeight, std::int64_t indexBase, double* costs,
+                 void* best, void* stream = nullptr);
+    /** Cost-only form that copies the arg-min pair to the host (synchronises the stream). */
+    bool rollout(std::size_t nRollouts, int feet, int horizon, double dT, double rho,
+                 const GenericContainer::DeviceSoA& twists, const GenericContainer::DeviceSoA& positions,
+                 const GenericContainer::DeviceSoA& rotations, const GenericContainer::DeviceSoA& nullPoses,
+                 const GenericContainer::DeviceSoA* parameters, const iDynTree::Wrench& referenceWrench,
+                 double forceWeight, double torqueWeight, Result& result);
+
+    /**
+     * knownCoefficient[s] = base[s] + sum_c J_c^T wrench_c  (FloatingBaseSystemDynamics.cpp:199-226)
+     * states: 30 planes of nSystems*contactsPerSystem contacts; jacobians: device array of
+     * 6 x columns row-major blocks per contact; base (may be nullptr, may alias out) and out:
+     * nSystems x columns row-major.
+     */
+    bool generalizedForce(std::size_t nSystems, int contactsPerSystem, int columns,
+                          const GenericContainer::DeviceSoA& states,
+                          const GenericContainer::DeviceSoA* parameters, const double* jacobians,
+                          const double* base, double* out, GenericContainer::DeviceSoA* wrench = nullptr,
+                          void* stream = nullptr);
+
+private:
+    std::shared_ptr<ContactModels::CudaDevice> m_device;
+    void* m_best{nullptr};
+};
+
+} // namespace System
+} // namespace BipedalLocomotion
+
+#endif // BIPEDAL_LOCOMOTION_SYSTEM_CONTACT_ROLLOUT_BATCH_H

@@ -1,0 +1,412 @@
+/**
+ * @file IntegratorTest.cpp
+ * The reference's integrator test (src/System/tests/IntegratorTest.cpp:22-127) against this build:
+ *  - "Linear System": the generic ForwardEuler template on a host-side system (host logic only; the
+ *    reference's LinearTimeInvariantSystem is out of scope, so the same 2x2 system is defined here);
+ *  - "Floating base System Kinematics": FloatingBaseSystemKinematics + ForwardEuler, every step on
+ *    the GPU through the C ABI, against the axis-angle closed form, tolerance 1e-3 as the reference;
+ *  - batched forms: Euler step and fused rollout against a loop over per-instance objects, and the
+ *    J^T wrench accumulation against a host loop.
+ * The floating-base and batched sections need a CUDA device.
+ */
+#ifdef BLF_HAVE_CATCH2
+#include <catch2/catch.hpp>
+#else
+#include "catch_shim.h"
+#endif
+
+#include <cmath>
+#include <memory>
+#include <random>
+#include <vector>
+
+#include <BipedalLocomotion/ContactModels/ContinuousContactModel.h>
+#include <BipedalLocomotion/ContactModels/ContinuousContactModelBatch.h>
+#include <BipedalLocomotion/ParametersHandler/StdImplementation.h>
+#include <BipedalLocomotion/System/ContactRolloutBatch.h>
+#include <BipedalLocomotion/System/FloatingBaseSystemKinematics.h>
+#include <BipedalLocomotion/System/ForwardEuler.h>
+
+using namespace BipedalLocomotion::System;
+using namespace BipedalLocomotion::ContactModels;
+using namespace BipedalLocomotion::ParametersHandler;
+using BipedalLocomotion::GenericContainer::DeviceSoA;
+
+namespace
+{
+using Vector2d = FixedVector<2>;
+
+/** dx = A x + b u with A = [0 1; -2 -2], b = [0; 2] (IntegratorTest.cpp:30-45). */
+class TwoStateLinearSystem
+    : public DynamicalSystem<std::tuple<Vector2d>, std::tuple<Vector2d>, std::tuple<double>>
+{
+public:
+    bool dynamics(const double&, StateDerivativeType& stateDerivative) final
+    {
+        const Vector2d& x = std::get<0>(m_state);
+        const double u = std::get<0>(m_controlInput);
+        std::get<0>(stateDerivative) = Vector2d{x[1], -2.0 * x[0] - 2.0 * x[1] + 2.0 * u};
+        return true;
+    }
+};
+
+bool isApprox(const double* a, const double* b, std::size_t n, double tol)
+{
+    double d = 0, na = 0, nb = 0;
+    for (std::size_t i = 0; i < n; ++i)
+    {
+        d += (a[i] - b[i]) * (a[i] - b[i]);
+        na += a[i] * a[i];
+        nb += b[i] * b[i];
+    }
+    return std::sqrt(d) <= tol * std::sqrt(std::min(na, nb)) + 1e-300;
+}
+
+/** Eigen::AngleAxisd(angle, axis) as a row-major matrix. */
+Matrix3d angleAxis(double angle, const Vector3d& axis)
+{
+    const double c = std::cos(angle), s = std::sin(angle), t = 1 - c;
+    const double x = axis[0], y = axis[1], z = axis[2];
+    Matrix3d r;
+    r(0, 0) = t * x * x + c;     r(0, 1) = t * x * y - s * z; r(0, 2) = t * x * z + s * y;
+    r(1, 0) = t * x * y + s * z; r(1, 1) = t * y * y + c;     r(1, 2) = t * y * z - s * x;
+    r(2, 0) = t * x * z - s * y; r(2, 1) = t * y * z + s * x; r(2, 2) = t * z * z + c;
+    return r;
+}
+
+double relErr(const double* got, const double* ref, std::size_t n)
+{
+    double num = 0, den = 0;
+    for (std::size_t i = 0; i < n; ++i)
+    {
+        num = std::max(num, std::fabs(got[i] - ref[i]));
+        den = std::max(den, std::fabs(ref[i]));
+    }
+    return num == 0 ? 0 : num / std::max(den, 1e-300);
+}
+} // namespace
+
+TEST_CASE("Integrator - Linear system")
+{
+    constexpr double dT = 0.0001;
+    constexpr double tolerance = 1e-3;
+    constexpr double simulationTime = 2;
+
+    SECTION("Linear System")
+    {
+        auto system = std::make_shared<TwoStateLinearSystem>();
+        auto closeFormSolution = [](const double& t) {
+            return Vector2d{1 - std::exp(-t) * (std::cos(t) + std::sin(t)), 2 * std::exp(-t) * std::sin(t)};
+        };
+        REQUIRE(system->setControlInput({1.0}));
+        REQUIRE(system->setState({Vector2d{0.0, 0.0}}));
+
+        ForwardEuler<TwoStateLinearSystem> integrator(dT);
+        REQUIRE(integrator.setDynamicalSystem(system));
+        REQUIRE_FALSE(integrator.setDynamicalSystem(system)); // only once
+
+        for (int i = 0; i < simulationTime / dT; i++)
+        {
+            const auto& [solution] = integrator.getSolution();
+            const Vector2d exact = closeFormSolution(dT * i);
+            if (i > 0) REQUIRE(isApprox(solution.data(), exact.data(), 2, tolerance));
+            REQUIRE(integrator.integrate(0, dT));
+        }
+        // FixedStepIntegrator argument checks (FixedStepIntegrator.tpp:32-46) and the schedule quirk
+        REQUIRE_FALSE(integrator.integrate(1.0, 0.5));
+        REQUIRE_FALSE(integrator.integrate(1.0, 1.0));
+        ForwardEuler<TwoStateLinearSystem> bad(0.0);
+        bad.setDynamicalSystem(system);
+        REQUIRE_FALSE(bad.integrate(0.0, 1.0));
+    }
+}
+
+// The reference keeps this section inside the test case above (IntegratorTest.cpp:80-126); it is
+// its own test case here so that the host-only section can run on a machine without a GPU.
+TEST_CASE("Integrator - Floating base System Kinematics")
+{
+    constexpr double dT = 0.0001;
+    constexpr double tolerance = 1e-3;
+    constexpr double simulationTime = 2;
+
+    SECTION("Floating base System Kinematics")
+    {
+        auto system = std::make_shared<FloatingBaseSystemKinematics>();
+        std::mt19937 gen(42);
+        std::uniform_real_distribution<> u(-1.0, 1.0);
+        Vector6d twist;
+        for (int i = 0; i < 6; ++i) twist[i] = u(gen);
+        VectorXd jointVelocity(20);
+        for (int i = 0; i < 20; ++i) jointVelocity[i] = u(gen);
+
+        // handler protocol of initalize (FloatingBaseSystemKinematics.cpp:13-34)
+        REQUIRE_FALSE(system->initalize(std::weak_ptr<IParametersHandler>()));
+        auto handler = std::make_shared<StdImplementation>();
+        REQUIRE_FALSE(system->initalize(handler));
+        handler->setParameter("rho", 0.01);
+        REQUIRE(system->initalize(handler));
+
+        const Vector3d position0;
+        const Matrix3d rotation0 = Matrix3d::Identity();
+        const VectorXd jointPosition0(20);
+        const double wnorm = std::sqrt(twist[3] * twist[3] + twist[4] * twist[4] + twist[5] * twist[5]);
+        const Vector3d axis{twist[3] / wnorm, twist[4] / wnorm, twist[5] / wnorm};
+
+        REQUIRE(system->setControlInput({twist, jointVelocity}));
+        REQUIRE(system->setState({position0, rotation0, jointPosition0}));
+
+        // dynamics() at the identity: Rdot = S(w)
+        FloatingBaseSystemKinematics::StateDerivativeType dx;
+        REQUIRE(system->dynamics(0.0, dx));
+        REQUIRE(std::get<0>(dx)[0] == twist[0]);
+        REQUIRE(std::fabs(std::get<1>(dx)(0, 1) + twist[5]) < 1e-15);
+        REQUIRE(std::fabs(std::get<1>(dx)(2, 1) - twist[3]) < 1e-15);
+        REQUIRE(std::get<2>(dx)[7] == jointVelocity[7]);
+
+        ForwardEuler<FloatingBaseSystemKinematics> integrator(dT);
+        REQUIRE(integrator.setDynamicalSystem(system));
+
+        // the reference checks every step of 2 s (20 000 device round trips); 2 000 steps here
+        for (int i = 0; i < 2000; i++)
+        {
+            const auto& [basePosition, baseRotation, jointPosition] = integrator.getSolution();
+            const double t = dT * i;
+            const Matrix3d rotExact = angleAxis(wnorm * t, axis);
+            Vector3d posExact;
+            for (int k = 0; k < 3; ++k) posExact[k] = t * twist[k];
+            VectorXd jointExact = jointVelocity * t;
+            REQUIRE(isApprox(baseRotation.data(), rotExact.data(), 9, tolerance));
+            if (i > 0) REQUIRE(isApprox(basePosition.data(), posExact.data(), 3, tolerance));
+            if (i > 0) REQUIRE(isApprox(jointPosition.data(), jointExact.data(), 20, tolerance));
+            REQUIRE(integrator.integrate(0, dT));
+        }
+        // one call covering the rest of the horizon (one launch for the whole schedule)
+        REQUIRE(integrator.integrate(0.2, simulationTime - dT));   // schedule quirk: one extra dT
+        const auto& [p, R, s] = integrator.getSolution();
+        const Matrix3d rotExact = angleAxis(wnorm * simulationTime, axis);
+        REQUIRE(isApprox(R.data(), rotExact.data(), 9, tolerance));
+        REQUIRE(std::fabs(p[0] - simulationTime * twist[0]) < 1e-9);
+        REQUIRE(std::fabs(s[3] - simulationTime * jointVelocity[3]) < 1e-9);
+    }
+}
+
+TEST_CASE("Batched steps either side of the contact model")
+{
+    auto dev = CudaDevice::open(0);
+    REQUIRE(dev != nullptr);
+    auto handler = std::make_shared<StdImplementation>();
+    handler->setParameter("length", 0.12);
+    handler->setParameter("width", 0.09);
+    handler->setParameter("spring_coeff", 2000.0);
+    handler->setParameter("damper_coeff", 100.0);
+    ContinuousContactModelBatch batch(dev);
+    REQUIRE(batch.initialize(handler));
+    ContactRolloutBatch rollouts(dev);
+
+    std::mt19937 gen(7);
+    std::uniform_real_distribution<> u(-1.0, 1.0);
+    const int nRollouts = 37, feet = 2, horizon = 25;
+    const std::size_t chains = nRollouts * feet, n = chains * horizon;
+    const double dT = 0.01, rho = 2.0;
+
+    // per chain: initial pose near flat, null pose; per (t, chain): twist
+    std::vector<iDynTree::Transform> pose(chains), nullPose(chains);
+    for (std::size_t c = 0; c < chains; ++c)
+    {
+        pose[c] = iDynTree::Transform(iDynTree::Rotation::RPY(0.2 * u(gen), 0.2 * u(gen), 3.0 * u(gen)),
+                                      iDynTree::Position(0.05 * u(gen), 0.05 * u(gen), 0.05 * u(gen)));
+        nullPose[c] = iDynTree::Transform(iDynTree::Rotation::RPY(0.02 * u(gen), 0.02 * u(gen), u(gen)),
+                                          iDynTree::Position(0.05 * u(gen), 0.05 * u(gen), 0.05 * u(gen)));
+    }
+    std::vector<double> twistRows(n * 6);
+    for (double& x : twistRows) x = u(gen);
+
+    DeviceSoA twists(dev, 6, n), positions(dev, 3, chains), rotations(dev, 9, chains), nulls(dev, 12, chains);
+    REQUIRE(twists.uploadRows(0, 6, twistRows.data()));
+    {
+        std::vector<double> rows(chains * 12);
+        for (std::size_t c = 0; c < chains; ++c)
+            for (int k = 0; k < 12; ++k) rows[c * 12 + k] = reinterpret_cast<const double*>(&pose[c])[k];
+        std::vector<double> p(chains * 3), r(chains * 9);
+        for (std::size_t c = 0; c < chains; ++c)
+        {
+            for (int k = 0; k < 3; ++k) p[c * 3 + k] = rows[c * 12 + k];
+            for (int k = 0; k < 9; ++k) r[c * 9 + k] = rows[c * 12 + 3 + k];
+        }
+        REQUIRE(positions.uploadRows(0, 3, p.data()));
+        REQUIRE(rotations.uploadRows(0, 9, r.data()));
+        REQUIRE(nulls.uploadRows(0, 12, reinterpret_cast<const double*>(nullPose.data())));
+    }
+
+    SECTION("Fused rollout equals a loop over per-instance objects")
+    {
+        DeviceSoA wrench(dev, 6, n), finalP(dev, 3, chains), finalR(dev, 9, chains);
+        iDynTree::Wrench reference;
+        reference(2) = 30.0;
+        void* best = nullptr;
+        std::vector<double> costs(nRollouts);
+        DeviceSoA costPlane(dev, 1, nRollouts);
+        DeviceSoA bestPlane(dev, 1, 2);
+        best = bestPlane.plane(0);
+        REQUIRE(rollouts.rollout(nRollouts, feet, horizon, dT, rho, twists, positions, rotations, nulls,
+                                 nullptr, ContinuousContactModelBatch::ContactWrench, &wrench, nullptr,
+                                 nullptr, &finalP, &finalR, reference, 1.0, 10.0, 0, costPlane.plane(0),
+                                 best));
+        std::vector<double> w(n * 6), fp(chains * 3), fr(chains * 9);
+        REQUIRE(wrench.downloadRows(0, 6, w.data()));
+        REQUIRE(finalP.downloadRows(0, 3, fp.data()));
+        REQUIRE(finalR.downloadRows(0, 9, fr.data()));
+        REQUIRE(costPlane.download(0, costs.data()));
+
+        // the same rollouts, one object per chain, through the per-instance facades
+        ContinuousContactModel model;
+        REQUIRE(model.initialize(handler));
+        auto kinHandler = std::make_shared<StdImplementation>();
+        kinHandler->setParameter("rho", rho);
+        double worst = 0;
+        std::vector<double> chainCost(chains, 0.0);
+        for (std::size_t c = 0; c < chains; c += 9) // a sample of the chains (each step is a launch)
+        {
+            auto system = std::make_shared<FloatingBaseSystemKinematics>(dev);
+            REQUIRE(system->initalize(kinHandler));
+            Vector3d p0;
+            Matrix3d r0;
+            for (int k = 0; k < 3; ++k) p0[k] = pose[c].getPosition()(k);
+            for (int k = 0; k < 9; ++k) r0[k] = pose[c].getRotation().data()[k];
+            system->setState({p0, r0, VectorXd(0)});
+            ForwardEuler<FloatingBaseSystemKinematics> integrator(dT);
+            integrator.setDynamicalSystem(system);
+            model.setNullForceTransform(nullPose[c]);
+            for (int t = 0; t < horizon; ++t)
+            {
+                const double* tw = &twistRows[(static_cast<std::size_t>(t) * chains + c) * 6];
+                Vector6d twist;
+                for (int k = 0; k < 6; ++k) twist[k] = tw[k];
+                const auto& [p, R, s] = integrator.getSolution();
+                iDynTree::Rotation rot;
+                for (int k = 0; k < 9; ++k) rot.data()[k] = R[k];
+                iDynTree::Twist itw;
+                for (int k = 0; k < 6; ++k) itw(k) = tw[k];
+                model.setState(itw, iDynTree::Transform(rot, iDynTree::Position(p[0], p[1], p[2])));
+                const iDynTree::Wrench& ref = model.getContactWrench();
+                const double* got = &w[(static_cast<std::size_t>(t) * chains + c) * 6];
+                worst = std::max(worst, relErr(got, ref.data(), 3));
+                worst = std::max(worst, relErr(got + 3, ref.data() + 3, 3));
+                system->setControlInput({twist, VectorXd(0)});
+                REQUIRE(integrator.integrate(0, dT));
+            }
+            const auto& [p, R, s] = integrator.getSolution();
+            worst = std::max(worst, relErr(&fp[c * 3], p.data(), 3));
+            worst = std::max(worst, relErr(&fr[c * 9], R.data(), 9));
+        }
+        REQUIRE(worst <= 1e-12);
+
+        // cost and arg-min against a host loop over the wrench trajectory
+        std::vector<double> hostCost(nRollouts, 0.0);
+        for (int r = 0; r < nRollouts; ++r)
+            for (int f = 0; f < feet; ++f)
+            {
+                const std::size_t c = static_cast<std::size_t>(r) * feet + f;
+                double acc = 0;
+                for (int t = 0; t < horizon; ++t)
+                {
+                    const double* x = &w[(static_cast<std::size_t>(t) * chains + c) * 6];
+                    const double df = x[0] * x[0] + x[1] * x[1] + (x[2] - 30.0) * (x[2] - 30.0);
+                    const double dt = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
+                    acc += 1.0 * df + 10.0 * dt;
+                }
+                hostCost[r] += acc;
+            }
+        int argmin = 0;
+        for (int r = 0; r < nRollouts; ++r)
+        {
+            REQUIRE(std::fabs(costs[r] - hostCost[r]) <= 1e-12 * hostCost[r]);
+            if (costs[r] < costs[argmin]) argmin = r;
+        }
+        ContactRolloutBatch::Result result{};
+        REQUIRE(rollouts.rollout(nRollouts, feet, horizon, dT, rho, twists, positions, rotations, nulls,
+                                 nullptr, reference, 1.0, 10.0, result));
+        REQUIRE(result.index == argmin);
+        REQUIRE(std::fabs(result.cost - hostCost[argmin]) <= 1e-12 * hostCost[argmin]);
+    }
+
+    SECTION("Euler step batch and generalized force")
+    {
+        // one Euler step over all chains with the t = 0 twists == per-instance integrate(0, dT)
+        DeviceSoA tw0(dev, 6, chains);
+        REQUIRE(tw0.uploadRows(0, 6, twistRows.data()));
+        REQUIRE(rollouts.eulerStep(rho, dT, tw0, positions, rotations));
+        std::vector<double> p(chains * 3), r(chains * 9);
+        REQUIRE(positions.downloadRows(0, 3, p.data()));
+        REQUIRE(rotations.downloadRows(0, 9, r.data()));
+        auto kinHandler = std::make_shared<StdImplementation>();
+        kinHandler->setParameter("rho", rho);
+        for (std::size_t c = 0; c < chains; c += 13)
+        {
+            auto system = std::make_shared<FloatingBaseSystemKinematics>(dev);
+            system->initalize(kinHandler);
+            Vector3d p0;
+            Matrix3d r0;
+            Vector6d twist;
+            for (int k = 0; k < 3; ++k) p0[k] = pose[c].getPosition()(k);
+            for (int k = 0; k < 9; ++k) r0[k] = pose[c].getRotation().data()[k];
+            for (int k = 0; k < 6; ++k) twist[k] = twistRows[c * 6 + k];
+            system->setState({p0, r0, VectorXd(0)});
+            system->setControlInput({twist, VectorXd(0)});
+            ForwardEuler<FloatingBaseSystemKinematics> integrator(dT);
+            integrator.setDynamicalSystem(system);
+            REQUIRE(integrator.integrate(0, dT));
+            const auto& [pp, RR, ss] = integrator.getSolution();
+            REQUIRE(relErr(&p[c * 3], pp.data(), 3) <= 1e-12);
+            REQUIRE(relErr(&r[c * 9], RR.data(), 9) <= 1e-12);
+        }
+
+        // known[s] = base[s] + sum_c J_c^T wrench_c, two contacts per system, 6 + 23 columns
+        const int cps = 2, cols = 29;
+        const std::size_t nSystems = chains / cps;
+        DeviceSoA states(dev, ContinuousContactModelBatch::NumberOfPlanes, chains);
+        std::vector<iDynTree::Twist> tws(chains);
+        for (std::size_t c = 0; c < chains; ++c)
+            for (int k = 0; k < 6; ++k) tws[c](k) = twistRows[c * 6 + k];
+        REQUIRE(states.uploadRows(ContinuousContactModelBatch::LinearVelocity, 6,
+                                  reinterpret_cast<const double*>(tws.data())));
+        REQUIRE(states.uploadRows(ContinuousContactModelBatch::Position, 12,
+                                  reinterpret_cast<const double*>(pose.data())));
+        REQUIRE(states.uploadRows(ContinuousContactModelBatch::NullForcePosition, 12,
+                                  reinterpret_cast<const double*>(nullPose.data())));
+        std::vector<double> J(chains * 6 * cols), base(nSystems * cols), out(nSystems * cols);
+        for (double& x : J) x = u(gen);
+        for (double& x : base) x = 10.0 * u(gen);
+        DeviceSoA Jd(dev, 1, J.size()), based(dev, 1, base.size()), outd(dev, 1, out.size());
+        REQUIRE(Jd.upload(0, J.data()));
+        REQUIRE(based.upload(0, base.data()));
+        REQUIRE(rollouts.generalizedForce(nSystems, cps, cols, states, nullptr, Jd.plane(0), based.plane(0),
+                                          outd.plane(0)));
+        REQUIRE(outd.download(0, out.data()));
+        ContinuousContactModel model;
+        REQUIRE(model.initialize(handler));
+        double worst = 0;
+        for (std::size_t s = 0; s < nSystems; s += 5)
+        {
+            std::vector<double> ref(base.begin() + s * cols, base.begin() + (s + 1) * cols), mag(cols, 0.0);
+            for (int q = 0; q < cols; ++q) mag[q] = std::fabs(ref[q]);
+            for (int c = 0; c < cps; ++c)
+            {
+                const std::size_t i = s * cps + c;
+                model.setState(tws[i], pose[i]);
+                model.setNullForceTransform(nullPose[i]);
+                const iDynTree::Wrench& w = model.getContactWrench();
+                for (int q = 0; q < cols; ++q)
+                    for (int rr = 0; rr < 6; ++rr)
+                    {
+                        ref[q] += J[(i * 6 + rr) * cols + q] * w(rr);
+                        mag[q] += std::fabs(J[(i * 6 + rr) * cols + q] * w(rr));
+                    }
+            }
+            double m = 0;
+            for (int q = 0; q < cols; ++q) m = std::max(m, mag[q]);
+            for (int q = 0; q < cols; ++q) worst = std::max(worst, std::fabs(out[s * cols + q] - ref[q]) / m);
+        }
+        REQUIRE(worst <= 1e-12);
+    }
+}

@@ -56,3 +56,20 @@ def test_reference_rls_test_on_the_gpu_estimator(cpp):
     r = _run("RecursiveLeastSquareUnitTests")
     assert r.returncode == 0, r.stdout + r.stderr
     assert "2 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
+
+
+def test_generic_integrator_templates_host_section(cpp):
+    """src/System/tests/IntegratorTest.cpp:27-78 (linear system through the generic ForwardEuler /
+    FixedStepIntegrator templates; host logic only)."""
+    r = _run("IntegratorUnitTests", "Linear")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "1 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_integrator_test_and_batched_system_steps(cpp):
+    """IntegratorTest.cpp:80-126 on the GPU-backed FloatingBaseSystemKinematics + ForwardEuler, and
+    the batched Euler step / fused rollout / J^T wrench against loops over per-instance objects."""
+    r = _run("IntegratorUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "3 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
