@@ -303,6 +303,87 @@ def run_ours(args):
            "collective": "nccl all_gather 16 B/rank + device arg-min" if world > 1 else "none (1 GPU)",
            "hbm_frac_of_measured": None}
 
+    # ---- fused rollout: integrate -> contact model -> cost, pose in ---------
+    # registers; same shape (2 feet x 4096 samples x 100 steps), the twist planes of the batch read
+    # time-major, initial / null poses = the first 8192 states; Baumgarte rho = reference default
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch, KinematicsBatch, RolloutBatch
+    rb = RolloutBatch(batch)
+    chains = FEET * SAMPLES
+    fused_calls = [rb.prepare(SAMPLES, FEET, HORIZON, 0.01, 0.01, planes[j][0:6],
+                              planes[j][6:9, :chains], planes[j][9:18, :chains],
+                              planes[j][18:30, :chains], ref_wrench, weights, mask=0,
+                              index_base=first_rollout, want_cost=False) for j in range(NSETS)]
+
+    def fused_step(i):
+        call, o = fused_calls[i % NSETS]
+        call()
+        if world > 1:
+            return batch.argmin_pairs(sharding.all_gather_pairs(o["best"], world, dist))
+        return o["best"]
+
+    for i in range(Wm):
+        fbest = fused_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(Km):
+        fbest = fused_step(i)
+    f1.record()
+    barrier()
+    fused_ms = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([fused_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fused_ms = float(t.item())
+    fc, fi = batch.decode_best(fbest)
+    mpc_fused = {"value": world * n * Km / (fused_ms * 1e-3), "unit": UNIT,
+                 "ms_per_step": fused_ms / Km, "steps": Km,
+                 "what": "blf_ccm_rollout_integrate_cost: ForwardEuler(FloatingBaseSystemKinematics) "
+                         "-> contact wrench -> cost -> arg-min, cost only; 48 B (twist) per "
+                         "evaluation from HBM, pose in registers",
+                 "rho": 0.01, "dT": 0.01, "argmin": {"cost": fc, "rollout": fi},
+                 "speedup_vs_unfused_mpc": (mpc_ms / Km) / (fused_ms / Km)}
+
+    # ---- the other rows next to the path, one GPU, briefly (fractions of the measured HBM peak) ---
+    next_rows = None
+    if world == 1:
+        def timed(fn, iters=50):
+            for i in range(5):
+                fn(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(iters):
+                fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+        gf = GeneralizedForceBatch(batch)
+        ncols, cps = 29, FEET                        # 6 + 23 DoF (iCub-sized), two feet per robot
+        Js = [torch.rand((n, 6, ncols), dtype=torch.float64, device=dev) for _ in range(2)]
+        base = torch.rand((n // cps, ncols), dtype=torch.float64, device=dev)
+        gouts = [torch.empty_like(base) for _ in range(2)]
+        gcalls = [gf.prepare(cps, ncols, planes[j], Js[j], base, out=gouts[j])[0] for j in range(2)]
+        g_ms = timed(lambda i: gcalls[i % 2]())
+        g_bytes = n * (200 + 48 * ncols) + (n // cps) * ncols * 16
+        kb = KinematicsBatch(local, batch.handle)
+        kp = [planes[j][6:18].clone() for j in range(NSETS)]
+        kcalls = [kb.prepare_euler_step(0.01, 1e-4, planes[j][0:6], kp[j][0:3], kp[j][3:12])
+                  for j in range(NSETS)]
+        k_ms = timed(lambda i: kcalls[i % NSETS]())
+        pk = _peaks()[0]
+        next_rows = {
+            "generalized_force": {"what": "blf_ccm_generalized_force_soa: base + sum J^T wrench, "
+                                          f"{n // cps} systems x {cps} contacts, 6 x {ncols} Jacobians",
+                                  "ms": g_ms, "contacts_per_s": n / (g_ms * 1e-3),
+                                  "algorithmic_gbs": g_bytes / (g_ms * 1e-3) / 1e9,
+                                  "hbm_frac_of_measured": g_bytes / (g_ms * 1e-3) / 1e9 / pk},
+            "kinematics_euler_step": {"what": "blf_sys_kinematics_euler_step_soa, rho 0.01, 240 B/system",
+                                      "ms": k_ms, "systems_per_s": n / (k_ms * 1e-3),
+                                      "hbm_frac_of_measured": n * 240 / (k_ms * 1e-3) / 1e9 / pk},
+        }
+        del Js, base, gouts, gcalls, kp, kcalls
+
     # ---- end to end through the C ABI with HOST buffers (copies inside the timed region) ---------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_tw, h_po, h_nu = pin(st["twists"]), pin(st["poses"]), pin(st["null_poses"])
@@ -365,7 +446,7 @@ def run_ours(args):
                    "l2": f"{NSETS} rotating input/output buffer sets; one step streams 491.5 MB "
                          "(> 126 MB L2), no explicit flush"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "mpc": mpc,
+        "clocks": clocks, "mpc": mpc, "mpc_fused": mpc_fused, "next_rows": next_rows,
     }
     print(json.dumps(line))
     if world > 1:

@@ -79,6 +79,7 @@ struct blf_ccm_handle {
     int tune_cpt = 0;            // BLF_CCM_TUNE_CPT=2: use the 128-bit two-contacts-per-lane SoA kernel
     int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM>0: persistent grid with that many CTAs/SM
                                  // (looping kernels only); default = one tile per warp
+    int tune_rollout_split = 0;  // BLF_CCM_TUNE_ROLLOUT_SPLIT>0: warps per tile of the fused rollout
 };
 
 static int env_int(const char* name)
@@ -122,6 +123,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->sm_count = prop.multiProcessorCount;
     h->tune_cpt = env_int("BLF_CCM_TUNE_CPT");
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
+    h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
     CUDA_TRY(cudaMalloc(&h->counter, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(h->counter, 0, sizeof(unsigned int)));

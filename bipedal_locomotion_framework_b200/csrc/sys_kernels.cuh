@@ -199,10 +199,18 @@ struct RolloutArgs {
     int horizon;
     int ctrl_bulk;
     int write_final;
+    int split;               // warps sharing one 32-chain tile (power of two, 1 = none)
 };
 
+// Few chains (a sampling-MPC batch of configs[2] size is 8 192 chains = 256 warps for 592 warp
+// schedulers) leave the FP64 pipes idle and the step latency exposed.  `split` = K > 1 lets K warps
+// share the same 32 chains: every warp integrates the poses of all steps (cheap: ~35 FP64
+// instructions per step) but evaluates the contact model and the cost only for the steps
+// t = phase (mod K), so the per-warp critical path shrinks ~2-3x while the idle schedulers fill up.
+// Each (chain, phase) writes its own partial cost: chain_cost[chain*K + phase]; the reduce kernel
+// sums a rollout's feet*K partials in index order (deterministic for a given shape and device).
 template <unsigned OUT, bool HET, bool BAUM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
 {
     constexpr unsigned MASK = OUT | M_WRENCH;   // the cost needs the wrench
@@ -212,8 +220,10 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const long long wbase =
-        (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp) * kWarp;
+    const int K = a.split;                      // power of two
+    const long long gw = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    const int phase = static_cast<int>(gw & (K - 1));
+    const long long wbase = (gw / K) * kWarp;
     if (wbase >= a.chains) return;  // warp-uniform
     const long long c = wbase + lane;
     const bool on = c < a.chains;
@@ -261,6 +271,7 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
     }
 
     double acc = 0.0;
+    bool staged = false;   // a ctrl tile of this warp may still be leaving shared memory
     for (int t = 0; t < H; ++t) {
         ptx::cp_async_wait<D - 1>();
         V3 v{}, w{};
@@ -269,6 +280,7 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
             v = V3{r[0], r[kWarp], r[2 * kWarp]};
             w = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
         }
+        if ((t & (K - 1)) == phase) {   // warp-uniform: this warp's share of the evaluations
         State st;
         st.v = v; st.w = w; st.p = s.p; st.p0 = p0;
         st.e1 = s.c0; st.e2 = s.c1;
@@ -280,8 +292,9 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
         const long long i = static_cast<long long>(t) * a.chains + c;
         if constexpr ((OUT & M_CTRL) != 0) {
             // previous step's tile must have left shared memory before it is overwritten
-            if (t > 0 && a.ctrl_bulk && lane == 0) ptx::bulk_wait_read_all();
+            if (staged && a.ctrl_bulk && lane == 0) ptx::bulk_wait_read_all();
             __syncwarp();
+            staged = true;
         }
         if (on) {
             if constexpr ((OUT & M_WRENCH) != 0) {
@@ -303,14 +316,15 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
         if constexpr ((OUT & M_CTRL) != 0)
             flush_ctrl_tile(a.ctrl, ctile, static_cast<long long>(t) * a.chains + wbase, cnt, lane,
                             a.ctrl_bulk != 0);
+        }
 
         kin_euler_step<BAUM>(s, v, w, a.half_rho, a.dT);
         issue(t + D);   // the slot just consumed
     }
 
     if (on) {
-        a.chain_cost[c] = acc;
-        if (a.write_final) {
+        a.chain_cost[c * K + phase] = acc;
+        if (a.write_final && phase == 0) {
             a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
             a.rot_out[0][c] = s.c0.x; a.rot_out[1][c] = s.c1.x; a.rot_out[2][c] = s.c2.x;
             a.rot_out[3][c] = s.c0.y; a.rot_out[4][c] = s.c1.y; a.rot_out[5][c] = s.c2.y;
@@ -319,7 +333,7 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
     }
     ptx::cp_async_wait<0>();
     if constexpr ((OUT & M_CTRL) != 0) {
-        if (a.ctrl_bulk && lane == 0) ptx::bulk_wait_read_all();
+        if (staged && a.ctrl_bulk && lane == 0) ptx::bulk_wait_read_all();
     }
 }
 
@@ -347,7 +361,11 @@ struct GenForceArgs {
     int stage_bytes;       // per-stage shared-memory bytes (48*ncols rounded up to 128)
 };
 
-template <bool HET>
+// NCH = ceil(ncols / 32): column chunks a lane owns (compile-time so dead chunks cost nothing).
+// Per contact and warp: one mbarrier wait, three broadcast LDS.128 for the wrench, NCH x (6 LDS +
+// 6 DFMA/DMUL + 1 DADD); a first version with runtime chunk predicates, shuffles for the wrench and
+// an integer division per contact was issue-bound (74 % issue slots busy, ncu) at 72 % of DRAM.
+template <bool HET, int NCH>
 __global__ void __launch_bounds__(128)
 ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
 {
@@ -359,13 +377,20 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     const long long sys0 = wid * a.sys_per_warp;
     if (sys0 >= a.n_systems) return;  // warp-uniform
     const int nsys = static_cast<int>(min64(a.sys_per_warp, a.n_systems - sys0));
-    const int ncont = nsys * a.cps;
-    const long long c0 = sys0 * a.cps;   // first contact of this warp
-    const int jbytes = 48 * a.ncols;     // one contact's Jacobian
+    const int cps = a.cps, ncols = a.ncols;
+    const int ncont = nsys * cps;
+    const long long c0 = sys0 * cps;           // first contact of this warp
+    const uint32_t jbytes = 48u * ncols;       // one contact's Jacobian
+    const bool bulk = a.jac_bulk != 0;
 
-    unsigned char* ws = smem_raw + static_cast<size_t>(warp) * (kGfStages * a.stage_bytes + 128);
-    const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * a.stage_bytes);
-    if (a.jac_bulk) {
+    // per warp: kGfStages Jacobian stages | 32 wrenches (32 x 48 B) | kGfStages mbarriers
+    const int per_warp = kGfStages * a.stage_bytes + kWarp * 48 + 128;
+    unsigned char* ws = smem_raw + static_cast<size_t>(warp) * per_warp;
+    double* wsm = reinterpret_cast<double*>(ws + kGfStages * a.stage_bytes);
+    const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * a.stage_bytes + kWarp * 48);
+    const uint32_t stage0 = ptx::smem_addr(ws);
+    const double* jac0 = a.jac + c0 * 6 * ncols;
+    if (bulk) {
         if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
@@ -374,8 +399,8 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
             for (int s = 0; s < kGfStages; ++s)
                 if (s < ncont) {
                     ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
-                    ptx::bulk_g2s(ptx::smem_addr(ws + s * a.stage_bytes),
-                                  a.jac + (c0 + s) * 6 * a.ncols, jbytes, bar0 + 8 * s);
+                    ptx::bulk_g2s(stage0 + s * a.stage_bytes, jac0 + static_cast<long long>(s) * 6 * ncols,
+                                  jbytes, bar0 + 8 * s);
                 }
         }
         __syncwarp();
@@ -412,66 +437,63 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
         __stcs(a.wrench[2] + i, r.force.z); __stcs(a.wrench[3] + i, r.torque.x);
         __stcs(a.wrench[4] + i, r.torque.y); __stcs(a.wrench[5] + i, r.torque.z);
     }
+    {
+        double2* o = reinterpret_cast<double2*>(wsm) + lane * 3;
+        o[0] = make_double2(r.force.x, r.force.y);
+        o[1] = make_double2(r.force.z, r.torque.x);
+        o[2] = make_double2(r.torque.y, r.torque.z);
+    }
+    __syncwarp();
 
-    // ---- lanes own columns; contacts are visited in order -------------------------------------
-    const int nch = (a.ncols + kWarp - 1) / kWarp;
-    double acc[kGfMaxChunks];
-    uint32_t phase = 0;   // bit s = parity of stage s
-    for (int k = 0; k < ncont; ++k) {
-        const int sys = k / a.cps;
-        const bool first = (k - sys * a.cps) == 0, last = (k - sys * a.cps) == a.cps - 1;
-        const long long row = (sys0 + sys) * a.ncols;
-        if (first) {
+    // ---- lanes own columns; systems and their contacts are visited in order -------------------
+    bool mine[NCH];
 #pragma unroll
-            for (int ch = 0; ch < kGfMaxChunks; ++ch) {
-                const int col = ch * kWarp + lane;
-                acc[ch] = (ch < nch && col < a.ncols && a.base) ? __ldcs(a.base + row + col) : 0.0;
+    for (int ch = 0; ch < NCH; ++ch) mine[ch] = ch * kWarp + lane < ncols;
+    int k = 0;
+    for (int sys = 0; sys < nsys; ++sys) {
+        const long long row = (sys0 + sys) * ncols + lane;
+        double acc[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            acc[ch] = (mine[ch] && a.base) ? __ldcs(a.base + row + ch * kWarp) : 0.0;
+        for (int cc = 0; cc < cps; ++cc, ++k) {
+            const int s = k & (kGfStages - 1);
+            const double* J;
+            if (bulk) {
+                ptx::mbar_wait(bar0 + 8 * s, (k / kGfStages) & 1);
+                J = reinterpret_cast<const double*>(ws + s * a.stage_bytes) + lane;
+            } else {
+                J = jac0 + static_cast<long long>(k) * 6 * ncols + lane;
             }
-        }
-        const double w0 = __shfl_sync(0xffffffffu, r.force.x, k);
-        const double w1 = __shfl_sync(0xffffffffu, r.force.y, k);
-        const double w2 = __shfl_sync(0xffffffffu, r.force.z, k);
-        const double w3 = __shfl_sync(0xffffffffu, r.torque.x, k);
-        const double w4 = __shfl_sync(0xffffffffu, r.torque.y, k);
-        const double w5 = __shfl_sync(0xffffffffu, r.torque.z, k);
-        const int s = k % kGfStages;
-        const double* J;
-        if (a.jac_bulk) {
-            ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
-            phase ^= 1u << s;
-            J = reinterpret_cast<const double*>(ws + s * a.stage_bytes);
-        } else {
-            J = a.jac + (c0 + k) * 6 * a.ncols;
+            const double2* wv = reinterpret_cast<const double2*>(wsm) + k * 3;
+            const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                if (mine[ch]) {
+                    // (J^T w)[col], rows in order; then known += product  (:224-225)
+                    const double* Jc = J + ch * kWarp;
+                    double t = Jc[0] * w01.x;
+                    t += Jc[ncols] * w01.y;
+                    t += Jc[2 * ncols] * w23.x;
+                    t += Jc[3 * ncols] * w23.y;
+                    t += Jc[4 * ncols] * w45.x;
+                    t += Jc[5 * ncols] * w45.y;
+                    acc[ch] = acc[ch] + t;
+                }
+            }
+            if (bulk) {
+                __syncwarp();   // every lane is done with stage s
+                if (lane == 0 && k + kGfStages < ncont) {
+                    ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
+                    ptx::bulk_g2s(stage0 + s * a.stage_bytes,
+                                  jac0 + static_cast<long long>(k + kGfStages) * 6 * ncols, jbytes,
+                                  bar0 + 8 * s);
+                }
+            }
         }
 #pragma unroll
-        for (int ch = 0; ch < kGfMaxChunks; ++ch) {
-            const int col = ch * kWarp + lane;
-            if (ch < nch && col < a.ncols) {
-                // (J^T w)[col], rows in order; then known += product  (:224-225)
-                double t = J[col] * w0;
-                t += J[a.ncols + col] * w1;
-                t += J[2 * a.ncols + col] * w2;
-                t += J[3 * a.ncols + col] * w3;
-                t += J[4 * a.ncols + col] * w4;
-                t += J[5 * a.ncols + col] * w5;
-                acc[ch] = acc[ch] + t;
-            }
-        }
-        if (a.jac_bulk) {
-            __syncwarp();   // every lane is done with stage s
-            if (lane == 0 && k + kGfStages < ncont) {
-                ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
-                ptx::bulk_g2s(ptx::smem_addr(ws + s * a.stage_bytes),
-                              a.jac + (c0 + k + kGfStages) * 6 * a.ncols, jbytes, bar0 + 8 * s);
-            }
-        }
-        if (last) {
-#pragma unroll
-            for (int ch = 0; ch < kGfMaxChunks; ++ch) {
-                const int col = ch * kWarp + lane;
-                if (ch < nch && col < a.ncols) __stcs(a.out + row + col, acc[ch]);
-            }
-        }
+        for (int ch = 0; ch < NCH; ++ch)
+            if (mine[ch]) __stcs(a.out + row + ch * kWarp, acc[ch]);
     }
 }
 

@@ -114,6 +114,27 @@ def sys_only():
                 torch.cuda.empty_cache()
         del tws, pos, rot, null
         torch.cuda.empty_cache()
+    # --- rollout: warps per 32-chain tile (BLF_CCM_TUNE_ROLLOUT_SPLIT) at configs[2] size ---------
+    for nr, feet, H in ((4096, 2, 100), (16384, 2, 100)):
+        chains, n = nr * feet, nr * feet * H
+        st = syn.make_states(chains, seed=48)
+        tile = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+        pos, rot, null = tile(st["poses"][:, :3]), tile(st["poses"][:, 3:]), tile(st["null_poses"])
+        tws = [rnd(6, n) for _ in range(2)]
+        print(f"=== rollout split sweep {nr} x {feet} x {H} ===")
+        for split in (1, 2, 4, 8):
+            bs = make_batch(BLF_CCM_TUNE_ROLLOUT_SPLIT=split)
+            rbs = RolloutBatch(bs)
+            for rho in (0.0, 2.0):
+                for mask, bytes_per in ((0, 48), (7, 432)):
+                    cls = [rbs.prepare(nr, feet, H, 0.01, rho, tw, pos, rot, null, [0, 0, 30., 0, 0, 0],
+                                       [1., 10.], mask=mask)[0] for tw in tws]
+                    ms = timeit(lambda i: cls[i % 2](), iters=50, warm=5)
+                    row(f"split={split} rho={rho} out_mask={mask}", ms, n, bytes_per)
+                    del cls
+        os.environ.pop("BLF_CCM_TUNE_ROLLOUT_SPLIT", None)
+        del tws, pos, rot, null
+        torch.cuda.empty_cache()
     # --- J^T wrench --------------------------------------------------------------------------------
     for ns, cps, ncols in ((409600, 2, 29), (1 << 21, 2, 29), (1 << 20, 4, 38), (1 << 21, 1, 6)):
         n = ns * cps
