@@ -309,6 +309,14 @@ class ContinuousContactModelBatch:
     def set_uniform_params(self, length, width, spring, damper):
         self._handle.set_uniform_params(float(length), float(width), float(spring), float(damper))
 
+    def load_parameter_table(self, handler):
+        """Per-contact parameter table (four equally long float lists, e.g. a group of a `.ini`
+        file read with ini.load_ini_file) -> (4, n) device planes for `param_planes`; None (and a
+        message) when a key is missing, mistyped or of a different length."""
+        from .ini import parameter_table
+        t = parameter_table(handler)
+        return None if t is None else self._torch.from_numpy(t).to(self.device)
+
     def _stream(self):
         return self._torch.cuda.current_stream(self.device).cuda_stream
 

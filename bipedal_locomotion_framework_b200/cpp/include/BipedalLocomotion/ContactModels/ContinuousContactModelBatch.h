@@ -93,6 +93,16 @@ public:
     std::shared_ptr<CudaDevice> device() const { return m_device; }
 
     /**
+     * Per-contact parameter table -> the four device planes `evaluate` takes as `parameters`.
+     * The handler (typically a group of a `.ini` file read with ParametersHandler::loadIniFile,
+     * the reference's on-disk configuration format) must hold the four keys of initialize() as
+     * equally long std::vector<double>: "length", "width", "spring_coeff", "damper_coeff".
+     * On success `parameters` owns 4 planes of that length.  No range validation, as initialize().
+     */
+    bool loadParameterTable(std::weak_ptr<ParametersHandler::IParametersHandler> handler,
+                            GenericContainer::DeviceSoA& parameters);
+
+    /**
      * Device-resident structure-of-arrays evaluation (asynchronous on `stream`).
      * @param states 30 planes (Plane order); planes that cannot affect `outputs` may be null
      * @param parameters 4 planes length,width,spring,damper or nullptr for the uniform ones

@@ -3,6 +3,7 @@
  * Batched entry point: thin C++17 layer over the C ABI (include/blf_ccm.h).
  */
 #include <iostream>
+#include <vector>
 
 #include <BipedalLocomotion/ContactModels/ContinuousContactModelBatch.h>
 
@@ -77,6 +78,51 @@ bool ContinuousContactModelBatch::initialize(std::weak_ptr<IParametersHandler> w
         return false;
     }
     return report(blf_ccm_set_uniform_params(raw(m_device), length, width, spring, damper), "initialize");
+}
+
+bool ContinuousContactModelBatch::loadParameterTable(std::weak_ptr<IParametersHandler> weakHandler,
+                                                     DeviceSoA& parameters)
+{
+    auto handler = weakHandler.lock();
+    if (handler == nullptr)
+    {
+        std::cerr << "[ContinuousContactModelBatch::loadParameterTable] The parameter handler is "
+                     "corrupted. Please make sure that the handler exists."
+                  << std::endl;
+        return false;
+    }
+    const char* keys[4] = {"length", "width", "spring_coeff", "damper_coeff"};
+    std::vector<double> column[4];
+    for (int k = 0; k < 4; ++k)
+    {
+        if (!handler->getParameter(keys[k], column[k]))
+        {
+            std::cerr << "[ContinuousContactModelBatch::loadParameterTable] Unable to get the vector "
+                         "named "
+                      << keys[k] << "." << std::endl;
+            return false;
+        }
+        if (column[k].size() != column[0].size())
+        {
+            std::cerr << "[ContinuousContactModelBatch::loadParameterTable] The vector named " << keys[k]
+                      << " has " << column[k].size() << " elements, " << keys[0] << " has "
+                      << column[0].size() << "." << std::endl;
+            return false;
+        }
+    }
+    if (m_device == nullptr)
+    {
+        std::cerr << "[ContinuousContactModelBatch::loadParameterTable] The CUDA backend is not "
+                     "available and there is no CPU evaluation path."
+                  << std::endl;
+        return false;
+    }
+    DeviceSoA table(m_device, 4, column[0].size());
+    if (!table.valid()) return report(BLF_CCM_ERR_CUDA, "loadParameterTable");
+    for (int k = 0; k < 4; ++k)
+        if (!table.upload(static_cast<std::size_t>(k), column[k].data())) return false;
+    parameters = std::move(table);
+    return true;
 }
 
 bool ContinuousContactModelBatch::evaluate(const DeviceSoA& states, const DeviceSoA* parameters,

@@ -19,12 +19,14 @@
 #include <array>
 #include <cmath>
 #include <random>
+#include <string>
 #include <vector>
 
 #include <iDynTree/Core/SpatialAcc.h>
 
 #include <BipedalLocomotion/ContactModels/ContinuousContactModel.h>
 #include <BipedalLocomotion/ContactModels/ContinuousContactModelBatch.h>
+#include <BipedalLocomotion/ParametersHandler/IniFile.h>
 #include <BipedalLocomotion/ParametersHandler/StdImplementation.h>
 
 using namespace iDynTree;
@@ -257,6 +259,61 @@ TEST_CASE("Batched entry point")
                     const bool structural = (r < 3 && c != r) || (r >= 3 && c < 3);
                     if (structural) REQUIRE((ctrl[i](r, c) == 0.0 && !std::signbit(ctrl[i](r, c))));
                 }
+    }
+
+    SECTION("Per-contact parameter table from the on-disk configuration format")
+    {
+        // four contacts, parameters from a `.ini` group (ParametersHandler/IniFile.h)
+        const std::string ini = "[CONTACT_PARAMETERS]\n"
+                                "length        (0.12, 0.15, 0.30, 0.08)\n"
+                                "width         (0.09, 0.10, 0.15, 0.04)\n"
+                                "spring_coeff  (2000.0, 50000.0, 1e6, 1e3)\n"
+                                "damper_coeff  (100.0, 300.0, 1e4, 10.0)\n";
+        auto file = std::make_shared<StdImplementation>();
+        REQUIRE(loadIniString(ini, *file));
+        DeviceSoA table;
+        REQUIRE(batch.loadParameterTable(file->getGroup("CONTACT_PARAMETERS"), table));
+        REQUIRE(table.planes() == 4);
+        REQUIRE(table.size() == 4);
+        REQUIRE_FALSE(batch.loadParameterTable(file->getGroup("MISSING"), table)); // expired group
+        auto shortTable = std::make_shared<StdImplementation>();
+        REQUIRE(loadIniString("length (0.1, 0.2)\nwidth (0.1)\nspring_coeff (1.0, 2.0)\n"
+                              "damper_coeff (1.0, 2.0)\n", *shortTable));
+        REQUIRE_FALSE(batch.loadParameterTable(shortTable, table));                // ragged columns
+        REQUIRE(table.size() == 4);                                                 // untouched
+
+        const std::size_t m = 4;
+        auto dev = batch.device();
+        DeviceSoA states(dev, ContinuousContactModelBatch::NumberOfPlanes, m), wrenchPlanes(dev, 6, m);
+        REQUIRE(states.uploadRows(ContinuousContactModelBatch::LinearVelocity, 6,
+                                  reinterpret_cast<const double*>(twists.data())));
+        REQUIRE(states.uploadRows(ContinuousContactModelBatch::Position, 12,
+                                  reinterpret_cast<const double*>(poses.data())));
+        REQUIRE(states.uploadRows(ContinuousContactModelBatch::NullForcePosition, 12,
+                                  reinterpret_cast<const double*>(nulls.data())));
+        REQUIRE(batch.evaluate(states, &table, ContinuousContactModelBatch::ContactWrench, &wrenchPlanes,
+                               nullptr, nullptr, nullptr));
+        std::vector<Wrench> got(m);
+        REQUIRE(wrenchPlanes.downloadRows(0, 6, reinterpret_cast<double*>(got.data())));
+        const double L[4] = {0.12, 0.15, 0.30, 0.08}, W[4] = {0.09, 0.10, 0.15, 0.04};
+        const double K[4] = {2000.0, 50000.0, 1e6, 1e3}, B[4] = {100.0, 300.0, 1e4, 10.0};
+        for (std::size_t i = 0; i < m; ++i)
+        {
+            auto h = std::make_shared<StdImplementation>();
+            h->setParameter("length", L[i]);
+            h->setParameter("width", W[i]);
+            h->setParameter("spring_coeff", K[i]);
+            h->setParameter("damper_coeff", B[i]);
+            ContinuousContactModel model;
+            REQUIRE(model.initialize(h));
+            model.setState(twists[i], poses[i]);
+            model.setNullForceTransform(nulls[i]);
+            for (int c = 0; c < 6; ++c)
+            {
+                const double ref = model.getContactWrench()(c);
+                REQUIRE(std::fabs(got[i](c) - ref) <= 1e-12 * std::max(std::fabs(ref), 1e-300));
+            }
+        }
     }
 
     SECTION("Device SoA container and the rollout arg-min")

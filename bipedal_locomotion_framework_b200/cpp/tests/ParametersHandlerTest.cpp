@@ -14,12 +14,15 @@
 #include <iostream>
 #include <unordered_map>
 
+#include <BipedalLocomotion/ParametersHandler/IniFile.h>
 #include <BipedalLocomotion/ParametersHandler/StdImplementation.h>
 
 using namespace BipedalLocomotion::ParametersHandler;
 
 TEST_CASE("Get parameters")
 {
+    const std::vector<int> fibonacciNumbers{1, 1, 2, 3, 5, 8, 13, 21};
+    const std::vector<std::string> donaldsNephews{"Huey", "Dewey", "Louie"};
     std::shared_ptr<StdImplementation> originalHandler = std::make_shared<StdImplementation>();
     IParametersHandler::shared_ptr parameterHandler = originalHandler;
 
@@ -109,5 +112,102 @@ TEST_CASE("Get parameters")
         REQUIRE_FALSE(parameterHandler->isEmpty());
         parameterHandler->clear();
         REQUIRE(parameterHandler->isEmpty());
+    }
+
+    SECTION("Set from ini text")
+    {
+        // What the reference's "Set from RF" section checks
+        // (src/ParametersHandler/tests/ParametersHandlerYarpTest.cpp:133-190) on the content of its
+        // fixture src/ParametersHandler/tests/config.ini, read here without YARP.
+        const std::string ini = "answer_to_the_ultimate_question_of_life 42\n"
+                                "pi                                      3.14\n"
+                                "John                                    Smith\n"
+                                "\"Fibonacci Numbers\"                     (1, 1, 2, 3, 5, 8, 13, 21)\n"
+                                "\n"
+                                "[CARTOONS]\n"
+                                "\"Donald's nephews\"                      (\"Huey\", \"Dewey\", \"Louie\")\n"
+                                "Fibonacci_Numbers                       (1, 1, 2, 3, 5, 8, 13, 21)\n"
+                                "John                                    Doe\n";
+        parameterHandler->clear();
+        REQUIRE(parameterHandler->isEmpty());
+        REQUIRE(loadIniString(ini, *parameterHandler));
+        {
+            int element;
+            REQUIRE(parameterHandler->getParameter("answer_to_the_ultimate_question_of_life", element));
+            REQUIRE(element == 42);
+            double wrongType;
+            REQUIRE_FALSE(parameterHandler->getParameter("answer_to_the_ultimate_question_of_life", wrongType));
+        }
+        {
+            double element;
+            REQUIRE(parameterHandler->getParameter("pi", element));
+            REQUIRE(element == 3.14);
+        }
+        {
+            std::string element;
+            REQUIRE(parameterHandler->getParameter("John", element));
+            REQUIRE(element == "Smith");
+        }
+        {
+            std::vector<int> element;
+            REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", element));
+            REQUIRE(element == fibonacciNumbers);
+        }
+        IParametersHandler::shared_ptr cartoonsGroup = parameterHandler->getGroup("CARTOONS").lock();
+        REQUIRE(cartoonsGroup);
+        {
+            std::vector<std::string> element;
+            REQUIRE(cartoonsGroup->getParameter("Donald's nephews", element));
+            REQUIRE(element == donaldsNephews);
+        }
+        {
+            std::vector<int> element;
+            REQUIRE(cartoonsGroup->getParameter("Fibonacci_Numbers", element));
+            REQUIRE(element == fibonacciNumbers);
+        }
+        {
+            std::string element;
+            REQUIRE(cartoonsGroup->getParameter("John", element));
+            REQUIRE(element == "Doe");
+        }
+    }
+
+    SECTION("Ini grammar: comments, bare lists, booleans, exponents, errors")
+    {
+        StdImplementation h;
+        REQUIRE(loadIniString("# a comment\n// another\n  rho 1e-2   # trailing\n"
+                              "gains 1.5 2 2.5\nflags (true, false)\nuse_cuda true\nempty ()\n"
+                              "name \"two words\"\n[CONTACT_PARAMETERS]\nlength (0.12, 0.15)\n",
+                              h));
+        double rho;
+        REQUIRE(h.getParameter("rho", rho));
+        REQUIRE(rho == 0.01);
+        std::vector<double> gains;
+        REQUIRE(h.getParameter("gains", gains)); // mixed int/double list -> doubles
+        REQUIRE((gains == std::vector<double>{1.5, 2.0, 2.5}));
+        std::vector<bool> flags;
+        REQUIRE(h.getParameter("flags", flags));
+        REQUIRE((flags == std::vector<bool>{true, false}));
+        bool useCuda = false;
+        REQUIRE(h.getParameter("use_cuda", useCuda));
+        REQUIRE(useCuda);
+        std::vector<int> empty{1};
+        REQUIRE(h.getParameter("empty", empty));
+        REQUIRE(empty.empty());
+        std::string name;
+        REQUIRE(h.getParameter("name", name));
+        REQUIRE(name == "two words");
+        auto table = h.getGroup("CONTACT_PARAMETERS").lock();
+        REQUIRE(table);
+        std::vector<double> length;
+        REQUIRE(table->getParameter("length", length));
+        REQUIRE((length == std::vector<double>{0.12, 0.15}));
+
+        StdImplementation bad;
+        REQUIRE_FALSE(loadIniString("key \"unterminated\n", bad));
+        REQUIRE_FALSE(loadIniString("key (1, 2\n", bad));
+        REQUIRE_FALSE(loadIniString("lonely_key\n", bad));
+        REQUIRE_FALSE(loadIniString("[]\n", bad));
+        REQUIRE_FALSE(loadIniFile("/nonexistent/config.ini", bad));
     }
 }

@@ -97,3 +97,57 @@ def test_initialize_rejects_missing_or_mistyped_keys():
     h.setParameter("length", 1)                            # int under a double key
     assert ContinuousContactModel().initialize(h) is False
     assert ContinuousContactModel().initialize(None) is False
+
+
+# --- on-disk configuration format ------------------------------------
+
+REFERENCE_CONFIG_INI = '''answer_to_the_ultimate_question_of_life 42
+pi                                      3.14
+John                                    Smith
+"Fibonacci Numbers"                     (1, 1, 2, 3, 5, 8, 13, 21)
+
+[CARTOONS]
+"Donald's nephews"                      ("Huey", "Dewey", "Louie")
+Fibonacci_Numbers                       (1, 1, 2, 3, 5, 8, 13, 21)
+John                                    Doe
+'''
+
+
+def test_ini_reader_on_the_reference_fixture_content():
+    """What ParametersHandlerYarpTest.cpp:133-190 ("Set from RF") checks on the content of
+    src/ParametersHandler/tests/config.ini, read without YARP."""
+    from bipedal_locomotion_framework_b200.ini import load_ini_string
+    h = load_ini_string(REFERENCE_CONFIG_INI)
+    assert h.getParameter("answer_to_the_ultimate_question_of_life", int) == (True, 42)
+    assert h.getParameter("answer_to_the_ultimate_question_of_life", float)[0] is False   # strict
+    assert h.getParameter("pi", float) == (True, 3.14)
+    assert h.getParameter("John", str) == (True, "Smith")
+    assert h.getParameter("Fibonacci Numbers", list) == (True, [1, 1, 2, 3, 5, 8, 13, 21])
+    g = h.getGroup("CARTOONS")
+    assert g.getParameter("Donald's nephews", list) == (True, ["Huey", "Dewey", "Louie"])
+    assert g.getParameter("Fibonacci_Numbers", list) == (True, [1, 1, 2, 3, 5, 8, 13, 21])
+    assert g.getParameter("John", str) == (True, "Doe")
+
+
+def test_ini_grammar_and_parameter_table():
+    import numpy as np
+    from bipedal_locomotion_framework_b200.ini import load_ini_string, parameter_table
+    h = load_ini_string('# c\n// c\n rho 1e-2 # t\ngains 1.5 2 2.5\nflags (true, false)\nempty ()\n'
+                        'name "two words"\n[CONTACT_PARAMETERS]\nlength (0.12, 0.15)\n'
+                        'width (0.09, 0.1)\nspring_coeff (2000.0, 5e4)\ndamper_coeff (100.0, 300.0)\n')
+    assert h.getParameter("rho", float) == (True, 0.01)
+    assert h.getParameter("gains", list) == (True, [1.5, 2.0, 2.5])
+    assert h.getParameter("flags", list) == (True, [True, False])
+    assert h.getParameter("empty", list) == (True, [])
+    assert h.getParameter("name", str) == (True, "two words")
+    t = parameter_table(h.getGroup("CONTACT_PARAMETERS"))
+    assert np.array_equal(t, [[0.12, 0.15], [0.09, 0.1], [2000.0, 5e4], [100.0, 300.0]])
+    for bad in ('key "unterminated\n', "key (1, 2\n", "lonely\n", "[]\n", "k ((1) 2)\n"):
+        assert load_ini_string(bad) is None
+    ragged = load_ini_string("length (0.1, 0.2)\nwidth (0.1)\nspring_coeff (1.0, 2.0)\n"
+                             "damper_coeff (1.0, 2.0)\n")
+    assert parameter_table(ragged) is None
+    ints = load_ini_string("length (1, 2)\nwidth (1.0, 2.0)\nspring_coeff (1.0, 2.0)\n"
+                           "damper_coeff (1.0, 2.0)\n")
+    assert parameter_table(ints) is None                  # ints are not doubles (strict typing)
+    assert parameter_table(None) is None

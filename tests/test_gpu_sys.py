@@ -335,3 +335,24 @@ def test_generalized_force_argument_errors(torch, batch):
         gf.run(33, 4, z(30, 33), z(33, 6, 4))
     with pytest.raises(_capi.BlfCcmError):
         gf.run(1, 129, z(30, 2), z(2, 6, 129))
+
+
+# --- per-contact parameter table from the on-disk configuration format -----------------------------
+
+def test_parameter_table_from_ini_drives_the_batched_evaluation(torch, batch, oracle):
+    from bipedal_locomotion_framework_b200.ini import load_ini_string
+    n = 257
+    st = syn.make_states(n, seed=66, heterogeneous=True)
+    fmt = lambda col: ", ".join(repr(float(x)) for x in col)
+    text = "[CONTACT_PARAMETERS]\n" + "".join(
+        f"{key} ({fmt(st['params'][:, j])})\n"
+        for j, key in enumerate(("length", "width", "spring_coeff", "damper_coeff")))
+    table = batch.load_parameter_table(load_ini_string(text).getGroup("CONTACT_PARAMETERS"))
+    assert table.shape == (4, n) and np.array_equal(table.cpu().numpy(), st["params"].T)  # repr round-trips
+    planes = _dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+    out = batch.evaluate_soa(planes, table, 7)
+    ref = oracle.eval_batch_states(st, mask=7, nthreads=1)
+    assert_parity(out["wrench"].cpu().numpy().T, ref["wrench"], "wrench")
+    assert_parity(out["autodyn"].cpu().numpy().T, ref["autodyn"], "autodyn")
+    assert_parity(out["ctrl"].cpu().numpy(), ref["ctrl"], "ctrl")
+    assert batch.load_parameter_table(load_ini_string("length (0.1)\n")) is None
