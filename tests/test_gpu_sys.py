@@ -356,3 +356,131 @@ def test_parameter_table_from_ini_drives_the_batched_evaluation(torch, batch, or
     assert_parity(out["autodyn"].cpu().numpy().T, ref["autodyn"], "autodyn")
     assert_parity(out["ctrl"].cpu().numpy(), ref["ctrl"], "ctrl")
     assert batch.load_parameter_table(load_ini_string("length (0.1)\n")) is None
+
+
+# --- memory safety and edge shapes ------------------------------------------------------------------
+
+GUARD, SENTINEL = 64, -7.25
+
+
+def _guarded(torch, rows, cols, fill):
+    buf = torch.full((rows, cols + 2 * GUARD), fill, dtype=torch.float64, device="cuda")
+    return buf, buf[:, GUARD:GUARD + cols]
+
+
+def _check_guards(buf, cols, what):
+    assert bool((buf[:, :GUARD] == SENTINEL).all()) and bool((buf[:, GUARD + cols:] == SENTINEL).all()), \
+        f"{what}: guard band overwritten"
+
+
+@pytest.mark.parametrize("nr,feet,H,het,rho", [(1, 1, 1, False, 0.0), (33, 1, 5, True, 3.0),
+                                               (17, 3, 9, False, 0.5), (300, 2, 12, True, 0.0)])
+def test_rollout_no_out_of_bounds_canaries(torch, batch, nr, feet, H, het, rho):
+    """compute-sanitizer is closed on this pool: inputs are followed by NaN guards (an over-read
+    would poison a result), every output lives between sentinel guard bands."""
+    from bipedal_locomotion_framework_b200 import _capi
+    import ctypes as C
+    chains, n = nr * feet, nr * feet * H
+    st = syn.make_states(chains, seed=5, heterogeneous=True)
+    nan = float("nan")
+    _, tw = _guarded(torch, 6, n, nan)
+    tw.copy_(_dev(torch, syn.make_states(n, seed=6)["twists"].T))
+    _, pos = _guarded(torch, 3, chains, nan)
+    pos.copy_(_dev(torch, st["poses"][:, :3].T))
+    _, rot = _guarded(torch, 9, chains, nan)
+    rot.copy_(_dev(torch, st["poses"][:, 3:].T))
+    _, nul = _guarded(torch, 12, chains, nan)
+    nul.copy_(_dev(torch, st["null_poses"].T))
+    _, prm = _guarded(torch, 4, chains, nan)
+    prm.copy_(_dev(torch, st["params"].T))
+    wb, w = _guarded(torch, 6, n, SENTINEL)
+    ab, a = _guarded(torch, 6, n, SENTINEL)
+    cb, c = _guarded(torch, 1, n * 36, SENTINEL)
+    fpb, fp = _guarded(torch, 3, chains, SENTINEL)
+    frb, fr = _guarded(torch, 9, chains, SENTINEL)
+    costb, cost = _guarded(torch, 1, nr, SENTINEL)
+    best = torch.empty(2, dtype=torch.int64, device="cuda")
+    ref, wts = np.zeros(6), np.ones(2)
+    pp = batch._plane_ptrs
+    for mask in (7, 0):
+        rc = _capi.lib().blf_ccm_rollout_integrate_cost(
+            batch.handle.ptr, nr, feet, H, 0.01, rho, pp(tw, 6), pp(pos, 3), pp(rot, 9), pp(nul, 12),
+            pp(prm, 4) if het else None, mask, pp(w, 6), pp(a, 6), c.data_ptr(), pp(fp, 3), pp(fr, 9),
+            ref.ctypes.data_as(C.c_void_p), wts.ctypes.data_as(C.c_void_p), 0, cost.data_ptr(),
+            best.data_ptr(), None)
+        assert rc == 0, _capi.lib().blf_ccm_last_error()
+        torch.cuda.synchronize()
+        for b_, cols, what in ((wb, n, "wrench"), (ab, n, "autodyn"), (cb, n * 36, "ctrl"),
+                               (fpb, chains, "final pos"), (frb, chains, "final rot"), (costb, nr, "cost")):
+            _check_guards(b_, cols, f"rollout {what} mask={mask}")
+        for t_ in (w, a, c, fp, fr, cost):
+            assert bool(torch.isfinite(t_).all())            # no NaN guard was read
+
+
+@pytest.mark.parametrize("ns,cps,ncols", [(1, 1, 1), (3, 2, 29), (11, 3, 33), (5, 32, 128), (40, 7, 64)])
+def test_generalized_force_no_out_of_bounds_canaries(torch, batch, ns, cps, ncols):
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    gf = GeneralizedForceBatch(batch)
+    n = ns * cps
+    st = syn.make_states(n, seed=8)
+    nan = float("nan")
+    _, planes = _guarded(torch, 30, n, nan)
+    planes.copy_(_dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])))
+    _, J = _guarded(torch, 1, n * 6 * ncols, nan)
+    J.copy_(torch.rand((1, n * 6 * ncols), dtype=torch.float64, device="cuda"))
+    _, base = _guarded(torch, 1, ns * ncols, nan)
+    base.copy_(torch.rand((1, ns * ncols), dtype=torch.float64, device="cuda"))
+    ob, out = _guarded(torch, 1, ns * ncols, SENTINEL)
+    res = gf.run(cps, ncols, planes, J.view(n, 6, ncols), base.view(ns, ncols), out=out.view(ns, ncols))
+    torch.cuda.synchronize()
+    _check_guards(ob, ns * ncols, "generalized force out")
+    assert bool(torch.isfinite(res).all())
+
+
+def test_euler_step_no_out_of_bounds_canaries(torch, batch):
+    from bipedal_locomotion_framework_b200.system import KinematicsBatch
+    kb = KinematicsBatch(0, batch.handle)
+    for n in (1, 31, 129, 1000):
+        st = syn.make_states(n, seed=9)
+        _, tw = _guarded(torch, 6, n, float("nan"))
+        tw.copy_(_dev(torch, st["twists"].T))
+        pb, p = _guarded(torch, 3, n, SENTINEL)
+        p.copy_(_dev(torch, st["poses"][:, :3].T))
+        rb, r = _guarded(torch, 9, n, SENTINEL)
+        r.copy_(_dev(torch, st["poses"][:, 3:].T))
+        kb.euler_step(1.5, 1e-3, tw, p, r)
+        torch.cuda.synchronize()
+        _check_guards(pb, n, "euler pos")
+        _check_guards(rb, n, "euler rot")
+        assert bool(torch.isfinite(p).all()) and bool(torch.isfinite(r).all())
+
+
+def test_rollout_forced_split_variants_agree_with_oracle(torch, so):
+    """Every warps-per-tile variant (1, 2, 4, 8) of the rollout kernel against the oracle, with
+    trajectories (forced through BLF_CCM_TUNE_ROLLOUT_SPLIT, read when a handle is created)."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    nr, feet, H = 45, 2, 23
+    chains = nr * feet
+    st = syn.make_states(chains, seed=12)
+    tw = np.ascontiguousarray(syn.make_states(H * chains, seed=13)["twists"].T)
+    pos0 = np.ascontiguousarray(st["poses"][:, :3].T)
+    rot0 = np.ascontiguousarray(st["poses"][:, 3:].T)
+    null = np.ascontiguousarray(st["null_poses"].T)
+    ref_w, wts = np.array([0.0, 0.0, 30.0, 0.1, -0.1, 0.0]), np.array([1.0, 25.0])
+    ref = so.rollout(nr, feet, H, 0.01, 1.0, tw, pos0, rot0, null, uniform=syn.REFERENCE_TEST_PARAMS,
+                     mask=7, wrench_ref=ref_w, weights=wts)
+    try:
+        for split in (1, 2, 4, 8):
+            os.environ["BLF_CCM_TUNE_ROLLOUT_SPLIT"] = str(split)
+            b = ContinuousContactModelBatch(0)
+            b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+            out = RolloutBatch(b).run(nr, feet, H, 0.01, 1.0, _dev(torch, tw), _dev(torch, pos0),
+                                      _dev(torch, rot0), _dev(torch, null), ref_w, wts, mask=7,
+                                      want_final=True)
+            _check_traj(out, ref, 7, f"split={split}")
+            assert rel(out["final_rot"].cpu().numpy().T, ref["rot"].T).max() <= TOL
+            assert np.all(rel(out["cost"].cpu().numpy()[:, None], ref["cost"][:, None]) <= TOL)
+            assert b.decode_best(out["best"])[1] == int(np.argmin(out["cost"].cpu().numpy()))
+    finally:
+        os.environ.pop("BLF_CCM_TUNE_ROLLOUT_SPLIT", None)
