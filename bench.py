@@ -274,12 +274,32 @@ def run_ours(args):
                                        index_base=first_rollout, out=outs[j], want_cost=False)
                  for j in range(NSETS)]
 
-    def mpc_step(i):
+    # the only exchange of the path: every rank's 16-byte (cost, index) pair.  Default: stores into
+    # the peers' mailboxes over NVLink (one single-warp kernel per rank); NCCL all-gather as the
+    # baseline it replaces (also timed below)
+    peer, peer_note = None, None
+    if world > 1 and not args.nccl_argmin:
+        try:
+            peer = sharding.PeerArgmin(batch, world, rank, dist)
+        except Exception as e:   # e.g. CUDA IPC not permitted in this container
+            peer_note = f"peer-memory mailbox unavailable ({e}); NCCL all-gather used"
+    if world > 1:   # the choice must be the same on every rank
+        flag = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer = None
+
+    def exchange(best, use_peer=True):
+        if world == 1:
+            return best
+        if peer is not None and use_peer:
+            return peer.exchange(best)
+        return batch.argmin_pairs(sharding.all_gather_pairs(best, world, dist))
+
+    def mpc_step(i, use_peer=True):
         call, _, _, best = mpc_calls[i % NSETS]
         call()
-        if world > 1:   # the only collective of the path: 16 bytes per rank
-            return batch.argmin_pairs(sharding.all_gather_pairs(best, world, dist))
-        return best
+        return exchange(best, use_peer)
 
     for i in range(Wm):
         gbest = mpc_step(i)
@@ -297,10 +317,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         mpc_ms = float(t.item())
     best_cost, best_idx = batch.decode_best(gbest)
+    nccl_ms = None
+    if world > 1 and peer is not None:   # the same step with the NCCL all-gather it replaces
+        for i in range(Wm):
+            mpc_step(i, use_peer=False)
+        barrier()
+        m0.record()
+        for i in range(Km):
+            mpc_step(i, use_peer=False)
+        m1.record()
+        barrier()
+        t = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nccl_ms = float(t.item()) / Km
+    collective = "none (1 GPU)"
+    if world > 1:
+        collective = ("peer-memory mailbox over NVLink (blf_ccm_argmin_exchange_p2p, one single-warp "
+                      "kernel per rank)" if peer is not None else "nccl all_gather 16 B/rank + device arg-min")
     mpc = {"value": world * n * Km / (mpc_ms * 1e-3), "unit": UNIT, "ms_per_step": mpc_ms / Km,
            "steps": Km, "rollouts": world * n_roll, "rollout_len": ROLLOUT_LEN,
            "argmin": {"cost": best_cost, "rollout": best_idx},
-           "collective": "nccl all_gather 16 B/rank + device arg-min" if world > 1 else "none (1 GPU)",
+           "collective": collective, "ms_per_step_with_nccl_all_gather": nccl_ms, "note": peer_note,
            "hbm_frac_of_measured": None}
 
     # ---- fused rollout: integrate -> contact model -> cost, pose in ---------
@@ -317,9 +354,7 @@ def run_ours(args):
     def fused_step(i):
         call, o = fused_calls[i % NSETS]
         call()
-        if world > 1:
-            return batch.argmin_pairs(sharding.all_gather_pairs(o["best"], world, dist))
-        return o["best"]
+        return exchange(o["best"])
 
     for i in range(Wm):
         fbest = fused_step(i)
@@ -596,6 +631,9 @@ def main():
                     help="config3 (default, the headline): MPC batch, weak scaling; config4: 64M "
                          "heterogeneous states + NCCL arg-min, strong; config5: 256M states, strong")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-argmin", action="store_true",
+                    help="N > 1: use the NCCL all-gather for the arg-min pair instead of the "
+                         "peer-memory mailbox")
     ap.add_argument("--only-main", action="store_true",
                     help="profiling aid: run only the main timed loop (no mpc/e2e/cpu legs)")
     args = ap.parse_args()

@@ -17,6 +17,7 @@
 #include "ccm_kernels.cuh"
 #include "rls_kernels.cuh"
 #include "sys_kernels.cuh"
+#include "p2p_kernels.cuh"
 
 using namespace blfccm;
 
@@ -80,6 +81,12 @@ struct blf_ccm_handle {
     int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM>0: persistent grid with that many CTAs/SM
                                  // (looping kernels only); default = one tile per warp
     int tune_rollout_split = 0;  // BLF_CCM_TUNE_ROLLOUT_SPLIT>0: warps per tile of the fused rollout
+    // peer-memory arg-min exchange
+    int p2p_nranks = 0, p2p_rank = -1;
+    bool p2p_connected = false;
+    P2pSlot* p2p_local = nullptr;             // this rank's mailbox [2][nranks]
+    P2pSlot* p2p_peer[kP2pMaxRanks] = {};     // every rank's mailbox as mapped here
+    unsigned long long p2p_epoch = 0;
 };
 
 static int env_int(const char* name)
@@ -131,6 +138,19 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     return BLF_CCM_OK;
 }
 
+static void p2p_release(blf_ccm_handle* h)
+{
+    for (int r = 0; r < h->p2p_nranks; ++r)
+        if (h->p2p_peer[r] && r != h->p2p_rank) cudaIpcCloseMemHandle(h->p2p_peer[r]);
+    if (h->p2p_local) cudaFree(h->p2p_local);
+    h->p2p_local = nullptr;
+    for (auto& p : h->p2p_peer) p = nullptr;
+    h->p2p_nranks = 0;
+    h->p2p_rank = -1;
+    h->p2p_connected = false;
+    h->p2p_epoch = 0;
+}
+
 extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
 {
     if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
@@ -139,6 +159,7 @@ extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
         if (h->hstream[s]) cudaStreamDestroy(h->hstream[s]);
         if (h->hbuf[s]) cudaFree(h->hbuf[s]);
     }
+    p2p_release(h);
     cudaFree(h->block_best);
     cudaFree(h->counter);
     if (h->partials) cudaFree(h->partials);
@@ -923,6 +944,83 @@ extern "C" int blf_ccm_argmin_allgather_nccl(blf_ccm_handle* h, void* comm, int 
     const int rc = allgather(best, gathered, 16, /*ncclInt8*/ 0, comm, st);
     if (rc != 0) return fail(BLF_CCM_ERR_NCCL, "ncclAllGather: %s", errstr ? errstr(rc) : "error");
     return blf_ccm_argmin_pairs(h, nranks, gathered, global_best, stream);
+}
+
+// ---- peer-memory arg-min exchange (NVLink / NVSwitch P2P through CUDA IPC) ------------------------
+
+extern "C" int blf_ccm_p2p_mailbox_create(blf_ccm_handle* h, int nranks, int rank, void* ipc_handle_out)
+{
+    CHECK_HANDLE(h);
+    if (nranks < 1 || nranks > kP2pMaxRanks || rank < 0 || rank >= nranks || !ipc_handle_out)
+        return fail(BLF_CCM_ERR_INVALID_ARG, "nranks 1..%d, 0 <= rank < nranks, ipc_handle_out non-NULL",
+                    kP2pMaxRanks);
+    static_assert(sizeof(cudaIpcMemHandle_t) == BLF_CCM_IPC_HANDLE_BYTES, "IPC handle size");
+    p2p_release(h);
+    const size_t bytes = sizeof(P2pSlot) * 2 * nranks;
+    CUDA_TRY(cudaMalloc(&h->p2p_local, bytes));
+    CUDA_TRY(cudaMemset(h->p2p_local, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());   // zeroed before any peer can write
+    cudaIpcMemHandle_t ipc;
+    CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->p2p_local));
+    memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+    h->p2p_nranks = nranks;
+    h->p2p_rank = rank;
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_p2p_mailbox_connect(blf_ccm_handle* h, const void* all_ipc_handles)
+{
+    CHECK_HANDLE(h);
+    if (!h->p2p_local) return fail(BLF_CCM_ERR_NOT_INITIALIZED, "call blf_ccm_p2p_mailbox_create first");
+    if (!all_ipc_handles) return fail(BLF_CCM_ERR_INVALID_ARG, "all_ipc_handles is NULL");
+    if (h->p2p_connected) return fail(BLF_CCM_ERR_INVALID_ARG, "mailbox already connected");
+    const char* src = static_cast<const char*>(all_ipc_handles);
+    for (int r = 0; r < h->p2p_nranks; ++r) {
+        if (r == h->p2p_rank) {
+            h->p2p_peer[r] = h->p2p_local;
+            continue;
+        }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, src + size_t(r) * sizeof(ipc), sizeof(ipc));
+        void* mapped = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&mapped, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(BLF_CCM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (peer access over NVLink/PCIe "
+                        "between the two devices is required)", r, cudaGetErrorString(e));
+        }
+        h->p2p_peer[r] = static_cast<P2pSlot*>(mapped);
+    }
+    h->p2p_connected = true;
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_argmin_exchange_p2p(blf_ccm_handle* h, const void* best, void* global_best,
+                                           void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!h->p2p_connected) return fail(BLF_CCM_ERR_NOT_INITIALIZED, "mailbox not connected");
+    if (!best || !global_best) return fail(BLF_CCM_ERR_INVALID_ARG, "NULL best / global_best");
+    P2pArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < h->p2p_nranks; ++r) a.peer[r] = h->p2p_peer[r];
+    a.mine = static_cast<const CostIdx*>(best);
+    a.out = static_cast<CostIdx*>(global_best);
+    a.epoch = ++h->p2p_epoch;
+    a.nranks = h->p2p_nranks;
+    a.rank = h->p2p_rank;
+    ccm_p2p_exchange_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_p2p_mailbox_destroy(blf_ccm_handle* h)
+{
+    CHECK_HANDLE(h);
+    CUDA_TRY(cudaDeviceSynchronize());
+    p2p_release(h);
+    return BLF_CCM_OK;
 }
 
 // ---- System component (rows 2 and 3 of SURVEY.md section 8(f)) -----------------------------------

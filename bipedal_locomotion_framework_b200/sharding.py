@@ -39,3 +39,47 @@ def all_gather_pairs(best, world: int, dist=None):
     gathered = torch.empty((world, 2), dtype=torch.int64, device=best.device)
     dist.all_gather_into_tensor(gathered.view(-1), best)
     return gathered
+
+
+class PeerArgmin:
+    """Arg-min exchange over NVLink peer memory (blf_ccm_p2p_mailbox_* / blf_ccm_argmin_exchange_p2p):
+    one single-warp kernel per rank instead of an NCCL all-gather.  `dist` (torch.distributed, any
+    backend) is used ONCE, to exchange the 64-byte CUDA IPC handles."""
+
+    def __init__(self, batch, world: int, rank: int, dist=None):
+        import ctypes as C
+
+        import torch
+
+        from . import _capi
+        self._capi, self._C, self._torch = _capi, C, torch
+        self._batch = batch
+        self.world = world
+        handle = (C.c_ubyte * 64)()
+        _capi.check(_capi.lib().blf_ccm_p2p_mailbox_create(batch.handle.ptr, world, rank, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8)
+        dist = dist or torch.distributed
+        if dist.get_backend() == "nccl":
+            gathered = torch.empty((world, 64), dtype=torch.uint8, device=batch.device)
+            dist.all_gather_into_tensor(gathered.view(-1), mine.to(batch.device))
+            gathered = gathered.cpu()
+        else:
+            gathered = torch.empty((world, 64), dtype=torch.uint8)
+            dist.all_gather_into_tensor(gathered.view(-1), mine)
+        blob = (C.c_ubyte * (64 * world))(*gathered.view(-1).tolist())
+        _capi.check(_capi.lib().blf_ccm_p2p_mailbox_connect(batch.handle.ptr, blob))
+        dist.barrier()   # every mailbox is mapped everywhere before the first exchange
+        self._out = torch.empty(2, dtype=torch.int64, device=batch.device)
+
+    def exchange(self, best, out=None):
+        """best: this rank's (2,) int64 pair tensor -> (2,) global best (same on every rank)."""
+        out = self._out if out is None else out
+        st = self._torch.cuda.current_stream(self._batch.device).cuda_stream
+        rc = self._capi.lib().blf_ccm_argmin_exchange_p2p(self._batch.handle.ptr, best.data_ptr(),
+                                                          out.data_ptr(), st)
+        if rc:
+            self._capi.check(rc)
+        return out
+
+    def close(self):
+        self._capi.check(self._capi.lib().blf_ccm_p2p_mailbox_destroy(self._batch.handle.ptr))

@@ -182,6 +182,25 @@ BLF_CCM_API int blf_ccm_argmin_allgather_nccl(blf_ccm_handle* h, void* comm, int
                                               void* stream);
 
 /*
+ * Peer-memory arg-min exchange (NVLink / NVSwitch P2P, one process per GPU on one node): replaces
+ * the NCCL all-gather of the 16-byte pair.  Every rank creates a mailbox in its own device memory
+ * and gets a CUDA IPC handle for it (BLF_CCM_IPC_HANDLE_BYTES bytes); the ranks exchange the
+ * handles by any means (e.g. torch.distributed.all_gather) and connect.  After that ONE single-warp
+ * kernel per rank and per exchange stores the rank's pair into every peer's mailbox over NVLink,
+ * waits for the peers' pairs in its own mailbox and reduces them with the lowest-index tie-break
+ * -- no host round trip, no collective library.  Every rank must call the exchange the same number
+ * of times (it is a collective); a peer that never arrives makes the kernel give up after ~2 s and
+ * report index -2.  best / global_best: device, 16 bytes {double cost, int64 index}.
+ */
+enum { BLF_CCM_IPC_HANDLE_BYTES = 64 };
+BLF_CCM_API int blf_ccm_p2p_mailbox_create(blf_ccm_handle* h, int nranks, int rank,
+                                           void* ipc_handle_out);
+BLF_CCM_API int blf_ccm_p2p_mailbox_connect(blf_ccm_handle* h, const void* all_ipc_handles);
+BLF_CCM_API int blf_ccm_argmin_exchange_p2p(blf_ccm_handle* h, const void* best,
+                                            void* global_best, void* stream);
+BLF_CCM_API int blf_ccm_p2p_mailbox_destroy(blf_ccm_handle* h);
+
+/*
  * Batched Estimators::RecursiveLeastSquare::advance (reference:
  * src/Estimators/src/RecursiveLeastSquare.cpp:96-133), n independent estimators, one step each:
  *   K = P Y^T (lambda R + Y P Y^T)^-1 ; theta += K (z - Y theta) ; P = (P - K Y P) / lambda
