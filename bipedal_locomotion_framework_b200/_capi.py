@@ -29,7 +29,7 @@ SYMBOLS = [
     "blf_sys_kinematics_integrate_host", "blf_ccm_rollout_integrate_cost",
     "blf_ccm_generalized_force_soa",
     "blf_ccm_p2p_mailbox_create", "blf_ccm_p2p_mailbox_connect", "blf_ccm_argmin_exchange_p2p",
-    "blf_ccm_p2p_mailbox_destroy",
+    "blf_ccm_p2p_mailbox_destroy", "blf_ccm_rollout_set_exchange",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
     L.blf_ccm_p2p_mailbox_connect.argtypes = [vp, vp]
     L.blf_ccm_argmin_exchange_p2p.argtypes = [vp, vp, vp, vp]
     L.blf_ccm_p2p_mailbox_destroy.argtypes = [vp]
+    L.blf_ccm_rollout_set_exchange.argtypes = [vp, vp]
     L.blf_ccm_last_path.argtypes = [vp]
     L.blf_ccm_launch_count.argtypes = [vp]
     L.blf_ccm_launch_count.restype = i64

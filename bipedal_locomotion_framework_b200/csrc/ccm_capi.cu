@@ -17,7 +17,6 @@
 #include "ccm_kernels.cuh"
 #include "rls_kernels.cuh"
 #include "sys_kernels.cuh"
-#include "p2p_kernels.cuh"
 
 using namespace blfccm;
 
@@ -87,6 +86,7 @@ struct blf_ccm_handle {
     P2pSlot* p2p_local = nullptr;             // this rank's mailbox [2][nranks]
     P2pSlot* p2p_peer[kP2pMaxRanks] = {};     // every rank's mailbox as mapped here
     unsigned long long p2p_epoch = 0;
+    CostIdx* p2p_fused_out = nullptr;         // non-NULL: rollout reductions also run the exchange
 };
 
 static int env_int(const char* name)
@@ -149,6 +149,7 @@ static void p2p_release(blf_ccm_handle* h)
     h->p2p_rank = -1;
     h->p2p_connected = false;
     h->p2p_epoch = 0;
+    h->p2p_fused_out = nullptr;
 }
 
 extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
@@ -546,6 +547,29 @@ extern "C" int blf_ccm_eval_surface_points(blf_ccm_handle* h, const double* host
 
 // ---- rollout cost + arg-min ----------------------------------------------------------------------
 
+extern "C" int blf_ccm_argmin_exchange_p2p(blf_ccm_handle* h, const void* best, void* global_best,
+                                           void* stream);
+
+// an empty shard has no reduction launch to carry the fused exchange: run it on its own
+static int exchange_if_fused(blf_ccm_handle* h, const void* best, void* stream)
+{
+    if (!h->p2p_connected || !h->p2p_fused_out) return BLF_CCM_OK;
+    return blf_ccm_argmin_exchange_p2p(h, best, h->p2p_fused_out, stream);
+}
+
+// nranks = 0 unless the fused exchange is enabled (blf_ccm_rollout_set_exchange)
+static void fill_reduce_p2p(blf_ccm_handle* h, const CostIdx* mine, P2pArgs& p)
+{
+    memset(&p, 0, sizeof(p));
+    if (!h->p2p_connected || !h->p2p_fused_out) return;
+    for (int r = 0; r < h->p2p_nranks; ++r) p.peer[r] = h->p2p_peer[r];
+    p.mine = mine;
+    p.out = h->p2p_fused_out;
+    p.epoch = ++h->p2p_epoch;
+    p.nranks = h->p2p_nranks;
+    p.rank = h->p2p_rank;
+}
+
 template <unsigned OUT, bool HET>
 struct CostLaunch {
     static int run(blf_ccm_handle* h, const SoaArgs& a, cudaStream_t st)
@@ -595,8 +619,10 @@ extern "C" int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_roll
     if (!host_wrench_ref || !host_weights || !best)
         return fail(BLF_CCM_ERR_INVALID_ARG, "wrench_ref, weights and best are required");
     if (!aligned16(best)) return fail(BLF_CCM_ERR_INVALID_ARG, "best must be 16-byte aligned");
-    if (n_rollouts == 0)  // nothing to compare: best = (+inf, -1)
-        return blf_ccm_argmin_pairs(h, 0, best, best, stream);
+    if (n_rollouts == 0) {  // nothing to compare: best = (+inf, -1); still take part in the exchange
+        if (int rc = blf_ccm_argmin_pairs(h, 0, best, best, stream)) return rc;
+        return exchange_if_fused(h, best, stream);
+    }
     SoaArgs a;
     bool vec = false;
     if (int rc = fill_soa_args(h, n_rollouts * rollout_len, in_planes, param_planes, out_mask,
@@ -638,6 +664,7 @@ extern "C" int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_roll
     ra.block_best = h->block_best;
     ra.counter = h->counter;
     ra.best = static_cast<CostIdx*>(best);
+    fill_reduce_p2p(h, ra.best, ra.p2p);
     const int threads = 128;
     const int grid = static_cast<int>(std::min<long long>((n_rollouts + threads - 1) / threads, kMaxPartials));
     ccm_cost_reduce_kernel<<<grid, threads, 0, st>>>(ra);
@@ -1012,6 +1039,17 @@ extern "C" int blf_ccm_argmin_exchange_p2p(blf_ccm_handle* h, const void* best, 
     ccm_p2p_exchange_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    return BLF_CCM_OK;
+}
+
+extern "C" int blf_ccm_rollout_set_exchange(blf_ccm_handle* h, void* global_best)
+{
+    CHECK_HANDLE(h);
+    if (global_best && !h->p2p_connected)
+        return fail(BLF_CCM_ERR_NOT_INITIALIZED, "mailbox not connected");
+    if (global_best && !aligned16(global_best))
+        return fail(BLF_CCM_ERR_INVALID_ARG, "global_best must be 16-byte aligned");
+    h->p2p_fused_out = static_cast<CostIdx*>(global_best);
     return BLF_CCM_OK;
 }
 

@@ -670,6 +670,10 @@ __device__ __forceinline__ CostIdx warp_best(CostIdx b)
     return b;
 }
 
+}  // namespace blfccm
+#include "p2p_kernels.cuh"
+namespace blfccm {
+
 struct ReduceArgs {
     const double* partials;    // [n_rollouts][slots]
     int slots;
@@ -681,6 +685,7 @@ struct ReduceArgs {
     CostIdx* block_best;       // gridDim.x entries (handle scratch)
     unsigned int* counter;     // zero before launch; reset by the last CTA
     CostIdx* best;             // result
+    P2pArgs p2p;               // nranks > 0: the last block also runs the peer exchange -> p2p.out
 };
 
 __global__ void __launch_bounds__(128)
@@ -735,10 +740,15 @@ ccm_cost_reduce_kernel(const __grid_constant__ ReduceArgs ra)
             if (better(c.cost, c.idx, b.cost, b.idx)) b = c;
         }
         b = warp_best(b);
+        if (b.idx == 0x7fffffffffffffffLL) b.idx = -1;  // nothing comparable (empty / all NaN)
         if (lane == 0) {
-            if (b.idx == 0x7fffffffffffffffLL) b.idx = -1;  // nothing comparable (empty / all NaN)
             *ra.best = b;
             *ra.counter = 0u;
+        }
+        // fused collective: this rank's pair goes straight to the peers' mailboxes over NVLink
+        if (ra.p2p.nranks > 0) {
+            const CostIdx g = p2p_exchange_warp(ra.p2p, b, lane);
+            if (lane == 0) *ra.p2p.out = g;
         }
     }
 }

@@ -12,9 +12,9 @@
 // can be at most one exchange ahead of a peer (it needs the peer's flag of exchange e to finish e),
 // so the pair of exchange e is never overwritten before every peer has read it.
 // A peer that never shows up would hang the spin: it is bounded (~2 s) and then reports index -2.
+// Included by ccm_kernels.cuh right after CostIdx / better() / warp_best() (it needs them), so that
+// the cost-reduction kernel can run the exchange in its last block: reduce + exchange in ONE launch.
 #pragma once
-
-#include "ccm_kernels.cuh"
 
 namespace blfccm {
 
@@ -47,12 +47,11 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
     return v;
 }
 
-__global__ void __launch_bounds__(32)
-ccm_p2p_exchange_kernel(const __grid_constant__ P2pArgs a)
+// One warp: publish `me`, wait for every rank's pair of this epoch, return the global best
+// (index -1: nothing to compare anywhere; -2: a peer did not arrive in time).
+__device__ __forceinline__ CostIdx p2p_exchange_warp(const P2pArgs& a, const CostIdx me, int lane)
 {
-    const int lane = threadIdx.x;
     const int parity = static_cast<int>(a.epoch & 1ull);
-    const CostIdx me = *a.mine;
     // 1. publish to every peer (lane r -> rank r's mailbox)
     if (lane < a.nranks) {
         P2pSlot* s = a.peer[lane] + parity * a.nranks + a.rank;
@@ -89,15 +88,21 @@ ccm_p2p_exchange_kernel(const __grid_constant__ P2pArgs a)
     const bool any_timeout = __any_sync(0xffffffffu, timeout);
     // 3. combine
     b = warp_best(b);
-    if (lane == 0) {
-        if (any_timeout) {
-            b.cost = __longlong_as_double(0x7ff8000000000000LL);
-            b.idx = -2;
-        } else if (b.idx == 0x7fffffffffffffffLL) {
-            b.idx = -1;
-        }
-        *a.out = b;
+    if (any_timeout) {
+        b.cost = __longlong_as_double(0x7ff8000000000000LL);
+        b.idx = -2;
+    } else if (b.idx == 0x7fffffffffffffffLL) {
+        b.idx = -1;
     }
+    return b;
+}
+
+__global__ void __launch_bounds__(32)
+ccm_p2p_exchange_kernel(const __grid_constant__ P2pArgs a)
+{
+    const int lane = threadIdx.x;
+    const CostIdx b = p2p_exchange_warp(a, *a.mine, lane);
+    if (lane == 0) *a.out = b;
 }
 
 }  // namespace blfccm

@@ -81,5 +81,16 @@ class PeerArgmin:
             self._capi.check(rc)
         return out
 
+    def fuse_into_rollouts(self, on: bool = True):
+        """Every later rollout call of the batch also runs the exchange inside its own reduction
+        kernel (blf_ccm_rollout_set_exchange); the global best lands in `self.global_best`."""
+        self._capi.check(self._capi.lib().blf_ccm_rollout_set_exchange(
+            self._batch.handle.ptr, self._out.data_ptr() if on else None))
+        return self._out
+
+    @property
+    def global_best(self):
+        return self._out
+
     def close(self):
         self._capi.check(self._capi.lib().blf_ccm_p2p_mailbox_destroy(self._batch.handle.ptr))

@@ -198,6 +198,12 @@ BLF_CCM_API int blf_ccm_p2p_mailbox_create(blf_ccm_handle* h, int nranks, int ra
 BLF_CCM_API int blf_ccm_p2p_mailbox_connect(blf_ccm_handle* h, const void* all_ipc_handles);
 BLF_CCM_API int blf_ccm_argmin_exchange_p2p(blf_ccm_handle* h, const void* best,
                                             void* global_best, void* stream);
+/* Fuse the exchange into the rollout entry points: with global_best != NULL (device, 16 bytes,
+ * 16-byte aligned) every later blf_ccm_rollout_cost_argmin_soa / blf_ccm_rollout_integrate_cost call
+ * ALSO runs the peer exchange -- inside the last block of its own cost-reduction kernel, i.e.
+ * reduction + collective in one launch -- and writes the global arg-min to global_best (`best`
+ * still receives the local one).  NULL switches it off.  Collective semantics as above. */
+BLF_CCM_API int blf_ccm_rollout_set_exchange(blf_ccm_handle* h, void* global_best);
 BLF_CCM_API int blf_ccm_p2p_mailbox_destroy(blf_ccm_handle* h);
 
 /*

@@ -56,6 +56,40 @@ def _worker(rank, world, port, rounds, q):
         b.record()
         torch.cuda.synchronize()
         us = a.elapsed_time(b) / 500 * 1e3
+
+        # fused into the rollout reduction: every rank evaluates its own rollouts, the global
+        # arg-min appears on every rank without any further call
+        from bipedal_locomotion_framework_b200 import synthetic as syn
+        from bipedal_locomotion_framework_b200.system import RolloutBatch
+        batch.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+        nr, rl = 64, 50
+        first = rank * nr
+        st = syn.make_states(nr * rl, seed=77, start=first * rl)
+        planes = torch.from_numpy(syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])).to(batch.device)
+        gbest = peer.fuse_into_rollouts(True)
+        _, cost, best = batch.rollout_cost_argmin(planes, rl, [0, 0, 30.0, 0, 0, 0], [1.0, 10.0],
+                                                  index_base=first)
+        torch.cuda.synchronize()
+        local = batch.decode_best(best)
+        g = batch.decode_best(gbest)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        ok = ok and g == min(gathered) and local[1] == first + int(cost.argmin().item())
+        # ... and by the fused integrate -> contact -> cost rollout; an empty shard takes part too
+        chains = nr * 2
+        ro = RolloutBatch(batch).run(nr if rank == 0 else 0, 2, 10, 0.01, 0.5,
+                                     planes[0:6, :10 * chains] if rank == 0 else planes[0:6, :0],
+                                     planes[6:9, :chains] if rank == 0 else planes[6:9, :0],
+                                     planes[9:18, :chains] if rank == 0 else planes[9:18, :0],
+                                     planes[18:30, :chains] if rank == 0 else planes[18:30, :0],
+                                     [0, 0, 30.0, 0, 0, 0], [1.0, 10.0], index_base=first)
+        torch.cuda.synchronize()
+        g2 = batch.decode_best(gbest)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, batch.decode_best(ro["best"]))
+        valid = [x for x in gathered if x[1] >= 0]
+        ok = ok and g2 == min(valid)
+        peer.fuse_into_rollouts(False)
         peer.close()
         q.put((rank, ok, us))
     finally:
