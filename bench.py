@@ -40,6 +40,16 @@ WORKLOAD = ("configs[2]: sampling-MPC rollout batch 2 feet x 4096 samples x 100 
             "wrench+autodyn+ctrl, uniform params, SoA")
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -169,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference cannot be compiled here (Eigen/iDynTree absent): oracle port timed",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -262,8 +272,8 @@ def run_ours(args):
     if args.only_main:
         sampler.stop_flag = True
         if rank == 0:
-            print(json.dumps({"only_main": True, "value": value, "ms_per_step": total_ms / K,
-                              "avg_launch_ms": avg_kernel_ms, "gpu_launches": int(launches)}))
+            emit({"only_main": True, "value": value, "ms_per_step": total_ms / K,
+                  "avg_launch_ms": avg_kernel_ms, "gpu_launches": int(launches)})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -488,7 +498,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "mpc": mpc, "mpc_fused": mpc_fused, "next_rows": next_rows,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -620,7 +630,7 @@ def run_large(args):
         if res is not None:
             c, i = batch.decode_best(res)
             line["argmin"] = {"cost": c, "rollout": i}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -642,9 +652,12 @@ def main():
     ap.add_argument("--only-main", action="store_true",
                     help="profiling aid: run only the main timed loop (no mpc/e2e/cpu legs)")
     args = ap.parse_args()
-    # stdout carries exactly ONE JSON line: NCCL's banner / debug lines (NCCL_DEBUG set on the box)
-    # go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner
+    # when NCCL_DEBUG is set on the box) is sent to stderr at the file-descriptor level
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     if args.workload != "config3":

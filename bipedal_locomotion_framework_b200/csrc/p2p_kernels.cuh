@@ -5,8 +5,10 @@
 // step measured on 2 B200s, +22 us on 8).  Here every rank owns a small MAILBOX in its own HBM,
 // mapped into every peer through CUDA IPC; ONE single-warp kernel per rank
 //   1. stores its pair into slot [parity][rank] of every peer's mailbox (remote stores over
-//      NVLink), fences system-wide, then stores the epoch flag of that slot,
-//   2. spins on the nranks flags of its OWN mailbox until they carry this epoch,
+//      NVLink) as four 8-byte words, each = 4 data bytes + the 32-bit epoch ("LL" framing: an
+//      8-byte store is atomic, so data and flag arrive together and no system-wide fence -- a
+//      full NVLink round trip -- is needed between them),
+//   2. spins on the 4 x nranks words of its OWN mailbox until they all carry this epoch,
 //   3. reduces the nranks pairs with the lowest-index tie-break and writes the global best.
 // No host round trip, no collective library.  Slots are double-buffered on the epoch parity: a rank
 // can be at most one exchange ahead of a peer (it needs the peer's flag of exchange e to finish e),
@@ -21,10 +23,7 @@ namespace blfccm {
 constexpr int kP2pMaxRanks = 32;
 
 struct alignas(32) P2pSlot {
-    double cost;
-    long long idx;
-    unsigned long long epoch;
-    unsigned long long pad;
+    unsigned long long w[4];   // w[k] = (epoch32 << 32) | k-th 32-bit quarter of {cost, idx}
 };
 
 struct P2pArgs {
@@ -52,14 +51,16 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
 __device__ __forceinline__ CostIdx p2p_exchange_warp(const P2pArgs& a, const CostIdx me, int lane)
 {
     const int parity = static_cast<int>(a.epoch & 1ull);
+    const unsigned long long tag = (a.epoch & 0xffffffffull) << 32;
     // 1. publish to every peer (lane r -> rank r's mailbox)
     if (lane < a.nranks) {
         P2pSlot* s = a.peer[lane] + parity * a.nranks + a.rank;
-        st_sys_u64(reinterpret_cast<unsigned long long*>(&s->cost),
-                   static_cast<unsigned long long>(__double_as_longlong(me.cost)));
-        st_sys_u64(reinterpret_cast<unsigned long long*>(&s->idx), static_cast<unsigned long long>(me.idx));
-        __threadfence_system();
-        st_sys_u64(&s->epoch, a.epoch);
+        const unsigned long long c = static_cast<unsigned long long>(__double_as_longlong(me.cost));
+        const unsigned long long i = static_cast<unsigned long long>(me.idx);
+        st_sys_u64(&s->w[0], tag | (c & 0xffffffffull));
+        st_sys_u64(&s->w[1], tag | (c >> 32));
+        st_sys_u64(&s->w[2], tag | (i & 0xffffffffull));
+        st_sys_u64(&s->w[3], tag | (i >> 32));
     }
     // 2. wait for every rank's pair of this epoch in the local mailbox
     CostIdx b{__longlong_as_double(0x7ff0000000000000LL), 0x7fffffffffffffffLL};
@@ -67,18 +68,22 @@ __device__ __forceinline__ CostIdx p2p_exchange_warp(const P2pArgs& a, const Cos
     if (lane < a.nranks) {
         const P2pSlot* s = a.peer[a.rank] + parity * a.nranks + lane;
         const long long t0 = clock64();
-        while (ld_sys_u64(&s->epoch) != a.epoch) {
+        unsigned long long w0, w1, w2, w3;
+        for (;;) {
+            w0 = ld_sys_u64(&s->w[0]);
+            w1 = ld_sys_u64(&s->w[1]);
+            w2 = ld_sys_u64(&s->w[2]);
+            w3 = ld_sys_u64(&s->w[3]);
+            const unsigned long long hi = 0xffffffff00000000ull;
+            if ((w0 & hi) == tag && (w1 & hi) == tag && (w2 & hi) == tag && (w3 & hi) == tag) break;
             if (clock64() - t0 > 4000000000LL) {
                 timeout = true;
                 break;
             }
-            __nanosleep(20);
         }
-        __threadfence_system();
         if (!timeout) {
-            b.cost = __longlong_as_double(static_cast<long long>(
-                ld_sys_u64(reinterpret_cast<const unsigned long long*>(&s->cost))));
-            b.idx = static_cast<long long>(ld_sys_u64(reinterpret_cast<const unsigned long long*>(&s->idx)));
+            b.cost = __longlong_as_double(static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32)));
+            b.idx = static_cast<long long>((w2 & 0xffffffffull) | (w3 << 32));
             if (b.idx < 0) {   // a rank with nothing to compare
                 b.cost = __longlong_as_double(0x7ff0000000000000LL);
                 b.idx = 0x7fffffffffffffffLL;
