@@ -70,6 +70,11 @@ class PeerArgmin:
         _capi.check(_capi.lib().blf_ccm_p2p_mailbox_connect(batch.handle.ptr, blob))
         dist.barrier()   # every mailbox is mapped everywhere before the first exchange
         self._out = torch.empty(2, dtype=torch.int64, device=batch.device)
+        # self-check: one exchange of (cost = rank, index = rank) must yield (0.0, 0) everywhere
+        probe = torch.tensor(list(pack_pair(float(rank), rank)), dtype=torch.int64, device=batch.device)
+        got = unpack_pair(*self.exchange(probe).cpu().tolist())
+        if got != (0.0, 0):
+            raise RuntimeError(f"peer-memory exchange self-check failed on rank {rank}: {got}")
 
     def exchange(self, best, out=None):
         """best: this rank's (2,) int64 pair tensor -> (2,) global best (same on every rank)."""
