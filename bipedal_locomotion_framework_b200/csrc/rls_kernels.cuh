@@ -45,6 +45,16 @@ __device__ __forceinline__ void rls_advance(const double (&Y)[M][P], const doubl
             A[i][c] = a;
             B[i][c] = b;
         }
+    // innovation z - Y theta: formed here so that Y and z are dead during the factorisation
+    // (register pressure: 172 -> see DESIGN.md section 10)
+    double innov[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc += Y[i][k] * th[k];
+        innov[i] = z[i] - acc;
+    }
     // lower triangle of S = lambda R + A Y^T
     double S[M][M];
 #pragma unroll
@@ -85,15 +95,7 @@ __device__ __forceinline__ void rls_advance(const double (&Y)[M][P], const doubl
             B[k][c] = acc;                  // B now holds K^T
         }
     }
-    // theta += K (z - Y theta)
-    double innov[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < P; ++k) acc += Y[i][k] * th[k];
-        innov[i] = z[i] - acc;
-    }
+    // theta += K (z - Y theta)   (innovation formed before the factorisation, see above)
 #pragma unroll
     for (int c = 0; c < P; ++c) {
         double acc = 0.0;
@@ -132,7 +134,7 @@ struct RlsArgs {
 };
 
 template <int P, int M, bool AOS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (P <= 2 ? 3 : 2))
 rls_advance_kernel(const __grid_constant__ RlsArgs a)
 {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -180,7 +182,7 @@ struct CcmRlsArgs {
 };
 
 template <bool HETG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 ccm_rls_kernel(const __grid_constant__ CcmRlsArgs a)
 {
     constexpr unsigned LIVE = live_planes(M_REGRESSOR);
