@@ -80,6 +80,7 @@ struct Result {
     double gd;
     double gs[6];
     V3 y_fk, y_fb, y_tk, y_tb;  // regressor corners: (force|torque) x (spring|damper) columns
+    V3 t1, t2;              // e1 x w, e2 x w = -Rdot.col(0), -Rdot.col(1): reused by the fused rollout
 };
 
 template <unsigned MASK>
@@ -103,6 +104,8 @@ __device__ __forceinline__ void eval_contact(const State& s, const Prm& q, Resul
         u2 = cross(s.e2, t2);
         m1 = cross_exact(s.e1, s.n1);  // S(e1) R0.col(0)
         m2 = cross_exact(s.e2, s.n2);
+        r.t1 = t1;
+        r.t2 = t2;
     }
     if constexpr (kW || kA) {
         sd = q.k * d - q.b * s.v;                       // k (p0 - p) - b v

@@ -34,6 +34,36 @@ struct Pose {
     V3 c0, c1, c2;  // columns of R
 };
 
+// d_j += rho/2 (G^-1 - I) c_j,  G = R R^T = sum_j c_j c_j^T (symmetric; symmetric adjugate inverse)
+__device__ __forceinline__ void kin_baumgarte_add(const Pose& s, double half_rho, V3& d0, V3& d1,
+                                                  V3& d2)
+{
+    const double gxx = s.c0.x * s.c0.x + s.c1.x * s.c1.x + s.c2.x * s.c2.x;
+    const double gxy = s.c0.x * s.c0.y + s.c1.x * s.c1.y + s.c2.x * s.c2.y;
+    const double gxz = s.c0.x * s.c0.z + s.c1.x * s.c1.z + s.c2.x * s.c2.z;
+    const double gyy = s.c0.y * s.c0.y + s.c1.y * s.c1.y + s.c2.y * s.c2.y;
+    const double gyz = s.c0.y * s.c0.z + s.c1.y * s.c1.z + s.c2.y * s.c2.z;
+    const double gzz = s.c0.z * s.c0.z + s.c1.z * s.c1.z + s.c2.z * s.c2.z;
+    const double axx = gyy * gzz - gyz * gyz;
+    const double axy = gxz * gyz - gxy * gzz;
+    const double axz = gxy * gyz - gxz * gyy;
+    const double ayy = gxx * gzz - gxz * gxz;
+    const double ayz = gxy * gxz - gxx * gyz;
+    const double azz = gxx * gyy - gxy * gxy;
+    const double inv = 1.0 / (gxx * axx + gxy * axy + gxz * axz);
+    // M = rho/2 (G^-1 - I)
+    const double mxx = half_rho * (axx * inv - 1.0), mxy = half_rho * (axy * inv);
+    const double mxz = half_rho * (axz * inv), myy = half_rho * (ayy * inv - 1.0);
+    const double myz = half_rho * (ayz * inv), mzz = half_rho * (azz * inv - 1.0);
+    auto mul = [&](const V3& c) {
+        return V3{mxx * c.x + mxy * c.y + mxz * c.z, mxy * c.x + myy * c.y + myz * c.z,
+                  mxz * c.x + myz * c.y + mzz * c.z};
+    };
+    d0 = d0 + mul(s.c0);
+    d1 = d1 + mul(s.c1);
+    d2 = d2 + mul(s.c2);
+}
+
 template <bool BAUM>
 __device__ __forceinline__ void kin_rates(const Pose& s, const V3& w, double half_rho, V3& d0,
                                           V3& d1, V3& d2)
@@ -41,47 +71,38 @@ __device__ __forceinline__ void kin_rates(const Pose& s, const V3& w, double hal
     d0 = cross(w, s.c0);
     d1 = cross(w, s.c1);
     d2 = cross(w, s.c2);
-    if constexpr (BAUM) {
-        // G = R R^T = sum_j c_j c_j^T
-        const double gxx = s.c0.x * s.c0.x + s.c1.x * s.c1.x + s.c2.x * s.c2.x;
-        const double gxy = s.c0.x * s.c0.y + s.c1.x * s.c1.y + s.c2.x * s.c2.y;
-        const double gxz = s.c0.x * s.c0.z + s.c1.x * s.c1.z + s.c2.x * s.c2.z;
-        const double gyy = s.c0.y * s.c0.y + s.c1.y * s.c1.y + s.c2.y * s.c2.y;
-        const double gyz = s.c0.y * s.c0.z + s.c1.y * s.c1.z + s.c2.y * s.c2.z;
-        const double gzz = s.c0.z * s.c0.z + s.c1.z * s.c1.z + s.c2.z * s.c2.z;
-        // symmetric adjugate
-        const double axx = gyy * gzz - gyz * gyz;
-        const double axy = gxz * gyz - gxy * gzz;
-        const double axz = gxy * gyz - gxz * gyy;
-        const double ayy = gxx * gzz - gxz * gxz;
-        const double ayz = gxy * gxz - gxx * gyz;
-        const double azz = gxx * gyy - gxy * gxy;
-        const double inv = 1.0 / (gxx * axx + gxy * axy + gxz * axz);
-        // M = rho/2 (G^-1 - I)
-        const double mxx = half_rho * (axx * inv - 1.0), mxy = half_rho * (axy * inv);
-        const double mxz = half_rho * (axz * inv), myy = half_rho * (ayy * inv - 1.0);
-        const double myz = half_rho * (ayz * inv), mzz = half_rho * (azz * inv - 1.0);
-        auto mul = [&](const V3& c) {
-            return V3{mxx * c.x + mxy * c.y + mxz * c.z, mxy * c.x + myy * c.y + myz * c.z,
-                      mxz * c.x + myz * c.y + mzz * c.z};
-        };
-        d0 = d0 + mul(s.c0);
-        d1 = d1 + mul(s.c1);
-        d2 = d2 + mul(s.c2);
-    }
+    if constexpr (BAUM) kin_baumgarte_add(s, half_rho, d0, d1, d2);
 }
 
 // x += dx * dT  (ForwardEuler.h:50)
+__device__ __forceinline__ void kin_apply(Pose& s, const V3& v, double dT, const V3& d0,
+                                          const V3& d1, const V3& d2)
+{
+    s.p = s.p + dT * v;
+    s.c0 = s.c0 + dT * d0;
+    s.c1 = s.c1 + dT * d1;
+    s.c2 = s.c2 + dT * d2;
+}
+
 template <bool BAUM>
 __device__ __forceinline__ void kin_euler_step(Pose& s, const V3& v, const V3& w, double half_rho,
                                                double dT)
 {
     V3 d0, d1, d2;
     kin_rates<BAUM>(s, w, half_rho, d0, d1, d2);
-    s.p = s.p + dT * v;
-    s.c0 = s.c0 + dT * d0;
-    s.c1 = s.c1 + dT * d1;
-    s.c2 = s.c2 + dT * d2;
+    kin_apply(s, v, dT, d0, d1, d2);
+}
+
+// Same step when t1 = c0 x w and t2 = c1 x w are already known (the contact model computed them
+// for the same pose and twist): w x c0 = -t1, w x c1 = -t2 -- one cross product instead of three.
+template <bool BAUM>
+__device__ __forceinline__ void kin_euler_step_shared(Pose& s, const V3& v, const V3& w,
+                                                      const V3& t1, const V3& t2, double half_rho,
+                                                      double dT)
+{
+    V3 d0 = neg(t1), d1 = neg(t2), d2 = cross(w, s.c2);
+    if constexpr (BAUM) kin_baumgarte_add(s, half_rho, d0, d1, d2);
+    kin_apply(s, v, dT, d0, d1, d2);
 }
 
 struct KinArgs {
