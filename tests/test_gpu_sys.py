@@ -484,3 +484,67 @@ def test_rollout_forced_split_variants_agree_with_oracle(torch, so):
             assert b.decode_best(out["best"])[1] == int(np.argmin(out["cost"].cpu().numpy()))
     finally:
         os.environ.pop("BLF_CCM_TUNE_ROLLOUT_SPLIT", None)
+
+
+def test_rollout_large_batch_sampled_against_oracle(torch, batch, so):
+    """13.1 M evaluations (65 536 rollouts x 2 feet x 100 steps, the size where the kernel is
+    FP64-bound): every 257th rollout re-run by the oracle from the same device bits -- wrench
+    trajectory, final pose and cost."""
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    rb = RolloutBatch(batch)
+    nr, feet, H = 65536, 2, 100
+    chains = nr * feet
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2024)
+    U = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    tw = U(6, H * chains)
+    base = syn.make_states(4096, seed=404)
+    rep = chains // 4096
+    pos = _dev(torch, np.tile(base["poses"][:, :3].T, (1, rep))) + 1e-3 * U(3, chains)
+    rot = _dev(torch, np.tile(base["poses"][:, 3:].T, (1, rep))) * (1.0 + 1e-4 * U(9, chains))
+    null = _dev(torch, np.tile(base["null_poses"].T, (1, rep)))
+    ref_w, wts = np.array([0.0, 0.0, 30.0, 0.0, 0.0, 0.0]), np.array([1.0, 10.0])
+    out = rb.run(nr, feet, H, 0.01, 0.01, tw, pos, rot, null, ref_w, wts, mask=1, want_final=True)
+    rolls = torch.arange(0, nr, 257, device="cuda")
+    cidx = (rolls[:, None] * feet + torch.arange(feet, device="cuda")[None, :]).reshape(-1)   # chains
+    m = cidx.numel()
+    tidx = (torch.arange(H, device="cuda")[:, None] * chains + cidx[None, :]).reshape(-1)     # (t, chain)
+    ref = so.rollout(rolls.numel(), feet, H, 0.01, 0.01, tw[:, tidx].cpu().numpy(),
+                     pos[:, cidx].cpu().numpy(), rot[:, cidx].cpu().numpy(),
+                     null[:, cidx].cpu().numpy(), uniform=syn.REFERENCE_TEST_PARAMS, mask=1,
+                     wrench_ref=ref_w, weights=wts, nthreads=NTHREADS)
+    assert_parity(out["wrench"][:, tidx].cpu().numpy().T, ref["wrench"].T, "wrench", what="13M rollout ")
+    assert rel(out["final_pos"][:, cidx].cpu().numpy().T, ref["pos"].T).max() <= TOL
+    assert rel(out["final_rot"][:, cidx].cpu().numpy().T, ref["rot"].T).max() <= TOL
+    got_cost = out["cost"][rolls].cpu().numpy()
+    assert np.all(rel(got_cost[:, None], ref["cost"][:, None]) <= TOL)
+    cost = out["cost"].cpu().numpy()
+    c, idx = batch.decode_best(out["best"])
+    assert idx == int(np.argmin(cost)) and c == cost.min()
+    assert m == rolls.numel() * feet
+
+
+def test_generalized_force_config2_size_sampled_against_oracle(torch, batch, so):
+    """409 600 robots x 2 feet x 6x29 Jacobians (the configs[2] batch seen from the simulator side):
+    every 1021st robot re-evaluated by the oracle from the same device bits."""
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    gf = GeneralizedForceBatch(batch)
+    ns, cps, ncols = 409600, 2, 29
+    n = ns * cps
+    st = syn.make_states(n, seed=45)
+    planes = _dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    J = torch.rand((n, 6, ncols), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    base = torch.rand((ns, ncols), dtype=torch.float64, device="cuda", generator=g) * 100 - 50
+    out = gf.run(cps, ncols, planes, J, base)
+    sys_idx = torch.arange(0, ns, 1021, device="cuda")
+    cidx = (sys_idx[:, None] * cps + torch.arange(cps, device="cuda")[None, :]).reshape(-1)
+    Js, bs = J[cidx].cpu().numpy(), base[sys_idx].cpu().numpy()
+    ref, wref = so.generalized_force(cps, ncols, planes[:, cidx].cpu().numpy(), Js, bs,
+                                     uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True)
+    m = sys_idx.numel()
+    mag = np.abs(bs) + np.einsum("scrq,scr->sq", np.abs(Js.reshape(m, cps, 6, ncols)),
+                                 np.abs(wref.T.reshape(m, cps, 6)))
+    err = np.abs(out[sys_idx].cpu().numpy() - ref).max(axis=1) / mag.max(axis=1)
+    assert err.max() <= TOL
