@@ -230,6 +230,28 @@ class RolloutBatch:
         call()
         return out
 
+    def run_host(self, n_rollouts, feet, horizon, dT, rho, twist_planes, pos_planes, rot_planes,
+                 null_planes, wrench_ref, weights, param_planes=None, want_cost: bool = True):
+        """Host arrays in ((6, horizon*chains) etc.; numpy or pinned torch CPU tensors), pair out:
+        blf_ccm_rollout_integrate_cost_host.  Returns (best_cost, best_index, cost or None)."""
+        def rows(t, count):
+            if t is None:
+                return None
+            if isinstance(t, np.ndarray):
+                assert t.shape[0] == count and t.dtype == np.float64 and t.strides[1] == 8
+                return _ptr_array([t[i].ctypes.data for i in range(count)])
+            assert t.shape[0] == count and t.stride(1) == 1
+            return _ptr_array([t[i].data_ptr() for i in range(count)])
+        ref = np.ascontiguousarray(wrench_ref, dtype=np.float64)
+        wts = np.ascontiguousarray(weights, dtype=np.float64)
+        cost = np.empty(n_rollouts) if want_cost else None
+        bc, bi = C.c_double(), C.c_int64()
+        _capi.check(_capi.lib().blf_ccm_rollout_integrate_cost_host(
+            self._b.handle.ptr, int(n_rollouts), int(feet), int(horizon), float(dT), float(rho),
+            rows(twist_planes, 6), rows(pos_planes, 3), rows(rot_planes, 9), rows(null_planes, 12),
+            rows(param_planes, 4), _np_ptr(ref), _np_ptr(wts), _np_ptr(cost), C.byref(bc), C.byref(bi)))
+        return bc.value, bi.value, cost
+
 
 class GeneralizedForceBatch:
     """out[s] = base[s] + sum_c J_c^T wrench_c on one GPU (blf_ccm_generalized_force_soa)."""

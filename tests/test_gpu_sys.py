@@ -548,3 +548,42 @@ def test_generalized_force_config2_size_sampled_against_oracle(torch, batch, so)
                                  np.abs(wref.T.reshape(m, cps, 6)))
     err = np.abs(out[sys_idx].cpu().numpy() - ref).max(axis=1) / mag.max(axis=1)
     assert err.max() <= TOL
+
+
+@pytest.mark.parametrize("nr,feet,H,het,rho", [(5000, 2, 40, False, 0.0), (7, 3, 11, True, 2.0),
+                                               (40000, 1, 100, True, 0.01)])
+def test_rollout_host_pipeline_vs_device_path(torch, batch, nr, feet, H, het, rho):
+    """blf_ccm_rollout_integrate_cost_host (chunked, three slots, strided H2D of the time-major
+    twist planes) must reproduce the device-resident entry point bit for bit (same kernel, split
+    forced to 1 there), whatever the chunking."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    chains = nr * feet
+    st = syn.make_states(chains, seed=31, heterogeneous=het)
+    tw = np.ascontiguousarray(syn.make_states(H * chains, seed=32)["twists"].T)
+    pos0 = np.ascontiguousarray(st["poses"][:, :3].T)
+    rot0 = np.ascontiguousarray(st["poses"][:, 3:].T)
+    null = np.ascontiguousarray(st["null_poses"].T)
+    prm = np.ascontiguousarray(st["params"].T) if het else None
+    ref_w, wts = np.array([0.0, 0.0, 30.0, 0.1, -0.1, 0.0]), np.array([1.0, 25.0])
+    os.environ["BLF_CCM_TUNE_ROLLOUT_SPLIT"] = "1"
+    try:
+        b1 = ContinuousContactModelBatch(0)
+    finally:
+        os.environ.pop("BLF_CCM_TUNE_ROLLOUT_SPLIT", None)
+    b1.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    dev = RolloutBatch(b1).run(nr, feet, H, 0.01, rho, _dev(torch, tw), _dev(torch, pos0),
+                               _dev(torch, rot0), _dev(torch, null), ref_w, wts,
+                               param_planes=_dev(torch, prm), mask=0)
+    bc, bi, cost = RolloutBatch(batch).run_host(nr, feet, H, 0.01, rho, tw, pos0, rot0, null, ref_w,
+                                                wts, param_planes=prm)
+    assert np.array_equal(cost, dev["cost"].cpu().numpy())
+    assert (bc, bi) == b1.decode_best(dev["best"])
+    # pinned torch tensors work the same; the costs are optional
+    pin = lambda a: None if a is None else torch.from_numpy(a).pin_memory()
+    bc2, bi2, none = RolloutBatch(batch).run_host(nr, feet, H, 0.01, rho, pin(tw), pin(pos0), pin(rot0),
+                                                  pin(null), ref_w, wts, param_planes=pin(prm),
+                                                  want_cost=False)
+    assert (bc2, bi2) == (bc, bi) and none is None
+    assert RolloutBatch(batch).run_host(0, feet, H, 0.01, rho, tw[:, :0], pos0[:, :0], rot0[:, :0],
+                                        null[:, :0], ref_w, wts)[1] == -1
