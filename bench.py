@@ -394,6 +394,40 @@ def run_ours(args):
                  "rho": 0.01, "dT": 0.01, "argmin": {"cost": fc, "rollout": fi},
                  "speedup_vs_unfused_mpc": (mpc_ms / Km) / (fused_ms / Km)}
 
+    # end to end for the fused rollout: twists and poses in pinned HOST memory, one pair back
+    if world == 1:
+        hp = torch.from_numpy(planes_np).pin_memory()
+        host_args = (SAMPLES, FEET, HORIZON, 0.01, 0.01, hp[0:6], hp[6:9, :chains], hp[9:18, :chains],
+                     hp[18:30, :chains], ref_wrench, weights)
+        for _ in range(3):
+            rb.run_host(*host_args, want_cost=False)
+        Kh = max(3, min(K, 30))
+        t0 = time.perf_counter()
+        for _ in range(Kh):
+            hb = rb.run_host(*host_args, want_cost=False)
+        host_s = (time.perf_counter() - t0) / Kh
+        mpc_fused["e2e"] = {"value": n / host_s, "unit": UNIT, "ms_per_step": host_s * 1e3, "steps": Kh,
+                            "h2d_bytes_per_step": int(n * 48 + chains * 24 * 8),
+                            "d2h_bytes_per_step": 16,
+                            "api": "blf_ccm_rollout_integrate_cost_host (time-major twist planes and "
+                                   "per-chain poses in pinned host memory in, arg-min pair out)",
+                            "argmin": {"cost": hb[0], "rollout": hb[1]}}
+        if not args.no_cpu:
+            from oracle import sys_oracle
+            cores = os.cpu_count() or 1
+            best_s = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                sys_oracle.rollout(SAMPLES, FEET, HORIZON, 0.01, 0.01, planes_np[0:6],
+                                   planes_np[6:9, :chains], planes_np[9:18, :chains],
+                                   planes_np[18:30, :chains], uniform=syn.REFERENCE_TEST_PARAMS, mask=0,
+                                   wrench_ref=ref_wrench, weights=weights, nthreads=cores)
+                dt_ = time.perf_counter() - t0
+                best_s = dt_ if best_s is None else min(best_s, dt_)
+            mpc_fused["cpu_baseline"] = {"value": n / best_s, "unit": UNIT, "cores": cores, "kind": "port",
+                                         "sample": "best of 3 passes of oracle/sys_oracle.c rollout over "
+                                                   "the same 4096 x 2 x 100 batch"}
+
     # ---- the other rows next to the path, one GPU, briefly (fractions of the measured HBM peak) ---
     next_rows = None
     if world == 1:
