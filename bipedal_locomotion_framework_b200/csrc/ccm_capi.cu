@@ -71,6 +71,7 @@ struct blf_ccm_handle {
     size_t partials_bytes = 0;
     // host pipeline
     cudaStream_t hstream[kHostSlots] = {};
+    cudaEvent_t hev_up[kHostSlots] = {}, hev_done[kHostSlots] = {};   // time-chunked host rollouts
     double* hbuf[kHostSlots] = {};
     long long hchunk = 0;      // contacts per chunk the slots are sized for
     size_t hbytes = 0;
@@ -159,6 +160,8 @@ extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
     for (int s = 0; s < kHostSlots; ++s) {
         if (h->hstream[s]) cudaStreamDestroy(h->hstream[s]);
         if (h->hbuf[s]) cudaFree(h->hbuf[s]);
+        if (h->hev_up[s]) cudaEventDestroy(h->hev_up[s]);
+        if (h->hev_done[s]) cudaEventDestroy(h->hev_done[s]);
     }
     p2p_release(h);
     cudaFree(h->block_best);

@@ -221,6 +221,8 @@ struct RolloutArgs {
     int ctrl_bulk;
     int write_final;
     int split;               // warps sharing one 32-chain tile (power of two, 1 = none)
+    int t_base;              // global index of this launch's first step (time-chunked rollouts)
+    int accumulate;          // chain_cost holds the cost of the steps before t_base: add to it
 };
 
 // Few chains (a sampling-MPC batch of configs[2] size is 8 192 chains = 256 warps for 592 warp
@@ -291,7 +293,7 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
         __syncwarp();
     }
 
-    double acc = 0.0;
+    double acc = (a.accumulate && on) ? a.chain_cost[c * K + phase] : 0.0;
     bool staged = false;   // a ctrl tile of this warp may still be leaving shared memory
     for (int t = 0; t < H; ++t) {
         ptx::cp_async_wait<D - 1>();
@@ -301,7 +303,7 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
             v = V3{r[0], r[kWarp], r[2 * kWarp]};
             w = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
         }
-        if ((t & (K - 1)) == phase) {   // warp-uniform: this warp's share of the evaluations
+        if (((a.t_base + t) & (K - 1)) == phase) {   // warp-uniform: this warp's share of the evaluations
         State st;
         st.v = v; st.w = w; st.p = s.p; st.p0 = p0;
         st.e1 = s.c0; st.e2 = s.c1;

@@ -310,10 +310,11 @@ BLF_CCM_API int blf_ccm_rollout_integrate_cost(
     double* const* final_rot_planes, const double* host_wrench_ref, const double* host_weights,
     int64_t index_base, double* cost, void* best, void* stream);
 
-/* Same rollouts with every plane in HOST memory (pinned gives full PCIe speed), cost only: chunks
- * of rollouts are pipelined through three slots, so the upload of the next chunk overlaps the
- * kernel of the current one; per evaluation only the 48-byte twist crosses PCIe, one pair comes
- * back.  cost (host, n_rollouts) may be NULL.  Returns when best_cost / best_index are written
+/* Same rollouts with every plane in HOST memory (pinned gives full PCIe speed), cost only: the
+ * horizon is cut into time chunks (contiguous in the time-major planes, so every upload is a plain
+ * 1-D copy), pipelined through three slots -- the upload of the next chunk overlaps the kernel of
+ * the current one, poses and costs carry over on the device; per evaluation only the 48-byte
+ * twist crosses PCIe, one pair comes back.  cost (host, n_rollouts) may be NULL.  Returns when best_cost / best_index are written
  * (index -1 when there is nothing to compare).  Not part of a peer exchange (local arg-min). */
 BLF_CCM_API int blf_ccm_rollout_integrate_cost_host(
     blf_ccm_handle* h, int64_t n_rollouts, int feet, int horizon, double dT, double rho,
