@@ -66,6 +66,19 @@ public:
                  double forceWeight, double torqueWeight, Result& result);
 
     /**
+     * Cost-only rollouts with every plane in HOST memory (blf_ccm_rollout_integrate_cost_host):
+     * twistPlanes[6] of horizon*chains doubles (time-major), positionPlanes[3], rotationPlanes[9],
+     * nullPosePlanes[12] (third rotation column may be null) and optional parameterPlanes[4] of
+     * chains doubles.  Uploads are pipelined with the kernels; costs (host, nRollouts) may be
+     * nullptr.  Returns when `result` is written.
+     */
+    bool rolloutHost(std::size_t nRollouts, int feet, int horizon, double dT, double rho,
+                     const double* const* twistPlanes, const double* const* positionPlanes,
+                     const double* const* rotationPlanes, const double* const* nullPosePlanes,
+                     const double* const* parameterPlanes, const iDynTree::Wrench& referenceWrench,
+                     double forceWeight, double torqueWeight, double* costs, Result& result);
+
+    /**
      * knownCoefficient[s] = base[s] + sum_c J_c^T wrench_c  (FloatingBaseSystemDynamics.cpp:199-226)
      * states: 30 planes of nSystems*contactsPerSystem contacts; jacobians: device array of
      * 6 x columns row-major blocks per contact; base (may be nullptr, may alias out) and out:

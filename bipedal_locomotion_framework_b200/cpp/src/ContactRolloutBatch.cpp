@@ -117,6 +117,29 @@ bool ContactRolloutBatch::rollout(std::size_t nRollouts, int feet, int horizon, 
     return true;
 }
 
+bool ContactRolloutBatch::rolloutHost(std::size_t nRollouts, int feet, int horizon, double dT, double rho,
+                                      const double* const* twistPlanes,
+                                      const double* const* positionPlanes,
+                                      const double* const* rotationPlanes,
+                                      const double* const* nullPosePlanes,
+                                      const double* const* parameterPlanes,
+                                      const iDynTree::Wrench& referenceWrench, double forceWeight,
+                                      double torqueWeight, double* costs, Result& result)
+{
+    if (m_device == nullptr) return report(BLF_CCM_ERR_INVALID_HANDLE, "rolloutHost");
+    const double weights[2] = {forceWeight, torqueWeight};
+    std::int64_t index = -1;
+    if (!report(blf_ccm_rollout_integrate_cost_host(raw(m_device), static_cast<std::int64_t>(nRollouts),
+                                                    feet, horizon, dT, rho, twistPlanes, positionPlanes,
+                                                    rotationPlanes, nullPosePlanes, parameterPlanes,
+                                                    referenceWrench.data(), weights, costs, &result.cost,
+                                                    &index),
+                "rolloutHost"))
+        return false;
+    result.index = index;
+    return true;
+}
+
 bool ContactRolloutBatch::generalizedForce(std::size_t nSystems, int contactsPerSystem, int columns,
                                            const DeviceSoA& states, const DeviceSoA* parameters,
                                            const double* jacobians, const double* base, double* out,

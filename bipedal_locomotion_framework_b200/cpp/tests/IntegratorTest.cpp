@@ -328,6 +328,32 @@ TEST_CASE("Batched steps either side of the contact model")
                                  nullptr, reference, 1.0, 10.0, result));
         REQUIRE(result.index == argmin);
         REQUIRE(std::fabs(result.cost - hostCost[argmin]) <= 1e-12 * hostCost[argmin]);
+
+        // the same rollouts straight from host planes (pipelined uploads): same arg-min and costs
+        std::vector<double> hostPlanes(6 * n + 24 * chains);
+        std::vector<const double*> twPtr(6), pPtr(3), rPtr(9), nPtr(12);
+        for (int j = 0; j < 6; ++j)
+        {
+            twPtr[j] = hostPlanes.data() + j * n;
+            for (std::size_t i = 0; i < n; ++i) hostPlanes[j * n + i] = twistRows[i * 6 + j];
+        }
+        double* q = hostPlanes.data() + 6 * n;
+        for (int j = 0; j < 24; ++j)
+        {
+            for (std::size_t c = 0; c < chains; ++c)
+                q[j * chains + c] = j < 12 ? reinterpret_cast<const double*>(&pose[c])[j]
+                                           : reinterpret_cast<const double*>(&nullPose[c])[j - 12];
+            if (j < 3) pPtr[j] = q + j * chains;
+            else if (j < 12) rPtr[j - 3] = q + j * chains;
+            else nPtr[j - 12] = q + j * chains;
+        }
+        std::vector<double> costsHost(nRollouts);
+        ContactRolloutBatch::Result fromHost{};
+        REQUIRE(rollouts.rolloutHost(nRollouts, feet, horizon, dT, rho, twPtr.data(), pPtr.data(), rPtr.data(),
+                                     nPtr.data(), nullptr, reference, 1.0, 10.0, costsHost.data(), fromHost));
+        REQUIRE(fromHost.index == argmin);
+        for (int r = 0; r < nRollouts; ++r)
+            REQUIRE(std::fabs(costsHost[r] - costs[r]) <= 1e-12 * costs[r]);
     }
 
     SECTION("Euler step batch and generalized force")
