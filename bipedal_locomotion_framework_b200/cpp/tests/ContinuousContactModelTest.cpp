@@ -17,7 +17,9 @@
 #endif
 
 #include <array>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <random>
 #include <string>
 #include <vector>
@@ -208,6 +210,40 @@ TEST_CASE("Initialization failures and lazy cache")
         for (int i = 0; i < 6; ++i) changed = changed || (m.getContactWrench()(i) != before(i));
         REQUIRE(changed);
     }
+}
+
+TEST_CASE("Per-instance latency")
+{
+    // not a correctness check: prints what one setState + getter costs through the GPU-only facade
+    std::mt19937 gen(11);
+    ContinuousContactModel m;
+    REQUIRE(m.initialize(testHandler()));
+    const Transform pose = testPose();
+    double sink = 0;
+    for (int warm = 0; warm < 50; ++warm)
+    {
+        m.setState(randomTwist(gen), pose);
+        sink += m.getContactWrench()(2);
+    }
+    const int iterations = 2000;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < iterations; ++i)
+    {
+        m.setState(randomTwist(gen), pose);
+        sink += m.getContactWrench()(2);
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    for (int i = 0; i < iterations; ++i)
+    {
+        m.setState(randomTwist(gen), pose);
+        sink += m.getContactWrench()(2) + m.getAutonomousDynamics()(1) + m.getControlMatrix()(0, 0);
+    }
+    const auto t2 = std::chrono::steady_clock::now();
+    const double us1 = std::chrono::duration<double, std::micro>(t1 - t0).count() / iterations;
+    const double us3 = std::chrono::duration<double, std::micro>(t2 - t1).count() / iterations;
+    std::printf("per-instance facade: setState + getContactWrench %.1f us; + getAutonomousDynamics + "
+                "getControlMatrix %.1f us (sink %g)\n", us1, us3, sink);
+    REQUIRE(us1 < 1000.0);
 }
 
 TEST_CASE("Batched entry point")

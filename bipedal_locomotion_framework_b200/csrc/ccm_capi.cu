@@ -72,6 +72,7 @@ struct blf_ccm_handle {
     // host pipeline
     cudaStream_t hstream[kHostSlots] = {};
     cudaEvent_t hev_up[kHostSlots] = {}, hev_done[kHostSlots] = {};   // time-chunked host rollouts
+    double* single_out = nullptr;   // 60 doubles of mapped pinned host memory (n = 1 fast path)
     double* hbuf[kHostSlots] = {};
     long long hchunk = 0;      // contacts per chunk the slots are sized for
     size_t hbytes = 0;
@@ -164,6 +165,7 @@ extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
         if (h->hev_done[s]) cudaEventDestroy(h->hev_done[s]);
     }
     p2p_release(h);
+    if (h->single_out) cudaFreeHost(h->single_out);
     cudaFree(h->block_best);
     cudaFree(h->counter);
     if (h->partials) cudaFree(h->partials);
@@ -431,6 +433,46 @@ extern "C" int blf_ccm_eval_batch_aos(blf_ccm_handle* h, int64_t n, const double
                       regressor, static_cast<cudaStream_t>(stream));
 }
 
+// ---- one contact state from host memory: the per-instance facade's getters -----------------------
+
+template <unsigned MASK, bool HET>
+struct SingleLaunch {
+    static int run(blf_ccm_handle* h, const SingleArgs& a, cudaStream_t st)
+    {
+        ccm_single_kernel<MASK><<<1, 32, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        return BLF_CCM_OK;
+    }
+};
+
+static int eval_single_host(blf_ccm_handle* h, const double* twist, const double* pose,
+                            const double* null_pose, const blf_ccm_params* params, unsigned out_mask,
+                            double* wrench, double* autodyn, double* ctrl, double* regressor)
+{
+    if (!h->single_out)
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->single_out), 60 * sizeof(double), cudaHostAllocMapped));
+    if (!h->hstream[0]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream[0], cudaStreamNonBlocking));
+    SingleArgs a;
+    memset(&a, 0, sizeof(a));
+    if (twist) memcpy(a.tw, twist, sizeof(a.tw));
+    memcpy(a.pose, pose, sizeof(a.pose));
+    if (null_pose) memcpy(a.null, null_pose, sizeof(a.null));
+    a.prm = params ? make_prm(params->length, params->width, params->spring_coeff, params->damper_coeff)
+                   : h->uni;
+    a.out = h->single_out;   // unified addressing: the mapped host pointer is valid on the device
+    cudaStream_t st = h->hstream[0];
+    if (int rc = dispatch_mask<SingleLaunch, false>(out_mask, h, a, st)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const double* o = h->single_out;
+    if (out_mask & BLF_CCM_WRENCH) memcpy(wrench, o, 6 * sizeof(double));
+    if (out_mask & BLF_CCM_AUTODYN) memcpy(autodyn, o + 6, 6 * sizeof(double));
+    if (out_mask & BLF_CCM_REGRESSOR) memcpy(regressor, o + 12, 12 * sizeof(double));
+    if (out_mask & BLF_CCM_CTRL) memcpy(ctrl, o + 24, 36 * sizeof(double));
+    h->last_path = BLF_CCM_PATH_BULK;
+    return BLF_CCM_OK;
+}
+
 // ---- host buffers: chunked, three slots, copies and kernels overlapped ---------------------------
 
 extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const double* twists,
@@ -452,6 +494,9 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
     if (!params && !h->have_params)
         return fail(BLF_CCM_ERR_NOT_INITIALIZED,
                     "no parameters: call blf_ccm_set_uniform_params or pass params");
+    if (n == 1)   // the per-instance facade: one launch, results through mapped pinned memory
+        return eval_single_host(h, twists, poses, null_poses, params, out_mask, wrench, autodyn, ctrl,
+                                regressor);
 
     // slot layout in doubles per contact (every section starts 16-byte aligned: all even counts)
     const long long chunk = std::min<long long>(n, h->host_chunk_pref);

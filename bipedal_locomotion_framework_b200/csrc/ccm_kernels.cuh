@@ -597,6 +597,63 @@ ccm_aos_scalar_kernel(const __grid_constant__ AosArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// One contact state (the per-instance facade's getters): the state travels in the kernel
+// parameters, the results go straight to mapped pinned host memory -- one launch and one stream
+// synchronisation per getter instead of three staged copies around a batch kernel.
+// ------------------------------------------------------------------------------------------------
+
+struct SingleArgs {
+    double tw[6];
+    double pose[12];
+    double null[12];
+    Prm prm;
+    double* out;   // mapped host memory: wrench 0-5 | autodyn 6-11 | regressor 12-23 | ctrl 24-59
+};
+
+template <unsigned MASK>
+__global__ void ccm_single_kernel(const __grid_constant__ SingleArgs a)
+{
+    if (threadIdx.x != 0) return;
+    State s;
+    s.v = V3{a.tw[0], a.tw[1], a.tw[2]};
+    s.w = V3{a.tw[3], a.tw[4], a.tw[5]};
+    s.p = V3{a.pose[0], a.pose[1], a.pose[2]};
+    s.e1 = V3{a.pose[3], a.pose[6], a.pose[9]};
+    s.e2 = V3{a.pose[4], a.pose[7], a.pose[10]};
+    s.R02 = a.pose[5];
+    s.R12 = a.pose[8];
+    s.R22 = a.pose[11];
+    s.p0 = V3{a.null[0], a.null[1], a.null[2]};
+    s.n1 = V3{a.null[3], a.null[6], a.null[9]};
+    s.n2 = V3{a.null[4], a.null[7], a.null[10]};
+    Result r;
+    eval_contact<MASK>(s, a.prm, r);
+    double* o = a.out;
+    if constexpr ((MASK & M_WRENCH) != 0) {
+        o[0] = r.force.x; o[1] = r.force.y; o[2] = r.force.z;
+        o[3] = r.torque.x; o[4] = r.torque.y; o[5] = r.torque.z;
+    }
+    if constexpr ((MASK & M_AUTODYN) != 0) {
+        o[6] = r.fhead.x; o[7] = r.fhead.y; o[8] = r.fhead.z;
+        o[9] = r.ftail.x; o[10] = r.ftail.y; o[11] = r.ftail.z;
+    }
+    if constexpr ((MASK & M_REGRESSOR) != 0) {
+        o[12] = r.y_fk.x; o[13] = r.y_fb.x; o[14] = r.y_fk.y; o[15] = r.y_fb.y;
+        o[16] = r.y_fk.z; o[17] = r.y_fb.z; o[18] = r.y_tk.x; o[19] = r.y_tb.x;
+        o[20] = r.y_tk.y; o[21] = r.y_tb.y; o[22] = r.y_tk.z; o[23] = r.y_tb.z;
+    }
+    if constexpr ((MASK & M_CTRL) != 0) {
+        double* c = o + 24;
+#pragma unroll
+        for (int e = 0; e < 36; ++e) c[e] = 0.0;
+        c[0] = r.gd; c[7] = r.gd; c[14] = r.gd;
+        c[21] = r.gs[0]; c[22] = r.gs[1]; c[23] = r.gs[2];
+        c[27] = r.gs[1]; c[28] = r.gs[3]; c[29] = r.gs[4];
+        c[33] = r.gs[2]; c[34] = r.gs[4]; c[35] = r.gs[5];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Surface points of one contact state (getForceAtPoint / getTorqueGeneratedAtPoint)
 // ------------------------------------------------------------------------------------------------
 

@@ -46,7 +46,8 @@ def test_reference_catch2_sections_on_the_gpu_facade(cpp):
     plus lazy-cache, batch-vs-instances and DeviceSoA / rollout arg-min cases."""
     r = _run("ContinuousContactModelUnitTests")
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "3 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
+    assert "4 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
+    print([ln for ln in r.stdout.splitlines() if "per-instance facade" in ln])
 
 
 @pytest.mark.gpu
