@@ -279,13 +279,24 @@ TEST_CASE("Batched entry point")
         {
             model.setState(twists[i], poses[i]);
             model.setNullForceTransform(nulls[i]);
-            for (int c = 0; c < 6; ++c)
-            {
-                REQUIRE(model.getContactWrench()(c) == wrenches[i](c));
-                REQUIRE(model.getAutonomousDynamics()(c) == autodyn[i](c));
-            }
+            // two different kernels (batch vs single-state): equal to the parity tolerance,
+            // norm-wise per 3-vector block
+            auto blockClose = [](const double* a, const double* b) {
+                double num = 0, den = 0;
+                for (int c = 0; c < 3; ++c)
+                {
+                    num = std::max(num, std::fabs(a[c] - b[c]));
+                    den = std::max(den, std::fabs(b[c]));
+                }
+                return num <= 1e-12 * den;
+            };
+            REQUIRE(blockClose(wrenches[i].data(), model.getContactWrench().data()));
+            REQUIRE(blockClose(wrenches[i].data() + 3, model.getContactWrench().data() + 3));
+            REQUIRE(blockClose(autodyn[i].data(), model.getAutonomousDynamics().data()));
+            REQUIRE(blockClose(autodyn[i].data() + 3, model.getAutonomousDynamics().data() + 3));
             for (int r = 0; r < 6; ++r)
-                for (int c = 0; c < 6; ++c) REQUIRE(model.getControlMatrix()(r, c) == ctrl[i](r, c));
+                REQUIRE(blockClose(ctrl[i].data() + 6 * r + 3 * (r / 3),
+                                   model.getControlMatrix().data() + 6 * r + 3 * (r / 3)));
         }
         // structural zeros of g are +0.0
         for (std::size_t i = 0; i < n; ++i)
