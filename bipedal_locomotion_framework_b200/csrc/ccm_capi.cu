@@ -82,6 +82,7 @@ struct blf_ccm_handle {
     int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM>0: persistent grid with that many CTAs/SM
                                  // (looping kernels only); default = one tile per warp
     int tune_rollout_split = 0;  // BLF_CCM_TUNE_ROLLOUT_SPLIT>0: warps per tile of the fused rollout
+    int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
     bool p2p_connected = false;
@@ -133,6 +134,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_cpt = env_int("BLF_CCM_TUNE_CPT");
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
+    h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");
     CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
     CUDA_TRY(cudaMalloc(&h->counter, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(h->counter, 0, sizeof(unsigned int)));
@@ -219,6 +221,25 @@ static int persistent_blocks(blf_ccm_handle* h, K kernel, int threads, size_t sm
     return BLF_CCM_OK;
 }
 
+// Launch with programmatic stream serialization (PDL): see ccm_soa_kernel.  BLF_CCM_TUNE_NO_PDL=1
+// falls back to a plain launch (for A/B measurements).
+template <typename K, typename A>
+static cudaError_t launch_pdl(const blf_ccm_handle* h, K kernel, long long grid, int threads,
+                              size_t smem, cudaStream_t st, const A& args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->tune_no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
@@ -263,7 +284,7 @@ struct SoaLaunch {
             if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;  // smem attribute
             const long long grid = (a.n + threads - 1) / threads;
             if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");
-            k<<<static_cast<int>(grid), threads, smem, st>>>(a);
+            CUDA_TRY(launch_pdl(h, k, grid, threads, smem, st, a));
         }
         CUDA_TRY(cudaGetLastError());
         h->launches++;
@@ -361,7 +382,7 @@ struct AosLaunch {
             const long long tiles = (a.n + 31) / 32;
             const long long want = (tiles + threads / 32 - 1) / (threads / 32);
             const int grid = static_cast<int>(std::min<long long>(want, cap));
-            k<<<grid, threads, smem, st>>>(a);
+            CUDA_TRY(launch_pdl(h, k, grid, threads, smem, st, a));
         } else {
             constexpr int threads = 128;
             auto k = ccm_aos_scalar_kernel<MASK, HET>;
@@ -629,7 +650,7 @@ struct CostLaunch {
         if (int rc = persistent_blocks(h, k, threads, smem, &cap)) return rc;
         const long long grid = (a.n + threads - 1) / threads;
         if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");
-        k<<<static_cast<int>(grid), threads, smem, st>>>(a);
+        CUDA_TRY(launch_pdl(h, k, grid, threads, smem, st, a));
         CUDA_TRY(cudaGetLastError());
         h->launches++;
         return BLF_CCM_OK;
@@ -715,7 +736,7 @@ extern "C" int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_roll
     fill_reduce_p2p(h, ra.best, ra.p2p);
     const int threads = 128;
     const int grid = static_cast<int>(std::min<long long>((n_rollouts + threads - 1) / threads, kMaxPartials));
-    ccm_cost_reduce_kernel<<<grid, threads, 0, st>>>(ra);
+    CUDA_TRY(launch_pdl(h, ccm_cost_reduce_kernel, grid, threads, 0, st, ra));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return BLF_CCM_OK;

@@ -153,6 +153,23 @@ ccm_soa_kernel(const __grid_constant__ SoaArgs a)
     const bool on = i < a.n;
     const int cnt = static_cast<int>(min64(kWarp, a.n - base));
 
+    // Programmatic dependent launch: let the NEXT launch of the stream take SM slots as this grid's
+    // CTAs retire; such a CTA does the part of its work that touches no global memory (the
+    // structural zeros below) and then blocks in grid_dep_wait() until the previous grid has
+    // completed -- stream order is preserved, the inter-launch gap and the ramp of the first wave
+    // disappear.  (Without the launch attribute both instructions are no-ops.)
+    ptx::grid_dep_launch_dependents();
+
+    double* ctile = reinterpret_cast<double*>(smem_raw) + warp * (kWarp * 36);
+    if constexpr ((OUT & M_CTRL) != 0) {
+        // structural zeros of the 32 dense blocks
+        double2* z = reinterpret_cast<double2*>(ctile);
+#pragma unroll
+        for (int j = 0; j < 18; ++j) z[lane + j * kWarp] = make_double2(0.0, 0.0);
+        __syncwarp();
+    }
+    ptx::grid_dep_wait();
+
     // ---- every live plane in flight before the first use ---------------------------------------
     double x[30] = {};
 #pragma unroll
@@ -163,15 +180,6 @@ ccm_soa_kernel(const __grid_constant__ SoaArgs a)
         const double l = on ? __ldcs(a.prm[0] + i) : 0.0, w = on ? __ldcs(a.prm[1] + i) : 0.0;
         const double k = on ? __ldcs(a.prm[2] + i) : 0.0, b = on ? __ldcs(a.prm[3] + i) : 0.0;
         q = make_prm(l, w, k, b);
-    }
-
-    double* ctile = reinterpret_cast<double*>(smem_raw) + warp * (kWarp * 36);
-    if constexpr ((OUT & M_CTRL) != 0) {
-        // structural zeros of the 32 dense blocks, written while the loads are in flight
-        double2* z = reinterpret_cast<double2*>(ctile);
-#pragma unroll
-        for (int j = 0; j < 18; ++j) z[lane + j * kWarp] = make_double2(0.0, 0.0);
-        __syncwarp();
     }
 
     State s;
@@ -420,6 +428,8 @@ ccm_aos_kernel(const __grid_constant__ AosArgs a)
         for (int i = lane; i < TILE * 18; i += kWarp) z[i] = make_double2(0.0, 0.0);
     }
     __syncwarp();
+    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
+    ptx::grid_dep_wait();
 
     const long long ntiles = (a.n + TILE - 1) / TILE;
     const long long wstride = static_cast<long long>(gridDim.x) * warps_per_cta;
@@ -753,6 +763,8 @@ ccm_cost_reduce_kernel(const __grid_constant__ ReduceArgs ra)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
+    ptx::grid_dep_wait();                // the partials come from the previous launch
 
     CostIdx mine{inf, 0x7fffffffffffffffLL};
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;

@@ -87,6 +87,19 @@ __device__ __forceinline__ void fence_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// launch_dependents: the next kernel of the stream (if launched with the programmatic-serialization
+// attribute) may start occupying SM resources as they free up; it still blocks in grid_dep_wait()
+// until THIS grid has completed and its memory is visible, so stream semantics are unchanged.
+__device__ __forceinline__ void grid_dep_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void grid_dep_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- per-thread async copies (LDGSTS): 8 bytes global -> shared, tracked by commit groups ------
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src)
 {

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(128, 5)
 sys_kin_euler_kernel(const __grid_constant__ KinArgs a)
 {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
+    ptx::grid_dep_wait();
     if (i >= a.n) return;
     double t[6], x[12];
 #pragma unroll
@@ -267,6 +269,8 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
         }
         ptx::cp_async_commit();
     };
+    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
+    ptx::grid_dep_wait();
 #pragma unroll
     for (int t = 0; t < D; ++t) issue(t);
 
@@ -413,11 +417,15 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * a.stage_bytes + kWarp * 48);
     const uint32_t stage0 = ptx::smem_addr(ws);
     const double* jac0 = a.jac + c0 * 6 * ncols;
+    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
+    if (bulk && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        ptx::fence_mbar_init();
+    }
+    ptx::grid_dep_wait();
     if (bulk) {
         if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
-            ptx::fence_mbar_init();
 #pragma unroll
             for (int s = 0; s < kGfStages; ++s)
                 if (s < ncont) {
