@@ -269,8 +269,9 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
         }
         ptx::cp_async_commit();
     };
-    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
-    ptx::grid_dep_wait();
+    // No programmatic dependent launch here (measured: 43 -> 70 us at 8 192 chains): this kernel
+    // is latency-bound with about one working warp per scheduler, and the early-resident CTAs of
+    // the next launches, parked in griddepcontrol.wait, take issue slots from it.
 #pragma unroll
     for (int t = 0; t < D; ++t) issue(t);
 
