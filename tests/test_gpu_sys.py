@@ -587,3 +587,65 @@ def test_rollout_host_pipeline_vs_device_path(torch, batch, nr, feet, H, het, rh
     assert (bc2, bi2) == (bc, bi) and none is None
     assert RolloutBatch(batch).run_host(0, feet, H, 0.01, rho, tw[:, :0], pos0[:, :0], rot0[:, :0],
                                         null[:, :0], ref_w, wts)[1] == -1
+
+
+# --- non-finite inputs and ties ---------------------------------------------------------------------
+
+def test_non_finite_inputs_stay_local_and_never_win_the_argmin(torch, batch, so):
+    """A NaN / Inf in one chain's state poisons that chain only (the evaluations are independent, as
+    separate reference objects are); a rollout whose cost is NaN never wins the arg-min, exact ties go
+    to the lowest index, and when every cost is NaN the index is -1."""
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    rb = RolloutBatch(batch)
+    nr, feet, H = 96, 2, 12
+    chains = nr * feet
+    st = syn.make_states(chains, seed=71)
+    tw = np.ascontiguousarray(syn.make_states(H * chains, seed=72)["twists"].T)
+    pos0 = np.ascontiguousarray(st["poses"][:, :3].T)
+    rot0 = np.ascontiguousarray(st["poses"][:, 3:].T)
+    null = np.ascontiguousarray(st["null_poses"].T)
+    ref_w, wts = np.zeros(6), np.array([1.0, 1.0])
+    clean = rb.run(nr, feet, H, 0.01, 0.5, _dev(torch, tw), _dev(torch, pos0), _dev(torch, rot0),
+                   _dev(torch, null), ref_w, wts, mask=1, want_final=True)
+    cost0 = clean["cost"].cpu().numpy()
+    best0 = int(np.argmin(cost0))
+    # poison the best rollout (NaN twist at step 3 of its first foot) and another one with Inf
+    other = (best0 + 7) % nr
+    tw2 = tw.copy()
+    tw2[4, 3 * chains + best0 * feet] = np.nan
+    pos2 = pos0.copy()
+    pos2[1, other * feet + 1] = np.inf
+    out = rb.run(nr, feet, H, 0.01, 0.5, _dev(torch, tw2), _dev(torch, pos2), _dev(torch, rot0),
+                 _dev(torch, null), ref_w, wts, mask=1, want_final=True)
+    cost = out["cost"].cpu().numpy()
+    bad = np.zeros(nr, dtype=bool)
+    bad[[best0, other]] = True
+    assert not np.isfinite(cost[bad]).any() and np.array_equal(cost[~bad], cost0[~bad])
+    good_chains = np.repeat(~bad, feet)
+    assert torch.equal(out["final_rot"][:, torch.from_numpy(good_chains).cuda()],
+                       clean["final_rot"][:, torch.from_numpy(good_chains).cuda()])
+    c, idx = batch.decode_best(out["best"])
+    expect = int(np.nanargmin(np.where(np.isfinite(cost), cost, np.nan)))
+    assert idx == expect and c == cost[expect] and idx not in (best0, other)
+    # exact tie: duplicate the data of rollout 5 into rollout 50 -> the lower index wins
+    tw3, pos3, rot3, null3 = tw.copy(), pos0.copy(), rot0.copy(), null.copy()
+    a, b = 5, 50
+    for arr in (pos3, rot3, null3):
+        arr[:, b * feet:(b + 1) * feet] = arr[:, a * feet:(a + 1) * feet]
+    for t in range(H):
+        tw3[:, t * chains + b * feet:t * chains + (b + 1) * feet] = \
+            tw3[:, t * chains + a * feet:t * chains + (a + 1) * feet]
+    # make that pair the cheapest: the reference wrench is their own mean wrench
+    probe = rb.run(nr, feet, H, 0.01, 0.5, _dev(torch, tw3), _dev(torch, pos3), _dev(torch, rot3),
+                   _dev(torch, null3), ref_w, wts, mask=1)
+    w = probe["wrench"].cpu().numpy().reshape(6, H, chains)[:, :, a * feet:(a + 1) * feet]
+    tie = rb.run(nr, feet, H, 0.01, 0.5, _dev(torch, tw3), _dev(torch, pos3), _dev(torch, rot3),
+                 _dev(torch, null3), w.mean(axis=(1, 2)), wts, mask=0)
+    ct = tie["cost"].cpu().numpy()
+    assert ct[a] == ct[b]
+    if np.argmin(ct) in (a, b):
+        assert batch.decode_best(tie["best"])[1] == a
+    # every cost NaN -> nothing comparable
+    allnan = rb.run(nr, feet, H, 0.01, 0.5, _dev(torch, np.full_like(tw, np.nan)), _dev(torch, pos0),
+                    _dev(torch, rot0), _dev(torch, null), ref_w, wts, mask=0)
+    assert batch.decode_best(allnan["best"])[1] == -1
