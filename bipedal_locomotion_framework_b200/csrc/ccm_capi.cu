@@ -82,6 +82,7 @@ struct blf_ccm_handle {
     int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM>0: persistent grid with that many CTAs/SM
                                  // (looping kernels only); default = one tile per warp
     int tune_rollout_split = 0;  // BLF_CCM_TUNE_ROLLOUT_SPLIT>0: warps per tile of the fused rollout
+    int tune_rollout_ws = 0;     // BLF_CCM_TUNE_ROLLOUT_WS: 1 force / 2 forbid the warp-specialised rollout
     int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
@@ -135,6 +136,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");
+    h->tune_rollout_ws = env_int("BLF_CCM_TUNE_ROLLOUT_WS");
     CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
     CUDA_TRY(cudaMalloc(&h->counter, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(h->counter, 0, sizeof(unsigned int)));

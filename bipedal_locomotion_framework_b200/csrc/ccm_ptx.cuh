@@ -25,6 +25,13 @@ __device__ __forceinline__ void fence_mbar_init()
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
+// plain arrive (release at CTA scope): the arriving thread's earlier shared-memory writes are
+// visible to a thread that observes the phase completion with mbar_wait (acquire)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
@@ -33,17 +40,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
+    // no PTX labels: the function is inlined several times into one kernel
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
 }
 
 // global -> shared::cta bulk copy, completion counted in bytes on an mbarrier.

@@ -366,6 +366,148 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-specialised rollout for SMALL batches, cost only.
+//
+// A sampling-MPC batch of configs[2] size has 8 192 chains: 256 warps for 592 warp schedulers, and
+// every warp walks 100 dependent steps -- latency, not throughput, sets the time.  Only the pose
+// integration is inherently sequential (~35 of the ~120 FP64 instructions of a step).  So a CTA of
+// four warps shares one 32-chain tile:
+//   warp 0 (producer)   reads the twists (cp.async ring), integrates the pose and PUBLISHES, per
+//                       step, what the contact model needs (v, w, p, e1, e2, R22: 16 doubles per
+//                       lane) into a shared-memory ring of kWsStages stages;
+//   warps 1..3          consumer k evaluates the steps t = k (mod 3): contact wrench + cost term.
+// Stages are handed over with mbarriers: full[s] (producer -> the one consumer of that step) and
+// empty[s] (that consumer -> producer).  Unlike `split` (every warp integrates everything) no work
+// is duplicated.  Each consumer keeps its own partial cost, chain_cost[chain*3 + k]; the reduction
+// kernel sums a rollout's feet*3 partials in index order (deterministic).
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kWsConsumers = 3;
+constexpr int kWsStages = 9;                        // a multiple of kWsConsumers
+constexpr int kWsStageDoubles = 16 * kWarp;         // [16][32]
+constexpr int kWsSmemBytes = kRolloutRingBytes + kWsStages * kWsStageDoubles * 8 + 2 * kWsStages * 8 + 64;
+
+template <bool HET, bool BAUM>
+__global__ void __launch_bounds__(128)
+ccm_rollout_ws_kernel(const __grid_constant__ RolloutArgs a)
+{
+    constexpr int D = kRolloutDepth;
+    constexpr int S = kWsStages;
+    constexpr int C = kWsConsumers;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wbase = static_cast<long long>(blockIdx.x) * kWarp;
+    const long long c = wbase + lane;
+    const bool on = c < a.chains;
+    const int H = a.horizon;
+
+    double* ring = reinterpret_cast<double*>(smem_raw);                      // producer's twist ring
+    double* stages = ring + D * 6 * kWarp;                                   // [S][16][32]
+    const uint32_t full0 = ptx::smem_addr(stages + S * kWsStageDoubles);     // S barriers
+    const uint32_t empty0 = full0 + 8 * S;                                   // S barriers
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(full0 + 8 * s, 1);
+            ptx::mbar_init(empty0 + 8 * s, 1);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer: twists -> pose trajectory -> stages --------------------------
+        const uint32_t ring_s = ptx::smem_addr(ring) + static_cast<uint32_t>(lane) * 8u;
+        auto issue = [&](int t) {
+            if (on && t < H) {
+                const uint32_t dst = ring_s + static_cast<uint32_t>((t & (D - 1)) * 6 * kWarp * 8);
+                const long long src = static_cast<long long>(t) * a.chains + c;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, a.tw[j] + src);
+            }
+            ptx::cp_async_commit();
+        };
+#pragma unroll
+        for (int t = 0; t < D; ++t) issue(t);
+        Pose s{};
+        if (on) {
+            s.p = V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)};
+            s.c0 = V3{__ldg(a.rot0[0] + c), __ldg(a.rot0[3] + c), __ldg(a.rot0[6] + c)};
+            s.c1 = V3{__ldg(a.rot0[1] + c), __ldg(a.rot0[4] + c), __ldg(a.rot0[7] + c)};
+            s.c2 = V3{__ldg(a.rot0[2] + c), __ldg(a.rot0[5] + c), __ldg(a.rot0[8] + c)};
+        }
+        for (int t = 0; t < H; ++t) {
+            const int st = t % S;
+            ptx::cp_async_wait<D - 1>();
+            V3 v{}, w{};
+            if (on) {
+                const double* r = ring + (t & (D - 1)) * 6 * kWarp + lane;
+                v = V3{r[0], r[kWarp], r[2 * kWarp]};
+                w = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
+            }
+            if (t >= S) ptx::mbar_wait(empty0 + 8 * st, ((t / S) - 1) & 1);   // stage consumed
+            double* o = stages + st * kWsStageDoubles + lane;
+            o[0 * kWarp] = v.x;  o[1 * kWarp] = v.y;  o[2 * kWarp] = v.z;
+            o[3 * kWarp] = w.x;  o[4 * kWarp] = w.y;  o[5 * kWarp] = w.z;
+            o[6 * kWarp] = s.p.x;  o[7 * kWarp] = s.p.y;  o[8 * kWarp] = s.p.z;
+            o[9 * kWarp] = s.c0.x; o[10 * kWarp] = s.c0.y; o[11 * kWarp] = s.c0.z;
+            o[12 * kWarp] = s.c1.x; o[13 * kWarp] = s.c1.y; o[14 * kWarp] = s.c1.z;
+            o[15 * kWarp] = s.c2.z;
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(full0 + 8 * st);
+            kin_euler_step<BAUM>(s, v, w, a.half_rho, a.dT);
+            issue(t + D);
+        }
+        if (on && a.write_final) {
+            a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
+            a.rot_out[0][c] = s.c0.x; a.rot_out[1][c] = s.c1.x; a.rot_out[2][c] = s.c2.x;
+            a.rot_out[3][c] = s.c0.y; a.rot_out[4][c] = s.c1.y; a.rot_out[5][c] = s.c2.y;
+            a.rot_out[6][c] = s.c0.z; a.rot_out[7][c] = s.c1.z; a.rot_out[8][c] = s.c2.z;
+        }
+        ptx::cp_async_wait<0>();
+    } else {
+        // ---------------- consumers: contact wrench + cost of the steps t = k (mod 3) ------------
+        const int k = warp - 1;
+        V3 p0{}, n1{}, n2{};
+        Prm q = a.uni;
+        if (on) {
+            p0 = V3{__ldg(a.nul[0] + c), __ldg(a.nul[1] + c), __ldg(a.nul[2] + c)};
+            n1 = V3{__ldg(a.nul[3] + c), __ldg(a.nul[6] + c), __ldg(a.nul[9] + c)};
+            n2 = V3{__ldg(a.nul[4] + c), __ldg(a.nul[7] + c), __ldg(a.nul[10] + c)};
+            if constexpr (HET)
+                q = make_prm(__ldg(a.prm[0] + c), __ldg(a.prm[1] + c), __ldg(a.prm[2] + c),
+                             __ldg(a.prm[3] + c));
+        }
+        double acc = 0.0;
+        for (int t = k; t < H; t += C) {
+            const int st = t % S;
+            ptx::mbar_wait(full0 + 8 * st, (t / S) & 1);
+            const double* in = stages + st * kWsStageDoubles + lane;
+            State x;
+            x.v = V3{in[0 * kWarp], in[1 * kWarp], in[2 * kWarp]};
+            x.w = V3{in[3 * kWarp], in[4 * kWarp], in[5 * kWarp]};
+            x.p = V3{in[6 * kWarp], in[7 * kWarp], in[8 * kWarp]};
+            x.e1 = V3{in[9 * kWarp], in[10 * kWarp], in[11 * kWarp]};
+            x.e2 = V3{in[12 * kWarp], in[13 * kWarp], in[14 * kWarp]};
+            x.R02 = 0.0; x.R12 = 0.0;
+            x.R22 = in[15 * kWarp];
+            x.p0 = p0; x.n1 = n1; x.n2 = n2;
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty0 + 8 * st);   // the stage may be refilled
+            Result r;
+            eval_contact<M_WRENCH>(x, q, r);
+            if (on) {
+                const V3 df = r.force - V3{a.ref[0], a.ref[1], a.ref[2]};
+                const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
+                acc = acc + (a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
+                             a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
+            }
+        }
+        if (on) a.chain_cost[c * C + k] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // J^T * wrench accumulation
 // ------------------------------------------------------------------------------------------------
 

@@ -133,6 +133,16 @@ def sys_only():
                     row(f"split={split} rho={rho} out_mask={mask}", ms, n, bytes_per)
                     del cls
         os.environ.pop("BLF_CCM_TUNE_ROLLOUT_SPLIT", None)
+        for ws, label in ((1, "warp-specialised (1 producer + 3 consumers)"), (2, "plain / split (auto)")):
+            bs = make_batch(BLF_CCM_TUNE_ROLLOUT_WS=ws)
+            rbs = RolloutBatch(bs)
+            for rho in (0.0, 0.01, 2.0):
+                cls = [rbs.prepare(nr, feet, H, 0.01, rho, tw, pos, rot, null, [0, 0, 30., 0, 0, 0],
+                                   [1., 10.], mask=0)[0] for tw in tws]
+                ms = timeit(lambda i: cls[i % 2](), iters=50, warm=5)
+                row(f"cost-only rho={rho} {label}", ms, n, 48)
+                del cls
+        os.environ.pop("BLF_CCM_TUNE_ROLLOUT_WS", None)
         del tws, pos, rot, null
         torch.cuda.empty_cache()
     # --- J^T wrench --------------------------------------------------------------------------------
