@@ -417,18 +417,23 @@ ccm_rollout_ws_kernel(const __grid_constant__ RolloutArgs a)
 
     if (warp == 0) {
         // ---------------- producer: twists -> pose trajectory -> stages --------------------------
+        // (kept lean: this warp's instruction stream IS the critical path of the kernel --
+        //  incremental pointers and stage indices, 128-bit shared-memory stores)
         const uint32_t ring_s = ptx::smem_addr(ring) + static_cast<uint32_t>(lane) * 8u;
-        auto issue = [&](int t) {
-            if (on && t < H) {
-                const uint32_t dst = ring_s + static_cast<uint32_t>((t & (D - 1)) * 6 * kWarp * 8);
-                const long long src = static_cast<long long>(t) * a.chains + c;
+        const double* src[6];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, a.tw[j] + src);
+        for (int j = 0; j < 6; ++j) src[j] = a.tw[j] + c;
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            if (on && t < H) {
+                const uint32_t dst = ring_s + static_cast<uint32_t>(t * 6 * kWarp * 8);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, src[j] + static_cast<long long>(t) * a.chains);
             }
             ptx::cp_async_commit();
-        };
+        }
 #pragma unroll
-        for (int t = 0; t < D; ++t) issue(t);
+        for (int j = 0; j < 6; ++j) src[j] += static_cast<long long>(D) * a.chains;   // step t + D
         Pose s{};
         if (on) {
             s.p = V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)};
@@ -436,27 +441,46 @@ ccm_rollout_ws_kernel(const __grid_constant__ RolloutArgs a)
             s.c1 = V3{__ldg(a.rot0[1] + c), __ldg(a.rot0[4] + c), __ldg(a.rot0[7] + c)};
             s.c2 = V3{__ldg(a.rot0[2] + c), __ldg(a.rot0[5] + c), __ldg(a.rot0[8] + c)};
         }
+        int st = 0;                 // stage of step t
+        uint32_t empty_parity = 0;  // completion of empty[st] to wait for: (t / S - 1) & 1
+        bool wrapped = false;
+        int slot = 0;               // twist ring slot of step t
         for (int t = 0; t < H; ++t) {
-            const int st = t % S;
             ptx::cp_async_wait<D - 1>();
             V3 v{}, w{};
+            const double* r = ring + slot * 6 * kWarp + lane;
             if (on) {
-                const double* r = ring + (t & (D - 1)) * 6 * kWarp + lane;
                 v = V3{r[0], r[kWarp], r[2 * kWarp]};
                 w = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
             }
-            if (t >= S) ptx::mbar_wait(empty0 + 8 * st, ((t / S) - 1) & 1);   // stage consumed
-            double* o = stages + st * kWsStageDoubles + lane;
-            o[0 * kWarp] = v.x;  o[1 * kWarp] = v.y;  o[2 * kWarp] = v.z;
-            o[3 * kWarp] = w.x;  o[4 * kWarp] = w.y;  o[5 * kWarp] = w.z;
-            o[6 * kWarp] = s.p.x;  o[7 * kWarp] = s.p.y;  o[8 * kWarp] = s.p.z;
-            o[9 * kWarp] = s.c0.x; o[10 * kWarp] = s.c0.y; o[11 * kWarp] = s.c0.z;
-            o[12 * kWarp] = s.c1.x; o[13 * kWarp] = s.c1.y; o[14 * kWarp] = s.c1.z;
-            o[15 * kWarp] = s.c2.z;
+            if (wrapped) ptx::mbar_wait(empty0 + 8 * st, empty_parity);   // stage consumed
+            double2* o = reinterpret_cast<double2*>(stages + st * kWsStageDoubles) + lane;
+            o[0 * kWarp] = make_double2(v.x, v.y);
+            o[1 * kWarp] = make_double2(v.z, w.x);
+            o[2 * kWarp] = make_double2(w.y, w.z);
+            o[3 * kWarp] = make_double2(s.p.x, s.p.y);
+            o[4 * kWarp] = make_double2(s.p.z, s.c0.x);
+            o[5 * kWarp] = make_double2(s.c0.y, s.c0.z);
+            o[6 * kWarp] = make_double2(s.c1.x, s.c1.y);
+            o[7 * kWarp] = make_double2(s.c1.z, s.c2.z);
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(full0 + 8 * st);
             kin_euler_step<BAUM>(s, v, w, a.half_rho, a.dT);
-            issue(t + D);
+            // refill the twist slot just consumed with step t + D
+            if (on && t + D < H) {
+                const uint32_t dst = ring_s + static_cast<uint32_t>(slot * 6 * kWarp * 8);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, src[j]);
+            }
+            ptx::cp_async_commit();
+#pragma unroll
+            for (int j = 0; j < 6; ++j) src[j] += a.chains;
+            slot = (slot + 1) & (D - 1);
+            if (++st == S) {
+                st = 0;
+                empty_parity = wrapped ? (empty_parity ^ 1u) : 0u;
+                wrapped = true;
+            }
         }
         if (on && a.write_final) {
             a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
@@ -479,21 +503,24 @@ ccm_rollout_ws_kernel(const __grid_constant__ RolloutArgs a)
                              __ldg(a.prm[3] + c));
         }
         double acc = 0.0;
+        int st = k;                 // stage of step t = k, k + 3, ... (C divides S)
+        uint32_t parity = 0;
         for (int t = k; t < H; t += C) {
-            const int st = t % S;
-            ptx::mbar_wait(full0 + 8 * st, (t / S) & 1);
-            const double* in = stages + st * kWsStageDoubles + lane;
-            State x;
-            x.v = V3{in[0 * kWarp], in[1 * kWarp], in[2 * kWarp]};
-            x.w = V3{in[3 * kWarp], in[4 * kWarp], in[5 * kWarp]};
-            x.p = V3{in[6 * kWarp], in[7 * kWarp], in[8 * kWarp]};
-            x.e1 = V3{in[9 * kWarp], in[10 * kWarp], in[11 * kWarp]};
-            x.e2 = V3{in[12 * kWarp], in[13 * kWarp], in[14 * kWarp]};
-            x.R02 = 0.0; x.R12 = 0.0;
-            x.R22 = in[15 * kWarp];
-            x.p0 = p0; x.n1 = n1; x.n2 = n2;
+            ptx::mbar_wait(full0 + 8 * st, parity);
+            const double2* in = reinterpret_cast<const double2*>(stages + st * kWsStageDoubles) + lane;
+            const double2 a0 = in[0 * kWarp], a1 = in[1 * kWarp], a2 = in[2 * kWarp], a3 = in[3 * kWarp];
+            const double2 a4 = in[4 * kWarp], a5 = in[5 * kWarp], a6 = in[6 * kWarp], a7 = in[7 * kWarp];
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(empty0 + 8 * st);   // the stage may be refilled
+            State x;
+            x.v = V3{a0.x, a0.y, a1.x};
+            x.w = V3{a1.y, a2.x, a2.y};
+            x.p = V3{a3.x, a3.y, a4.x};
+            x.e1 = V3{a4.y, a5.x, a5.y};
+            x.e2 = V3{a6.x, a6.y, a7.x};
+            x.R02 = 0.0; x.R12 = 0.0;
+            x.R22 = a7.y;
+            x.p0 = p0; x.n1 = n1; x.n2 = n2;
             Result r;
             eval_contact<M_WRENCH>(x, q, r);
             if (on) {
@@ -501,6 +528,11 @@ ccm_rollout_ws_kernel(const __grid_constant__ RolloutArgs a)
                 const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
                 acc = acc + (a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
                              a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
+            }
+            st += C;
+            if (st >= S) {
+                st -= S;
+                parity ^= 1u;
             }
         }
         if (on) a.chain_cost[c * C + k] = acc;
