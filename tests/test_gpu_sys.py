@@ -649,3 +649,43 @@ def test_non_finite_inputs_stay_local_and_never_win_the_argmin(torch, batch, so)
     allnan = rb.run(nr, feet, H, 0.01, 0.5, _dev(torch, np.full_like(tw, np.nan)), _dev(torch, pos0),
                     _dev(torch, rot0), _dev(torch, null), ref_w, wts, mask=0)
     assert batch.decode_best(allnan["best"])[1] == -1
+
+
+@pytest.mark.parametrize("het,rho,nr,feet,H", [(True, 3.0, 100, 2, 31), (False, 0.0, 33, 1, 2),
+                                               (True, 0.0, 10, 3, 10), (False, 0.5, 700, 2, 64)])
+def test_rollout_warp_specialised_variant_vs_oracle(torch, so, het, rho, nr, feet, H):
+    """ccm_rollout_ws_kernel (producer + three consumers, mbarrier hand-over) forced for every
+    template instance, incl. horizons shorter than the stage ring and ragged tiles."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    from bipedal_locomotion_framework_b200.system import RolloutBatch
+    chains = nr * feet
+    st = syn.make_states(chains, seed=88, heterogeneous=het)
+    tw = np.ascontiguousarray(syn.make_states(H * chains, seed=89)["twists"].T)
+    pos0 = np.ascontiguousarray(st["poses"][:, :3].T)
+    rot0 = np.ascontiguousarray(st["poses"][:, 3:].T)
+    null = np.ascontiguousarray(st["null_poses"].T)
+    prm = np.ascontiguousarray(st["params"].T) if het else None
+    ref_w, wts = np.array([0.0, 0.0, 30.0, 0.1, -0.1, 0.0]), np.array([1.0, 25.0])
+    ref = so.rollout(nr, feet, H, 0.01, rho, tw, pos0, rot0, null, param_planes=prm,
+                     uniform=syn.REFERENCE_TEST_PARAMS, mask=0, wrench_ref=ref_w, weights=wts)
+    os.environ["BLF_CCM_TUNE_ROLLOUT_WS"] = "1"
+    try:
+        b = ContinuousContactModelBatch(0)
+    finally:
+        os.environ.pop("BLF_CCM_TUNE_ROLLOUT_WS", None)
+    b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    launches = b.handle.launch_count
+    out = RolloutBatch(b).run(nr, feet, H, 0.01, rho, _dev(torch, tw), _dev(torch, pos0),
+                              _dev(torch, rot0), _dev(torch, null), ref_w, wts,
+                              param_planes=_dev(torch, prm), mask=0, want_final=True)
+    assert b.handle.launch_count - launches == 2
+    cost = out["cost"].cpu().numpy()
+    assert np.all(rel(cost[:, None], ref["cost"][:, None]) <= TOL)
+    assert rel(out["final_pos"].cpu().numpy().T, ref["pos"].T).max() <= TOL
+    assert rel(out["final_rot"].cpu().numpy().T, ref["rot"].T).max() <= TOL
+    c, idx = b.decode_best(out["best"])
+    assert idx == int(np.argmin(cost)) and c == cost.min()
+    out2 = RolloutBatch(b).run(nr, feet, H, 0.01, rho, _dev(torch, tw), _dev(torch, pos0),
+                               _dev(torch, rot0), _dev(torch, null), ref_w, wts,
+                               param_planes=_dev(torch, prm), mask=0)
+    assert np.array_equal(out2["cost"].cpu().numpy(), cost)     # deterministic
