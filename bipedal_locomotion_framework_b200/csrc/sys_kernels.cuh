@@ -17,8 +17,8 @@
 //                             TMA bulk copies through a per-warp ring, lanes own columns.
 //
 // Derivation differs from the oracle on purpose: Rdot's columns are w x c_j (not -(c_j x w) through
-// a matrix), R R^T is accumulated as a sum of column outer products, and its inverse uses the
-// symmetric adjugate (6 cofactors) instead of Eigen's general 3x3 formula.
+// a matrix), and the Baumgarte term uses (R R^T)^-1 R = R^-T = cofactors of R over det R instead of
+// forming R R^T and inverting it with Eigen's general 3x3 formula.
 #pragma once
 
 #include "ccm_kernels.cuh"
@@ -34,34 +34,21 @@ struct Pose {
     V3 c0, c1, c2;  // columns of R
 };
 
-// d_j += rho/2 (G^-1 - I) c_j,  G = R R^T = sum_j c_j c_j^T (symmetric; symmetric adjugate inverse)
+// d_j += rho/2 ((R R^T)^-1 R - R).col(j).  (R R^T)^-1 R = R^-T, and the columns of R^-T are the
+// cross products of R's columns over det R:  R^-T = [c1 x c2 | c2 x c0 | c0 x c1] / (c0 . (c1 x c2)).
+// Three cross products, one determinant and one division instead of forming R R^T, its adjugate
+// and a 3x3 product (about half the FP64 instructions of the first version, which matters: this
+// sits on the sequential chain of every rollout step).  Singular R gives inf/NaN, as the reference.
 __device__ __forceinline__ void kin_baumgarte_add(const Pose& s, double half_rho, V3& d0, V3& d1,
                                                   V3& d2)
 {
-    const double gxx = s.c0.x * s.c0.x + s.c1.x * s.c1.x + s.c2.x * s.c2.x;
-    const double gxy = s.c0.x * s.c0.y + s.c1.x * s.c1.y + s.c2.x * s.c2.y;
-    const double gxz = s.c0.x * s.c0.z + s.c1.x * s.c1.z + s.c2.x * s.c2.z;
-    const double gyy = s.c0.y * s.c0.y + s.c1.y * s.c1.y + s.c2.y * s.c2.y;
-    const double gyz = s.c0.y * s.c0.z + s.c1.y * s.c1.z + s.c2.y * s.c2.z;
-    const double gzz = s.c0.z * s.c0.z + s.c1.z * s.c1.z + s.c2.z * s.c2.z;
-    const double axx = gyy * gzz - gyz * gyz;
-    const double axy = gxz * gyz - gxy * gzz;
-    const double axz = gxy * gyz - gxz * gyy;
-    const double ayy = gxx * gzz - gxz * gxz;
-    const double ayz = gxy * gxz - gxx * gyz;
-    const double azz = gxx * gyy - gxy * gxy;
-    const double inv = 1.0 / (gxx * axx + gxy * axy + gxz * axz);
-    // M = rho/2 (G^-1 - I)
-    const double mxx = half_rho * (axx * inv - 1.0), mxy = half_rho * (axy * inv);
-    const double mxz = half_rho * (axz * inv), myy = half_rho * (ayy * inv - 1.0);
-    const double myz = half_rho * (ayz * inv), mzz = half_rho * (azz * inv - 1.0);
-    auto mul = [&](const V3& c) {
-        return V3{mxx * c.x + mxy * c.y + mxz * c.z, mxy * c.x + myy * c.y + myz * c.z,
-                  mxz * c.x + myz * c.y + mzz * c.z};
-    };
-    d0 = d0 + mul(s.c0);
-    d1 = d1 + mul(s.c1);
-    d2 = d2 + mul(s.c2);
+    const V3 k0 = cross(s.c1, s.c2), k1 = cross(s.c2, s.c0), k2 = cross(s.c0, s.c1);
+    const double det = s.c0.x * k0.x + s.c0.y * k0.y + s.c0.z * k0.z;
+    const double g = half_rho / det;          // rho/2 / det R
+    // d_j += g * k_j - half_rho * c_j
+    d0 = d0 + (g * k0 - half_rho * s.c0);
+    d1 = d1 + (g * k1 - half_rho * s.c1);
+    d2 = d2 + (g * k2 - half_rho * s.c2);
 }
 
 template <bool BAUM>
