@@ -585,12 +585,29 @@ def run_large(args):
                                                  [1.0, 10.0], param_planes=prm, mask=FULL,
                                                  index_base=first, out=out, want_cost=False)
 
+        peer = None
+        if world > 1 and not args.nccl_argmin:
+            try:
+                peer = sharding.PeerArgmin(batch, world, rank, dist)
+            except Exception as e:
+                print(f"bench.py: peer-memory mailbox unavailable ({e}); NCCL all-gather used", file=sys.stderr)
+        if world > 1:   # the choice must be the same on every rank
+            flag = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                peer = None
+        if peer is not None:
+            peer.fuse_into_rollouts(True)   # the exchange runs inside the cost-reduction kernel
+
         def step():
             call()
             if world > 1:
+                if peer is not None:
+                    return peer.global_best
                 return batch.argmin_pairs(sharding.all_gather_pairs(best, world, dist))
             return best
     else:
+        peer = None
         call, _ = batch.prepare_soa(planes, None, FULL, out=out)
 
         def step():
@@ -653,7 +670,10 @@ def run_large(args):
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (device-generated)",
             "config": {"workload": name, "evals_per_step": total, "evals_per_step_per_gpu": n,
-                       "parallelism": f"sharded x{world}" + (", NCCL all_gather 16 B/rank" if args.workload == "config4" and world > 1 else ""),
+                       "parallelism": f"sharded x{world}" + (
+                           (", arg-min pair over the NVLink peer-memory mailbox (fused into the reduction kernel)"
+                            if peer is not None else ", NCCL all_gather 16 B/rank")
+                           if args.workload == "config4" and world > 1 else ""),
                        "l2": "per-GPU working set >> 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
                          "frac": per_gpu_gbs / peak, "traffic": None,
