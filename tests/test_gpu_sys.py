@@ -291,6 +291,11 @@ def test_generalized_force_matches_exact(torch, batch, g, tag):
     (3, 38, 3_000, True, True, True),       # 32 % 3 != 0, two column chunks
     (32, 128, 65, False, True, True),       # maxima
     (5, 1, 777, False, True, True),         # single column
+    (2, 12, 20_001, True, True, True),      # narrow Jacobian: two contacts per warp iteration
+    (3, 16, 5_000, False, False, True),     # ... on the direct (8-byte aligned) path
+    (1, 9, 33_333, False, True, False),     # ... one contact per system
+    (7, 8, 4_001, True, True, True),        # four contacts per iteration, 32 % 7 != 0
+    (32, 5, 100, False, True, True),        # a whole warp is one system
 ])
 def test_generalized_force_vs_oracle(torch, batch, so, cps, ncols, ns, het, aligned, with_base):
     from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
@@ -417,7 +422,8 @@ def test_rollout_no_out_of_bounds_canaries(torch, batch, nr, feet, H, het, rho):
             assert bool(torch.isfinite(t_).all())            # no NaN guard was read
 
 
-@pytest.mark.parametrize("ns,cps,ncols", [(1, 1, 1), (3, 2, 29), (11, 3, 33), (5, 32, 128), (40, 7, 64)])
+@pytest.mark.parametrize("ns,cps,ncols", [(1, 1, 1), (3, 2, 29), (11, 3, 33), (5, 32, 128), (40, 7, 64),
+                                          (9, 2, 6), (13, 3, 12), (2, 32, 16)])
 def test_generalized_force_no_out_of_bounds_canaries(torch, batch, ns, cps, ncols):
     from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
     gf = GeneralizedForceBatch(batch)

@@ -146,7 +146,8 @@ def sys_only():
         del tws, pos, rot, null
         torch.cuda.empty_cache()
     # --- J^T wrench --------------------------------------------------------------------------------
-    for ns, cps, ncols in ((409600, 2, 29), (1 << 21, 2, 29), (1 << 20, 4, 38), (1 << 21, 1, 6)):
+    for ns, cps, ncols in ((409600, 2, 29), (1 << 21, 2, 29), (1 << 20, 4, 38), (1 << 21, 1, 6),
+                           (1 << 21, 2, 6), (1 << 20, 2, 12)):
         n = ns * cps
         st = syn.make_states(min(n, 1 << 18), seed=49)
         reps = (n + st["n"] - 1) // st["n"]
