@@ -690,19 +690,18 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     }
 }
 
-// Narrow Jacobians (ncols <= 16).  With one contact per warp iteration only ncols of the 32 lanes
-// work and every contact pays one mbarrier round trip for a few hundred bytes (6 columns: 51 % of
-// HBM).  Here (a) the Jacobians of ALL the warp's contacts -- they are consecutive in memory --
-// arrive with ONE bulk copy (<= 32 x 768 B) on one mbarrier, and (b) the warp is cut into G = 2
-// (ncols <= 16) or 4 (ncols <= 8) lane groups that take G consecutive contacts at once; the
-// group-0 lanes then add the G products to the system's accumulator IN CONTACT ORDER (shuffles),
-// so the summation order is the reference's.
+// Narrow Jacobians (ncols <= 16): with one contact per warp iteration only ncols of the 32 lanes
+// work (6 columns: 51 % of HBM).  Here the warp is cut into G = 2 (ncols <= 16) or 4 (ncols <= 8)
+// lane groups that take G consecutive contacts at once -- each group waits for its own contact's
+// Jacobian stage and forms its own J^T w -- and the group-0 lanes then add the G products to the
+// system's accumulator IN CONTACT ORDER (shuffles), so the summation order is the reference's.
 template <bool HET, int G>
 __global__ void __launch_bounds__(128)
 ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
 {
     constexpr unsigned LIVE = live_planes(M_WRENCH);
     constexpr int W = kWarp / G;                 // lanes per group
+    constexpr int NST = 2 * G < 4 ? 4 : 2 * G;   // Jacobian stages in flight per warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -713,29 +712,33 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
     const int cps = a.cps, ncols = a.ncols;
     const int ncont = nsys * cps;
     const long long c0 = sys0 * cps;
-    const int jdoubles = 6 * ncols;              // one contact's Jacobian
+    const uint32_t jbytes = 48u * ncols;
     const bool bulk = a.jac_bulk != 0;
     const int grp = lane / W, col = lane % W;
     const bool colon = col < ncols;
 
-    // per warp: 32 Jacobians | 32 wrenches (32 x 48 B) | one mbarrier
-    const int jregion = (kWarp * jdoubles * 8 + 127) / 128 * 128;
-    unsigned char* ws = smem_raw + static_cast<size_t>(warp) * (jregion + kWarp * 48 + 128);
-    const double* jsm = reinterpret_cast<const double*>(ws);
-    double* wsm = reinterpret_cast<double*>(ws + jregion);
-    const uint32_t bar = ptx::smem_addr(ws + jregion + kWarp * 48);
-    const double* jac0 = a.jac + c0 * jdoubles;
+    const int per_warp = NST * a.stage_bytes + kWarp * 48 + 128;
+    unsigned char* ws = smem_raw + static_cast<size_t>(warp) * per_warp;
+    double* wsm = reinterpret_cast<double*>(ws + NST * a.stage_bytes);
+    const uint32_t bar0 = ptx::smem_addr(ws + NST * a.stage_bytes + kWarp * 48);
+    const uint32_t stage0 = ptx::smem_addr(ws);
+    const double* jac0 = a.jac + c0 * 6 * ncols;
     ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
     if (bulk && lane == 0) {
-        ptx::mbar_init(bar, 1);
+#pragma unroll
+        for (int s = 0; s < NST; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
         ptx::fence_mbar_init();
     }
     ptx::grid_dep_wait();
     if (bulk) {
         if (lane == 0) {
-            const uint32_t bytes = static_cast<uint32_t>(ncont) * jdoubles * 8u;
-            ptx::mbar_arrive_expect_tx(bar, bytes);
-            ptx::bulk_g2s(ptx::smem_addr(ws), jac0, bytes, bar);
+#pragma unroll
+            for (int s = 0; s < NST; ++s)
+                if (s < ncont) {
+                    ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
+                    ptx::bulk_g2s(stage0 + s * a.stage_bytes, jac0 + static_cast<long long>(s) * 6 * ncols,
+                                  jbytes, bar0 + 8 * s);
+                }
         }
         __syncwarp();
     }
@@ -778,7 +781,6 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
         o[2] = make_double2(r.torque.y, r.torque.z);
     }
     __syncwarp();
-    if (bulk) ptx::mbar_wait(bar, 0);
 
     // ---- waves of G contacts ------------------------------------------------------------------
     int sys = 0, cin = 0;          // system / contact-in-system of the next contact to accumulate
@@ -786,16 +788,40 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
     for (int k0 = 0; k0 < ncont; k0 += G) {
         const int k = k0 + grp;
         double t = 0.0;
-        if (k < ncont && colon) {
-            const double* J = (bulk ? jsm : jac0) + k * jdoubles + col;
-            const double2* wv = reinterpret_cast<const double2*>(wsm) + k * 3;
-            const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
-            t = J[0] * w01.x;
-            t += J[ncols] * w01.y;
-            t += J[2 * ncols] * w23.x;
-            t += J[3 * ncols] * w23.y;
-            t += J[4 * ncols] * w45.x;
-            t += J[5 * ncols] * w45.y;
+        if (k < ncont) {
+            const int s = k % NST;
+            const double* J;
+            if (bulk) {
+                ptx::mbar_wait(bar0 + 8 * s, (k / NST) & 1);
+                J = reinterpret_cast<const double*>(ws + s * a.stage_bytes) + col;
+            } else {
+                J = jac0 + static_cast<long long>(k) * 6 * ncols + col;
+            }
+            if (colon) {
+                const double2* wv = reinterpret_cast<const double2*>(wsm) + k * 3;
+                const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
+                t = J[0] * w01.x;
+                t += J[ncols] * w01.y;
+                t += J[2 * ncols] * w23.x;
+                t += J[3 * ncols] * w23.y;
+                t += J[4 * ncols] * w45.x;
+                t += J[5 * ncols] * w45.y;
+            }
+        }
+        if (bulk) {
+            __syncwarp();   // every group is done with its stage
+            if (lane == 0) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int kn = k0 + g + NST;
+                    if (kn < ncont) {
+                        const int s = kn % NST;
+                        ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
+                        ptx::bulk_g2s(stage0 + s * a.stage_bytes,
+                                      jac0 + static_cast<long long>(kn) * 6 * ncols, jbytes, bar0 + 8 * s);
+                    }
+                }
+            }
         }
         // ordered accumulation by the group-0 lanes
 #pragma unroll
