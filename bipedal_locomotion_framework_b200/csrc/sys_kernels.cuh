@@ -690,157 +690,10 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     }
 }
 
-// Narrow Jacobians (ncols <= 16): with one contact per warp iteration only ncols of the 32 lanes
-// work (6 columns: 51 % of HBM).  Here the warp is cut into G = 2 (ncols <= 16) or 4 (ncols <= 8)
-// lane groups that take G consecutive contacts at once -- each group waits for its own contact's
-// Jacobian stage and forms its own J^T w -- and the group-0 lanes then add the G products to the
-// system's accumulator IN CONTACT ORDER (shuffles), so the summation order is the reference's.
-template <bool HET, int G>
-__global__ void __launch_bounds__(128)
-ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
-{
-    constexpr unsigned LIVE = live_planes(M_WRENCH);
-    constexpr int W = kWarp / G;                 // lanes per group
-    constexpr int NST = 2 * G < 4 ? 4 : 2 * G;   // Jacobian stages in flight per warp
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
-    const long long sys0 = wid * a.sys_per_warp;
-    if (sys0 >= a.n_systems) return;  // warp-uniform
-    const int nsys = static_cast<int>(min64(a.sys_per_warp, a.n_systems - sys0));
-    const int cps = a.cps, ncols = a.ncols;
-    const int ncont = nsys * cps;
-    const long long c0 = sys0 * cps;
-    const uint32_t jbytes = 48u * ncols;
-    const bool bulk = a.jac_bulk != 0;
-    const int grp = lane / W, col = lane % W;
-    const bool colon = col < ncols;
-
-    const int per_warp = NST * a.stage_bytes + kWarp * 48 + 128;
-    unsigned char* ws = smem_raw + static_cast<size_t>(warp) * per_warp;
-    double* wsm = reinterpret_cast<double*>(ws + NST * a.stage_bytes);
-    const uint32_t bar0 = ptx::smem_addr(ws + NST * a.stage_bytes + kWarp * 48);
-    const uint32_t stage0 = ptx::smem_addr(ws);
-    const double* jac0 = a.jac + c0 * 6 * ncols;
-    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
-    if (bulk && lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NST; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
-        ptx::fence_mbar_init();
-    }
-    ptx::grid_dep_wait();
-    if (bulk) {
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < NST; ++s)
-                if (s < ncont) {
-                    ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
-                    ptx::bulk_g2s(stage0 + s * a.stage_bytes, jac0 + static_cast<long long>(s) * 6 * ncols,
-                                  jbytes, bar0 + 8 * s);
-                }
-        }
-        __syncwarp();
-    }
-
-    // ---- wrench of this lane's contact (one contact per lane, as in the unpacked kernel) -------
-    const bool on = lane < ncont;
-    const long long i = c0 + lane;
-    double x[30] = {};
-#pragma unroll
-    for (int pl = 0; pl < 30; ++pl)
-        if (LIVE & (1u << pl)) x[pl] = on ? __ldcs(a.in[pl] + i) : 0.0;
-    Prm q = a.uni;
-    if constexpr (HET) {
-        const double l = on ? __ldcs(a.prm[0] + i) : 0.0, w = on ? __ldcs(a.prm[1] + i) : 0.0;
-        const double k = on ? __ldcs(a.prm[2] + i) : 0.0, b = on ? __ldcs(a.prm[3] + i) : 0.0;
-        q = make_prm(l, w, k, b);
-    }
-    State st;
-    st.v = V3{x[0], x[1], x[2]};
-    st.w = V3{x[3], x[4], x[5]};
-    st.p = V3{x[6], x[7], x[8]};
-    st.e1 = V3{x[9], x[12], x[15]};
-    st.e2 = V3{x[10], x[13], x[16]};
-    st.R02 = 0.0; st.R12 = 0.0;
-    st.R22 = x[17];
-    st.p0 = V3{x[18], x[19], x[20]};
-    st.n1 = V3{x[21], x[24], x[27]};
-    st.n2 = V3{x[22], x[25], x[28]};
-    Result r;
-    eval_contact<M_WRENCH>(st, q, r);
-    if (a.want_wrench && on) {
-        __stcs(a.wrench[0] + i, r.force.x); __stcs(a.wrench[1] + i, r.force.y);
-        __stcs(a.wrench[2] + i, r.force.z); __stcs(a.wrench[3] + i, r.torque.x);
-        __stcs(a.wrench[4] + i, r.torque.y); __stcs(a.wrench[5] + i, r.torque.z);
-    }
-    {
-        double2* o = reinterpret_cast<double2*>(wsm) + lane * 3;
-        o[0] = make_double2(r.force.x, r.force.y);
-        o[1] = make_double2(r.force.z, r.torque.x);
-        o[2] = make_double2(r.torque.y, r.torque.z);
-    }
-    __syncwarp();
-
-    // ---- waves of G contacts ------------------------------------------------------------------
-    int sys = 0, cin = 0;          // system / contact-in-system of the next contact to accumulate
-    double acc = 0.0;              // group-0 lanes: the current system's column `col`
-    for (int k0 = 0; k0 < ncont; k0 += G) {
-        const int k = k0 + grp;
-        double t = 0.0;
-        if (k < ncont) {
-            const int s = k % NST;
-            const double* J;
-            if (bulk) {
-                ptx::mbar_wait(bar0 + 8 * s, (k / NST) & 1);
-                J = reinterpret_cast<const double*>(ws + s * a.stage_bytes) + col;
-            } else {
-                J = jac0 + static_cast<long long>(k) * 6 * ncols + col;
-            }
-            if (colon) {
-                const double2* wv = reinterpret_cast<const double2*>(wsm) + k * 3;
-                const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
-                t = J[0] * w01.x;
-                t += J[ncols] * w01.y;
-                t += J[2 * ncols] * w23.x;
-                t += J[3 * ncols] * w23.y;
-                t += J[4 * ncols] * w45.x;
-                t += J[5 * ncols] * w45.y;
-            }
-        }
-        if (bulk) {
-            __syncwarp();   // every group is done with its stage
-            if (lane == 0) {
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const int kn = k0 + g + NST;
-                    if (kn < ncont) {
-                        const int s = kn % NST;
-                        ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
-                        ptx::bulk_g2s(stage0 + s * a.stage_bytes,
-                                      jac0 + static_cast<long long>(kn) * 6 * ncols, jbytes, bar0 + 8 * s);
-                    }
-                }
-            }
-        }
-        // ordered accumulation by the group-0 lanes
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const double tg = __shfl_sync(0xffffffffu, t, g * W + col);
-            if (k0 + g < ncont) {   // warp-uniform
-                const long long row = (sys0 + sys) * ncols + col;
-                if (grp == 0 && colon) {
-                    if (cin == 0) acc = a.base ? __ldcs(a.base + row) : 0.0;
-                    acc = acc + tg;
-                    if (cin == cps - 1) __stcs(a.out + row, acc);
-                }
-                if (++cin == cps) {
-                    cin = 0;
-                    ++sys;
-                }
-            }
-        }
-    }
-}
+// Narrow Jacobians (ncols <= 16) reach only 50-90 % of HBM with this kernel.  A lane-packed variant
+// (2 or 4 contacts per warp iteration, ordered accumulation through shuffles) was built and measured
+// within +-5 % of it (6 columns: 52.0 vs 49.6 %; 12 columns: 77.4 vs 80.3 %), and one bulk copy per
+// warp for all its Jacobians was slower (34-46 %): idle lanes are not what bounds that shape, the
+// per-contact hand-over is.  Both were removed again.
 
 }  // namespace blfccm
