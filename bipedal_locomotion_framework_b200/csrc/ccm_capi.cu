@@ -83,6 +83,7 @@ struct blf_ccm_handle {
                                  // (looping kernels only); default = one tile per warp
     int tune_rollout_split = 0;  // BLF_CCM_TUNE_ROLLOUT_SPLIT>0: warps per tile of the fused rollout
     int tune_rollout_ws = 0;     // BLF_CCM_TUNE_ROLLOUT_WS: 1 force / 2 forbid the warp-specialised rollout
+    int tune_no_rows = 0;        // BLF_CCM_TUNE_NO_ROWS=1: J^T wrench without base/out row staging
     int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
@@ -136,6 +137,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");
+    h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
     h->tune_rollout_ws = env_int("BLF_CCM_TUNE_ROLLOUT_WS");
     CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
     CUDA_TRY(cudaMalloc(&h->counter, sizeof(unsigned int)));

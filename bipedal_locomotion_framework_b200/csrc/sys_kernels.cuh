@@ -548,6 +548,7 @@ struct GenForceArgs {
     int jac_bulk;          // jac 16-byte aligned -> TMA ring; else direct loads
     int want_wrench;
     int stage_bytes;       // per-stage shared-memory bytes (48*ncols rounded up to 128)
+    int row_bytes;         // > 0: per-warp shared-memory bytes for the warp's base / out rows
 };
 
 // NCH = ceil(ncols / 32): column chunks a lane owns (compile-time so dead chunks cost nothing).
@@ -572,22 +573,36 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     const uint32_t jbytes = 48u * ncols;       // one contact's Jacobian
     const bool bulk = a.jac_bulk != 0;
 
-    // per warp: kGfStages Jacobian stages | 32 wrenches (32 x 48 B) | kGfStages mbarriers
-    const int per_warp = kGfStages * a.stage_bytes + kWarp * 48 + 128;
+    // per warp: kGfStages Jacobian stages | 32 wrenches (32 x 48 B) | kGfStages + 1 mbarriers |
+    //           the warp's base / out rows (row staging, see below)
+    const int per_warp = kGfStages * a.stage_bytes + kWarp * 48 + 128 + a.row_bytes;
     unsigned char* ws = smem_raw + static_cast<size_t>(warp) * per_warp;
     double* wsm = reinterpret_cast<double*>(ws + kGfStages * a.stage_bytes);
     const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * a.stage_bytes + kWarp * 48);
+    const uint32_t rbar = bar0 + 8 * kGfStages;
+    double* rows = reinterpret_cast<double*>(ws + kGfStages * a.stage_bytes + kWarp * 48 + 128);
     const uint32_t stage0 = ptx::smem_addr(ws);
     const double* jac0 = a.jac + c0 * 6 * ncols;
+    // Row staging.  The warp's systems own CONSECUTIVE rows of base and out.  Read per system they
+    // cost a global-load latency each (acc = base + ... waits for it), which is what bounded narrow
+    // Jacobians at ~50 % of HBM; staged they are one bulk copy in and one bulk copy out per warp.
+    // Needs 16-byte aligned blocks (else the direct per-system accesses are used).
+    const long long row0 = sys0 * ncols;
+    const uint32_t rbytes = static_cast<uint32_t>(nsys) * ncols * 8u;
+    const bool staged = a.row_bytes > 0 && ((row0 | (static_cast<long long>(nsys) * ncols)) & 1) == 0;
     ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
-    if (bulk && lane == 0) {
+    if (lane == 0 && (bulk || staged)) {
 #pragma unroll
-        for (int s = 0; s < kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s <= kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
         ptx::fence_mbar_init();
     }
     ptx::grid_dep_wait();
-    if (bulk) {
-        if (lane == 0) {
+    if (lane == 0) {
+        if (staged && a.base) {
+            ptx::mbar_arrive_expect_tx(rbar, rbytes);
+            ptx::bulk_g2s(ptx::smem_addr(rows), a.base + row0, rbytes, rbar);
+        }
+        if (bulk) {
 #pragma unroll
             for (int s = 0; s < kGfStages; ++s)
                 if (s < ncont) {
@@ -596,8 +611,8 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
                                   jbytes, bar0 + 8 * s);
                 }
         }
-        __syncwarp();
     }
+    __syncwarp();
 
     // ---- wrench of this lane's contact --------------------------------------------------------
     const bool on = lane < ncont;
@@ -642,13 +657,17 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     bool mine[NCH];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) mine[ch] = ch * kWarp + lane < ncols;
+    if (staged && a.base) ptx::mbar_wait(rbar, 0);
     int k = 0;
     for (int sys = 0; sys < nsys; ++sys) {
         const long long row = (sys0 + sys) * ncols + lane;
+        double* srow = rows + sys * ncols + lane;
         double acc[NCH];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch)
-            acc[ch] = (mine[ch] && a.base) ? __ldcs(a.base + row + ch * kWarp) : 0.0;
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (staged) acc[ch] = (mine[ch] && a.base) ? srow[ch * kWarp] : 0.0;
+            else acc[ch] = (mine[ch] && a.base) ? __ldcs(a.base + row + ch * kWarp) : 0.0;
+        }
         for (int cc = 0; cc < cps; ++cc, ++k) {
             const int s = k & (kGfStages - 1);
             const double* J;
@@ -685,8 +704,20 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
             }
         }
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch)
-            if (mine[ch]) __stcs(a.out + row + ch * kWarp, acc[ch]);
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (!mine[ch]) continue;
+            if (staged) srow[ch * kWarp] = acc[ch];
+            else __stcs(a.out + row + ch * kWarp, acc[ch]);
+        }
+    }
+    if (staged) {   // the warp's rows leave with one bulk store
+        ptx::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::bulk_s2g(a.out + row0, ptx::smem_addr(rows), rbytes);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read_all();
+        }
     }
 }
 
