@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>

@@ -547,15 +547,25 @@ struct GenForceArgs {
     int sys_per_warp;      // 32 / cps
     int jac_bulk;          // jac 16-byte aligned -> TMA ring; else direct loads
     int want_wrench;
-    int stage_bytes;       // per-stage shared-memory bytes (48*ncols rounded up to 128)
+    int cps_stage;         // consecutive contacts per ring stage (about 2 KB of Jacobians)
+    int stage_bytes;       // per-stage shared-memory bytes (cps_stage*48*ncols rounded up to 128)
     int row_bytes;         // > 0: per-warp shared-memory bytes for the warp's base / out rows
 };
 
-// NCH = ceil(ncols / 32): column chunks a lane owns (compile-time so dead chunks cost nothing).
-// Per contact and warp: one mbarrier wait, three broadcast LDS.128 for the wrench, NCH x (6 LDS +
-// 6 DFMA/DMUL + 1 DADD); a first version with runtime chunk predicates, shuffles for the wrench and
-// an integer division per contact was issue-bound (74 % issue slots busy, ncu) at 72 % of DRAM.
-template <bool HET, int NCH>
+// NCH = ceil(ncols / 32): column chunks a lane owns (compile-time so dead chunks cost nothing);
+// BULK: Jacobians through the TMA ring (16-byte aligned) or direct loads.
+//
+// The kernel is ISSUE-bound before it is HBM-bound if the per-contact instruction count is not kept
+// down (ncu on the first versions: 74-77 % issue slots busy; ~120-150 warp instructions per contact,
+// whatever the Jacobian's width -- so narrow Jacobians got 50 % of HBM).  Hence:
+//   * a ring stage holds `cps_stage` CONSECUTIVE contacts (about 2 KB): one mbarrier wait and one
+//     re-arm + bulk copy per stage, not per contact;
+//   * Jacobian reads are shared-memory loads off one per-lane base address (BULK is compile-time, so
+//     no generic addressing); the wrench is three broadcast LDS.128;
+//   * stage / system bookkeeping is incremental (no divisions, loop invariants in registers);
+//   * the warp's base / out rows are staged through shared memory with one bulk copy each (read per
+//     system they cost a global-load latency each).
+template <bool HET, int NCH, bool BULK>
 __global__ void __launch_bounds__(128)
 ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
 {
@@ -567,31 +577,37 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     const long long sys0 = wid * a.sys_per_warp;
     if (sys0 >= a.n_systems) return;  // warp-uniform
     const int nsys = static_cast<int>(min64(a.sys_per_warp, a.n_systems - sys0));
-    const int cps = a.cps, ncols = a.ncols;
+    const int cps = a.cps, ncols = a.ncols, cpst = a.cps_stage, stage_bytes = a.stage_bytes;
     const int ncont = nsys * cps;
     const long long c0 = sys0 * cps;           // first contact of this warp
-    const uint32_t jbytes = 48u * ncols;       // one contact's Jacobian
-    const bool bulk = a.jac_bulk != 0;
+    const int jd = 6 * ncols;                  // doubles of one contact's Jacobian
+    const int nstage = (ncont + cpst - 1) / cpst;
 
     // per warp: kGfStages Jacobian stages | 32 wrenches (32 x 48 B) | kGfStages + 1 mbarriers |
-    //           the warp's base / out rows (row staging, see below)
-    const int per_warp = kGfStages * a.stage_bytes + kWarp * 48 + 128 + a.row_bytes;
+    //           the warp's base / out rows
+    const int per_warp = kGfStages * stage_bytes + kWarp * 48 + 128 + a.row_bytes;
     unsigned char* ws = smem_raw + static_cast<size_t>(warp) * per_warp;
-    double* wsm = reinterpret_cast<double*>(ws + kGfStages * a.stage_bytes);
-    const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * a.stage_bytes + kWarp * 48);
+    double* wsm = reinterpret_cast<double*>(ws + kGfStages * stage_bytes);
+    const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * stage_bytes + kWarp * 48);
     const uint32_t rbar = bar0 + 8 * kGfStages;
-    double* rows = reinterpret_cast<double*>(ws + kGfStages * a.stage_bytes + kWarp * 48 + 128);
+    double* rows = reinterpret_cast<double*>(ws + kGfStages * stage_bytes + kWarp * 48 + 128);
     const uint32_t stage0 = ptx::smem_addr(ws);
-    const double* jac0 = a.jac + c0 * 6 * ncols;
-    // Row staging.  The warp's systems own CONSECUTIVE rows of base and out.  Read per system they
-    // cost a global-load latency each (acc = base + ... waits for it), which is what bounded narrow
-    // Jacobians at ~50 % of HBM; staged they are one bulk copy in and one bulk copy out per warp.
-    // Needs 16-byte aligned blocks (else the direct per-system accesses are used).
+    const double* jac0 = a.jac + c0 * jd;
     const long long row0 = sys0 * ncols;
     const uint32_t rbytes = static_cast<uint32_t>(nsys) * ncols * 8u;
     const bool staged = a.row_bytes > 0 && ((row0 | (static_cast<long long>(nsys) * ncols)) & 1) == 0;
+
+    auto arm = [&](int q) {   // lane 0: bulk copy of stage q (contacts q*cpst ..) into its ring slot
+        const int first = q * cpst;
+        const uint32_t bytes = static_cast<uint32_t>(min(cpst, ncont - first)) * jd * 8u;
+        const uint32_t bar = bar0 + 8 * (q & (kGfStages - 1));
+        ptx::mbar_arrive_expect_tx(bar, bytes);
+        ptx::bulk_g2s(stage0 + (q & (kGfStages - 1)) * stage_bytes, jac0 + static_cast<long long>(first) * jd,
+                      bytes, bar);
+    };
+
     ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
-    if (lane == 0 && (bulk || staged)) {
+    if (lane == 0 && (BULK || staged)) {
 #pragma unroll
         for (int s = 0; s <= kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
         ptx::fence_mbar_init();
@@ -602,14 +618,10 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
             ptx::mbar_arrive_expect_tx(rbar, rbytes);
             ptx::bulk_g2s(ptx::smem_addr(rows), a.base + row0, rbytes, rbar);
         }
-        if (bulk) {
+        if constexpr (BULK) {
 #pragma unroll
-            for (int s = 0; s < kGfStages; ++s)
-                if (s < ncont) {
-                    ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
-                    ptx::bulk_g2s(stage0 + s * a.stage_bytes, jac0 + static_cast<long long>(s) * 6 * ncols,
-                                  jbytes, bar0 + 8 * s);
-                }
+            for (int q = 0; q < kGfStages; ++q)
+                if (q < nstage) arm(q);
         }
     }
     __syncwarp();
@@ -653,61 +665,81 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     }
     __syncwarp();
 
-    // ---- lanes own columns; systems and their contacts are visited in order -------------------
+    // ---- lanes own columns; stages, and the contacts inside a stage, are visited in order ------
     bool mine[NCH];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) mine[ch] = ch * kWarp + lane < ncols;
     if (staged && a.base) ptx::mbar_wait(rbar, 0);
-    int k = 0;
-    for (int sys = 0; sys < nsys; ++sys) {
-        const long long row = (sys0 + sys) * ncols + lane;
-        double* srow = rows + sys * ncols + lane;
-        double acc[NCH];
+    int sys = 0, cin = 0;            // system / contact-in-system of the contact being added
+    double acc[NCH];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            if (staged) acc[ch] = (mine[ch] && a.base) ? srow[ch * kWarp] : 0.0;
-            else acc[ch] = (mine[ch] && a.base) ? __ldcs(a.base + row + ch * kWarp) : 0.0;
+    for (int ch = 0; ch < NCH; ++ch) acc[ch] = 0.0;
+    const double2* wv = reinterpret_cast<const double2*>(wsm);
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int sq = 0; sq < nstage; ++sq) {
+        const int first = sq * cpst;
+        const int cnt = min(cpst, ncont - first);
+        const double* J;
+        if constexpr (BULK) {
+            ptx::mbar_wait(bar0 + 8 * slot, parity);
+            J = reinterpret_cast<const double*>(ws + slot * stage_bytes) + lane;
+        } else {
+            J = jac0 + static_cast<long long>(first) * jd + lane;
         }
-        for (int cc = 0; cc < cps; ++cc, ++k) {
-            const int s = k & (kGfStages - 1);
-            const double* J;
-            if (bulk) {
-                ptx::mbar_wait(bar0 + 8 * s, (k / kGfStages) & 1);
-                J = reinterpret_cast<const double*>(ws + s * a.stage_bytes) + lane;
-            } else {
-                J = jac0 + static_cast<long long>(k) * 6 * ncols + lane;
+        for (int j = 0; j < cnt; ++j, J += jd, wv += 3) {
+            if (cin == 0) {   // a new system starts: acc = base row
+                const long long row = (sys0 + sys) * ncols + lane;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (staged) acc[ch] = (mine[ch] && a.base) ? rows[sys * ncols + lane + ch * kWarp] : 0.0;
+                    else acc[ch] = (mine[ch] && a.base) ? __ldcs(a.base + row + ch * kWarp) : 0.0;
+                }
             }
-            const double2* wv = reinterpret_cast<const double2*>(wsm) + k * 3;
             const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 if (mine[ch]) {
                     // (J^T w)[col], rows in order; then known += product  (:224-225)
                     const double* Jc = J + ch * kWarp;
-                    double t = Jc[0] * w01.x;
-                    t += Jc[ncols] * w01.y;
-                    t += Jc[2 * ncols] * w23.x;
-                    t += Jc[3 * ncols] * w23.y;
-                    t += Jc[4 * ncols] * w45.x;
-                    t += Jc[5 * ncols] * w45.y;
+                    double t;
+                    if constexpr (BULK) {
+                        t = Jc[0] * w01.x;
+                        t += Jc[ncols] * w01.y;
+                        t += Jc[2 * ncols] * w23.x;
+                        t += Jc[3 * ncols] * w23.y;
+                        t += Jc[4 * ncols] * w45.x;
+                        t += Jc[5 * ncols] * w45.y;
+                    } else {
+                        t = __ldcs(Jc) * w01.x;
+                        t += __ldcs(Jc + ncols) * w01.y;
+                        t += __ldcs(Jc + 2 * ncols) * w23.x;
+                        t += __ldcs(Jc + 3 * ncols) * w23.y;
+                        t += __ldcs(Jc + 4 * ncols) * w45.x;
+                        t += __ldcs(Jc + 5 * ncols) * w45.y;
+                    }
                     acc[ch] = acc[ch] + t;
                 }
             }
-            if (bulk) {
-                __syncwarp();   // every lane is done with stage s
-                if (lane == 0 && k + kGfStages < ncont) {
-                    ptx::mbar_arrive_expect_tx(bar0 + 8 * s, jbytes);
-                    ptx::bulk_g2s(stage0 + s * a.stage_bytes,
-                                  jac0 + static_cast<long long>(k + kGfStages) * 6 * ncols, jbytes,
-                                  bar0 + 8 * s);
+            if (++cin == cps) {   // the system is complete: its row leaves
+                const long long row = (sys0 + sys) * ncols + lane;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (!mine[ch]) continue;
+                    if (staged) rows[sys * ncols + lane + ch * kWarp] = acc[ch];
+                    else __stcs(a.out + row + ch * kWarp, acc[ch]);
                 }
+                cin = 0;
+                ++sys;
             }
         }
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            if (!mine[ch]) continue;
-            if (staged) srow[ch * kWarp] = acc[ch];
-            else __stcs(a.out + row + ch * kWarp, acc[ch]);
+        if constexpr (BULK) {
+            __syncwarp();   // every lane is done with this stage
+            if (lane == 0 && sq + kGfStages < nstage) arm(sq + kGfStages);
+            if (++slot == kGfStages) {
+                slot = 0;
+                parity ^= 1u;
+            }
         }
     }
     if (staged) {   // the warp's rows leave with one bulk store
@@ -721,10 +753,9 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     }
 }
 
-// Narrow Jacobians (ncols <= 16) reach only 50-90 % of HBM with this kernel.  A lane-packed variant
-// (2 or 4 contacts per warp iteration, ordered accumulation through shuffles) was built and measured
-// within +-5 % of it (6 columns: 52.0 vs 49.6 %; 12 columns: 77.4 vs 80.3 %), and one bulk copy per
-// warp for all its Jacobians was slower (34-46 %): idle lanes are not what bounds that shape, the
-// per-contact hand-over is.  Both were removed again.
+// A lane-packed variant for narrow Jacobians (2 or 4 contacts per warp iteration, ordered
+// accumulation through shuffles) and one bulk copy per warp for all its Jacobians were built,
+// measured no better (+-5 %) or slower, and removed: the instruction count per contact was the
+// bound, not idle lanes.
 
 }  // namespace blfccm

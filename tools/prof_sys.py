@@ -38,7 +38,8 @@ def main():
         call, out = RolloutBatch(b).prepare(nr, feet, H, 0.01, rho, tw, pos, rot, null,
                                             [0, 0, 30., 0, 0, 0], [1., 10.], mask=mask)
     elif what.startswith("genforce"):
-        ns, cps, ncols = (409600, 2, 29) if what == "genforce_small" else (1 << 21, 2, 29)
+        ns, cps, ncols = {"genforce_small": (409600, 2, 29), "genforce_narrow": (1 << 21, 1, 6)}.get(
+            what, (1 << 21, 2, 29))
         n = ns * cps
         st = syn.make_states(min(n, 1 << 17), seed=49)
         reps = (n + st["n"] - 1) // st["n"]
