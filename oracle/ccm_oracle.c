@@ -1,6 +1,7 @@
 /*
  * ccm_oracle.c -- CPU oracle for ContactModels::ContinuousContactModel.  TEST INFRASTRUCTURE ONLY,
- * PARITY UNPINNED (see ccm_oracle.h for both statements and for what it is pinned to instead).
+ * parity pinned against the reference's own sources compiled into oracle/_ref, not against a binary
+ * with the real Eigen (see ccm_oracle.h for both statements).
  *
  * The arithmetic keeps the reference's expression structure: explicit skew matrices, 3x3
  * matrix-matrix products associated left to right the way the C++ expressions parse, one rounding

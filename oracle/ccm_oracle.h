@@ -4,14 +4,20 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing on the product path may include, link or call this.
  * Allowed users: tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline / --impl reference leg.
  *
- * PARITY UNPINNED: the reference's own implementation cannot be built in this environment
- * (Eigen, iDynTree and Catch2 are absent, no network) and its tests hold no golden vectors for
- * this path (src/ContactModels/tests/ContinousContactModelTest.cpp has only self-consistency
- * checks with an unseeded random twist).  This file is a plain-C restatement of the reference's
- * closed-form algebra; it is pinned to that algebra -- not to the original binary -- by
+ * PARITY STATUS: pinned against THE REFERENCE'S OWN SOURCES, not against a binary linked with the
+ * real Eigen/iDynTree.  Eigen, iDynTree and Catch2 are absent from this image (no network), and the
+ * reference's tests hold no golden vectors for this path (ContinousContactModelTest.cpp has only
+ * self-consistency checks with an unseeded random twist).  This file is a plain-C restatement of
+ * the reference's closed-form algebra; it is pinned by
+ *   (o)  oracle/_ref: ContinuousContactModel.cpp / ContactModel.cpp / StdImplementation.cpp
+ *        compiled UNMODIFIED from /root/reference against stand-in Eigen/iDynTree headers
+ *        (oracle/refbuild/README.md says exactly what the stand-ins are); this restatement must
+ *        agree with that build BIT FOR BIT (tests/test_reference_build.py), and the reference's own
+ *        test file passes on that build;
  *   (i)  exact rational evaluation of the same formulas (oracle/exact_golden.py ->
- *        tests/golden/ccm_exact_golden.json), and
+ *        tests/golden/ccm_exact_golden.npz), and
  *   (ii) the reference's three test properties restated in tests/test_oracle.py.
+ * What remains unpinned: Eigen's internal evaluation order (an O(eps) effect, far below 1e-12).
  *
  * Follows (paths relative to /root/reference):
  *   src/ContactModels/src/ContinuousContactModel.cpp:16-274   all arithmetic

@@ -1,8 +1,9 @@
 """ctypes view of oracle/libccm_oracle.so (the C restatement in ccm_oracle.c).
 
 TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference leg, never from the product package.  PARITY UNPINNED against the
-reference binary (see ccm_oracle.h).
+cpu_baseline / --impl reference leg, never from the product package.  Pinned bit for bit against the
+reference's own sources compiled into oracle/_ref (oracle/ref_binding.py); not against a binary linked
+with the real Eigen/iDynTree (see ccm_oracle.h).
 """
 from __future__ import annotations
 

@@ -6,7 +6,7 @@ apart from one abs() and one division by 12, so with the double inputs taken as 
 result is an exact rational; it is then rounded ONCE to the nearest double.  Any faithful
 floating-point evaluation order (Eigen's, the C oracle's, the CUDA kernel's) must agree with this
 to a few ulps of the block norm -- that is what pins the C oracle in the absence of reference
-golden vectors ("parity unpinned" against the binary; pinned against the algebra).
+golden vectors (a second pin, independent of the build of the reference's own sources in oracle/_ref).
 
 This third derivation uses cross products, not the skew-matrix products of ccm_oracle.c.
 

@@ -1,8 +1,8 @@
 """Exact / high-precision evaluation of the System-component steps either side of the contact
 model, and the golden-fixture writer for them.
 
-TEST INFRASTRUCTURE ONLY (see sys_oracle.h).  PARITY UNPINNED against the reference binary; these
-fixtures pin the oracle and the CUDA path to the reference's ALGEBRA:
+TEST INFRASTRUCTURE ONLY (see sys_oracle.h).  These fixtures pin the oracle and the
+CUDA path to the reference's ALGEBRA (independently of the oracle/_ref build of its sources):
 
 * FloatingBaseSystemKinematics::dynamics + one ForwardEuler step
   (src/System/src/FloatingBaseSystemKinematics.cpp:36-73, ForwardEuler.h:45-53) is rational in the

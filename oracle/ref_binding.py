@@ -26,6 +26,7 @@ REFBUILD_DIR = os.path.join(_HERE, "refbuild")
 REFERENCE_ROOT = os.environ.get("BLF_REFERENCE_ROOT", "/root/reference")
 REFERENCE_TESTS = ("ContinuousContactModelReferenceTests", "IntegratorReferenceTests",
                    "ParametersHandlerReferenceTests")
+FACADE_TEST = "ContinuousContactModelReferenceTests_on_b200_facade"  # needs a CUDA device to run
 
 WRENCH, AUTODYN, CTRL, REGRESSOR = 1, 2, 4, 8
 
@@ -39,7 +40,11 @@ def build(force: bool = False) -> str | None:
     """make -C oracle/refbuild (needs the reference tree).  Returns the library path, or None when
     the reference tree is absent and nothing was prebuilt."""
     if reference_sources_present():
-        cmd = ["make", "-C", REFBUILD_DIR, f"REF={REFERENCE_ROOT}"] + (["-B"] if force else [])
+        targets = ["all"]
+        if os.path.exists(os.path.join(os.path.dirname(_HERE), "bipedal_locomotion_framework_b200", "lib",
+                                       "libblf_contact.so")):
+            targets.append("facade")  # the reference's unmodified test linked to the product facade
+        cmd = ["make", "-C", REFBUILD_DIR, f"REF={REFERENCE_ROOT}", *targets] + (["-B"] if force else [])
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("building oracle/_ref failed:\n" + r.stdout)

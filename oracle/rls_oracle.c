@@ -1,4 +1,4 @@
-/* rls_oracle.c -- see rls_oracle.h.  TEST INFRASTRUCTURE ONLY, PARITY UNPINNED. */
+/* rls_oracle.c -- see rls_oracle.h.  TEST INFRASTRUCTURE ONLY; parity status in rls_oracle.h. */
 #include "rls_oracle.h"
 
 #include <math.h>

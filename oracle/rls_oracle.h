@@ -1,10 +1,14 @@
 /*
  * rls_oracle.h -- CPU oracle for Estimators::RecursiveLeastSquare.
  *
- * TEST INFRASTRUCTURE ONLY (same rules as ccm_oracle.h).  PARITY UNPINNED: the reference's test
- * (src/Estimators/tests/RecursiveLeastSquareTest.cpp:91-142) needs YARP and holds no golden
- * vectors, only "10 000 steps recover (43.2, 12.2) within 0.1 %".  Pinned instead by exact rational
- * evaluation of the same update (oracle/exact_golden.py) and by that convergence property.
+ * TEST INFRASTRUCTURE ONLY (same rules as ccm_oracle.h).  PARITY STATUS: pinned against the
+ * reference's own RecursiveLeastSquare.cpp compiled unmodified into oracle/_ref against stand-in
+ * Eigen/iDynTree headers (bit-for-bit agreement required, tests/test_reference_build.py) -- with one
+ * caveat: the dynamic-size inverse() underneath is the STAND-IN's partial-pivot LU, a restatement of
+ * the algorithm Eigen documents, so the inverse itself stays unpinned against the real Eigen.
+ * The reference's test (src/Estimators/tests/RecursiveLeastSquareTest.cpp:91-142) needs YARP and
+ * holds no golden vectors, only "10 000 steps recover (43.2, 12.2) within 0.1 %".  Also pinned by
+ * exact rational evaluation of the same update (oracle/exact_golden.py) and by that property.
  *
  * Follows src/Estimators/src/RecursiveLeastSquare.cpp:96-133 (advance) and :17-88 (initialize:
  * diagonal measurement covariance, lambda, initial state, diagonal state covariance):

@@ -5,10 +5,16 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing on the product path may include, link or call this.
  * Allowed users: tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline / --impl reference leg.
  *
- * PARITY UNPINNED: the reference's System component needs Eigen and iDynTree (absent here) and its
- * only test of these functions (src/System/tests/IntegratorTest.cpp:80-126) compares against a
- * closed-form solution with tolerance 1e-3 on an unseeded random twist -- no golden vectors.  This
- * file restates the reference's arithmetic in plain C; it is pinned to that algebra by
+ * PARITY STATUS: kinematics, Euler step, integrate schedule and rollout are pinned against the
+ * reference's own FloatingBaseSystemKinematics.cpp + ForwardEuler/FixedStepIntegrator templates
+ * compiled unmodified into oracle/_ref against stand-in Eigen/iDynTree headers (bit-for-bit agreement
+ * required, tests/test_reference_build.py; the reference's IntegratorTest.cpp passes on that build;
+ * the 3x3 inverse() underneath is the stand-in's cofactor formula).  syso_generalized_force stays
+ * PARITY UNPINNED: FloatingBaseSystemDynamics.cpp needs iDynTree::KinDynComputations, which no
+ * stand-in can supply; only its per-contact wrench is covered by the reference build.
+ * The reference's only test of these functions (src/System/tests/IntegratorTest.cpp:80-126) compares
+ * against a closed-form solution with tolerance 1e-3 on an unseeded random twist -- no golden
+ * vectors.  This file restates the reference's arithmetic in plain C; it is also pinned by
  *   (i)  exact-rational single steps and 80-digit multi-step rollouts
  *        (oracle/exact_golden_sys.py -> tests/golden/sys_exact_golden.npz), and
  *   (ii) the reference test's property (rotation follows the axis-angle closed form within 1e-3,

@@ -1,8 +1,9 @@
 """ctypes view of the System-component oracle (oracle/sys_oracle.c, inside libccm_oracle.so).
 
 TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference leg, never from the product package.  PARITY UNPINNED against the
-reference binary (see sys_oracle.h).
+cpu_baseline / --impl reference leg, never from the product package.  Kinematics / integrator /
+rollout pinned bit for bit against the reference's own sources compiled into oracle/_ref; the
+J^T-wrench row stays parity-unpinned (see sys_oracle.h).
 """
 from __future__ import annotations
 
