@@ -5,8 +5,8 @@
  * Public interface identical to the reference class
  * (src/ContactModels/include/BipedalLocomotion/ContactModels/ContactModel.h:33-146): initialize,
  * setState, setNullForceTransform and the four lazy getters that return const references to
- * internal storage valid until the next setter.  Protocol of the four "computed" flags as in
- * src/ContactModels/src/ContactModel.cpp:12-92.
+ * internal storage valid until the next setter.  Same observable protocol as the four "computed"
+ * flags of src/ContactModels/src/ContactModel.cpp:12-92, kept here as one validity mask.
  */
 #ifndef BIPEDAL_LOCOMOTION_CONTACT_MODELS_CONTACT_MODEL_H
 #define BIPEDAL_LOCOMOTION_CONTACT_MODELS_CONTACT_MODEL_H
@@ -36,10 +36,12 @@ static_assert(sizeof(iDynTree::Matrix6x6) == 288, "Matrix6x6 must be 36 packed d
 
 class ContactModel
 {
-    bool m_isContactWrenchComputed{false};
-    bool m_isAutonomousDynamicsComputed{false};
-    bool m_isControlMatrixComputed{false};
-    bool m_isRegressorComputed{false};
+    /** Which cached results are current: one bit per getter, the bits of the C ABI's out_mask
+     * (BLF_CCM_OUT_WRENCH = 1, _AUTODYN = 2, _CTRL = 4, _REGRESSOR = 8).  Cleared by every setter. */
+    unsigned m_valid{0u};
+
+    /** Run `compute` unless the result guarded by `bit` is current. */
+    void refresh(unsigned bit, void (ContactModel::*compute)());
 
 protected:
     iDynTree::Wrench m_contactWrench; /**< contact wrench, mixed representation */

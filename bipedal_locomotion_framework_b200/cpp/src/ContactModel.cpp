@@ -1,76 +1,73 @@
 /**
  * @file ContactModel.cpp
- * Lazy-evaluation shell of the contact-model facade.  Protocol as in the reference
- * (src/ContactModels/src/ContactModel.cpp:12-92): every setter and initialize() clear the four
- * "computed" flags; each getter computes once and then serves the cached value.
+ * Lazy-evaluation shell of the contact-model facade.
+ *
+ * Observable protocol as in the reference (src/ContactModels/src/ContactModel.cpp:12-92):
+ * initialize() and both setters invalidate every cached result; a getter computes its result at
+ * most once between two invalidations and otherwise serves the cached value -- which is also why
+ * writing through springCoeff()/damperCoeff() leaves stale results in place, as upstream.
+ * Kept as ONE validity mask whose bits are the C ABI's output mask, so that a derived class can
+ * hand the same bit straight to blf_ccm_eval_batch_host.
  */
 #include <BipedalLocomotion/ContactModels/ContactModel.h>
 
-using namespace BipedalLocomotion::ContactModels;
+namespace BipedalLocomotion
+{
+namespace ContactModels
+{
+namespace
+{
+constexpr unsigned kWrench = 1u, kAutonomousDynamics = 2u, kControlMatrix = 4u, kRegressor = 8u;
+}
+
+void ContactModel::refresh(unsigned bit, void (ContactModel::*compute)())
+{
+    if (m_valid & bit) return;
+    (this->*compute)();
+    m_valid |= bit;
+}
 
 bool ContactModel::initialize(std::weak_ptr<ParametersHandler::IParametersHandler> handler)
 {
-    m_isContactWrenchComputed = false;
-    m_isControlMatrixComputed = false;
-    m_isAutonomousDynamicsComputed = false;
-    m_isRegressorComputed = false;
+    m_valid = 0u;
     return initializePrivate(handler);
-}
-
-void ContactModel::setNullForceTransform(const iDynTree::Transform& nullForceTransform)
-{
-    m_isContactWrenchComputed = false;
-    m_isControlMatrixComputed = false;
-    m_isAutonomousDynamicsComputed = false;
-    m_isRegressorComputed = false;
-    setNullForceTransformPrivate(nullForceTransform);
 }
 
 void ContactModel::setState(const iDynTree::Twist& twist, const iDynTree::Transform& transform)
 {
-    m_isContactWrenchComputed = false;
-    m_isControlMatrixComputed = false;
-    m_isAutonomousDynamicsComputed = false;
-    m_isRegressorComputed = false;
+    m_valid = 0u;
     setStatePrivate(twist, transform);
+}
+
+void ContactModel::setNullForceTransform(const iDynTree::Transform& transform)
+{
+    m_valid = 0u;
+    setNullForceTransformPrivate(transform);
 }
 
 const iDynTree::Wrench& ContactModel::getContactWrench()
 {
-    if (!m_isContactWrenchComputed)
-    {
-        computeContactWrench();
-        m_isContactWrenchComputed = true;
-    }
+    refresh(kWrench, &ContactModel::computeContactWrench);
     return m_contactWrench;
 }
 
 const iDynTree::Vector6& ContactModel::getAutonomousDynamics()
 {
-    if (!m_isAutonomousDynamicsComputed)
-    {
-        computeAutonomousDynamics();
-        m_isAutonomousDynamicsComputed = true;
-    }
+    refresh(kAutonomousDynamics, &ContactModel::computeAutonomousDynamics);
     return m_autonomousDynamics;
 }
 
 const iDynTree::Matrix6x6& ContactModel::getControlMatrix()
 {
-    if (!m_isControlMatrixComputed)
-    {
-        computeControlMatrix();
-        m_isControlMatrixComputed = true;
-    }
+    refresh(kControlMatrix, &ContactModel::computeControlMatrix);
     return m_controlMatrix;
 }
 
 const iDynTree::MatrixDynSize& ContactModel::getRegressor()
 {
-    if (!m_isRegressorComputed)
-    {
-        computeRegressor();
-        m_isRegressorComputed = true;
-    }
+    refresh(kRegressor, &ContactModel::computeRegressor);
     return m_regressor;
 }
+
+} // namespace ContactModels
+} // namespace BipedalLocomotion
