@@ -568,7 +568,7 @@ def run_large(args):
 
     from bipedal_locomotion_framework_b200 import sharding
     from bipedal_locomotion_framework_b200 import synthetic as syn
-    from bipedal_locomotion_framework_b200.contact_models import FULL, ContinuousContactModelBatch
+    from bipedal_locomotion_framework_b200.contact_models import FULL, WRENCH, ContinuousContactModelBatch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -580,6 +580,7 @@ def run_large(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = min(args.steps, 50), max(min(args.warmup, 10), 3)
+    mask, nsets = FULL, 1
 
     batch = ContinuousContactModelBatch(local)
     batch.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
@@ -591,13 +592,20 @@ def run_large(args):
         name = ("configs[3]: 64M heterogeneous contact states (per-contact length/width/spring/"
                 "damper), rollouts of 200 sharded by rollout, wrench+autodyn+ctrl + per-rollout "
                 "cost + NCCL arg-min")
+    elif args.workload == "config2":
+        total = 1 << 20                           # per GPU (weak): the configuration is a 1-GPU one
+        n, het, bytes_per, mask, nsets = total, False, 248, WRENCH, 3
+        total *= world
+        K = min(args.steps, 2000)
+        name = ("configs[1]: 1M random contact states per GPU, wrench only, uniform foot geometry and "
+                "stiffness/damping, SoA (25 live planes in, 6 planes out = 248 B/eval)")
     else:
         total = 1 << 28
         first, count = sharding.shard_rollouts(total, world, rank)   # plain block partition
         n, het, bytes_per = count, False, 600
         name = "configs[4]: strong scaling, 256M contact states, wrench+autodyn+ctrl, uniform params"
     planes, prm = syn.make_planes_torch(n, dev, seed=42 + 4 + 1000 * rank, heterogeneous=het)
-    out = batch.alloc_soa_outputs(n, FULL)
+    out = batch.alloc_soa_outputs(n, mask)
     torch.cuda.synchronize()
 
     if args.workload == "config4":
@@ -626,6 +634,17 @@ def run_large(args):
                     return peer.global_best
                 return batch.argmin_pairs(sharding.all_gather_pairs(best, world, dist))
             return best
+    elif nsets > 1:
+        # rotating buffer sets: a step never finds its 260 MB in the 126 MB L2
+        peer = None
+        sets = [(planes, out)] + [(planes.clone(), batch.alloc_soa_outputs(n, mask)) for _ in range(nsets - 1)]
+        calls = [batch.prepare_soa(pl, None, mask, out=o)[0] for pl, o in sets]
+        counter = [0]
+
+        def step():
+            calls[counter[0] % nsets]()
+            counter[0] += 1
+            return None
     else:
         peer = None
         call, _ = batch.prepare_soa(planes, None, FULL, out=out)
@@ -662,19 +681,22 @@ def run_large(args):
     clocks = sampler.summary(t0, t1)
     sampler.stop_flag = True
 
-    # parity on a sample of the same device bits (every 4099th state of this rank's shard)
+    # parity on the same device bits: every state up to 2M, else every 4099th state of this rank's shard
     parity = None
     if rank == 0:
         from oracle import ccm_oracle
-        idx = torch.arange(0, n, 4099, device=dev)
+        idx = torch.arange(0, n, 1 if n <= (1 << 21) else 4099, device=dev)
         st = syn.sample_states_from_planes(planes, prm, idx)
         ref = ccm_oracle.eval_batch_states(st, mask=7, nthreads=os.cpu_count() or 1)
         worst = 0.0
-        got = {"wrench": torch.stack([p[idx] for p in out["wrench"]], 1).cpu().numpy(),
-               "autodyn": torch.stack([p[idx] for p in out["autodyn"]], 1).cpu().numpy(),
-               "ctrl": out["ctrl"][idx].cpu().numpy()}
+        got = {"wrench": torch.stack([p[idx] for p in out["wrench"]], 1).cpu().numpy()}
+        if mask == FULL:
+            got["autodyn"] = torch.stack([p[idx] for p in out["autodyn"]], 1).cpu().numpy()
+            got["ctrl"] = out["ctrl"][idx].cpu().numpy()
         for key, blocks in (("wrench", [slice(0, 3), slice(3, 6)]), ("autodyn", [slice(0, 3), slice(3, 6)]),
                             ("ctrl", [slice(6 * q + 3 * (q // 3), 6 * q + 3 * (q // 3) + 3) for q in range(6)])):
+            if key not in got:
+                continue
             for sl in blocks:
                 num = np.abs(got[key][:, sl] - ref[key][:, sl]).max(axis=1)
                 den = np.maximum(np.abs(ref[key][:, sl]).max(axis=1), 1e-300)
@@ -688,13 +710,14 @@ def run_large(args):
         line = {
             "metric": METRIC, "value": total * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (device-generated)",
+            "scaling": "weak" if args.workload == "config2" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (device-generated)",
             "config": {"workload": name, "evals_per_step": total, "evals_per_step_per_gpu": n,
                        "parallelism": f"sharded x{world}" + (
                            (", arg-min pair over the NVLink peer-memory mailbox (fused into the reduction kernel)"
                             if peer is not None else ", NCCL all_gather 16 B/rank")
                            if args.workload == "config4" and world > 1 else ""),
-                       "l2": "per-GPU working set >> 126 MB L2"},
+                       "l2": ("3 rotating input/output buffer sets; one step streams 260 MB (> 126 MB L2)"
+                              if nsets > 1 else "per-GPU working set >> 126 MB L2")},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
                          "frac": per_gpu_gbs / peak, "traffic": None,
                          "note": "whole step (kernel + epilogue launches) on rank 0's shard", "peak_source": peak_src},
@@ -716,8 +739,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"],
-                    help="config3 (default, the headline): MPC batch, weak scaling; config4: 64M "
+    ap.add_argument("--workload", default="config3", choices=["config2", "config3", "config4", "config5"],
+                    help="config2: 1M states wrench-only; "
+                         "config3 (default, the headline): MPC batch, weak scaling; config4: 64M "
                          "heterogeneous states + NCCL arg-min, strong; config5: 256M states, strong")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--nccl-argmin", action="store_true",
