@@ -637,7 +637,8 @@ def run_large(args):
     elif nsets > 1:
         # rotating buffer sets: a step never finds its 260 MB in the 126 MB L2
         peer = None
-        sets = [(planes, out)] + [(planes.clone(), batch.alloc_soa_outputs(n, mask)) for _ in range(nsets - 1)]
+        sets = [(planes, out)] + [([None if q is None else q.clone() for q in planes],
+                                  batch.alloc_soa_outputs(n, mask)) for _ in range(nsets - 1)]
         calls = [batch.prepare_soa(pl, None, mask, out=o)[0] for pl, o in sets]
         counter = [0]
 
