@@ -4,8 +4,9 @@
 // TEST INFRASTRUCTURE ONLY.  Purpose: compile the reference's own, UNMODIFIED Catch2 test
 // (src/ContactModels/tests/ContinousContactModelTest.cpp) against the B200 facade instead of the
 // reference's classes -- the drop-in check: same test source, other implementation behind the same
-// interface.  Include order when building it: facade include dir, this directory, then
-// oracle/refbuild/standin (for <Eigen/Core> and <catch2/catch.hpp> only).
+// interface.  Include path when building it: the facade's include dir, this directory, and
+// oracle/refbuild/standin/eigen + standin/catch (NOT standin/idyntree: the iDynTree-layout types
+// are the facade's own).
 #ifndef BLF_REFBUILD_FACADE_GLUE_EIGEN_HELPERS
 #define BLF_REFBUILD_FACADE_GLUE_EIGEN_HELPERS
 
