@@ -76,6 +76,7 @@ def lib():
         L.blf_ref_kin_dynamics.argtypes = [d, vp, vp, vp, vp]
         L.blf_ref_kin_integrate.argtypes = [d, d, d, d, vp, vp, vp, i, vp, vp]
         L.blf_ref_rollout.argtypes = [sz, i, d, d, vp, vp, vp, vp, vp, C.c_uint, vp, vp, vp, i]
+        L.blf_ref_generalized_force.argtypes = [sz, i, i] + [vp] * 9 + [i]
         _lib = L
     return _lib
 
@@ -217,6 +218,31 @@ def rollout(twists, poses, null_poses, dT, rho, params=None, uniform=None,
         raise RuntimeError(f"reference rollout failed (rc={rc})")
     out["final_poses"] = poses
     return out
+
+
+def generalized_force(contacts_per_system, ncols, twists, poses, null_poses, jacobians, base=None,
+                      params=None, uniform=None, want_wrench=False, nthreads=1):
+    """FloatingBaseDynamicalSystem::dynamics run from the reference's own source over the
+    KinDynComputations test double (identity mass matrix, injected Jacobians and bias forces):
+    out[s] = base[s] + sum_c J_c^T wrench_c.  AoS states (n = n_systems * contacts_per_system),
+    jacobians (n, 6, ncols), base (n_systems, ncols) or None."""
+    twists, poses, null_poses = _f64(twists), _f64(poses), _f64(null_poses)
+    n = twists.shape[0]
+    assert n % contacts_per_system == 0
+    ns = n // contacts_per_system
+    J = _f64(jacobians)
+    assert J.size == n * 6 * ncols
+    b = None if base is None else _f64(base).reshape(ns, ncols)
+    pr = None if params is None else _f64(params).reshape(n, 4)
+    uni = np.asarray(uniform if uniform is not None else (0, 0, 0, 0), dtype=np.float64)
+    out = np.empty((ns, ncols))
+    wr = np.empty((n, 6)) if want_wrench else None
+    rc = lib().blf_ref_generalized_force(ns, int(contacts_per_system), int(ncols), _ptr(twists), _ptr(poses),
+                                         _ptr(null_poses), _ptr(pr), _ptr(uni), _ptr(J), _ptr(b), _ptr(out),
+                                         _ptr(wr), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"reference FloatingBaseDynamicalSystem failed (rc={rc})")
+    return (out, wr) if want_wrench else out
 
 
 def run_reference_test(name: str, timeout: float = 600.0) -> subprocess.CompletedProcess:

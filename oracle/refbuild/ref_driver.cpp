@@ -9,6 +9,9 @@
 //   BipedalLocomotion::ParametersHandler::StdImplementation      (src/ParametersHandler/src/*.cpp)
 //   BipedalLocomotion::Estimators::RecursiveLeastSquare          (src/Estimators/src/*.cpp)
 //   BipedalLocomotion::System::FloatingBaseSystemKinematics + ForwardEuler<> (src/System/...)
+//   BipedalLocomotion::System::FloatingBaseDynamicalSystem (src/System/src/FloatingBaseSystemDynamics.cpp)
+//     -- over a KinDynComputations TEST DOUBLE that returns injected Jacobians / bias forces / frame
+//        states and an identity mass matrix (standin/idyntree/iDynTree/Model/StandinModel.h)
 // called through their public interface, the way src/System/src/FloatingBaseSystemDynamics.cpp:211-225
 // and the reference's tests call them.  Eigen and iDynTree are stand-ins (oracle/refbuild/standin).
 #include <algorithm>
@@ -25,6 +28,7 @@
 #include <BipedalLocomotion/ContactModels/ContinuousContactModel.h>
 #include <BipedalLocomotion/Estimators/RecursiveLeastSquare.h>
 #include <BipedalLocomotion/ParametersHandler/StdImplementation.h>
+#include <BipedalLocomotion/System/FloatingBaseSystemDynamics.h>
 #include <BipedalLocomotion/System/FloatingBaseSystemKinematics.h>
 #include <BipedalLocomotion/System/ForwardEuler.h>
 
@@ -32,6 +36,8 @@ using BipedalLocomotion::ContactModels::ContinuousContactModel;
 using BipedalLocomotion::Estimators::RecursiveLeastSquare;
 using BipedalLocomotion::ParametersHandler::IParametersHandler;
 using BipedalLocomotion::ParametersHandler::StdImplementation;
+using BipedalLocomotion::System::ContactWrench;
+using BipedalLocomotion::System::FloatingBaseDynamicalSystem;
 using BipedalLocomotion::System::FloatingBaseSystemKinematics;
 using BipedalLocomotion::System::ForwardEuler;
 
@@ -142,7 +148,8 @@ extern "C" {
 const char* blf_ref_description()
 {
     return "reference sources compiled in place (ContactModels, ParametersHandler/StdImplementation, "
-           "Estimators/RecursiveLeastSquare, System/FloatingBaseSystemKinematics + ForwardEuler) "
+           "Estimators/RecursiveLeastSquare, System/FloatingBaseSystemKinematics + ForwardEuler, "
+           "System/FloatingBaseSystemDynamics over a KinDynComputations test double) "
            "against stand-in Eigen/iDynTree headers";
 }
 
@@ -419,6 +426,101 @@ int blf_ref_rollout(std::size_t chains, int horizon, double dT, double rho, cons
                 }
                 rig.get(pose, pose + 3, 0, nullptr);
             }
+        }
+    });
+}
+
+// FloatingBaseDynamicalSystem::dynamics, contact part (FloatingBaseSystemDynamics.cpp:188-229), run
+// from the reference's own source: per system the KinDynComputations test double is loaded with
+//   mass matrix = identity (so the final llt().solve() returns m_knownCoefficent unchanged),
+//   generalized bias forces h = -base (so that -h = base),
+//   per contact c (frame index c): Jacobian J_c (6 x ncols row-major), frame velocity, world transform,
+// the joint torques are zero, and dynamics() is called; out = [baseAcceleration; jointAcceleration]
+// = base + sum_c J_c^T * wrench_c in the reference's own order.  Argument meaning as
+// oracle/sys_oracle.h::syso_generalized_force, AoS: twists n*6, poses n*12, null_poses n*12 with
+// n = n_systems*contacts_per_system; jacobians n*6*ncols; base / out n_systems*ncols; wrench n*6 or NULL.
+int blf_ref_generalized_force(std::size_t n_systems, int contacts_per_system, int ncols, const double* twists,
+                              const double* poses, const double* null_poses, const double* params,
+                              const double uniform[4], const double* jacobians, const double* base, double* out,
+                              double* wrench, int nthreads)
+{
+    if (ncols < 6 || contacts_per_system < 1) return -3;
+    return runPartitioned(n_systems, nthreads, [=](std::size_t b, std::size_t e, int* status) {
+        const std::size_t nc = std::size_t(ncols), dofs = nc - 6, cps = std::size_t(contacts_per_system);
+        for (std::size_t s = b; s < e; ++s)
+        {
+            auto kinDyn = std::make_shared<iDynTree::KinDynComputations>();
+            kinDyn->standinSetModel(dofs);
+            iDynTree::MatrixDynSize mass(nc, nc);
+            for (std::size_t i = 0; i < nc; ++i)
+                mass(i, i) = 1.0;
+            kinDyn->standinSetMassMatrix(mass);
+            iDynTree::FreeFloatingGeneralizedTorques h(kinDyn->model());
+            for (std::size_t q = 0; q < nc; ++q)
+            {
+                const double v = base ? -base[s * nc + q] : -0.0;
+                if (q < 6)
+                    h.baseWrench()(static_cast<unsigned>(q)) = v;
+                else
+                    h.jointTorques()(q - 6) = v;
+            }
+            kinDyn->standinSetBiasForces(h);
+
+            std::vector<std::shared_ptr<ContinuousContactModel>> models;
+            std::vector<ContactWrench> contacts;
+            for (std::size_t c = 0; c < cps; ++c)
+            {
+                const std::size_t i = s * cps + c;
+                iDynTree::MatrixDynSize J(6, nc);
+                std::memcpy(J.data(), jacobians + i * 6 * nc, sizeof(double) * 6 * nc);
+                kinDyn->standinSetFrame(static_cast<iDynTree::FrameIndex>(c), J, makeTwist(twists + 6 * i),
+                                        makeTransform(poses + 12 * i));
+                auto model = std::make_shared<ContinuousContactModel>();
+                if (!initModel(*model, params ? params + 4 * i : uniform))
+                {
+                    *status = -1;
+                    return;
+                }
+                model->setNullForceTransform(makeTransform(null_poses + 12 * i));
+                models.push_back(model);
+                contacts.emplace_back(static_cast<iDynTree::FrameIndex>(c), model);
+            }
+
+            FloatingBaseDynamicalSystem system;
+            if (!system.setKinDyn(kinDyn))
+            {
+                *status = -1;
+                return;
+            }
+            const Eigen::Index nd = Eigen::Index(dofs);
+            Eigen::Matrix<double, 6, 1> baseVelocity;
+            baseVelocity.setZero();
+            Eigen::VectorXd zeros(nd);
+            zeros.setZero();
+            Eigen::Vector3d basePosition;
+            basePosition.setZero();
+            Eigen::Matrix3d baseOrientation;
+            baseOrientation.setIdentity();
+            if (!system.setState({baseVelocity, zeros, basePosition, baseOrientation, zeros})
+                || !system.setControlInput({zeros, contacts}))
+            {
+                *status = -1;
+                return;
+            }
+            FloatingBaseDynamicalSystem::StateDerivativeType dx;
+            if (!system.dynamics(0.0, dx))
+            {
+                *status = -2;
+                return;
+            }
+            for (std::size_t q = 0; q < 6; ++q)
+                out[s * nc + q] = std::get<0>(dx)(Eigen::Index(q));
+            for (std::size_t q = 6; q < nc; ++q)
+                out[s * nc + q] = std::get<1>(dx)(Eigen::Index(q - 6));
+            if (wrench)
+                for (std::size_t c = 0; c < cps; ++c)
+                    for (unsigned k = 0; k < 6; ++k)
+                        wrench[6 * (s * cps + c) + k] = models[c]->getContactWrench()(k);
         }
     });
 }

@@ -1,7 +1,7 @@
 /*
  * sys_oracle.c -- CPU oracle for FloatingBaseSystemKinematics + ForwardEuler / FixedStepIntegrator
  * and for the J^T * wrench accumulation of FloatingBaseDynamicalSystem::dynamics.
- * TEST INFRASTRUCTURE ONLY; parity status (pinned rows / the unpinned J^T row) in sys_oracle.h.
+ * TEST INFRASTRUCTURE ONLY; parity status in sys_oracle.h.
  *
  * Keeps the reference's expression structure (explicit matrix products, general 3x3 cofactor
  * inverse, one rounding per operation with -ffp-contract=off); the CUDA kernels use a different

@@ -9,9 +9,10 @@
  * reference's own FloatingBaseSystemKinematics.cpp + ForwardEuler/FixedStepIntegrator templates
  * compiled unmodified into oracle/_ref against stand-in Eigen/iDynTree headers (bit-for-bit agreement
  * required, tests/test_reference_build.py; the reference's IntegratorTest.cpp passes on that build;
- * the 3x3 inverse() underneath is the stand-in's cofactor formula).  syso_generalized_force stays
- * PARITY UNPINNED: FloatingBaseSystemDynamics.cpp needs iDynTree::KinDynComputations, which no
- * stand-in can supply; only its per-contact wrench is covered by the reference build.
+ * the 3x3 inverse() underneath is the stand-in's cofactor formula).  syso_generalized_force is
+ * pinned the same way against FloatingBaseSystemDynamics.cpp compiled unmodified and run over a
+ * KinDynComputations TEST DOUBLE (identity mass matrix; Jacobians, bias forces and frame states
+ * injected -- iDynTree's rigid-body algorithms are not involved and not claimed).
  * The reference's only test of these functions (src/System/tests/IntegratorTest.cpp:80-126) compares
  * against a closed-form solution with tolerance 1e-3 on an unseeded random twist -- no golden
  * vectors.  This file restates the reference's arithmetic in plain C; it is also pinned by

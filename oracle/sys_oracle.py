@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference leg, never from the product package.  Kinematics / integrator /
-rollout pinned bit for bit against the reference's own sources compiled into oracle/_ref; the
-J^T-wrench row stays parity-unpinned (see sys_oracle.h).
+rollout / J^T-wrench accumulation pinned bit for bit against the reference's own sources compiled
+into oracle/_ref (see sys_oracle.h for what the stand-ins are).
 """
 from __future__ import annotations
 

@@ -218,3 +218,30 @@ def test_fused_rollout_vs_reference_build(torch, batch, ref, rho, het):
     cost = out["cost"].cpu().numpy()
     assert np.allclose(cost, cost_ref, rtol=1e-12)
     assert batch.decode_best(out["best"])[1] == int(np.argmin(cost))
+
+
+@pytest.mark.parametrize("cps,ncols,het", [(2, 29, False), (4, 38, True), (1, 6, False)])
+def test_generalized_force_vs_reference_build(torch, batch, ref, cps, ncols, het):
+    """blf_ccm_generalized_force_soa against FloatingBaseDynamicalSystem::dynamics run from the
+    reference's own FloatingBaseSystemDynamics.cpp (KinDynComputations test double: identity mass
+    matrix, injected Jacobians / bias forces).  Error per system against the magnitude of the summed
+    terms (the sum cancels)."""
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    ns = 3_001
+    n = ns * cps
+    st = syn.make_states(n, seed=81 + cps, heterogeneous=het)
+    rng = np.random.default_rng(cps * 100 + ncols)
+    J = rng.uniform(-1.0, 1.0, (n, 6, ncols))
+    base = rng.uniform(-50.0, 50.0, (ns, ncols))
+    want, wref = ref.generalized_force(cps, ncols, st["twists"], st["poses"], st["null_poses"], J, base,
+                                       params=st["params"] if het else None,
+                                       uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True, nthreads=NTHREADS)
+    planes = _dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+    out, wr = GeneralizedForceBatch(batch).run(cps, ncols, planes, _dev(torch, J), _dev(torch, base),
+                                               param_planes=_dev(torch, st["params"].T) if het else None,
+                                               want_wrench=True)
+    mag = np.abs(base) + np.einsum("scrq,scr->sq", np.abs(J.reshape(ns, cps, 6, ncols)),
+                                   np.abs(wref.reshape(ns, cps, 6)))
+    err = np.abs(out.cpu().numpy() - want).max(axis=1) / np.maximum(mag.max(axis=1), 1e-300)
+    assert err.max() <= TOL, (int(np.argmax(err)), err.max())
+    assert_parity(wr.cpu().numpy().T, wref, "wrench")

@@ -215,6 +215,31 @@ def test_integrate_refusals_match(sys_oracle, ref):
     assert sys_oracle.integrate(0.0, -0.01, 0.0, 0.5, tw, p, R)[0] == -1
 
 
+# --- J^T * wrench accumulation of FloatingBaseDynamicalSystem::dynamics ----------------------------
+
+@pytest.mark.parametrize("cps,ncols,het,with_base", [(2, 29, False, True), (4, 38, True, True),
+                                                     (1, 6, False, False), (3, 12, True, True),
+                                                     (2, 7, False, False)])
+def test_generalized_force_oracle_vs_reference_build(sys_oracle, ref, cps, ncols, het, with_base):
+    """src/System/src/FloatingBaseSystemDynamics.cpp compiled unmodified and run over a
+    KinDynComputations TEST DOUBLE (identity mass matrix, injected Jacobians / bias forces / frame
+    states): [baseAcceleration; jointAcceleration] = -h + sum_c J_c^T wrench_c."""
+    rng = np.random.default_rng(1000 * cps + ncols)
+    ns = 400
+    n = ns * cps
+    st = syn.make_states(n, seed=70 + cps, heterogeneous=het)
+    J = rng.normal(size=(n, 6, ncols))
+    base = rng.normal(size=(ns, ncols)) if with_base else None
+    planes = syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])
+    o, wo = sys_oracle.generalized_force(cps, ncols, planes, J, base,
+                                         param_planes=st["params"].T if het else None,
+                                         uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True, nthreads=2)
+    r, wr = ref.generalized_force(cps, ncols, st["twists"], st["poses"], st["null_poses"], J, base,
+                                  params=st["params"] if het else None,
+                                  uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True, nthreads=4)
+    assert np.array_equal(o, r) and np.array_equal(wo.T, wr)
+
+
 # --- integrate -> contact model rollout ------------------------------------------------------------
 
 @pytest.mark.parametrize("rho", [0.0, 2.0])
