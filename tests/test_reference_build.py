@@ -260,3 +260,30 @@ def test_rollout_oracle_vs_reference_build(sys_oracle, ref, rho):
     assert np.array_equal(o["ctrl"], r["ctrl"])
     assert np.array_equal(o["pos"].T, r["final_poses"][:, :3])
     assert np.array_equal(o["rot"].T, r["final_poses"][:, 3:])
+
+
+# --- special values: the restatement must propagate them exactly as the reference's code does ------
+
+def test_special_values_oracle_vs_reference_build(oracle, ref):
+    """Infinities, NaNs, signed zeros, denormals and huge/tiny magnitudes sprinkled over otherwise
+    ordinary states: same bits out of the C restatement and the reference build (NaN == NaN)."""
+    n = 20_000
+    st = syn.make_states(n, seed=99, heterogeneous=True)
+    rng = np.random.default_rng(99)
+    specials = np.array([np.inf, -np.inf, np.nan, 0.0, -0.0, 5e-324, -2.2e-308, 1e300, -1e300, 1e-300,
+                         1.7976931348623157e308])
+    for key, width in (("twists", 6), ("poses", 12), ("null_poses", 12), ("params", 4)):
+        a = st[key]
+        hit = rng.random((n, width)) < 0.03
+        a[hit] = rng.choice(specials, size=int(hit.sum()))
+    with np.errstate(all="ignore"):
+        a = oracle.eval_batch_states(st, MASK_ALL, nthreads=4)
+        b = ref.eval_batch_states(st, MASK_ALL, nthreads=4)
+    for key in ("wrench", "autodyn", "ctrl", "regressor"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+        finite = np.isfinite(a[key])
+        assert np.array_equal(np.signbit(a[key][finite]), np.signbit(b[key][finite])), key
+    # the structural zeros of the control matrix stay +0.0 whatever the inputs (never written)
+    from parity import CTRL_STRUCTURAL_ZERO
+    z = b["ctrl"][:, CTRL_STRUCTURAL_ZERO]
+    assert np.all(z == 0.0) and not np.signbit(z).any()
