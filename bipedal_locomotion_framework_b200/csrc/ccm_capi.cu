@@ -86,6 +86,7 @@ struct blf_ccm_handle {
     int tune_rollout_ws = 0;     // BLF_CCM_TUNE_ROLLOUT_WS: 1 force / 2 forbid the warp-specialised rollout
     int tune_no_rows = 0;        // BLF_CCM_TUNE_NO_ROWS=1: J^T wrench without base/out row staging
     int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
+    int tune_rls_pipe = 0;       // BLF_CCM_TUNE_RLS_PIPE=1: the plain one-estimator-per-thread RLS kernel instead of the pipelined one
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
     bool p2p_connected = false;
@@ -138,6 +139,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");
+    h->tune_rls_pipe = env_int("BLF_CCM_TUNE_RLS_PIPE");
     h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
     h->tune_rollout_ws = env_int("BLF_CCM_TUNE_ROLLOUT_WS");
     CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
@@ -761,9 +763,38 @@ extern "C" int blf_ccm_argmin_pairs(blf_ccm_handle* h, int n_pairs, const void* 
 
 // ---- batched recursive least squares -------------------------------------------------------------
 
+// software-pipelined SoA kernel: grid = what is resident (BPS blocks per SM), blocks walk over tiles
+template <int P, int M, int BPS>
+static int rls_launch_pipe(blf_ccm_handle* h, const RlsArgs& a, cudaStream_t st)
+{
+    using Cfg = RlsPipe<P, M>;
+    auto kern = rls_advance_pipe_kernel<P, M, BPS>;
+    static bool configured[16] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 16 && !configured[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured[dev] = true;
+    }
+    const long long ntiles = (a.n + Cfg::THREADS - 1) / Cfg::THREADS;
+    const long long resident = static_cast<long long>(h->sm_count) * BPS;
+    const int grid = static_cast<int>(std::min<long long>(ntiles, resident));
+    if (grid > 0) kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, ntiles);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return BLF_CCM_OK;
+}
+
 template <int P, int M, bool AOS>
 static int rls_launch(blf_ccm_handle* h, const RlsArgs& a, cudaStream_t st)
 {
+    if constexpr (!AOS) {
+        constexpr int kDefaultBps = (P <= 2 ? 3 : 2);
+        // measured (profiles/r01_rls_throughput_v3.log): 96.7 % vs 88.1 % of the HBM peak at 8.4 M
+        // estimators, 82 % vs 78 % at 819 200; a 4-blocks/SM build (128 registers, 168 B spilled)
+        // dropped to 77 % and was removed
+        if (h->tune_rls_pipe != 1) return rls_launch_pipe<P, M, kDefaultBps>(h, a, st);
+    }
     const int threads = 128;
     const long long grid = (a.n + threads - 1) / threads;
     if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");

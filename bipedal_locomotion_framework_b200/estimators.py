@@ -114,6 +114,40 @@ class RecursiveLeastSquareBatch:
             _np_ptr(self._r), self._lambda, pp(state_planes, p), pp(cov_planes, p * p),
             self._b._stream()))
 
+    def prepare_advance(self, regressor_planes, measurement_planes, state_planes, cov_planes):
+        """Pre-bound form of advance(): returns a zero-argument callable (launch-bound loops)."""
+        m, p = measurement_planes.shape[0], state_planes.shape[0]
+        n = state_planes.shape[1]
+        pp = self._b._plane_ptrs
+        args = (self._b.handle.ptr, n, p, m, pp(regressor_planes, m * p), pp(measurement_planes, m),
+                _np_ptr(self._r), self._lambda, pp(state_planes, p), pp(cov_planes, p * p),
+                self._b._stream())
+        fn = _capi.lib().blf_rls_advance_batch
+        keep = (regressor_planes, measurement_planes, state_planes, cov_planes)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call
+
+    def prepare_advance_contacts(self, planes, measured_wrench_planes, state_planes, cov_planes,
+                                 geometry_planes=None):
+        """Pre-bound form of advance_contacts()."""
+        n = self._b._num_contacts(planes)
+        pp = self._b._plane_ptrs
+        args = (self._b.handle.ptr, n, pp(planes, 30), pp(geometry_planes, 2),
+                pp(measured_wrench_planes, 6), _np_ptr(self._r), self._lambda, pp(state_planes, 2),
+                pp(cov_planes, 4), self._b._stream())
+        fn = _capi.lib().blf_ccm_rls_advance_contacts
+        keep = (planes, measured_wrench_planes, state_planes, cov_planes, geometry_planes)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call
+
     def advance_contacts(self, planes, measured_wrench_planes, state_planes, cov_planes,
                          geometry_planes=None):
         """Fused: regressor from the contact state in registers + one RLS step on (spring, damper)."""
