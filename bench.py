@@ -508,6 +508,32 @@ def run_ours(args):
            "h2d_bytes_per_step": int(n * 30 * 8), "d2h_bytes_per_step": int(n * 48 * 8),
            "ms_per_step": e2e_s / Ke * 1e3, "steps": Ke, "launches_per_step": e2e_launches / Ke,
            "api": "blf_ccm_eval_batch_host (AoS iDynTree-layout arrays in pinned host memory in/out)"}
+    if world == 1:
+        # what bounds e2e: the PCIe link, measured here with plain pinned copies of the same byte
+        # counts in both directions at once (240 B up, 384 B down per evaluation), no kernel
+        d_up = torch.empty(n * 30, dtype=torch.float64, device=dev)
+        d_dn = torch.empty(n * 48, dtype=torch.float64, device=dev)
+        h_up = torch.empty(n * 30, dtype=torch.float64).pin_memory()
+        h_dn = torch.empty(n * 48, dtype=torch.float64).pin_memory()
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def both():
+            with torch.cuda.stream(s_up):
+                d_up.copy_(h_up, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_dn.copy_(d_dn, non_blocking=True)
+        for _ in range(2):
+            both()
+        torch.cuda.synchronize()
+        tp = time.perf_counter()
+        for _ in range(5):
+            both()
+        torch.cuda.synchronize()
+        link_s = (time.perf_counter() - tp) / 5
+        e2e["pcie"] = {"what": "pinned cudaMemcpyAsync of one step's bytes in both directions at once, no kernel",
+                       "h2d_gbs": n * 240 / link_s / 1e9, "d2h_gbs": n * 384 / link_s / 1e9,
+                       "ceiling_evals_per_s": n / link_s, "frac_of_ceiling": (n * Ke / e2e_s) / (n / link_s)}
+        del d_up, d_dn, h_up, h_dn
     sampler.stop_flag = True
 
     if rank != 0:

@@ -542,9 +542,13 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
     for (int s = 0; s < kHostSlots; ++s)
         if (!h->hstream[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream[s], cudaStreamNonBlocking));
 
+    // Chunk sizes ramp up geometrically (chunk/8, chunk/4, chunk/2, chunk, chunk, ...): the D2H
+    // direction is the bottleneck of the whole call and cannot start before the first chunk's upload
+    // and kernel are done, so the first chunk is kept small; from then on both PCIe directions stay busy.
     int slot = 0;
-    for (long long off = 0; off < n; off += chunk, slot = (slot + 1) % kHostSlots) {
-        const long long c = std::min<long long>(chunk, n - off);
+    long long cur = (n > 2 * chunk) ? std::max<long long>(chunk / 8, 1024) : chunk;
+    for (long long off = 0, c = 0; off < n; off += c, slot = (slot + 1) % kHostSlots, cur = std::min(chunk, cur * 2)) {
+        c = std::min<long long>(cur, n - off);
         cudaStream_t st = h->hstream[slot];
         double* b = h->hbuf[slot];
         double* d_tw = b;
