@@ -788,13 +788,9 @@ static int rls_launch_pipe(blf_ccm_handle* h, const RlsArgs& a, cudaStream_t st)
 {
     using Cfg = RlsPipe<P, M>;
     auto kern = rls_advance_pipe_kernel<P, M, BPS>;
-    static bool configured[16] = {};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 16 && !configured[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured[dev] = true;
-    }
+    // opt in to > 48 KB of dynamic shared memory (a per-device function attribute; the call is a
+    // few hundred nanoseconds, so it is simply repeated rather than cached across threads)
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const long long ntiles = (a.n + Cfg::THREADS - 1) / Cfg::THREADS;
     const long long resident = static_cast<long long>(h->sm_count) * BPS;
     const int grid = static_cast<int>(std::min<long long>(ntiles, resident));
