@@ -4,11 +4,33 @@
  * Eigen::Matrix3d, Eigen::Matrix<double,6,1> and Eigen::VectorXd here
  * (src/System/include/BipedalLocomotion/System/FloatingBaseSystemKinematics.h:31-33); Eigen is a
  * third-party dependency that is not available in this build, so these stand-ins provide the
- * storage layout (Matrix3d is ROW-major here: it is handed to the C ABI as is) and the two
- * operations the integrators need (`x += dx * dT`, ForwardEuler.h:50).
+ * storage (Matrix3d is ROW-major here) and the two operations the integrators need
+ * (`x += dx * dT`, ForwardEuler.h:50).
+ *
+ * With Eigen available define BLF_HAVE_EIGEN (CMake: -DFRAMEWORK_USE_Eigen=ON): the four names
+ * then ARE the reference's Eigen types (Matrix3d column-major), so code written against the
+ * reference's System classes -- its own IntegratorTest.cpp included -- compiles unchanged.  The
+ * facade never assumes a storage order: rotations cross the C ABI through toRowMajor/fromRowMajor.
  */
 #ifndef BIPEDAL_LOCOMOTION_SYSTEM_STATE_TYPES_H
 #define BIPEDAL_LOCOMOTION_SYSTEM_STATE_TYPES_H
+
+#if defined(BLF_HAVE_EIGEN)
+
+#include <Eigen/Dense>
+
+namespace BipedalLocomotion
+{
+namespace System
+{
+using Vector3d = Eigen::Vector3d;
+using Vector6d = Eigen::Matrix<double, 6, 1>;
+using Matrix3d = Eigen::Matrix3d;
+using VectorXd = Eigen::VectorXd;
+} // namespace System
+} // namespace BipedalLocomotion
+
+#else // bundled value types
 
 #include <array>
 #include <cstddef>
@@ -115,6 +137,26 @@ struct VectorXd
     }
 };
 
+} // namespace System
+} // namespace BipedalLocomotion
+
+#endif // BLF_HAVE_EIGEN
+
+namespace BipedalLocomotion
+{
+namespace System
+{
+/** The C ABI takes rotations as 9 doubles, row-major, whatever Matrix3d's own storage order is. */
+inline void toRowMajor(const Matrix3d& m, double out[9])
+{
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) out[3 * r + c] = m(r, c);
+}
+inline void fromRowMajor(const double in[9], Matrix3d& m)
+{
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) m(r, c) = in[3 * r + c];
+}
 } // namespace System
 } // namespace BipedalLocomotion
 

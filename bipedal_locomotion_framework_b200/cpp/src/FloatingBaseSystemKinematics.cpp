@@ -62,15 +62,17 @@ bool FloatingBaseSystemKinematics::dynamics(const double& /*time*/, StateDerivat
     if (!ensureDevice("dynamics")) return false;
 
     Vector3d& baseLinearVelocity = std::get<0>(stateDerivative);
-    Matrix3d& baseRotationRate = std::get<1>(stateDerivative);
+    double rotation[9], rotationRate[9]; // row-major across the C ABI
+    toRowMajor(baseRotation, rotation);
     const int rc = blf_sys_kinematics_dynamics_host(static_cast<blf_ccm_handle*>(m_device->handle()), 1,
-                                                    m_rho, baseTwist.data(), baseRotation.data(),
-                                                    baseLinearVelocity.data(), baseRotationRate.data());
+                                                    m_rho, baseTwist.data(), rotation,
+                                                    baseLinearVelocity.data(), rotationRate);
     if (rc != BLF_CCM_OK)
     {
         std::cerr << "[FloatingBaseSystemKinematics::dynamics] " << blf_ccm_last_error() << std::endl;
         return false;
     }
+    fromRowMajor(rotationRate, std::get<1>(stateDerivative));
     std::get<2>(stateDerivative) = jointVelocity;
     return true;
 }
@@ -90,9 +92,11 @@ bool FloatingBaseSystemKinematics::advanceOnDevice(double stepDT, double lastDT,
     }
     if (!ensureDevice("dynamics")) return false;
     const std::int64_t nj = static_cast<std::int64_t>(jointPositions.size());
+    double rotation[9]; // row-major across the C ABI
+    toRowMajor(baseRotation, rotation);
     const int rc = blf_sys_kinematics_integrate_host(static_cast<blf_ccm_handle*>(m_device->handle()), 1,
                                                      m_rho, stepDT, lastDT, steps, baseTwist.data(),
-                                                     basePosition.data(), baseRotation.data(), nj,
+                                                     basePosition.data(), rotation, nj,
                                                      nj ? jointVelocity.data() : nullptr,
                                                      nj ? jointPositions.data() : nullptr);
     if (rc != BLF_CCM_OK)
@@ -100,5 +104,6 @@ bool FloatingBaseSystemKinematics::advanceOnDevice(double stepDT, double lastDT,
         std::cerr << "[FloatingBaseSystemKinematics::dynamics] " << blf_ccm_last_error() << std::endl;
         return false;
     }
+    fromRowMajor(rotation, baseRotation);
     return true;
 }

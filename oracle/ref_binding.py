@@ -27,6 +27,7 @@ REFERENCE_ROOT = os.environ.get("BLF_REFERENCE_ROOT", "/root/reference")
 REFERENCE_TESTS = ("ContinuousContactModelReferenceTests", "IntegratorReferenceTests",
                    "ParametersHandlerReferenceTests")
 FACADE_TEST = "ContinuousContactModelReferenceTests_on_b200_facade"  # needs a CUDA device to run
+FACADE_INTEGRATOR_TEST = "IntegratorReferenceTests_on_b200_facade"    # second section needs a CUDA device
 
 WRENCH, AUTODYN, CTRL, REGRESSOR = 1, 2, 4, 8
 

@@ -109,6 +109,19 @@ def test_reference_unmodified_test_passes_on_the_b200_facade(ref):
     assert "0 failure(s)" in r.stdout and "26 assertion(s)" in r.stdout
 
 
+def test_reference_unmodified_integrator_test_passes_on_the_b200_facade(ref):
+    """src/System/tests/IntegratorTest.cpp, compiled UNMODIFIED on the facade's System classes
+    (state types = the Eigen types via BLF_HAVE_EIGEN; the reference's own LinearTimeInvariantSystem
+    over the facade's DynamicalSystem / ForwardEuler templates): the linear system's closed-form
+    step response, and 20 000 single-step integrate() calls of FloatingBaseSystemKinematics on the
+    GPU against the axis-angle closed form."""
+    exe = os.path.join(ref.REF_DIR, ref.FACADE_INTEGRATOR_TEST)
+    assert os.path.exists(exe), "oracle/_ref/" + ref.FACADE_INTEGRATOR_TEST + " was not built / shipped"
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "0 failure(s)" in r.stdout and "120001 assertion(s)" in r.stdout
+
+
 def test_per_instance_facade_vs_reference_build(torch, ref):
     from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModel, StdImplementation
     st = syn.make_states(24, seed=3, heterogeneous=True)

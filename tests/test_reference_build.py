@@ -52,6 +52,26 @@ def test_reference_own_tests_pass(ref, exe):
     assert "0 failure(s)" in r.stdout
 
 
+def test_reference_lti_system_integrates_under_the_facade_templates(ref):
+    """The reference's IntegratorTest.cpp built on the FACADE's System templates: its first section
+    (the reference's own LinearTimeInvariantSystem under the facade's DynamicalSystem / ForwardEuler,
+    20 000 steps against the closed-form step response) is host-only and must pass here; the second
+    section needs the GPU and must fail loudly -- not fall back -- without one."""
+    import torch
+    exe = os.path.join(ref.REF_DIR, ref.FACADE_INTEGRATOR_TEST)
+    if not os.path.exists(exe):
+        pytest.skip("facade test binaries are built only where the product libraries exist")
+    r = ref.run_reference_test(ref.FACADE_INTEGRATOR_TEST)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "0 failure(s)" in r.stdout
+        return
+    assert r.returncode != 0
+    assert r.stdout.count("FAILED") == 1
+    assert "[section: Floating base System Kinematics]" in r.stdout
+    assert "there is no CPU evaluation path" in r.stdout
+    assert "40005 assertion(s), 1 failure(s)" in r.stdout   # 40 004 passed: the whole linear-system section
+
+
 # --- contact model: oracle == reference build ------------------------------------------------------
 
 @pytest.mark.parametrize("heterogeneous", [False, True])
