@@ -244,3 +244,45 @@ def test_fused_contact_identification(torch, batch, oracle):
     est = th_f.cpu().numpy()
     assert np.median(np.abs(est[0] - true_k) / true_k) < 0.05
     assert np.median(np.abs(est[1] - true_b) / true_b) < 0.05
+
+
+@pytest.mark.gpu
+def test_pipelined_and_plain_kernels_and_prebound_calls_agree_bit_for_bit(torch, monkeypatch):
+    """rls_advance_pipe_kernel (default, per-thread cp.async ring over a resident grid) and the plain
+    one-estimator-per-thread kernel (BLF_CCM_TUNE_RLS_PIPE=1) share the arithmetic body: identical
+    bits, at ragged sizes around the tile (128) and grid (3 blocks x SMs) boundaries; the pre-bound
+    call forms launch the same thing."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquareBatch
+    rng = np.random.default_rng(77)
+    r, lam = rng.uniform(0.1, 1.0, 6), 0.97
+
+    def run(n, plain, prebound):
+        if plain:
+            monkeypatch.setenv("BLF_CCM_TUNE_RLS_PIPE", "1")
+        else:
+            monkeypatch.delenv("BLF_CCM_TUNE_RLS_PIPE", raising=False)
+        b = ContinuousContactModelBatch(0)
+        b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+        rls = RecursiveLeastSquareBatch(b, r, lam)
+        g = np.random.default_rng(n)
+        Y, z = g.normal(0, 1, (12, n)), g.normal(0, 1, (6, n))
+        th = g.normal(0, 1, (2, n))
+        A = g.normal(0, 1, (n, 2, 2))
+        P = (A @ A.transpose(0, 2, 1) + 0.5 * np.eye(2)).reshape(n, 4).T
+        d = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (Y, z, th, P)]
+        for _ in range(3):
+            if prebound:
+                rls.prepare_advance(*d)()
+            else:
+                rls.advance(*d)
+        torch.cuda.synchronize()
+        return d[2].cpu().numpy(), d[3].cpu().numpy()
+
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    for n in (1, 127, 128, 129, 128 * 3 * sm - 1, 128 * 3 * sm + 1, 128 * 3 * sm * 2 + 77):
+        th_a, P_a = run(n, plain=False, prebound=False)
+        th_b, P_b = run(n, plain=True, prebound=False)
+        th_c, P_c = run(n, plain=False, prebound=True)
+        assert np.array_equal(th_a, th_b) and np.array_equal(P_a, P_b), n
+        assert np.array_equal(th_a, th_c) and np.array_equal(P_a, P_c), n
