@@ -503,7 +503,7 @@ static int eval_single_host(blf_ccm_handle* h, const double* twist, const double
     return BLF_CCM_OK;
 }
 
-// ---- host buffers: chunked, three slots, copies and kernels overlapped ---------------------------
+// ---- host buffers: chunked, four slots; upload, kernel and download streams overlapped ---------------------------
 
 extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const double* twists,
                                        const double* poses, const double* null_poses,

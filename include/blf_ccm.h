@@ -312,7 +312,7 @@ BLF_CCM_API int blf_ccm_rollout_integrate_cost(
 
 /* Same rollouts with every plane in HOST memory (pinned gives full PCIe speed), cost only: the
  * horizon is cut into time chunks (contiguous in the time-major planes, so every upload is a plain
- * 1-D copy), pipelined through three slots -- the upload of the next chunk overlaps the kernel of
+ * 1-D copy), pipelined through four slots -- the upload of the next chunk overlaps the kernel of
  * the current one, poses and costs carry over on the device; per evaluation only the 48-byte
  * twist crosses PCIe, one pair comes back.  cost (host, n_rollouts) may be NULL.  Returns when best_cost / best_index are written
  * (index -1 when there is nothing to compare).  Not part of a peer exchange (local arg-min). */
