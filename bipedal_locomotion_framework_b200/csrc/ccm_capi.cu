@@ -87,6 +87,7 @@ struct blf_ccm_handle {
     int tune_rollout_ws = 0;     // BLF_CCM_TUNE_ROLLOUT_WS: 1 force / 2 forbid the warp-specialised rollout
     int tune_no_rows = 0;        // BLF_CCM_TUNE_NO_ROWS=1: J^T wrench without base/out row staging
     int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
+    int tune_rollout_chunk_mb = 0;  // BLF_CCM_TUNE_ROLLOUT_CHUNK_MB: twist bytes per time chunk of the host rollout (default 8)
     int tune_rls_pipe = 0;       // BLF_CCM_TUNE_RLS_PIPE=1: the plain one-estimator-per-thread RLS kernel instead of the pipelined one
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
@@ -141,6 +142,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");
     h->tune_rls_pipe = env_int("BLF_CCM_TUNE_RLS_PIPE");
+    h->tune_rollout_chunk_mb = env_int("BLF_CCM_TUNE_ROLLOUT_CHUNK_MB");
     h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
     h->tune_rollout_ws = env_int("BLF_CCM_TUNE_ROLLOUT_WS");
     CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
