@@ -82,6 +82,33 @@ def lib():
     return _lib
 
 
+ALT_LIB_PATH = os.path.join(REF_DIR, "libblf_reference_alt.so")
+
+
+def eval_batch_states_alt(states: dict, mask=WRENCH | AUTODYN | CTRL | REGRESSOR, nthreads=1) -> dict:
+    """The same reference sources built with the OTHER choices a real-Eigen build could make
+    (tree-shaped inner sums, FMA contraction): oracle/_ref/libblf_reference_alt.so.  Only used to
+    bound how far such choices move the results."""
+    if not os.path.exists(ALT_LIB_PATH):
+        build()
+    L = C.CDLL(ALT_LIB_PATH)
+    L.blf_ref_ccm_eval_batch_aos.argtypes = [C.c_size_t] + [C.c_void_p] * 5 + [C.c_uint] + [C.c_void_p] * 4 + [C.c_int]
+    n = states["twists"].shape[0]
+    tw, po, nu = _f64(states["twists"]), _f64(states["poses"]), _f64(states["null_poses"])
+    pr = None if states.get("params") is None else _f64(states["params"])
+    uni = np.asarray(states.get("uniform") if states.get("uniform") is not None else (0, 0, 0, 0), dtype=np.float64)
+    out = {"wrench": np.empty((n, 6)) if mask & WRENCH else None,
+           "autodyn": np.empty((n, 6)) if mask & AUTODYN else None,
+           "ctrl": np.empty((n, 36)) if mask & CTRL else None,
+           "regressor": np.empty((n, 12)) if mask & REGRESSOR else None}
+    rc = L.blf_ref_ccm_eval_batch_aos(n, _ptr(tw), _ptr(po), _ptr(nu), _ptr(pr), _ptr(uni), mask,
+                                      _ptr(out["wrench"]), _ptr(out["autodyn"]), _ptr(out["ctrl"]),
+                                      _ptr(out["regressor"]), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"reference initialize() refused (rc={rc})")
+    return out
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

@@ -282,6 +282,28 @@ def test_rollout_oracle_vs_reference_build(sys_oracle, ref, rho):
     assert np.array_equal(o["rot"].T, r["final_poses"][:, 3:])
 
 
+# --- how much can the part the stand-in leaves open matter? ---------------------------------------
+
+def test_evaluation_order_and_fma_choices_move_results_far_below_tolerance(ref):
+    """The stand-in Eigen is not Eigen: it fixes one association of the 3-term inner sums and the
+    default build forbids FMA contraction.  libblf_reference_alt.so is the same reference source built
+    with the OTHER choices (tree-shaped sums as Eigen's unrolled reductions, -ffp-contract=fast -mfma).
+    The two builds differ -- most outputs in the last bits -- but norm-wise by < 1e-13 (measured:
+    8e-15), three orders of magnitude under the 1e-12 parity tolerance."""
+    from parity import block_rel_err
+    if not os.path.exists(ref.ALT_LIB_PATH) and not ref.reference_sources_present():
+        pytest.skip("alternative reference build not available")
+    st = syn.make_states(200_000, seed=49, heterogeneous=True)
+    a = ref.eval_batch_states(st, MASK_ALL, nthreads=4)
+    b = ref.eval_batch_states_alt(st, MASK_ALL, nthreads=4)
+    differing = 0
+    for key in ("wrench", "autodyn", "ctrl", "regressor"):
+        differing += int((a[key] != b[key]).any(axis=1).sum())
+        assert block_rel_err(b[key], a[key], key).max() < 1e-13, key
+    assert differing > 1000          # the alternative build really does round differently
+    assert np.array_equal(a["ctrl"], b["ctrl"]) or block_rel_err(b["ctrl"], a["ctrl"], "ctrl").max() < 1e-13
+
+
 # --- special values: the restatement must propagate them exactly as the reference's code does ------
 
 def test_special_values_oracle_vs_reference_build(oracle, ref):
