@@ -6,7 +6,10 @@
  * (src/ParametersHandler/include/BipedalLocomotion/ParametersHandler/IParametersHandler.h:26-249):
  * same method names, argument meaning and bool-return error convention.  Vector parameters are
  * carried as std::vector<T> (the reference routes them through GenericContainer::Vector, a host
- * utility that is outside this build's scope).
+ * utility that is outside this build's scope) and keep the reference's resize contract: by default
+ * (VectorResizeMode::Fixed) the destination must already have the size of the stored list, pass
+ * VectorResizeMode::Resizable to have it resized (IParametersHandler.h:129-139,
+ * StdImplementation.tpp:62-85).  std::vector<bool> is always resized, as upstream.
  */
 #ifndef BIPEDAL_LOCOMOTION_PARAMETERS_HANDLER_IPARAMETERS_HANDLER_H
 #define BIPEDAL_LOCOMOTION_PARAMETERS_HANDLER_IPARAMETERS_HANDLER_H
@@ -14,6 +17,8 @@
 #include <memory>
 #include <string>
 #include <vector>
+
+#include <BipedalLocomotion/GenericContainer/Vector.h>
 
 namespace BipedalLocomotion
 {
@@ -33,9 +38,12 @@ public:
     virtual bool getParameter(const std::string& parameterName, std::string& parameter) const = 0;
     virtual bool getParameter(const std::string& parameterName, bool& parameter) const = 0;
     virtual bool getParameter(const std::string& parameterName, std::vector<bool>& parameter) const = 0;
-    virtual bool getParameter(const std::string& parameterName, std::vector<int>& parameter) const = 0;
-    virtual bool getParameter(const std::string& parameterName, std::vector<double>& parameter) const = 0;
-    virtual bool getParameter(const std::string& parameterName, std::vector<std::string>& parameter) const = 0;
+    virtual bool getParameter(const std::string& parameterName, std::vector<int>& parameter,
+                              GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const = 0;
+    virtual bool getParameter(const std::string& parameterName, std::vector<double>& parameter,
+                              GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const = 0;
+    virtual bool getParameter(const std::string& parameterName, std::vector<std::string>& parameter,
+                              GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const = 0;
 
     virtual void setParameter(const std::string& parameterName, const int& parameter) = 0;
     virtual void setParameter(const std::string& parameterName, const double& parameter) = 0;

@@ -49,10 +49,26 @@ class StdImplementation : public IParametersHandler
         return true;
     }
 
+    /** Vector parameters: the reference's resize contract (StdImplementation.tpp:62-85). */
+    template <typename T>
+    bool getVectorPrivate(const std::string& parameterName, std::vector<T>& parameter,
+                          GenericContainer::VectorResizeMode mode) const
+    {
+        std::vector<T> stored;
+        if (!getParameterPrivate(parameterName, stored)) return false;
+        if (stored.size() != parameter.size() && mode != GenericContainer::VectorResizeMode::Resizable)
+        {
+            std::cerr << "[StdImplementation::getParameterPrivate] Unable to resize the vector. List size: "
+                      << stored.size() << ". Vector size: " << parameter.size() << std::endl;
+            return false;
+        }
+        parameter = stored;
+        return true;
+    }
+
 public:
-    using unique_ptr = std::unique_ptr<StdImplementation>;
-    using shared_ptr = std::shared_ptr<StdImplementation>;
-    using weak_ptr = std::weak_ptr<StdImplementation>;
+    // unique_ptr / shared_ptr / weak_ptr are the ones inherited from IParametersHandler (pointers to
+    // the INTERFACE), as upstream: `StdImplementation::shared_ptr g = h->getGroup("x").lock();`
 
     StdImplementation() = default;
     explicit StdImplementation(const std::unordered_map<std::string, std::any>& map) : m_map(map) {}
@@ -62,9 +78,21 @@ public:
     bool getParameter(const std::string& n, std::string& p) const final { return getParameterPrivate(n, p); }
     bool getParameter(const std::string& n, bool& p) const final { return getParameterPrivate(n, p); }
     bool getParameter(const std::string& n, std::vector<bool>& p) const final { return getParameterPrivate(n, p); }
-    bool getParameter(const std::string& n, std::vector<int>& p) const final { return getParameterPrivate(n, p); }
-    bool getParameter(const std::string& n, std::vector<double>& p) const final { return getParameterPrivate(n, p); }
-    bool getParameter(const std::string& n, std::vector<std::string>& p) const final { return getParameterPrivate(n, p); }
+    bool getParameter(const std::string& n, std::vector<int>& p,
+                      GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const final
+    {
+        return getVectorPrivate(n, p, mode);
+    }
+    bool getParameter(const std::string& n, std::vector<double>& p,
+                      GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const final
+    {
+        return getVectorPrivate(n, p, mode);
+    }
+    bool getParameter(const std::string& n, std::vector<std::string>& p,
+                      GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const final
+    {
+        return getVectorPrivate(n, p, mode);
+    }
 
     void setParameter(const std::string& n, const int& p) final { m_map[n] = p; }
     void setParameter(const std::string& n, const double& p) final { m_map[n] = p; }
@@ -80,7 +108,7 @@ public:
     {
         auto it = m_map.find(name);
         if (it == m_map.end()) return std::make_shared<StdImplementation>(); // expires at once
-        const auto* group = std::any_cast<shared_ptr>(&it->second);
+        const auto* group = std::any_cast<std::shared_ptr<StdImplementation>>(&it->second);
         if (group == nullptr)
         {
             std::cerr << "[StdImplementation::getGroup] The element named " << name
@@ -100,7 +128,7 @@ public:
                       << std::endl;
             return false;
         }
-        m_map[name] = std::make_any<shared_ptr>(down);
+        m_map[name] = std::make_any<std::shared_ptr<StdImplementation>>(down);
         return true;
     }
 

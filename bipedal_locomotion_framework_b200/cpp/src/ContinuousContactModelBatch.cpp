@@ -95,7 +95,7 @@ bool ContinuousContactModelBatch::loadParameterTable(std::weak_ptr<IParametersHa
     std::vector<double> column[4];
     for (int k = 0; k < 4; ++k)
     {
-        if (!handler->getParameter(keys[k], column[k]))
+        if (!handler->getParameter(keys[k], column[k], BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable))
         {
             std::cerr << "[ContinuousContactModelBatch::loadParameterTable] Unable to get the vector "
                          "named "

@@ -40,7 +40,7 @@ bool RecursiveLeastSquare::initialize(std::weak_ptr<IParametersHandler> handlerW
                   << std::endl;
         return false;
     }
-    if (!handler->getParameter("measurement_covariance", m_measurementCovariance))
+    if (!handler->getParameter("measurement_covariance", m_measurementCovariance, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable))
     {
         std::cerr << "[RecursiveLeastSquare::initialize] Unable to find the covariance matrix of "
                      "the measuraments."
@@ -53,12 +53,12 @@ bool RecursiveLeastSquare::initialize(std::weak_ptr<IParametersHandler> handlerW
         return false;
     }
     std::vector<double> state, stateCovariance;
-    if (!handler->getParameter("state", state))
+    if (!handler->getParameter("state", state, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable))
     {
         std::cerr << "[RecursiveLeastSquare::initialize] Unable to get the initial guess." << std::endl;
         return false;
     }
-    if (!handler->getParameter("state_covariance", stateCovariance))
+    if (!handler->getParameter("state_covariance", stateCovariance, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable))
     {
         std::cerr << "[RecursiveLeastSquare::initialize] Unable to get the initial state covariance."
                   << std::endl;

@@ -55,8 +55,14 @@ TEST_CASE("Get parameters")
     SECTION("Get Vector")
     {
         std::vector<int> element;
-        REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", element));
+        // the reference's contract (IParametersHandler.h:129-139): Fixed (default) needs a destination of
+        // the right size already, Resizable resizes it
+        REQUIRE_FALSE(parameterHandler->getParameter("Fibonacci Numbers", element));
+        REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", element, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable));
         REQUIRE(element == std::vector<int>{1, 1, 2, 3, 5, 8, 13, 21});
+        std::vector<int> sized(8, 0);
+        REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", sized));
+        REQUIRE(sized == element);
     }
 
     SECTION("Strict typing and missing keys")
@@ -76,7 +82,7 @@ TEST_CASE("Get parameters")
         REQUIRE(groupHandler);
         groupHandler->setParameter("Donald's nephews", std::vector<std::string>{"Huey", "Dewey", "Louie"});
         std::vector<std::string> element;
-        REQUIRE(groupHandler->getParameter("Donald's nephews", element));
+        REQUIRE(groupHandler->getParameter("Donald's nephews", element, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable));
         REQUIRE(element == std::vector<std::string>{"Huey", "Dewey", "Louie"});
         REQUIRE_FALSE(parameterHandler->getGroup("NO SUCH GROUP").lock());
     }
@@ -150,19 +156,19 @@ TEST_CASE("Get parameters")
         }
         {
             std::vector<int> element;
-            REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", element));
+            REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", element, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable));
             REQUIRE(element == fibonacciNumbers);
         }
         IParametersHandler::shared_ptr cartoonsGroup = parameterHandler->getGroup("CARTOONS").lock();
         REQUIRE(cartoonsGroup);
         {
             std::vector<std::string> element;
-            REQUIRE(cartoonsGroup->getParameter("Donald's nephews", element));
+            REQUIRE(cartoonsGroup->getParameter("Donald's nephews", element, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable));
             REQUIRE(element == donaldsNephews);
         }
         {
             std::vector<int> element;
-            REQUIRE(cartoonsGroup->getParameter("Fibonacci_Numbers", element));
+            REQUIRE(cartoonsGroup->getParameter("Fibonacci_Numbers", element, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable));
             REQUIRE(element == fibonacciNumbers);
         }
         {
@@ -183,7 +189,7 @@ TEST_CASE("Get parameters")
         REQUIRE(h.getParameter("rho", rho));
         REQUIRE(rho == 0.01);
         std::vector<double> gains;
-        REQUIRE(h.getParameter("gains", gains)); // mixed int/double list -> doubles
+        REQUIRE(h.getParameter("gains", gains, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable)); // mixed int/double list -> doubles
         REQUIRE((gains == std::vector<double>{1.5, 2.0, 2.5}));
         std::vector<bool> flags;
         REQUIRE(h.getParameter("flags", flags));
@@ -192,7 +198,7 @@ TEST_CASE("Get parameters")
         REQUIRE(h.getParameter("use_cuda", useCuda));
         REQUIRE(useCuda);
         std::vector<int> empty{1};
-        REQUIRE(h.getParameter("empty", empty));
+        REQUIRE(h.getParameter("empty", empty, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable));
         REQUIRE(empty.empty());
         std::string name;
         REQUIRE(h.getParameter("name", name));
@@ -200,7 +206,7 @@ TEST_CASE("Get parameters")
         auto table = h.getGroup("CONTACT_PARAMETERS").lock();
         REQUIRE(table);
         std::vector<double> length;
-        REQUIRE(table->getParameter("length", length));
+        REQUIRE(table->getParameter("length", length, BipedalLocomotion::GenericContainer::VectorResizeMode::Resizable));
         REQUIRE((length == std::vector<double>{0.12, 0.15}));
 
         StdImplementation bad;

@@ -28,6 +28,7 @@ REFERENCE_TESTS = ("ContinuousContactModelReferenceTests", "IntegratorReferenceT
                    "ParametersHandlerReferenceTests")
 FACADE_TEST = "ContinuousContactModelReferenceTests_on_b200_facade"  # needs a CUDA device to run
 FACADE_INTEGRATOR_TEST = "IntegratorReferenceTests_on_b200_facade"    # second section needs a CUDA device
+FACADE_HANDLER_TEST = "ParametersHandlerReferenceTests_on_b200_facade"  # host only
 
 WRENCH, AUTODYN, CTRL, REGRESSOR = 1, 2, 4, 8
 

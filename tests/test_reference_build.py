@@ -52,6 +52,18 @@ def test_reference_own_tests_pass(ref, exe):
     assert "0 failure(s)" in r.stdout
 
 
+def test_reference_parameters_handler_test_passes_on_the_facade_handler(ref):
+    """src/ParametersHandler/tests/ParametersHandlerTest.cpp, unmodified, on the facade's
+    StdImplementation: typed getters, the VectorResizeMode contract, groups through the inherited
+    shared_ptr typedefs, set-from-object, isEmpty / clear."""
+    exe = os.path.join(ref.REF_DIR, ref.FACADE_HANDLER_TEST)
+    if not os.path.exists(exe):
+        pytest.skip("facade test binaries are built only where the product libraries exist")
+    r = ref.run_reference_test(ref.FACADE_HANDLER_TEST)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "20 assertion(s), 0 failure(s)" in r.stdout
+
+
 def test_reference_lti_system_integrates_under_the_facade_templates(ref):
     """The reference's IntegratorTest.cpp built on the FACADE's System templates: its first section
     (the reference's own LinearTimeInvariantSystem under the facade's DynamicalSystem / ForwardEuler,
