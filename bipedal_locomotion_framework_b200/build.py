@@ -64,6 +64,7 @@ CPP_TESTS = {
     "ParametersHandlerUnitTests": "ParametersHandlerTest.cpp",             # host only
     "RecursiveLeastSquareUnitTests": "RecursiveLeastSquareTest.cpp",       # needs a GPU
     "IntegratorUnitTests": "IntegratorTest.cpp",                           # host section + GPU
+    "ContactWrenchUnitTests": "ContactWrenchTest.cpp",                     # host only
 }
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra"]
 

@@ -59,6 +59,13 @@ def test_reference_rls_test_on_the_gpu_estimator(cpp):
     assert "2 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
 
 
+def test_contact_wrench_holder(cpp):
+    """System::ContactWrench (src/System/src/ContactWrench.cpp:13-35): frame index + shared model."""
+    r = _run("ContactWrenchUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failure(s)" in r.stdout
+
+
 def test_generic_integrator_templates_host_section(cpp):
     """src/System/tests/IntegratorTest.cpp:27-78 (linear system through the generic ForwardEuler /
     FixedStepIntegrator templates; host logic only)."""
