@@ -137,7 +137,7 @@ def _cpu_impl(prefer_reference: bool = True):
     from oracle import ccm_oracle, ref_binding
     if prefer_reference and ref_binding.available():
         return ref_binding, "reference", ("oracle/_ref: the reference's ContinuousContactModel.cpp compiled in place "
-                                          "against stand-in Eigen/iDynTree headers (eager evaluation), g++ -O2")
+                                          "against stand-in Eigen/iDynTree headers (eager evaluation), g++ -O3 -DNDEBUG = CMake Release")
     ccm_oracle.build()
     return ccm_oracle, "port", "oracle/ccm_oracle.c per-instance path, gcc -O2 -ffp-contract=off"
 
