@@ -151,3 +151,35 @@ def test_ini_grammar_and_parameter_table():
                            "damper_coeff (1.0, 2.0)\n")
     assert parameter_table(ints) is None                  # ints are not doubles (strict typing)
     assert parameter_table(None) is None
+
+
+def test_header_is_plain_c99_with_no_cuda_or_torch_types(tmp_path):
+    """The drop-in boundary is a C ABI: include/blf_ccm.h must compile as ISO C99 on its own (plain
+    pointers and sizes in every signature -- no C++, CUDA or torch type)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "blf_ccm.h"\nint main(void) { return blf_ccm_version() != 0 ? 0 : 1; }\n')
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    header = open(os.path.join(ROOT, "include", "blf_ccm.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)          # declarations only, comments stripped
+    code = re.sub(r"//[^\n]*", "", code)
+    for forbidden in ("cudaStream_t", "torch", "at::", "std::", "#include <cuda", "class ", "template"):
+        assert forbidden not in code, f"{forbidden} leaks into the C ABI"
+
+
+def test_every_entry_point_cites_the_reference_or_says_it_is_new():
+    """Each declaration's comment block names the reference function it replaces (file:line under
+    src/...) or states that it has no reference counterpart."""
+    header = open(os.path.join(ROOT, "include", "blf_ccm.h")).read()
+    cites = set(re.findall(r"\b\w+\.(?:cpp|h|tpp):\d+", header))
+    assert len(cites) >= 12, f"only {len(cites)} distinct file:line citations in include/blf_ccm.h"
+    for needed in ("ContinuousContactModel.cpp", "ContactModel.cpp", "RecursiveLeastSquare.cpp",
+                   "FloatingBaseSystemKinematics.cpp", "FloatingBaseSystemDynamics.cpp"):
+        assert any(c.startswith(needed) for c in cites), f"no citation of {needed}"
