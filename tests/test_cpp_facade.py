@@ -59,6 +59,14 @@ def test_reference_rls_test_on_the_gpu_estimator(cpp):
     assert "2 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
 
 
+def test_public_signatures_equal_the_reference(cpp):
+    """cpp/tests/ApiConformanceTest.cpp: static_asserts spelling the reference's declarations
+    (ContactModel, ContinuousContactModel, IParametersHandler, RecursiveLeastSquare, the System
+    templates, ContactWrench) against the facade -- building it IS the test."""
+    r = _run("ApiConformanceUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_contact_wrench_holder(cpp):
     """System::ContactWrench (src/System/src/ContactWrench.cpp:13-35): frame index + shared model."""
     r = _run("ContactWrenchUnitTests")
