@@ -135,7 +135,7 @@ def _cpu_impl(prefer_reference: bool = True):
     """(module, kind, what): oracle/_ref (the reference's own sources compiled against stand-in
     Eigen/iDynTree headers, kind "reference") when it was built, else the C port (kind "port")."""
     from oracle import ccm_oracle, ref_binding
-    if prefer_reference and ref_binding.available():
+    if prefer_reference and ref_binding.usable():
         return ref_binding, "reference", ("oracle/_ref: the reference's ContinuousContactModel.cpp compiled in place "
                                           "against stand-in Eigen/iDynTree headers (eager evaluation), g++ -O3 -DNDEBUG = CMake Release")
     ccm_oracle.build()

@@ -57,6 +57,18 @@ def available() -> bool:
     return os.path.exists(LIB_PATH) or (reference_sources_present() and build() is not None)
 
 
+def usable() -> bool:
+    """available() AND the library actually loads here (a prebuilt .so can be present but unloadable on
+    a box with another toolchain); callers that only want a baseline fall back to the C port then."""
+    if not available():
+        return False
+    try:
+        lib()
+        return True
+    except OSError:
+        return False
+
+
 _lib = None
 
 
