@@ -164,10 +164,16 @@ class ContinuousContactModel:
         self._twist = np.zeros(6)
         self._params = [0.0, 0.0, 0.0, 0.0]  # length, width, spring, damper
         self._params_dirty = True
+        # one launch per state: all four outputs of the current state, tagged with the parameters
+        # they were computed with (see cpp/.../ContinuousContactModel.h, m_all)
+        self._all = {WRENCH: np.zeros(6), AUTODYN: np.zeros(6), CTRL: np.zeros(36),
+                     REGRESSOR: np.zeros(12)}
+        self._all_params = None
 
     def _invalidate(self):
         for k in self._flags:
             self._flags[k] = False
+        self._all_params = None
 
     def initialize(self, handler) -> bool:
         self._invalidate()  # ContactModel.cpp:15-18: flags cleared before initializePrivate
@@ -198,18 +204,21 @@ class ContinuousContactModel:
         if self._handle is None:
             raise RuntimeError("[ContinuousContactModel] initialize() must succeed before any getter "
                                "(there is no CPU path)")
-        if self._params_dirty:
-            self._handle.set_uniform_params(*self._params)
-            self._params_dirty = False
         out = {WRENCH: self._wrench, AUTODYN: self._autodyn, CTRL: self._ctrl,
                REGRESSOR: self._regressor}
-        _capi.check(_capi.lib().blf_ccm_eval_batch_host(
-            self._handle.ptr, 1, _np_ptr(self._twist), _np_ptr(self._frame), _np_ptr(self._null),
-            None, bit,
-            _np_ptr(out[WRENCH]) if bit == WRENCH else None,
-            _np_ptr(out[AUTODYN]) if bit == AUTODYN else None,
-            _np_ptr(out[CTRL]) if bit == CTRL else None,
-            _np_ptr(out[REGRESSOR]) if bit == REGRESSOR else None))
+        if self._all_params != tuple(self._params):
+            # first getter of this state (or the coefficients were written since): ONE evaluation
+            # of all four outputs with the live parameters
+            if self._params_dirty:
+                self._handle.set_uniform_params(*self._params)
+                self._params_dirty = False
+            al = self._all
+            _capi.check(_capi.lib().blf_ccm_eval_batch_host(
+                self._handle.ptr, 1, _np_ptr(self._twist), _np_ptr(self._frame), _np_ptr(self._null),
+                None, WRENCH | AUTODYN | CTRL | REGRESSOR, _np_ptr(al[WRENCH]), _np_ptr(al[AUTODYN]),
+                _np_ptr(al[CTRL]), _np_ptr(al[REGRESSOR])))
+            self._all_params = tuple(self._params)
+        out[bit][:] = self._all[bit]
         self._flags[bit] = True
 
     def getContactWrench(self):
@@ -472,6 +481,11 @@ class ContinuousContactModelBatch:
 
     def set_host_chunk(self, contacts: int):
         _capi.check(_capi.lib().blf_ccm_set_host_chunk(self._handle.ptr, int(contacts)))
+
+    def set_host_threads(self, threads: int):
+        """Worker threads that expand the compact control-matrix download of evaluate_host
+        (-1 automatic, 0 = dense download)."""
+        _capi.check(_capi.lib().blf_ccm_set_host_threads(self._handle.ptr, int(threads)))
 
     def rollout_cost_argmin(self, planes, rollout_len: int, wrench_ref, weights,
                             param_planes=None, mask: int = 0, index_base: int = 0,

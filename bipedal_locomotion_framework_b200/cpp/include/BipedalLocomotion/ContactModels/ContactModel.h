@@ -44,6 +44,11 @@ class ContactModel
     void refresh(unsigned bit, void (ContactModel::*compute)());
 
 protected:
+    /** A compute*() that could not produce its result (no device, failed launch) sets this; the
+     * result is then NOT marked current, so the next getter tries again instead of serving the
+     * untouched storage as if it were computed. */
+    bool m_computeFailed{false};
+
     iDynTree::Wrench m_contactWrench; /**< contact wrench, mixed representation */
     iDynTree::Vector6 m_autonomousDynamics; /**< f of  d(wrench)/dt = f + g u */
     iDynTree::Matrix6x6 m_controlMatrix; /**< g of  d(wrench)/dt = f + g u */

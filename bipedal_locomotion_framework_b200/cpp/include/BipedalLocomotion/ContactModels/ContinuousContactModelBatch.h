@@ -31,6 +31,11 @@ class CudaDevice
 public:
     /** nullptr (and a message on std::cerr) when the device cannot be opened. */
     static std::shared_ptr<CudaDevice> open(int device);
+    /** Device the per-instance facades (ContinuousContactModel, RecursiveLeastSquare,
+     * FloatingBaseSystemKinematics) open in initialize(): the value given to setDefaultIndex, else
+     * $BLF_CCM_DEVICE, else 0. */
+    static int defaultIndex();
+    static void setDefaultIndex(int device);
     ~CudaDevice();
     void* handle() const; /**< blf_ccm_handle* */
     int index() const;

@@ -23,8 +23,9 @@ constexpr unsigned kWrench = 1u, kAutonomousDynamics = 2u, kControlMatrix = 4u, 
 void ContactModel::refresh(unsigned bit, void (ContactModel::*compute)())
 {
     if (m_valid & bit) return;
+    m_computeFailed = false;
     (this->*compute)();
-    m_valid |= bit;
+    if (!m_computeFailed) m_valid |= bit;
 }
 
 bool ContactModel::initialize(std::weak_ptr<ParametersHandler::IParametersHandler> handler)

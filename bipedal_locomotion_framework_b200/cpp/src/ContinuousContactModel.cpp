@@ -6,6 +6,7 @@
  * (src/ContactModels/src/ContinuousContactModel.cpp:16-77, :256-274).
  */
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 
 #include <BipedalLocomotion/ContactModels/ContinuousContactModel.h>
@@ -18,22 +19,13 @@ using namespace BipedalLocomotion::ParametersHandler;
 
 namespace
 {
-int g_defaultDevice = -1;
-
-int defaultDevice()
-{
-    if (g_defaultDevice >= 0) return g_defaultDevice;
-    if (const char* env = std::getenv("BLF_CCM_DEVICE")) return std::atoi(env);
-    return 0;
-}
-
 blf_ccm_handle* raw(const std::shared_ptr<CudaDevice>& d)
 {
     return static_cast<blf_ccm_handle*>(d->handle());
 }
 } // namespace
 
-void ContinuousContactModel::setDefaultDevice(int device) { g_defaultDevice = device; }
+void ContinuousContactModel::setDefaultDevice(int device) { CudaDevice::setDefaultIndex(device); }
 
 ContinuousContactModel::ContinuousContactModel()
 {
@@ -45,6 +37,7 @@ ContinuousContactModel::ContinuousContactModel()
 
 bool ContinuousContactModel::initializePrivate(std::weak_ptr<IParametersHandler> weakHandler)
 {
+    m_allValid = false;
     auto handler = weakHandler.lock();
     if (handler == nullptr)
     {
@@ -81,7 +74,7 @@ bool ContinuousContactModel::initializePrivate(std::weak_ptr<IParametersHandler>
     }
     if (m_device == nullptr)
     {
-        m_device = CudaDevice::open(defaultDevice());
+        m_device = CudaDevice::open(CudaDevice::defaultIndex());
         if (m_device == nullptr)
         {
             std::cerr << "[ContinuousContactModel::initialize] The CUDA backend is not available and "
@@ -96,6 +89,7 @@ bool ContinuousContactModel::initializePrivate(std::weak_ptr<IParametersHandler>
 void ContinuousContactModel::setNullForceTransformPrivate(const iDynTree::Transform& transform)
 {
     m_nullForceTransform = transform;
+    m_allValid = false;
 }
 
 void ContinuousContactModel::setStatePrivate(const iDynTree::Twist& twist,
@@ -103,6 +97,7 @@ void ContinuousContactModel::setStatePrivate(const iDynTree::Twist& twist,
 {
     m_twist = twist;
     m_frameTransform = transform;
+    m_allValid = false;
 }
 
 bool ContinuousContactModel::pushParameters()
@@ -120,38 +115,55 @@ bool ContinuousContactModel::pushParameters()
            == BLF_CCM_OK;
 }
 
-void ContinuousContactModel::evaluate(unsigned mask, double* wrench, double* autodyn, double* ctrl,
-                                      double* regressor)
+const double* ContinuousContactModel::evaluateAll()
 {
-    if (!pushParameters()) return;
+    const double live[4] = {m_length, m_width, m_springCoeff, m_damperCoeff};
+    if (m_allValid && std::memcmp(live, m_allParameters, sizeof(live)) == 0) return m_all;
+    m_allValid = false;
+    if (!pushParameters())
+    {
+        m_computeFailed = true;
+        return nullptr;
+    }
     const int rc = blf_ccm_eval_batch_host(raw(m_device), 1,
                                            reinterpret_cast<const double*>(&m_twist),
                                            reinterpret_cast<const double*>(&m_frameTransform),
                                            reinterpret_cast<const double*>(&m_nullForceTransform),
-                                           nullptr, mask, wrench, autodyn, ctrl, regressor);
+                                           nullptr,
+                                           BLF_CCM_WRENCH | BLF_CCM_AUTODYN | BLF_CCM_CTRL | BLF_CCM_REGRESSOR,
+                                           m_all, m_all + 6, m_all + 24, m_all + 12);
     if (rc != BLF_CCM_OK)
+    {
         std::cerr << "[ContinuousContactModel] evaluation failed: " << blf_ccm_last_error()
                   << std::endl;
+        m_computeFailed = true;
+        return nullptr;
+    }
+    std::memcpy(m_allParameters, live, sizeof(live));
+    m_allValid = true;
+    return m_all;
 }
 
 void ContinuousContactModel::computeContactWrench()
 {
-    evaluate(BLF_CCM_WRENCH, m_contactWrench.data(), nullptr, nullptr, nullptr);
+    if (const double* all = evaluateAll()) std::memcpy(m_contactWrench.data(), all, 6 * sizeof(double));
 }
 
 void ContinuousContactModel::computeAutonomousDynamics()
 {
-    evaluate(BLF_CCM_AUTODYN, nullptr, m_autonomousDynamics.data(), nullptr, nullptr);
+    if (const double* all = evaluateAll())
+        std::memcpy(m_autonomousDynamics.data(), all + 6, 6 * sizeof(double));
 }
 
 void ContinuousContactModel::computeControlMatrix()
 {
-    evaluate(BLF_CCM_CTRL, nullptr, nullptr, m_controlMatrix.data(), nullptr);
+    if (const double* all = evaluateAll())
+        std::memcpy(m_controlMatrix.data(), all + 24, 36 * sizeof(double));
 }
 
 void ContinuousContactModel::computeRegressor()
 {
-    evaluate(BLF_CCM_REGRESSOR, nullptr, nullptr, nullptr, m_regressor.data());
+    if (const double* all = evaluateAll()) std::memcpy(m_regressor.data(), all + 12, 12 * sizeof(double));
 }
 
 namespace

@@ -39,6 +39,20 @@ std::shared_ptr<CudaDevice> CudaDevice::open(int device)
     return dev;
 }
 
+namespace
+{
+int g_defaultIndex = -1;
+}
+
+int CudaDevice::defaultIndex()
+{
+    if (g_defaultIndex >= 0) return g_defaultIndex;
+    if (const char* env = std::getenv("BLF_CCM_DEVICE")) return std::atoi(env);
+    return 0;
+}
+
+void CudaDevice::setDefaultIndex(int device) { g_defaultIndex = device; }
+
 void* CudaDevice::handle() const { return m_impl->handle; }
 int CudaDevice::index() const { return m_impl->index; }
 std::int64_t CudaDevice::kernelLaunches() const { return blf_ccm_launch_count(m_impl->handle); }

@@ -70,7 +70,7 @@ bool RecursiveLeastSquare::initialize(std::weak_ptr<IParametersHandler> handlerW
                   << std::endl;
         return false;
     }
-    m_device = CudaDevice::open(0);
+    m_device = CudaDevice::open(CudaDevice::defaultIndex());
     if (m_device == nullptr)
     {
         std::cerr << "[RecursiveLeastSquare::initialize] The CUDA backend is not available and there "

@@ -6,14 +6,22 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <emmintrin.h>
+
 #include <algorithm>
-#include <type_traits>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <type_traits>
+#include <vector>
 
 #include "ccm_kernels.cuh"
 #include "rls_kernels.cuh"
@@ -49,7 +57,74 @@ static int fail(int code, const char* fmt, ...)
 // ------------------------------------------------------------------------------------------------
 
 static constexpr int kHostSlots = 4;
+static constexpr int kStageSlots = 8;    // pinned staging chunks of the compact control-matrix download
 static constexpr int kMaxPartials = 8192;
+
+// Worker threads of the host-buffer entry point: they expand the compact control-matrix download
+// (8 doubles per contact) into the caller's dense Matrix6x6 array while later chunks are still on
+// the PCIe link.  Data-format work only; no contact-model arithmetic runs on the host.
+class HostPool {
+public:
+    ~HostPool() { stop(); }
+    int size() const { return static_cast<int>(th_.size()); }
+    void resize(int n)
+    {
+        if (n == size()) return;
+        stop();
+        quit_ = false;
+        for (int j = 0; j < n; ++j) th_.emplace_back([this, j] { loop(j); });
+    }
+    // run job(j) on every worker; returns at once, wait() blocks until all are done
+    void start(std::function<void(int)> job)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        job_ = std::move(job);
+        active_ = size();
+        ++gen_;
+        cv_.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return active_ == 0; });
+    }
+
+private:
+    void stop()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_ = true;
+            cv_.notify_all();
+        }
+        for (auto& t : th_) t.join();
+        th_.clear();
+    }
+    void loop(int j)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::function<void(int)> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+                if (quit_) return;
+                seen = gen_;
+                job = job_;
+            }
+            job(j);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--active_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::function<void(int)> job_;
+    unsigned long long gen_ = 0;
+    int active_ = 0;
+    bool quit_ = false;
+};
 
 struct KernelInfo {
     int blocks_per_sm = 0;
@@ -59,22 +134,34 @@ struct blf_ccm_handle {
     unsigned magic = 0xB1FCC3A1u;
     int device = -1;
     int sm_count = 0;
+    size_t mem_pitch = 0;      // cudaDeviceProp::memPitch: upper bound of a 2-D copy's pitches
     bool have_params = false;
     double length = 0, width = 0, spring = 0, damper = 0;
     Prm uni{};
     int last_path = BLF_CCM_PATH_NONE;
     long long launches = 0;
     std::map<const void*, KernelInfo> kinfo;
-    // rollout scratch
+    // rollout scratch (block_best, counter, partials): ONE set per handle.  Calls that use it on
+    // different streams are ordered by the library (scratch_acquire), they never overlap.
     CostIdx* block_best = nullptr;   // kMaxPartials pairs
     unsigned int* counter = nullptr;
     double* partials = nullptr;      // [n_rollouts][slots] per-(rollout, tile) cost partial sums
     size_t partials_bytes = 0;
+    cudaEvent_t scratch_ev = nullptr;
+    cudaStream_t scratch_stream = nullptr;   // stream of the last launch that used the scratch
+    bool scratch_busy = false;
     // host pipeline
     cudaStream_t hstream[kHostSlots] = {};
     cudaEvent_t hev_up[kHostSlots] = {}, hev_done[kHostSlots] = {};   // time-chunked host rollouts
     cudaEvent_t hev_down[kHostSlots] = {};                            // host evaluation: slot downloaded
-    double* single_out = nullptr;   // 60 doubles of mapped pinned host memory (n = 1 fast path)
+    double* single_out = nullptr;   // 64 doubles of mapped pinned host memory (n = 1 fast path): results + flag
+    unsigned long long single_seq = 0;
+    // compact control-matrix download of the host evaluation: pinned staging ring + expansion pool
+    cudaEvent_t hev_stage[kStageSlots] = {};
+    double* hstage = nullptr;       // kStageSlots * hstage_chunk * 8 doubles, pinned
+    long long hstage_chunk = 0;
+    int host_threads = -1;          // -1 automatic, 0 = dense download (no host expansion)
+    HostPool* pool = nullptr;
     double* hbuf[kHostSlots] = {};
     long long hchunk = 0;      // contacts per chunk the slots are sized for
     size_t hbytes = 0;
@@ -106,12 +193,47 @@ static int env_int(const char* name)
 
 static bool valid(const blf_ccm_handle* h) { return h && h->magic == 0xB1FCC3A1u; }
 
+// Makes the handle's device current for the duration of one API call and restores the caller's
+// device afterwards: a multi-GPU host process (torch with another current device) must not find its
+// thread switched to another GPU behind its back.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 #define CHECK_HANDLE(h)                                                        \
     if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle"); \
-    CUDA_TRY(cudaSetDevice((h)->device))
+    DeviceGuard dev_guard_((h)->device);                                       \
+    if (dev_guard_.err != cudaSuccess)                                         \
+    return fail(BLF_CCM_ERR_CUDA, "cudaSetDevice(%d): %s", (h)->device, cudaGetErrorString(dev_guard_.err))
+
+// The rollout scratch is one set per handle.  A call that uses it on another stream than the last
+// user first orders itself after everything that user has submitted (an event recorded on the old
+// stream now covers its earlier launches), so two rollout calls on different streams are serialised
+// instead of corrupting each other's partial sums or the last-block counter.  The single-stream
+// path pays nothing.
+static int scratch_acquire(blf_ccm_handle* h, cudaStream_t st);
+static int scratch_quiesce(blf_ccm_handle* h);
 
 extern "C" const char* blf_ccm_version(void) { return "blf_ccm 0.1.0 (sm_100a)"; }
 extern "C" const char* blf_ccm_last_error(void) { return g_err; }
+
+extern "C" int blf_ccm_destroy(blf_ccm_handle* h);
 
 extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
 {
@@ -127,7 +249,9 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     }
     if (device < 0 || device >= count)
         return fail(BLF_CCM_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard dev_guard_(device);
+    if (dev_guard_.err != cudaSuccess)
+        return fail(BLF_CCM_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(dev_guard_.err));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
@@ -137,6 +261,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     if (!h) return fail(BLF_CCM_ERR_INVALID_ARG, "out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    h->mem_pitch = prop.memPitch;
     h->tune_cpt = env_int("BLF_CCM_TUNE_CPT");
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
@@ -145,10 +270,44 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_rollout_chunk_mb = env_int("BLF_CCM_TUNE_ROLLOUT_CHUNK_MB");
     h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
     h->tune_rollout_ws = env_int("BLF_CCM_TUNE_ROLLOUT_WS");
-    CUDA_TRY(cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials));
-    CUDA_TRY(cudaMalloc(&h->counter, sizeof(unsigned int)));
-    CUDA_TRY(cudaMemset(h->counter, 0, sizeof(unsigned int)));
+    if (const char* v = getenv("BLF_CCM_HOST_THREADS")) h->host_threads = atoi(v);
+    cudaError_t ce = cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials);
+    if (ce == cudaSuccess) ce = cudaMalloc(&h->counter, sizeof(unsigned int));
+    if (ce == cudaSuccess) ce = cudaMemset(h->counter, 0, sizeof(unsigned int));
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->scratch_ev, cudaEventDisableTiming);
+    if (ce != cudaSuccess) {   // nothing leaks on a failed create
+        cudaGetLastError();
+        blf_ccm_destroy(h);
+        return fail(BLF_CCM_ERR_CUDA, "blf_ccm_create: %s", cudaGetErrorString(ce));
+    }
     *out = h;
+    return BLF_CCM_OK;
+}
+
+static int scratch_acquire(blf_ccm_handle* h, cudaStream_t st)
+{
+    if (h->scratch_busy && h->scratch_stream != st) {
+        cudaError_t e = cudaEventRecord(h->scratch_ev, h->scratch_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->scratch_ev, 0);
+        if (e != cudaSuccess) {   // e.g. the old stream was destroyed by its owner
+            cudaGetLastError();
+            CUDA_TRY(cudaDeviceSynchronize());
+        }
+    }
+    h->scratch_stream = st;
+    h->scratch_busy = true;
+    return BLF_CCM_OK;
+}
+
+// before the scratch is freed / reallocated: nothing submitted earlier may still touch it
+static int scratch_quiesce(blf_ccm_handle* h)
+{
+    if (!h->scratch_busy) return BLF_CCM_OK;
+    if (cudaStreamSynchronize(h->scratch_stream) != cudaSuccess) {
+        cudaGetLastError();
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    h->scratch_busy = false;
     return BLF_CCM_OK;
 }
 
@@ -169,7 +328,13 @@ static void p2p_release(blf_ccm_handle* h)
 extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
 {
     if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard_(h->device);
+    delete h->pool;
+    h->pool = nullptr;
+    for (int s = 0; s < kStageSlots; ++s)
+        if (h->hev_stage[s]) cudaEventDestroy(h->hev_stage[s]);
+    if (h->hstage) cudaFreeHost(h->hstage);
+    if (h->scratch_ev) cudaEventDestroy(h->scratch_ev);
     for (int s = 0; s < kHostSlots; ++s) {
         if (h->hstream[s]) cudaStreamDestroy(h->hstream[s]);
         if (h->hbuf[s]) cudaFree(h->hbuf[s]);
@@ -179,8 +344,8 @@ extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
     }
     p2p_release(h);
     if (h->single_out) cudaFreeHost(h->single_out);
-    cudaFree(h->block_best);
-    cudaFree(h->counter);
+    if (h->block_best) cudaFree(h->block_best);
+    if (h->counter) cudaFree(h->counter);
     if (h->partials) cudaFree(h->partials);
     h->magic = 0;
     delete h;
@@ -412,7 +577,7 @@ struct AosLaunch {
 static int launch_aos(blf_ccm_handle* h, long long n, const double* twists, const double* poses,
                       const double* null_poses, const blf_ccm_params* params, unsigned out_mask,
                       double* wrench, double* autodyn, double* ctrl, double* regressor,
-                      cudaStream_t st)
+                      cudaStream_t st, bool ctrl_compact = false)
 {
     if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
     if (out_mask == 0 || out_mask > 15u) return fail(BLF_CCM_ERR_INVALID_ARG, "out_mask %u invalid", out_mask);
@@ -450,6 +615,7 @@ static int launch_aos(blf_ccm_handle* h, long long n, const double* twists, cons
     a.reg = regressor;
     a.uni = h->uni;
     a.n = n;
+    a.ctrl_compact = ctrl_compact ? 1 : 0;
     if (params) return dispatch_mask<AosLaunch, true>(out_mask, h, a, bulk, st);
     return dispatch_mask<AosLaunch, false>(out_mask, h, a, bulk, st);
 }
@@ -482,8 +648,10 @@ static int eval_single_host(blf_ccm_handle* h, const double* twist, const double
                             const double* null_pose, const blf_ccm_params* params, unsigned out_mask,
                             double* wrench, double* autodyn, double* ctrl, double* regressor)
 {
-    if (!h->single_out)
-        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->single_out), 60 * sizeof(double), cudaHostAllocMapped));
+    if (!h->single_out) {
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->single_out), 64 * sizeof(double), cudaHostAllocMapped));
+        memset(h->single_out, 0, 64 * sizeof(double));
+    }
     if (!h->hstream[0]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream[0], cudaStreamNonBlocking));
     SingleArgs a;
     memset(&a, 0, sizeof(a));
@@ -493,9 +661,23 @@ static int eval_single_host(blf_ccm_handle* h, const double* twist, const double
     a.prm = params ? make_prm(params->length, params->width, params->spring_coeff, params->damper_coeff)
                    : h->uni;
     a.out = h->single_out;   // unified addressing: the mapped host pointer is valid on the device
+    a.seq = ++h->single_seq;
     cudaStream_t st = h->hstream[0];
     if (int rc = dispatch_mask<SingleLaunch, false>(out_mask, h, a, st)) return rc;
-    CUDA_TRY(cudaStreamSynchronize(st));
+    // The kernel writes its results and then the sequence number into the mapped block; polling
+    // that word costs less than a stream synchronisation (measured per getter: DESIGN.md section 1).
+    // A launch that died never writes it: after a bounded spin the stream is asked instead.
+    {
+        const volatile unsigned long long* flag =
+            reinterpret_cast<const volatile unsigned long long*>(h->single_out + 60);
+        bool seen = false;
+        for (int spin = 0; spin < 200000 && !seen; ++spin) {
+            seen = (*flag == a.seq);
+            if (!seen) _mm_pause();
+        }
+        if (seen) std::atomic_thread_fence(std::memory_order_acquire);
+        else CUDA_TRY(cudaStreamSynchronize(st));
+    }
     const double* o = h->single_out;
     if (out_mask & BLF_CCM_WRENCH) memcpy(wrench, o, 6 * sizeof(double));
     if (out_mask & BLF_CCM_AUTODYN) memcpy(autodyn, o + 6, 6 * sizeof(double));
@@ -506,6 +688,34 @@ static int eval_single_host(blf_ccm_handle* h, const double* twist, const double
 }
 
 // ---- host buffers: chunked, four slots; upload, kernel and download streams overlapped ---------------------------
+
+// compact control matrix {gd, gs_xx, gs_xy, gs_xz, gs_yy, gs_yz, gs_zz, pad} -> dense row-major 6x6
+// (iDynTree::Matrix6x6; ContinuousContactModel.cpp:165-170: the top-left diagonal and the symmetric
+// bottom-right block, every other entry the +0.0 left by the constructor's zero(), :18).  Data
+// movement only; non-temporal stores when the destination allows (the dense array is written once
+// and read by somebody else).
+static void expand_ctrl(const double* src, double* dst, long long cnt)
+{
+    const __m128d z = _mm_setzero_pd();
+    const bool nt = aligned16(dst);
+    for (long long i = 0; i < cnt; ++i, src += 8, dst += 36) {
+        const __m128d a = _mm_load_pd(src), b = _mm_load_pd(src + 2), c = _mm_load_pd(src + 4),
+                      d = _mm_load_pd(src + 6);
+        const __m128d v[18] = {
+            _mm_unpacklo_pd(a, z), z, z,                          // gd 0 | 0 0 | 0 0
+            _mm_unpacklo_pd(z, a), z, z,                          // 0 gd | 0 0 | 0 0
+            z, _mm_unpacklo_pd(a, z), z,                          // 0 0 | gd 0 | 0 0
+            z, _mm_unpackhi_pd(z, a), b,                          // 0 0 | 0 xx | xy xz
+            z, _mm_unpacklo_pd(z, b), c,                          // 0 0 | 0 xy | yy yz
+            z, _mm_unpackhi_pd(z, b), _mm_shuffle_pd(c, d, 1)};   // 0 0 | 0 xz | yz zz
+        if (nt) {
+            for (int j = 0; j < 18; ++j) _mm_stream_pd(dst + 2 * j, v[j]);
+        } else {
+            for (int j = 0; j < 18; ++j) _mm_storeu_pd(dst + 2 * j, v[j]);
+        }
+    }
+    _mm_sfence();
+}
 
 extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const double* twists,
                                        const double* poses, const double* null_poses,
@@ -539,6 +749,7 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
             if (h->hbuf[s]) CUDA_TRY(cudaFree(h->hbuf[s]));
             h->hbuf[s] = nullptr;
         }
+        h->hbytes = 0;
         for (int s = 0; s < kHostSlots; ++s) CUDA_TRY(cudaMalloc(&h->hbuf[s], need));
         h->hbytes = need;
     }
@@ -547,20 +758,82 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         if (!h->hstream[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream[s], cudaStreamNonBlocking));
         if (!h->hev_up[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev_up[s], cudaEventDisableTiming));
         if (!h->hev_done[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev_done[s], cudaEventDisableTiming));
-        if (!h->hev_down[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev_down[s], cudaEventDisableTiming));
+    }
+    for (int s = 0; s < kStageSlots; ++s)
+        if (!h->hev_stage[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev_stage[s], cudaEventDisableTiming));
+
+    // Control matrix: 24 of the 36 doubles are structural zeros and 5 more are duplicates.  With
+    // host threads available the kernel writes the 7 distinct values (padded to 8 doubles) and only
+    // those 64 bytes per contact cross PCIe -- 160 instead of 384 bytes per evaluation come back --
+    // into a pinned staging ring; worker threads expand them into the caller's dense Matrix6x6
+    // array (structural zeros +0.0, bit-identical to the dense kernel output) while later chunks
+    // are in flight.  host_threads == 0 keeps the dense download (A/B: profiles/r02_host_compact*).
+    int nthreads = h->host_threads;
+    if (nthreads < 0) {
+        int hw = static_cast<int>(std::thread::hardware_concurrency());
+        if (const char* lws = getenv("LOCAL_WORLD_SIZE")) hw /= std::max(1, atoi(lws));  // one process per GPU
+        nthreads = std::max(1, std::min(8, hw / 2));
+    }
+    const bool compact = (out_mask & BLF_CCM_CTRL) && nthreads > 0;
+    const long long nchunks = (n + chunk - 1) / chunk;
+    if (compact) {
+        if (h->hstage_chunk < chunk) {
+            if (h->hstage) CUDA_TRY(cudaFreeHost(h->hstage));
+            h->hstage = nullptr;
+            h->hstage_chunk = 0;
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->hstage),
+                                   size_t(kStageSlots) * chunk * 8 * sizeof(double), cudaHostAllocDefault));
+            h->hstage_chunk = chunk;
+        }
+        if (nchunks < 2) nthreads = 1;   // a single chunk: the orchestrating thread's one worker is enough
+        if (!h->pool) h->pool = new (std::nothrow) HostPool();
+        if (!h->pool) return fail(BLF_CCM_ERR_INVALID_ARG, "out of host memory");
+        h->pool->resize(nthreads);
     }
 
+    // shared with the expansion workers
+    std::atomic<long long> ready{0};                 // chunks whose download has completed
+    std::atomic<long long> done[kStageSlots];        // cumulative worker completions per staging slot
+    std::atomic<bool> abort{false};
+    for (auto& d : done) d.store(0);
+    if (compact) {
+        double* stage = h->hstage;
+        const long long schunk = h->hstage_chunk;
+        h->pool->start([=, &ready, &done, &abort](int j) {
+            for (long long c = 0; c < nchunks; ++c) {
+                int spins = 0;
+                while (ready.load(std::memory_order_acquire) <= c) {
+                    if (abort.load(std::memory_order_relaxed)) return;
+                    if (++spins < 2000) _mm_pause();
+                    else std::this_thread::yield();
+                }
+                const long long off = c * chunk, cnt = std::min<long long>(chunk, n - off);
+                const long long lo = cnt * j / nthreads, hi = cnt * (j + 1) / nthreads;
+                expand_ctrl(stage + size_t(c % kStageSlots) * schunk * 8 + lo * 8, ctrl + (off + lo) * 36, hi - lo);
+                done[c % kStageSlots].fetch_add(1, std::memory_order_release);
+            }
+        });
+    }
+    // on any error below the workers must be released before the atomics leave scope
+    struct PoolJoin {
+        HostPool* p;
+        std::atomic<bool>& abort;
+        bool failed = true;
+        ~PoolJoin()
+        {
+            if (!p) return;
+            if (failed) abort.store(true);
+            p->wait();
+        }
+    } join{compact ? h->pool : nullptr, abort};
+
     // One stream per PCIe direction and one for the kernels, chained by events, so that each
-    // direction is ONE in-order queue; kHostSlots chunk buffers in flight.  Measured on the pool's
-    // box (profiles/r01_host_pipeline_sweep.log): 6.59 ms per 819 200-state step = 124 M evals/s =
-    // 0.90 of what plain pinned copies of the same bytes reach in both directions at once (137 M).
-    // One stream per slot, 3 vs 4 slots, and geometric chunk ramp-up/-down (to shorten pipeline fill
-    // and drain) were all measured within 1 % of this and are not kept.
-    int slot = 0, index = 0;
-    const int nslots = kHostSlots;
-    for (long long off = 0, c = 0; off < n; off += c, slot = (slot + 1) % nslots, ++index) {
-        c = std::min<long long>(chunk, n - off);
-        cudaStream_t up = h->hstream[0], comp = h->hstream[1], down = h->hstream[2];
+    // direction is ONE in-order queue; kHostSlots chunk buffers in flight on the device.
+    cudaStream_t up = h->hstream[0], comp = h->hstream[1], down = h->hstream[2];
+    const size_t D = sizeof(double);
+    auto enqueue = [&](long long index) -> int {
+        const long long off = index * chunk, c = std::min<long long>(chunk, n - off);
+        const int slot = static_cast<int>(index % kHostSlots), sslot = static_cast<int>(index % kStageSlots);
         double* b = h->hbuf[slot];
         double* d_tw = b;
         double* d_po = d_tw + chunk * 6;
@@ -570,8 +843,9 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         double* d_a = d_w + chunk * 6;
         double* d_c = d_a + chunk * 6;
         double* d_r = d_c + chunk * 36;
-        const size_t D = sizeof(double);
-        if (index >= nslots) CUDA_TRY(cudaStreamWaitEvent(up, h->hev_down[slot], 0));
+        // the device slot is free once the chunk that used it last (index - kHostSlots) is downloaded
+        if (index >= kHostSlots)
+            CUDA_TRY(cudaStreamWaitEvent(up, h->hev_stage[(index - kHostSlots) % kStageSlots], 0));
         if (need_state) {
             CUDA_TRY(cudaMemcpyAsync(d_tw, twists + off * 6, c * 6 * D, cudaMemcpyHostToDevice, up));
             CUDA_TRY(cudaMemcpyAsync(d_nu, null_poses + off * 12, c * 12 * D, cudaMemcpyHostToDevice, up));
@@ -583,7 +857,7 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         CUDA_TRY(cudaStreamWaitEvent(comp, h->hev_up[slot], 0));
         if (int rc = launch_aos(h, c, d_tw, d_po, d_nu,
                                 params ? reinterpret_cast<const blf_ccm_params*>(d_pr) : nullptr,
-                                out_mask, d_w, d_a, d_c, d_r, comp))
+                                out_mask, d_w, d_a, d_c, d_r, comp, compact))
             return rc;
         CUDA_TRY(cudaEventRecord(h->hev_done[slot], comp));
         CUDA_TRY(cudaStreamWaitEvent(down, h->hev_done[slot], 0));
@@ -591,13 +865,36 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
             CUDA_TRY(cudaMemcpyAsync(wrench + off * 6, d_w, c * 6 * D, cudaMemcpyDeviceToHost, down));
         if (out_mask & BLF_CCM_AUTODYN)
             CUDA_TRY(cudaMemcpyAsync(autodyn + off * 6, d_a, c * 6 * D, cudaMemcpyDeviceToHost, down));
-        if (out_mask & BLF_CCM_CTRL)
-            CUDA_TRY(cudaMemcpyAsync(ctrl + off * 36, d_c, c * 36 * D, cudaMemcpyDeviceToHost, down));
+        if (out_mask & BLF_CCM_CTRL) {
+            if (compact)
+                CUDA_TRY(cudaMemcpyAsync(h->hstage + size_t(sslot) * h->hstage_chunk * 8, d_c, c * 8 * D,
+                                         cudaMemcpyDeviceToHost, down));
+            else
+                CUDA_TRY(cudaMemcpyAsync(ctrl + off * 36, d_c, c * 36 * D, cudaMemcpyDeviceToHost, down));
+        }
         if (out_mask & BLF_CCM_REGRESSOR)
             CUDA_TRY(cudaMemcpyAsync(regressor + off * 12, d_r, c * 12 * D, cudaMemcpyDeviceToHost, down));
-        CUDA_TRY(cudaEventRecord(h->hev_down[slot], down));
+        CUDA_TRY(cudaEventRecord(h->hev_stage[sslot], down));
+        return BLF_CCM_OK;
+    };
+    // staging slot of chunk k is free once every worker has expanded chunk k - kStageSlots
+    auto stage_free = [&](long long k) {
+        return !compact || k < kStageSlots ||
+               done[k % kStageSlots].load(std::memory_order_acquire) >= (k / kStageSlots) * nthreads;
+    };
+    long long next_enq = 0, next_ready = 0;
+    while (next_ready < nchunks) {
+        while (next_enq < nchunks && next_enq < next_ready + kStageSlots && stage_free(next_enq))
+            if (int rc = enqueue(next_enq++)) return rc;
+        if (next_enq == next_ready) {   // everything enqueued is published; the next slot is still being expanded
+            _mm_pause();
+            continue;
+        }
+        CUDA_TRY(cudaEventSynchronize(h->hev_stage[next_ready % kStageSlots]));
+        ready.store(++next_ready, std::memory_order_release);
     }
-    for (int s = 0; s < kHostSlots; ++s) CUDA_TRY(cudaStreamSynchronize(h->hstream[s]));
+    for (int s = 0; s < 3; ++s) CUDA_TRY(cudaStreamSynchronize(h->hstream[s]));
+    join.failed = false;   // the destructor waits for the last expansions
     return BLF_CCM_OK;
 }
 
@@ -607,6 +904,15 @@ extern "C" int blf_ccm_set_host_chunk(blf_ccm_handle* h, int64_t contacts)
     if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
     if (contacts < 32) return fail(BLF_CCM_ERR_INVALID_ARG, "chunk must be >= 32 contacts");
     h->host_chunk_pref = contacts;
+    return BLF_CCM_OK;
+}
+
+// worker threads that expand the compact control-matrix download; 0 = dense download, -1 = automatic
+extern "C" int blf_ccm_set_host_threads(blf_ccm_handle* h, int threads)
+{
+    if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
+    if (threads < -1 || threads > 64) return fail(BLF_CCM_ERR_INVALID_ARG, "threads must be -1 (automatic) or 0..64");
+    h->host_threads = threads;
     return BLF_CCM_OK;
 }
 
@@ -732,13 +1038,15 @@ extern "C" int blf_ccm_rollout_cost_argmin_soa(blf_ccm_handle* h, int64_t n_roll
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (h->partials_bytes < need) {
         if (h->partials) {
-            CUDA_TRY(cudaStreamSynchronize(st));  // a previous launch may still read the old buffer
+            if (int rc = scratch_quiesce(h)) return rc;  // a previous launch may still read the old buffer
             CUDA_TRY(cudaFree(h->partials));
             h->partials = nullptr;
+            h->partials_bytes = 0;
         }
         CUDA_TRY(cudaMalloc(&h->partials, need));
         h->partials_bytes = need;
     }
+    if (int rc = scratch_acquire(h, st)) return rc;
     a.rollout_len = rollout_len;
     memcpy(a.ref, host_wrench_ref, sizeof(a.ref));
     a.wf = host_weights[0];

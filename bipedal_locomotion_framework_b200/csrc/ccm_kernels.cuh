@@ -370,7 +370,18 @@ struct AosArgs {
     double* reg;               // n*12
     Prm uni;
     long long n;
+    int ctrl_compact;          // ctrl receives n*8 doubles {gd, gs[0..5], 0} instead of n*36 (host pipeline)
 };
+
+// the 7 distinct values of one control matrix, padded to 8 doubles
+__device__ __forceinline__ void stage_ctrl_compact(double* slot, const Result& r)
+{
+    double2* o = reinterpret_cast<double2*>(slot);
+    o[0] = make_double2(r.gd, r.gs[0]);
+    o[1] = make_double2(r.gs[1], r.gs[2]);
+    o[2] = make_double2(r.gs[3], r.gs[4]);
+    o[3] = make_double2(r.gs[5], 0.0);
+}
 
 // per-warp shared-memory layout for a 32-contact tile (byte offsets, all multiples of 128)
 template <unsigned MASK, bool HET>
@@ -520,8 +531,10 @@ ccm_aos_kernel(const __grid_constant__ AosArgs a)
                 o[4] = make_double2(r.y_tk.y, r.y_tb.y);
                 o[5] = make_double2(r.y_tk.z, r.y_tb.z);
             }
-            if constexpr ((MASK & M_CTRL) != 0)
-                stage_ctrl(reinterpret_cast<double*>(ws + S::oc) + lane * 36, r);
+            if constexpr ((MASK & M_CTRL) != 0) {
+                if (a.ctrl_compact) stage_ctrl_compact(reinterpret_cast<double*>(ws + S::oc) + lane * 8, r);
+                else stage_ctrl(reinterpret_cast<double*>(ws + S::oc) + lane * 36, r);
+            }
         }
         ptx::fence_async_smem();
         __syncwarp();
@@ -533,8 +546,10 @@ ccm_aos_kernel(const __grid_constant__ AosArgs a)
                 ptx::bulk_s2g(a.autodyn + base * 6, ptx::smem_addr(ws + S::oa), c * 48u);
             if constexpr ((MASK & M_REGRESSOR) != 0)
                 ptx::bulk_s2g(a.reg + base * 12, ptx::smem_addr(ws + S::og), c * 96u);
-            if constexpr ((MASK & M_CTRL) != 0)
-                ptx::bulk_s2g(a.ctrl + base * 36, ptx::smem_addr(ws + S::oc), c * 288u);
+            if constexpr ((MASK & M_CTRL) != 0) {
+                if (a.ctrl_compact) ptx::bulk_s2g(a.ctrl + base * 8, ptx::smem_addr(ws + S::oc), c * 64u);
+                else ptx::bulk_s2g(a.ctrl + base * 36, ptx::smem_addr(ws + S::oc), c * 288u);
+            }
             ptx::bulk_commit();
         }
     }
@@ -595,6 +610,14 @@ ccm_aos_scalar_kernel(const __grid_constant__ AosArgs a)
             o[8] = r.y_tk.y; o[9] = r.y_tb.y; o[10] = r.y_tk.z; o[11] = r.y_tb.z;
         }
         if constexpr ((MASK & M_CTRL) != 0) {
+            if (a.ctrl_compact) {
+                double* o = a.ctrl + i * 8;
+                o[0] = r.gd;
+#pragma unroll
+                for (int e = 0; e < 6; ++e) o[1 + e] = r.gs[e];
+                o[7] = 0.0;
+                continue;
+            }
             double* o = a.ctrl + i * 36;
 #pragma unroll
             for (int e = 0; e < 36; ++e) o[e] = 0.0;
@@ -617,7 +640,8 @@ struct SingleArgs {
     double pose[12];
     double null[12];
     Prm prm;
-    double* out;   // mapped host memory: wrench 0-5 | autodyn 6-11 | regressor 12-23 | ctrl 24-59
+    double* out;   // mapped host memory: wrench 0-5 | autodyn 6-11 | regressor 12-23 | ctrl 24-59 | flag 60
+    unsigned long long seq;   // written to out[60] after the results: the host polls it
 };
 
 template <unsigned MASK>
@@ -661,6 +685,10 @@ __global__ void ccm_single_kernel(const __grid_constant__ SingleArgs a)
         c[27] = r.gs[1]; c[28] = r.gs[3]; c[29] = r.gs[4];
         c[33] = r.gs[2]; c[34] = r.gs[4]; c[35] = r.gs[5];
     }
+    // results first, then the sequence number: the host spins on it instead of paying a stream
+    // synchronisation per getter
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(o + 60) = a.seq;
 }
 
 // ------------------------------------------------------------------------------------------------

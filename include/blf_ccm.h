@@ -40,6 +40,15 @@
  *
  * Threading: a handle is used from one host thread at a time; distinct handles are independent.
  * Launches are asynchronous on the caller's stream (void* = cudaStream_t, NULL = default stream).
+ * Every call makes the handle's device current for its own duration and restores the caller's
+ * current device before it returns.
+ * Streams: the evaluation entry points (blf_ccm_eval_batch_soa/_aos, blf_rls_*, blf_sys_*_soa,
+ * blf_ccm_generalized_force_soa) keep no state between calls and may be in flight on any number of
+ * streams at once.  The rollout entry points (blf_ccm_rollout_cost_argmin_soa,
+ * blf_ccm_rollout_integrate_cost and its _host form) share ONE set of reduction scratch per handle:
+ * a rollout call issued on another stream than the previous one is ordered after it by the library
+ * (event wait), i.e. rollout calls of one handle are serialised, never corrupted; use one handle
+ * per stream for concurrent rollouts.
  * Errors: 0 = ok, negative = blf_ccm_status; text via blf_ccm_last_error(); nothing throws.
  */
 #ifndef BLF_CCM_H
@@ -138,6 +147,14 @@ BLF_CCM_API int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doub
 
 /* Contacts per chunk of the blf_ccm_eval_batch_host pipeline (default 65536, measured best on B200 + PCIe Gen5; tuning knob). */
 BLF_CCM_API int blf_ccm_set_host_chunk(blf_ccm_handle* h, int64_t contacts);
+
+/* blf_ccm_eval_batch_host moves the control matrix over PCIe in compact form (its 7 distinct values,
+ * 64 instead of 288 bytes per contact) and `threads` host worker threads of the library expand it
+ * into the caller's dense Matrix6x6 array, structural zeros +0.0, bit-identical to the device
+ * layout.  -1 (default) = min(8, cores/2) (cores divided by LOCAL_WORLD_SIZE when a launcher sets
+ * it); 0 = download the dense array instead (no host threads).  Environment override at create:
+ * BLF_CCM_HOST_THREADS. */
+BLF_CCM_API int blf_ccm_set_host_threads(blf_ccm_handle* h, int threads);
 
 /* Surface-point forces of ONE contact state held in host memory (twist[6], pose[12],
  * null_pose[12]), for m points xy (device, m*2): force_out / torque_out device m*3 (either may be
