@@ -27,7 +27,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["metric"].startswith("contact evals/sec") and d["unit"] == "evals/s"
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert "configs[2]" in d["config"]["workload"] and d["config"]["evals_per_step"] == 819200
+    assert "configs[4]" in d["config"]["workload"] and d["config"]["evals_per_step"] == 1 << 28
+    assert d["scaling"] == "strong"
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.shared_config(1)      # the SAME config dict in both arms
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert "819200" in cb["sample"]
@@ -42,7 +46,7 @@ def test_reference_arm_other_ranks_exit_quietly():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-@pytest.mark.parametrize("workload", ["config3", "config2"])
+@pytest.mark.parametrize("workload", ["headline", "config2"])
 def test_gpu_arm_fails_loudly_without_a_device(workload):
     import torch
     if torch.cuda.is_available():

@@ -570,3 +570,175 @@ def test_no_out_of_bounds_writes_canaries(torch, batch, n):
         assert bool((f[:guard] == sentinel).all()) and bool((f[guard + n * width:] == sentinel).all()), \
             f"aos {key}: guard band overwritten (n={n})"
         assert bool(torch.isfinite(outs[key]).all())
+
+
+# --- round 2 ------------------------------------------------------------------------------------------
+
+def test_config5_full_size_256m_properties(torch, batch, oracle):
+    """configs[4] at its full size: 2^28 states (2^20 rollouts x 256), uniform, wrench + autonomous
+    dynamics + control matrix on ONE GPU (58 GB of live input planes + 103 GB of outputs): oracle
+    parity on a strided sample plus the first and last 2^20 states of the same device bits,
+    per-rollout cost on sampled rollouts, arg-min consistency, structural zeros over all 2^28 dense
+    blocks scanned on the device."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 170e9:
+        pytest.skip("needs ~165 GB of free device memory")
+    n_rollouts, rl = 1 << 20, 256
+    n = n_rollouts * rl
+    dev = torch.device("cuda", 0)
+    planes, _ = syn.make_planes_torch(n, dev, seed=46)
+    ref_wrench, weights = [0.0, 0.0, 30.0, 0.0, 0.0, 0.0], [1.0, 10.0]
+    out, cost, best = batch.rollout_cost_argmin(planes, rl, ref_wrench, weights, None, mask=FULL)
+    torch.cuda.synchronize()
+    # (i) oracle parity: every 4099th state (65 489 states), then the first and the last 2^20
+    for what, idx in (("strided", torch.arange(0, n, 4099, device=dev)),
+                      ("first 2^20", torch.arange(0, 1 << 20, device=dev)),
+                      ("last 2^20", torch.arange(n - (1 << 20), n, device=dev))):
+        st = syn.sample_states_from_planes(planes, None, idx)
+        ref = oracle.eval_batch_states(st, mask=FULL, nthreads=NTHREADS)
+        got = {"wrench": out["wrench"][:, idx].T.cpu().numpy(),
+               "autodyn": out["autodyn"][:, idx].T.cpu().numpy(), "ctrl": out["ctrl"][idx].cpu().numpy()}
+        _check(got, ref, FULL, f"config5 full size, {what}")
+        del st, ref, got
+    # (ii) cost of sampled rollouts
+    for r in (0, 1, 4097, 777777, n_rollouts - 1):
+        ridx = torch.arange(r * rl, (r + 1) * rl, device=dev)
+        rs = syn.sample_states_from_planes(planes, None, ridx)
+        rw = oracle.eval_batch_states(rs, mask=W)["wrench"]
+        rc = oracle.rollout_cost(rw, rl, ref_wrench, weights)[0]
+        assert abs(float(cost[r]) - rc) <= 1e-12 * abs(rc)
+    # (iii) arg-min = first minimum of the device's own cost vector
+    bc, bi = batch.decode_best(best)
+    cmin = float(cost.min())
+    assert bi == int(torch.nonzero(cost == cmin)[0]) and bc == cmin
+    # (iv) structural zeros, exactly +0.0 (bit pattern 0), over all 2^28 blocks; chunked so the
+    # temporaries stay under 1 GB next to the 161 GB working set
+    zero_cols = torch.tensor([j for j in range(36)
+                              if not ((j // 6 < 3 and j % 6 == j // 6) or (j // 6 >= 3 and j % 6 >= 3))],
+                             device=dev)
+    bits = out["ctrl"].view(torch.int64)
+    step = 1 << 22
+    for a in range(0, n, step):
+        blk = bits[a:a + step]
+        assert not bool(blk.index_select(1, zero_cols).any()), f"structural zero not +0.0 in block {a}"
+        assert bool((blk[:, 0] == blk[:, 7]).all()) and bool((blk[:, 0] == blk[:, 14]).all())
+        assert bool((blk[:, 22] == blk[:, 27]).all()) and bool((blk[:, 23] == blk[:, 33]).all()) \
+            and bool((blk[:, 29] == blk[:, 34]).all())          # bottom-right block symmetric
+    for p in out["wrench"]:
+        assert bool(torch.isfinite(p).all())
+    for p in out["autodyn"]:
+        assert bool(torch.isfinite(p).all())
+
+
+@pytest.mark.parametrize("n", [2, 33, 4097, 65536, 65537, 200003])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_path_compact_download_is_bit_identical_to_dense(torch, batch, oracle, n, pinned):
+    """blf_ccm_eval_batch_host moves the control matrix over PCIe as its 7 distinct values and
+    expands it on the host: the dense array must be bit-identical to the dense download (every
+    structural zero +0.0), for ragged sizes across the chunk boundary, pageable and pinned buffers,
+    and a destination that is only 8-byte aligned."""
+    st = syn.make_states(n, seed=77, heterogeneous=True)
+    mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()) if pinned else np.ascontiguousarray
+    tw, po, nu, pr = mk(st["twists"]), mk(st["poses"]), mk(st["null_poses"]), mk(st["params"])
+    try:
+        batch.set_host_threads(0)
+        dense = batch.evaluate_host(tw, po, nu, pr, FULL | R)
+        for threads in (1, 3, -1):
+            batch.set_host_threads(threads)
+            # 8-byte-aligned (not 16) destination for the dense array on odd thread counts
+            raw = np.full(n * 36 + 1, -7.25)
+            ctrl = raw[1:].reshape(n, 36) if threads == 3 and raw.ctypes.data % 16 == 0 else raw[:n * 36].reshape(n, 36)
+            outp = {"wrench": np.empty((n, 6)), "autodyn": np.empty((n, 6)), "ctrl": ctrl,
+                    "regressor": np.empty((n, 12))}
+            got = batch.evaluate_host(tw, po, nu, pr, FULL | R, out=outp)
+            for key in ("wrench", "autodyn", "ctrl", "regressor"):
+                assert np.array_equal(got[key].view(np.int64), dense[key].view(np.int64)), \
+                    f"{key} differs, n={n}, threads={threads}"
+            assert_ctrl_structure(got["ctrl"])
+        # control matrix alone (no state arrays needed) and repeated calls on the same handle
+        only = batch.evaluate_host(None, po, None, pr, Cc)
+        assert np.array_equal(only["ctrl"].view(np.int64), dense["ctrl"].view(np.int64))
+    finally:
+        batch.set_host_threads(-1)
+    ref = oracle.eval_batch_states(st, mask=FULL | R, nthreads=NTHREADS)
+    _check(dense, ref, FULL, "host path")
+
+
+def test_rollout_calls_on_two_streams_are_serialised_not_corrupted(torch, batch, oracle):
+    """The rollout scratch (per-rollout partial sums, last-block counter) is one set per handle: two
+    asynchronous rollout calls on DIFFERENT streams must be ordered by the library, each producing
+    the result it would produce alone."""
+    rl = 200
+    sa, sb = syn.make_states(3000 * rl, seed=5), syn.make_states(1111 * rl, seed=6)
+    pa, _ = _soa_inputs(torch, sa)
+    pb, _ = _soa_inputs(torch, sb)
+    ref_w, wts = [0.0, 0.0, 30.0, 0.0, 0.0, 0.0], [1.0, 10.0]
+    _, ca0, ba0 = batch.rollout_cost_argmin(pa, rl, ref_w, wts)
+    _, cb0, bb0 = batch.rollout_cost_argmin(pb, rl, ref_w, wts)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(20):
+        with torch.cuda.stream(s1):
+            _, ca, ba = batch.rollout_cost_argmin(pa, rl, ref_w, wts)
+        with torch.cuda.stream(s2):
+            _, cb, bb = batch.rollout_cost_argmin(pb, rl, ref_w, wts)
+        torch.cuda.synchronize()
+        assert torch.equal(ca, ca0) and torch.equal(cb, cb0)
+        assert torch.equal(ba, ba0) and torch.equal(bb, bb0)
+
+
+def test_calls_restore_the_callers_current_device(torch, batch):
+    """Every C-ABI call makes the handle's device current only for its own duration."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    other = ContinuousContactModelBatch(1)
+    other.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    st = syn.make_states(1000, seed=9)
+    torch.cuda.set_device(0)
+    got = other.evaluate_host(st["twists"], st["poses"], st["null_poses"], None, FULL)
+    assert torch.cuda.current_device() == 0
+    x = torch.zeros(4, device="cuda")          # the caller's next allocation lands on ITS device
+    assert x.device.index == 0
+    ref = batch.evaluate_host(st["twists"], st["poses"], st["null_poses"], None, FULL)
+    for key in ("wrench", "autodyn", "ctrl"):
+        assert np.array_equal(got[key], ref[key])
+
+
+def test_facade_one_launch_per_state(torch, oracle):
+    """The per-instance facade evaluates all four outputs with ONE launch on the first getter after
+    a setter; the other getters of the same state launch nothing.  Writing springCoeff in between
+    keeps the reference's quirk: results already served stay stale, results not yet computed use
+    the new coefficient (src/ContactModels/src/ContinuousContactModel.cpp:256-274)."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModel, StdImplementation
+    h = StdImplementation()
+    for k, v in zip(("length", "width", "spring_coeff", "damper_coeff"), syn.REFERENCE_TEST_PARAMS):
+        h.setParameter(k, v)
+    m = ContinuousContactModel(0)
+    assert m.initialize(h)
+    st = syn.reference_test_state()
+    m.setNullForceTransform(st["null_poses"][0])
+    m.setState(st["twists"][0], st["poses"][0])
+    before = m._handle.launch_count
+    w = m.getContactWrench().copy()
+    assert m._handle.launch_count == before + 1
+    a, c, r = m.getAutonomousDynamics().copy(), m.getControlMatrix().copy(), m.getRegressor().copy()
+    assert m._handle.launch_count == before + 1
+    ref = oracle.eval_batch_states(st, mask=FULL | R)
+    assert_parity(w[None], ref["wrench"], "wrench")
+    assert_parity(a[None], ref["autodyn"], "autodyn")
+    assert_parity(c.reshape(1, 36), ref["ctrl"], "ctrl")
+    assert_parity(r.reshape(1, 12), ref["regressor"], "regressor")
+    # stale-cache quirk through the one-launch cache
+    m.setState(st["twists"][0], st["poses"][0])
+    w1 = m.getContactWrench().copy()
+    m.springCoeff = 2.0 * syn.REFERENCE_TEST_PARAMS[2]
+    assert np.array_equal(m.getContactWrench(), w1)                    # served stale, as upstream
+    a2 = m.getAutonomousDynamics().copy()                               # computed now: new coefficient
+    st2 = dict(st, uniform=(syn.REFERENCE_TEST_PARAMS[0], syn.REFERENCE_TEST_PARAMS[1],
+                            2.0 * syn.REFERENCE_TEST_PARAMS[2], syn.REFERENCE_TEST_PARAMS[3]))
+    ref2 = oracle.eval_batch_states(st2, mask=FULL)
+    assert_parity(a2[None], ref2["autodyn"], "autodyn")
+    assert not np.array_equal(a2, a)
+    m.setState(st["twists"][0], st["poses"][0])
+    assert_parity(m.getContactWrench()[None], ref2["wrench"], "wrench")  # the next setState refreshes
