@@ -45,8 +45,9 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     if not force and _newer(CUDA_LIB, cuda_sources()):
         return CUDA_LIB
+    # one CUDA translation unit + the host-only expansion helper (plain C++, passed through to g++)
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", CUDA_LIB, os.path.join(_HERE, "csrc", "ccm_capi.cu"),
-           "-lcudart", "-ldl"]
+           os.path.join(_HERE, "csrc", "host_expand.cpp"), "-lcudart", "-ldl", "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -100,6 +101,11 @@ def build_cpp(force: bool = False) -> str:
             run([cxx, *CXX_FLAGS, "-DCATCH_CONFIG_MAIN", "-o", target,
                  os.path.join(CPP_DIR, "tests", src), *inc, "-I", os.path.join(CPP_DIR, "tests"),
                  "-L", LIB_DIR, "-lblf_contact", "-lblf_ccm", "-Wl,-rpath,$ORIGIN"])
+    # host-only test of the expansion helper and its worker pool (no CUDA, no facade library)
+    target = os.path.join(LIB_DIR, "HostExpandUnitTests")
+    hsrc = [os.path.join(CPP_DIR, "tests", "HostExpandTest.cpp"), os.path.join(_HERE, "csrc", "host_expand.cpp")]
+    if force or not _newer(target, hsrc + [os.path.join(_HERE, "csrc", "host_expand.h")]):
+        run([cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-pthread", "-o", target, *hsrc])
     return CPP_LIB
 
 

@@ -6,24 +6,18 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
-#include <emmintrin.h>
-
 #include <algorithm>
 #include <atomic>
-#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <functional>
 #include <map>
-#include <mutex>
 #include <new>
-#include <thread>
 #include <type_traits>
-#include <vector>
 
 #include "ccm_kernels.cuh"
+#include "host_expand.h"
 #include "rls_kernels.cuh"
 #include "sys_kernels.cuh"
 
@@ -59,72 +53,6 @@ static int fail(int code, const char* fmt, ...)
 static constexpr int kHostSlots = 4;
 static constexpr int kStageSlots = 8;    // pinned staging chunks of the compact control-matrix download
 static constexpr int kMaxPartials = 8192;
-
-// Worker threads of the host-buffer entry point: they expand the compact control-matrix download
-// (8 doubles per contact) into the caller's dense Matrix6x6 array while later chunks are still on
-// the PCIe link.  Data-format work only; no contact-model arithmetic runs on the host.
-class HostPool {
-public:
-    ~HostPool() { stop(); }
-    int size() const { return static_cast<int>(th_.size()); }
-    void resize(int n)
-    {
-        if (n == size()) return;
-        stop();
-        quit_ = false;
-        for (int j = 0; j < n; ++j) th_.emplace_back([this, j] { loop(j); });
-    }
-    // run job(j) on every worker; returns at once, wait() blocks until all are done
-    void start(std::function<void(int)> job)
-    {
-        std::lock_guard<std::mutex> lk(m_);
-        job_ = std::move(job);
-        active_ = size();
-        ++gen_;
-        cv_.notify_all();
-    }
-    void wait()
-    {
-        std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [this] { return active_ == 0; });
-    }
-
-private:
-    void stop()
-    {
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            quit_ = true;
-            cv_.notify_all();
-        }
-        for (auto& t : th_) t.join();
-        th_.clear();
-    }
-    void loop(int j)
-    {
-        unsigned long long seen = 0;
-        for (;;) {
-            std::function<void(int)> job;
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
-                if (quit_) return;
-                seen = gen_;
-                job = job_;
-            }
-            job(j);
-            std::lock_guard<std::mutex> lk(m_);
-            if (--active_ == 0) done_.notify_all();
-        }
-    }
-    std::vector<std::thread> th_;
-    std::mutex m_;
-    std::condition_variable cv_, done_;
-    std::function<void(int)> job_;
-    unsigned long long gen_ = 0;
-    int active_ = 0;
-    bool quit_ = false;
-};
 
 struct KernelInfo {
     int blocks_per_sm = 0;
@@ -175,6 +103,7 @@ struct blf_ccm_handle {
     int tune_no_rows = 0;        // BLF_CCM_TUNE_NO_ROWS=1: J^T wrench without base/out row staging
     int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
     int tune_rollout_chunk_mb = 0;  // BLF_CCM_TUNE_ROLLOUT_CHUNK_MB: twist bytes per time chunk of the host rollout (default 8)
+    int tune_host_noexpand = 0;  // BLF_CCM_TUNE_HOST_NOEXPAND=1: measurement aid, the workers skip the expansion (results WRONG)
     int tune_rls_pipe = 0;       // BLF_CCM_TUNE_RLS_PIPE=1: the plain one-estimator-per-thread RLS kernel instead of the pipelined one
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
@@ -266,6 +195,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");
+    h->tune_host_noexpand = env_int("BLF_CCM_TUNE_HOST_NOEXPAND");
     h->tune_rls_pipe = env_int("BLF_CCM_TUNE_RLS_PIPE");
     h->tune_rollout_chunk_mb = env_int("BLF_CCM_TUNE_ROLLOUT_CHUNK_MB");
     h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
@@ -689,34 +619,6 @@ static int eval_single_host(blf_ccm_handle* h, const double* twist, const double
 
 // ---- host buffers: chunked, four slots; upload, kernel and download streams overlapped ---------------------------
 
-// compact control matrix {gd, gs_xx, gs_xy, gs_xz, gs_yy, gs_yz, gs_zz, pad} -> dense row-major 6x6
-// (iDynTree::Matrix6x6; ContinuousContactModel.cpp:165-170: the top-left diagonal and the symmetric
-// bottom-right block, every other entry the +0.0 left by the constructor's zero(), :18).  Data
-// movement only; non-temporal stores when the destination allows (the dense array is written once
-// and read by somebody else).
-static void expand_ctrl(const double* src, double* dst, long long cnt)
-{
-    const __m128d z = _mm_setzero_pd();
-    const bool nt = aligned16(dst);
-    for (long long i = 0; i < cnt; ++i, src += 8, dst += 36) {
-        const __m128d a = _mm_load_pd(src), b = _mm_load_pd(src + 2), c = _mm_load_pd(src + 4),
-                      d = _mm_load_pd(src + 6);
-        const __m128d v[18] = {
-            _mm_unpacklo_pd(a, z), z, z,                          // gd 0 | 0 0 | 0 0
-            _mm_unpacklo_pd(z, a), z, z,                          // 0 gd | 0 0 | 0 0
-            z, _mm_unpacklo_pd(a, z), z,                          // 0 0 | gd 0 | 0 0
-            z, _mm_unpackhi_pd(z, a), b,                          // 0 0 | 0 xx | xy xz
-            z, _mm_unpacklo_pd(z, b), c,                          // 0 0 | 0 xy | yy yz
-            z, _mm_unpackhi_pd(z, b), _mm_shuffle_pd(c, d, 1)};   // 0 0 | 0 xz | yz zz
-        if (nt) {
-            for (int j = 0; j < 18; ++j) _mm_stream_pd(dst + 2 * j, v[j]);
-        } else {
-            for (int j = 0; j < 18; ++j) _mm_storeu_pd(dst + 2 * j, v[j]);
-        }
-    }
-    _mm_sfence();
-}
-
 extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const double* twists,
                                        const double* poses, const double* null_poses,
                                        const blf_ccm_params* params, unsigned out_mask,
@@ -799,6 +701,7 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
     if (compact) {
         double* stage = h->hstage;
         const long long schunk = h->hstage_chunk;
+        const bool skip = h->tune_host_noexpand != 0;
         h->pool->start([=, &ready, &done, &abort](int j) {
             for (long long c = 0; c < nchunks; ++c) {
                 int spins = 0;
@@ -808,8 +711,12 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
                     else std::this_thread::yield();
                 }
                 const long long off = c * chunk, cnt = std::min<long long>(chunk, n - off);
-                const long long lo = cnt * j / nthreads, hi = cnt * (j + 1) / nthreads;
-                expand_ctrl(stage + size_t(c % kStageSlots) * schunk * 8 + lo * 8, ctrl + (off + lo) * 36, hi - lo);
+                // even slice boundaries (chunks are even too): a contact PAIR is nine whole 64-byte
+                // lines of the dense array, which the AVX-512 expansion stores line by line
+                const long long lo = (cnt * j / nthreads) & ~1LL;
+                const long long hi = j == nthreads - 1 ? cnt : ((cnt * (j + 1) / nthreads) & ~1LL);
+                if (!skip)
+                    expand_ctrl(stage + size_t(c % kStageSlots) * schunk * 8 + lo * 8, ctrl + (off + lo) * 36, hi - lo);
                 done[c % kStageSlots].fetch_add(1, std::memory_order_release);
             }
         });
@@ -903,7 +810,7 @@ extern "C" int blf_ccm_set_host_chunk(blf_ccm_handle* h, int64_t contacts)
 {
     if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle");
     if (contacts < 32) return fail(BLF_CCM_ERR_INVALID_ARG, "chunk must be >= 32 contacts");
-    h->host_chunk_pref = contacts;
+    h->host_chunk_pref = contacts & ~1LL;   // even: see the expansion workers
     return BLF_CCM_OK;
 }
 

@@ -527,6 +527,207 @@ ccm_rollout_ws_kernel(const __grid_constant__ RolloutArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-specialised rollout, second form (round 2): the producer's instruction stream is the critical
+// path of a small batch (100 dependent steps whatever the batch size), so everything that is not
+// the pose recurrence leaves it:
+//   * the twists of step t+1 are lifted out of the cp.async ring into registers while step t is
+//     integrated (the 29-cycle shared-memory latency is off the chain);
+//   * a stage holds only the pose (p, e1, e2, R22: 10 doubles per lane, five 128-bit stores); the
+//     consumers fetch the twist of their own steps straight from global memory, one step ahead;
+//   * stages are handed over in GROUPS of C (one stage per consumer): the producer waits on ONE
+//     `empty` barrier per C steps (an mbarrier try_wait costs ~90 cycles even when it succeeds) and
+//     signals ONE `full` barrier per group; consumer k evaluates step g*C + k of every group g;
+//   * C consumer warps (3, 5 or 7) keep up with the leaner producer.
+// Works with and without the Baumgarte term.  chain_cost[chain*C + k] = consumer k's partial cost;
+// the reduction kernel sums a rollout's feet*C partials in index order (deterministic).
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kWs2Groups = 3;               // stage groups in flight
+constexpr int kWs2StageDoubles = 10 * kWarp;
+
+template <int C>
+struct Ws2Cfg {
+    static constexpr int kStages = kWs2Groups * C;
+    static constexpr int kThreads = kWarp * (C + 1);
+    static constexpr int kSmemBytes = kRolloutRingBytes + kStages * kWs2StageDoubles * 8 + 2 * kWs2Groups * 8 + 64;
+};
+
+template <bool HET, bool BAUM, int C>
+__global__ void __launch_bounds__(kWarp * (C + 1))
+ccm_rollout_ws2_kernel(const __grid_constant__ RolloutArgs a)
+{
+    constexpr int D = kRolloutDepth;
+    constexpr int S = Ws2Cfg<C>::kStages;
+    constexpr int NG = kWs2Groups;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wbase = static_cast<long long>(blockIdx.x) * kWarp;
+    const long long c = wbase + lane;
+    const bool on = c < a.chains;
+    const int H = a.horizon;
+
+    double* ring = reinterpret_cast<double*>(smem_raw);                       // producer's twist ring
+    double* stages = ring + D * 6 * kWarp;                                    // [S][10][32]
+    const uint32_t full0 = ptx::smem_addr(stages + S * kWs2StageDoubles);     // NG barriers, 1 arrival
+    const uint32_t empty0 = full0 + 8 * NG;                                   // NG barriers, C arrivals
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < NG; ++g) {
+            ptx::mbar_init(full0 + 8 * g, 1);
+            ptx::mbar_init(empty0 + 8 * g, C);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer: the pose recurrence and nothing else -------------------------
+        const uint32_t ring_s = ptx::smem_addr(ring) + static_cast<uint32_t>(lane) * 8u;
+        const double* src[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) src[j] = a.tw[j] + c;
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            if (on && t < H) {
+                const uint32_t dst = ring_s + static_cast<uint32_t>(t * 6 * kWarp * 8);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, src[j] + static_cast<long long>(t) * a.chains);
+            }
+            ptx::cp_async_commit();
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) src[j] += static_cast<long long>(D) * a.chains;   // step t + D
+        Pose s{};
+        if (on) {
+            s.p = V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)};
+            s.c0 = V3{__ldg(a.rot0[0] + c), __ldg(a.rot0[3] + c), __ldg(a.rot0[6] + c)};
+            s.c1 = V3{__ldg(a.rot0[1] + c), __ldg(a.rot0[4] + c), __ldg(a.rot0[7] + c)};
+            s.c2 = V3{__ldg(a.rot0[2] + c), __ldg(a.rot0[5] + c), __ldg(a.rot0[8] + c)};
+        }
+        // twist of step 0 into registers
+        ptx::cp_async_wait<D - 1>();
+        V3 vn{}, wn{};
+        if (on) {
+            const double* r = ring + lane;
+            vn = V3{r[0], r[kWarp], r[2 * kWarp]};
+            wn = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
+        }
+        int slot = 0;               // twist ring slot of step t
+        int st = 0;                 // stage of step t
+        int gi = 0, g = 0;          // position inside the group, group slot
+        uint32_t empty_parity = 0;
+        bool wrapped = false;
+        for (int t = 0; t < H; ++t) {
+            const V3 v = vn, w = wn;
+            // the twist of step t + 1 (its copy was issued D - 1 steps ago): in flight while step t is integrated
+            ptx::cp_async_wait<D - 2>();
+            const int nslot = (slot + 1) & (D - 1);
+            if (on) {
+                const double* r = ring + nslot * 6 * kWarp + lane;
+                vn = V3{r[0], r[kWarp], r[2 * kWarp]};
+                wn = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
+            }
+            if (gi == 0 && wrapped) ptx::mbar_wait(empty0 + 8 * g, empty_parity);   // the group's stages are free
+            double2* o = reinterpret_cast<double2*>(stages + st * kWs2StageDoubles) + lane;
+            o[0 * kWarp] = make_double2(s.p.x, s.p.y);
+            o[1 * kWarp] = make_double2(s.p.z, s.c0.x);
+            o[2 * kWarp] = make_double2(s.c0.y, s.c0.z);
+            o[3 * kWarp] = make_double2(s.c1.x, s.c1.y);
+            o[4 * kWarp] = make_double2(s.c1.z, s.c2.z);
+            kin_euler_step<BAUM>(s, v, w, a.half_rho, a.dT);
+            if (++gi == C || t == H - 1) {   // the group is complete: hand it over
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(full0 + 8 * g);
+                gi = 0;
+                if (++g == NG) {
+                    g = 0;
+                    empty_parity = wrapped ? (empty_parity ^ 1u) : 0u;
+                    wrapped = true;
+                }
+            }
+            // refill the ring slot of step t (read one iteration ago) with step t + D
+            if (on && t + D < H) {
+                const uint32_t dst = ring_s + static_cast<uint32_t>(slot * 6 * kWarp * 8);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, src[j]);
+            }
+            ptx::cp_async_commit();
+#pragma unroll
+            for (int j = 0; j < 6; ++j) src[j] += a.chains;
+            slot = nslot;
+            if (++st == S) st = 0;
+        }
+        if (on && a.write_final) {
+            a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
+            a.rot_out[0][c] = s.c0.x; a.rot_out[1][c] = s.c1.x; a.rot_out[2][c] = s.c2.x;
+            a.rot_out[3][c] = s.c0.y; a.rot_out[4][c] = s.c1.y; a.rot_out[5][c] = s.c2.y;
+            a.rot_out[6][c] = s.c0.z; a.rot_out[7][c] = s.c1.z; a.rot_out[8][c] = s.c2.z;
+        }
+        ptx::cp_async_wait<0>();
+    } else {
+        // ---------------- consumer k: contact wrench + cost of the steps g*C + k -----------------
+        const int k = warp - 1;
+        V3 p0{}, n1{}, n2{};
+        Prm q = a.uni;
+        if (on) {
+            p0 = V3{__ldg(a.nul[0] + c), __ldg(a.nul[1] + c), __ldg(a.nul[2] + c)};
+            n1 = V3{__ldg(a.nul[3] + c), __ldg(a.nul[6] + c), __ldg(a.nul[9] + c)};
+            n2 = V3{__ldg(a.nul[4] + c), __ldg(a.nul[7] + c), __ldg(a.nul[10] + c)};
+            if constexpr (HET)
+                q = make_prm(__ldg(a.prm[0] + c), __ldg(a.prm[1] + c), __ldg(a.prm[2] + c),
+                             __ldg(a.prm[3] + c));
+        }
+        // the twists of this consumer's own steps come straight from global memory, one step ahead
+        const long long tstride = static_cast<long long>(C) * a.chains;
+        long long ti = static_cast<long long>(k) * a.chains + c;
+        V3 vn{}, wn{};
+        if (on && k < H) {
+            vn = V3{__ldg(a.tw[0] + ti), __ldg(a.tw[1] + ti), __ldg(a.tw[2] + ti)};
+            wn = V3{__ldg(a.tw[3] + ti), __ldg(a.tw[4] + ti), __ldg(a.tw[5] + ti)};
+        }
+        double acc = 0.0;
+        int g = 0;
+        uint32_t parity = 0;
+        const double2* stage_k = reinterpret_cast<const double2*>(stages + k * kWs2StageDoubles) + lane;
+        for (int t = k; t < H; t += C) {
+            State x;
+            x.v = vn;
+            x.w = wn;
+            ti += tstride;
+            if (on && t + C < H) {
+                vn = V3{__ldg(a.tw[0] + ti), __ldg(a.tw[1] + ti), __ldg(a.tw[2] + ti)};
+                wn = V3{__ldg(a.tw[3] + ti), __ldg(a.tw[4] + ti), __ldg(a.tw[5] + ti)};
+            }
+            ptx::mbar_wait(full0 + 8 * g, parity);
+            const double2* in = stage_k + g * (C * kWs2StageDoubles / 2);
+            const double2 a0 = in[0 * kWarp], a1 = in[1 * kWarp], a2 = in[2 * kWarp], a3 = in[3 * kWarp],
+                          a4 = in[4 * kWarp];
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty0 + 8 * g);   // one of the C arrivals that free the group
+            x.p = V3{a0.x, a0.y, a1.x};
+            x.e1 = V3{a1.y, a2.x, a2.y};
+            x.e2 = V3{a3.x, a3.y, a4.x};
+            x.R02 = 0.0; x.R12 = 0.0;
+            x.R22 = a4.y;
+            x.p0 = p0; x.n1 = n1; x.n2 = n2;
+            Result r;
+            eval_contact<M_WRENCH>(x, q, r);
+            if (on) {
+                const V3 df = r.force - V3{a.ref[0], a.ref[1], a.ref[2]};
+                const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
+                acc = acc + (a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
+                             a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
+            }
+            if (++g == NG) {
+                g = 0;
+                parity ^= 1u;
+            }
+        }
+        if (on) a.chain_cost[c * C + k] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // J^T * wrench accumulation
 // ------------------------------------------------------------------------------------------------
 

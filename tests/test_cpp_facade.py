@@ -28,6 +28,15 @@ def test_parameters_handler_cases(cpp):
     assert "0 failure(s)" in r.stdout
 
 
+def test_host_expansion_helper_and_worker_pool(cpp):
+    """csrc/host_expand.{h,cpp} on their own (no CUDA): every ISA form of the compact -> dense
+    control-matrix expansion against a plain loop, bit for bit, for every destination alignment;
+    the worker pool never re-runs the job of an earlier call after a resize."""
+    r = _run("HostExpandUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "All tests passed" in r.stdout
+
+
 def test_facade_fails_loudly_without_a_gpu(cpp):
     import torch
     if torch.cuda.is_available():
