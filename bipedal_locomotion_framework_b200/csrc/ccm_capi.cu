@@ -51,6 +51,9 @@ static int fail(int code, const char* fmt, ...)
 // ------------------------------------------------------------------------------------------------
 
 static constexpr int kHostSlots = 4;
+static constexpr int kHostCopyStreams = 5;   // host evaluation: up to 3 upload + 2 download streams
+static constexpr int kHostThreadsAuto = 4;   // expansion workers when not set (measured best: profiles/r02_host_sweep.log)
+static constexpr int kHostUpStreamsAuto = 1;
 static constexpr int kStageSlots = 8;    // pinned staging chunks of the compact control-matrix download
 static constexpr int kMaxPartials = 8192;
 
@@ -85,6 +88,7 @@ struct blf_ccm_handle {
     double* single_out = nullptr;   // 64 doubles of mapped pinned host memory (n = 1 fast path): results + flag
     unsigned long long single_seq = 0;
     // compact control-matrix download of the host evaluation: pinned staging ring + expansion pool
+    cudaStream_t hxstream[kHostCopyStreams] = {};   // [0..2] uploads, [3..4] downloads of the host evaluation
     cudaEvent_t hev_stage[kStageSlots] = {};
     double* hstage = nullptr;       // kStageSlots * hstage_chunk * 8 doubles, pinned
     long long hstage_chunk = 0;
@@ -100,9 +104,12 @@ struct blf_ccm_handle {
                                  // (looping kernels only); default = one tile per warp
     int tune_rollout_split = 0;  // BLF_CCM_TUNE_ROLLOUT_SPLIT>0: warps per tile of the fused rollout
     int tune_rollout_ws = 0;     // BLF_CCM_TUNE_ROLLOUT_WS: 1 force / 2 forbid the warp-specialised rollout
+    int tune_no_pack = 0;        // BLF_CCM_TUNE_NO_PACK=1: J^T wrench for narrow Jacobians with the column-per-lane kernel
     int tune_no_rows = 0;        // BLF_CCM_TUNE_NO_ROWS=1: J^T wrench without base/out row staging
     int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
     int tune_rollout_chunk_mb = 0;  // BLF_CCM_TUNE_ROLLOUT_CHUNK_MB: twist bytes per time chunk of the host rollout (default 8)
+    int tune_host_up = 0, tune_host_down = 0;   // BLF_CCM_TUNE_HOST_UP / _DOWN: copy streams per direction of the host evaluation
+    int tune_host_ramp = 1;      // BLF_CCM_TUNE_HOST_RAMP=0: equal chunks instead of the ramped schedule
     int tune_host_noexpand = 0;  // BLF_CCM_TUNE_HOST_NOEXPAND=1: measurement aid, the workers skip the expansion (results WRONG)
     int tune_rls_pipe = 0;       // BLF_CCM_TUNE_RLS_PIPE=1: the plain one-estimator-per-thread RLS kernel instead of the pipelined one
     // peer-memory arg-min exchange
@@ -196,9 +203,13 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");
     h->tune_host_noexpand = env_int("BLF_CCM_TUNE_HOST_NOEXPAND");
+    h->tune_host_up = env_int("BLF_CCM_TUNE_HOST_UP");
+    h->tune_host_down = env_int("BLF_CCM_TUNE_HOST_DOWN");
+    if (const char* v = getenv("BLF_CCM_TUNE_HOST_RAMP")) h->tune_host_ramp = atoi(v);
     h->tune_rls_pipe = env_int("BLF_CCM_TUNE_RLS_PIPE");
     h->tune_rollout_chunk_mb = env_int("BLF_CCM_TUNE_ROLLOUT_CHUNK_MB");
     h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
+    h->tune_no_pack = env_int("BLF_CCM_TUNE_NO_PACK");
     h->tune_rollout_ws = env_int("BLF_CCM_TUNE_ROLLOUT_WS");
     if (const char* v = getenv("BLF_CCM_HOST_THREADS")) h->host_threads = atoi(v);
     cudaError_t ce = cudaMalloc(&h->block_best, sizeof(CostIdx) * kMaxPartials);
@@ -263,6 +274,8 @@ extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
     h->pool = nullptr;
     for (int s = 0; s < kStageSlots; ++s)
         if (h->hev_stage[s]) cudaEventDestroy(h->hev_stage[s]);
+    for (int s = 0; s < kHostCopyStreams; ++s)
+        if (h->hxstream[s]) cudaStreamDestroy(h->hxstream[s]);
     if (h->hstage) cudaFreeHost(h->hstage);
     if (h->scratch_ev) cudaEventDestroy(h->scratch_ev);
     for (int s = 0; s < kHostSlots; ++s) {
@@ -642,8 +655,40 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         return eval_single_host(h, twists, poses, null_poses, params, out_mask, wrench, autodyn, ctrl,
                                 regressor);
 
+    // ---- chunk schedule ---------------------------------------------------------------------------
+    // Every chunk costs a fixed ~40 us of dead time on the PCIe engines (six copies, each started
+    // and retired on its own: 173 M evals/s with 65 536-contact chunks, 188 M with 262 144,
+    // profiles/r02_host_sweep.log), so chunks should be large; but the first chunk's upload and the
+    // last chunk's download + expansion are not overlapped with anything, so the schedule ramps:
+    // chunk/4, chunk/2, chunk ... chunk, chunk/2, chunk/4 (BLF_CCM_TUNE_HOST_RAMP=0: equal chunks).
+    const long long chunk = std::max<long long>(2, (std::min<long long>(n, h->host_chunk_pref) + 1) & ~1LL);   // even
+    std::vector<long long> offs, cnts;
+    {
+        const bool ramp = h->tune_host_ramp != 0 && n >= 4 * chunk;
+        long long off = 0;
+        auto push = [&](long long c) {
+            c = std::min(c, n - off);
+            if (c <= 0) return;
+            offs.push_back(off);
+            cnts.push_back(c);
+            off += c;
+        };
+        if (ramp) {
+            push(chunk / 4 & ~1LL);
+            push(chunk / 2 & ~1LL);
+            const long long tail = (chunk / 2 & ~1LL) + (chunk / 4 & ~1LL);
+            while (n - off > tail + chunk) push(chunk);
+            // what is left (between tail and tail + chunk contacts): one middle chunk, then the ramp down
+            push(std::max<long long>(0, n - off - tail) & ~1LL);
+            push(chunk / 2 & ~1LL);
+            push(n - off);
+        } else {
+            while (off < n) push(chunk);
+        }
+    }
+    const long long nchunks = static_cast<long long>(offs.size());
+
     // slot layout in doubles per contact (every section starts 16-byte aligned: all even counts)
-    const long long chunk = std::min<long long>(n, h->host_chunk_pref);
     const size_t per_contact = 6 + 12 + 12 + 4 + 6 + 6 + 36 + 12;
     const size_t need = size_t(chunk) * per_contact * sizeof(double);
     if (h->hbytes < need) {
@@ -661,6 +706,8 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         if (!h->hev_up[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev_up[s], cudaEventDisableTiming));
         if (!h->hev_done[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev_done[s], cudaEventDisableTiming));
     }
+    for (int s = 0; s < kHostCopyStreams; ++s)
+        if (!h->hxstream[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hxstream[s], cudaStreamNonBlocking));
     for (int s = 0; s < kStageSlots; ++s)
         if (!h->hev_stage[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev_stage[s], cudaEventDisableTiming));
 
@@ -669,15 +716,14 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
     // those 64 bytes per contact cross PCIe -- 160 instead of 384 bytes per evaluation come back --
     // into a pinned staging ring; worker threads expand them into the caller's dense Matrix6x6
     // array (structural zeros +0.0, bit-identical to the dense kernel output) while later chunks
-    // are in flight.  host_threads == 0 keeps the dense download (A/B: profiles/r02_host_compact*).
+    // are in flight.  host_threads == 0 keeps the dense download (A/B: profiles/r02_host_sweep.log).
     int nthreads = h->host_threads;
     if (nthreads < 0) {
         int hw = static_cast<int>(std::thread::hardware_concurrency());
         if (const char* lws = getenv("LOCAL_WORLD_SIZE")) hw /= std::max(1, atoi(lws));  // one process per GPU
-        nthreads = std::max(1, std::min(8, hw / 2));
+        nthreads = std::max(1, std::min(kHostThreadsAuto, hw / 2));
     }
     const bool compact = (out_mask & BLF_CCM_CTRL) && nthreads > 0;
-    const long long nchunks = (n + chunk - 1) / chunk;
     if (compact) {
         if (h->hstage_chunk < chunk) {
             if (h->hstage) CUDA_TRY(cudaFreeHost(h->hstage));
@@ -687,7 +733,7 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
                                    size_t(kStageSlots) * chunk * 8 * sizeof(double), cudaHostAllocDefault));
             h->hstage_chunk = chunk;
         }
-        if (nchunks < 2) nthreads = 1;   // a single chunk: the orchestrating thread's one worker is enough
+        if (nchunks < 2) nthreads = 1;   // a single chunk: one worker is enough
         if (!h->pool) h->pool = new (std::nothrow) HostPool();
         if (!h->pool) return fail(BLF_CCM_ERR_INVALID_ARG, "out of host memory");
         h->pool->resize(nthreads);
@@ -702,6 +748,8 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         double* stage = h->hstage;
         const long long schunk = h->hstage_chunk;
         const bool skip = h->tune_host_noexpand != 0;
+        const long long* poffs = offs.data();
+        const long long* pcnts = cnts.data();
         h->pool->start([=, &ready, &done, &abort](int j) {
             for (long long c = 0; c < nchunks; ++c) {
                 int spins = 0;
@@ -710,9 +758,9 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
                     if (++spins < 2000) _mm_pause();
                     else std::this_thread::yield();
                 }
-                const long long off = c * chunk, cnt = std::min<long long>(chunk, n - off);
-                // even slice boundaries (chunks are even too): a contact PAIR is nine whole 64-byte
-                // lines of the dense array, which the AVX-512 expansion stores line by line
+                const long long off = poffs[c], cnt = pcnts[c];
+                // even slice boundaries (chunk offsets are even too): a contact PAIR is nine whole
+                // 64-byte lines of the dense array, which the AVX-512 expansion stores line by line
                 const long long lo = (cnt * j / nthreads) & ~1LL;
                 const long long hi = j == nthreads - 1 ? cnt : ((cnt * (j + 1) / nthreads) & ~1LL);
                 if (!skip)
@@ -734,13 +782,17 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         }
     } join{compact ? h->pool : nullptr, abort};
 
-    // One stream per PCIe direction and one for the kernels, chained by events, so that each
-    // direction is ONE in-order queue; kHostSlots chunk buffers in flight on the device.
-    cudaStream_t up = h->hstream[0], comp = h->hstream[1], down = h->hstream[2];
+    // Streams: `nup` upload and `ndown` download streams (chunk k uses stream k mod the count) and
+    // one for the kernels, chained by events; kHostSlots chunk buffers in flight on the device.  With
+    // two upload streams the start-up and retirement of one copy overlap the transfer of the other.
+    const int nup = std::max(1, std::min(3, h->tune_host_up > 0 ? h->tune_host_up : kHostUpStreamsAuto));
+    const int ndown = std::max(1, std::min(2, h->tune_host_down > 0 ? h->tune_host_down : 1));
+    cudaStream_t comp = h->hstream[1];
     const size_t D = sizeof(double);
     auto enqueue = [&](long long index) -> int {
-        const long long off = index * chunk, c = std::min<long long>(chunk, n - off);
+        const long long off = offs[index], c = cnts[index];
         const int slot = static_cast<int>(index % kHostSlots), sslot = static_cast<int>(index % kStageSlots);
+        cudaStream_t up = h->hxstream[index % nup], down = h->hxstream[3 + index % ndown];
         double* b = h->hbuf[slot];
         double* d_tw = b;
         double* d_po = d_tw + chunk * 6;
@@ -800,7 +852,8 @@ extern "C" int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doubl
         CUDA_TRY(cudaEventSynchronize(h->hev_stage[next_ready % kStageSlots]));
         ready.store(++next_ready, std::memory_order_release);
     }
-    for (int s = 0; s < 3; ++s) CUDA_TRY(cudaStreamSynchronize(h->hstream[s]));
+    CUDA_TRY(cudaStreamSynchronize(comp));
+    for (int s = 0; s < kHostCopyStreams; ++s) CUDA_TRY(cudaStreamSynchronize(h->hxstream[s]));
     join.failed = false;   // the destructor waits for the last expansions
     return BLF_CCM_OK;
 }

@@ -954,9 +954,166 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
     }
 }
 
-// A lane-packed variant for narrow Jacobians (2 or 4 contacts per warp iteration, ordered
-// accumulation through shuffles) and one bulk copy per warp for all its Jacobians were built,
-// measured no better (+-5 %) or slower, and removed: the instruction count per contact was the
-// bound, not idle lanes.
+// ------------------------------------------------------------------------------------------------
+// Narrow Jacobians (ncols <= 16): lane-packed form.
+//
+// With lanes owning columns, a 6-column Jacobian keeps 6 of 32 lanes busy and the kernel above is
+// issue-bound at ~60 % of HBM (12 columns: ~80 %).  Here the warp is cut into G = 32 / NCP lane
+// groups (NCP = 4, 8 or 16 >= ncols) and every group owns a whole SYSTEM: lane (g, col) accumulates
+// column col of system it*G + g over that system's contacts, in order -- the same products and the
+// same order of additions as the kernel above (and the reference's loop,
+// FloatingBaseSystemDynamics.cpp:199-226), so the results are bit-identical; no shuffles are needed
+// because no sum crosses a group.  A ring stage holds the Jacobians of G consecutive systems
+// (G * cps contacts, contiguous in memory): one mbarrier wait + one re-arm per G systems.  The
+// instruction stream per iteration is the one of the kernel above, but it now covers G contacts.
+// (A first lane-packed attempt in round 1 split the CONTACTS of one system over the groups and
+// needed ordered shuffles; it gained nothing and was removed.)
+// ------------------------------------------------------------------------------------------------
+template <bool HET, int NCP>
+__global__ void __launch_bounds__(128)
+ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
+{
+    constexpr unsigned LIVE = live_planes(M_WRENCH);
+    constexpr int G = kWarp / NCP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    const long long sys0 = wid * a.sys_per_warp;
+    if (sys0 >= a.n_systems) return;  // warp-uniform
+    const int nsys = static_cast<int>(min64(a.sys_per_warp, a.n_systems - sys0));
+    const int cps = a.cps, ncols = a.ncols, stage_bytes = a.stage_bytes;
+    const int ncont = nsys * cps;
+    const long long c0 = sys0 * cps;
+    const int jd = 6 * ncols;
+    const int nstage = (nsys + G - 1) / G;     // G systems per stage
+
+    const int per_warp = kGfStages * stage_bytes + kWarp * 48 + 128 + a.row_bytes;
+    unsigned char* ws = smem_raw + static_cast<size_t>(warp) * per_warp;
+    double* wsm = reinterpret_cast<double*>(ws + kGfStages * stage_bytes);
+    const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * stage_bytes + kWarp * 48);
+    const uint32_t rbar = bar0 + 8 * kGfStages;
+    double* rows = reinterpret_cast<double*>(ws + kGfStages * stage_bytes + kWarp * 48 + 128);
+    const uint32_t stage0 = ptx::smem_addr(ws);
+    const double* jac0 = a.jac + c0 * jd;
+    const long long row0 = sys0 * ncols;
+    const uint32_t rbytes = static_cast<uint32_t>(nsys) * ncols * 8u;
+    const bool staged = a.row_bytes > 0 && ((row0 | (static_cast<long long>(nsys) * ncols)) & 1) == 0;
+
+    auto arm = [&](int q) {   // lane 0: the Jacobians of systems q*G .. q*G+G-1 into ring slot q % kGfStages
+        const int first = q * G * cps;
+        const uint32_t bytes = static_cast<uint32_t>(min(G * cps, ncont - first)) * jd * 8u;
+        const uint32_t bar = bar0 + 8 * (q & (kGfStages - 1));
+        ptx::mbar_arrive_expect_tx(bar, bytes);
+        ptx::bulk_g2s(stage0 + (q & (kGfStages - 1)) * stage_bytes, jac0 + static_cast<long long>(first) * jd,
+                      bytes, bar);
+    };
+
+    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s <= kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        ptx::fence_mbar_init();
+    }
+    ptx::grid_dep_wait();
+    if (lane == 0) {
+        if (staged && a.base) {
+            ptx::mbar_arrive_expect_tx(rbar, rbytes);
+            ptx::bulk_g2s(ptx::smem_addr(rows), a.base + row0, rbytes, rbar);
+        }
+#pragma unroll
+        for (int q = 0; q < kGfStages; ++q)
+            if (q < nstage) arm(q);
+    }
+    __syncwarp();
+
+    // ---- wrench of this lane's contact (as in ccm_genforce_kernel) -----------------------------
+    const bool on = lane < ncont;
+    const long long i = c0 + lane;
+    double x[30] = {};
+#pragma unroll
+    for (int pl = 0; pl < 30; ++pl)
+        if (LIVE & (1u << pl)) x[pl] = on ? __ldcs(a.in[pl] + i) : 0.0;
+    Prm q = a.uni;
+    if constexpr (HET) {
+        const double l = on ? __ldcs(a.prm[0] + i) : 0.0, w = on ? __ldcs(a.prm[1] + i) : 0.0;
+        const double k = on ? __ldcs(a.prm[2] + i) : 0.0, b = on ? __ldcs(a.prm[3] + i) : 0.0;
+        q = make_prm(l, w, k, b);
+    }
+    State st;
+    st.v = V3{x[0], x[1], x[2]};
+    st.w = V3{x[3], x[4], x[5]};
+    st.p = V3{x[6], x[7], x[8]};
+    st.e1 = V3{x[9], x[12], x[15]};
+    st.e2 = V3{x[10], x[13], x[16]};
+    st.R02 = 0.0; st.R12 = 0.0;
+    st.R22 = x[17];
+    st.p0 = V3{x[18], x[19], x[20]};
+    st.n1 = V3{x[21], x[24], x[27]};
+    st.n2 = V3{x[22], x[25], x[28]};
+    Result r;
+    eval_contact<M_WRENCH>(st, q, r);
+    if (a.want_wrench && on) {
+        __stcs(a.wrench[0] + i, r.force.x); __stcs(a.wrench[1] + i, r.force.y);
+        __stcs(a.wrench[2] + i, r.force.z); __stcs(a.wrench[3] + i, r.torque.x);
+        __stcs(a.wrench[4] + i, r.torque.y); __stcs(a.wrench[5] + i, r.torque.z);
+    }
+    {
+        double2* o = reinterpret_cast<double2*>(wsm) + lane * 3;
+        o[0] = make_double2(r.force.x, r.force.y);
+        o[1] = make_double2(r.force.z, r.torque.x);
+        o[2] = make_double2(r.torque.y, r.torque.z);
+    }
+    __syncwarp();
+
+    // ---- lane (g, col): column col of system it*G + g ------------------------------------------
+    const int g = lane / NCP, col = lane % NCP;
+    const bool active = col < ncols;
+    if (staged && a.base) ptx::mbar_wait(rbar, 0);
+    int slot = 0;
+    uint32_t parity = 0;
+    const int goff = g * cps * jd + (active ? col : 0);      // this group's first Jacobian inside a stage
+    for (int sq = 0; sq < nstage; ++sq) {
+        const int s = sq * G + g;
+        const bool valid = active && s < nsys;
+        const int sc = valid ? s : 0;                         // in-bounds addresses for idle lanes
+        ptx::mbar_wait(bar0 + 8 * slot, parity);
+        const double* J = reinterpret_cast<const double*>(ws + slot * stage_bytes) + (valid ? goff : 0);
+        const double2* wv = reinterpret_cast<const double2*>(wsm) + sc * cps * 3;
+        const long long row = (sys0 + sc) * ncols + col;
+        double acc = 0.0;
+        if (valid && a.base) acc = staged ? rows[sc * ncols + col] : __ldcs(a.base + row);
+        for (int j = 0; j < cps; ++j, J += jd, wv += 3) {
+            const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
+            // (J^T w)[col], rows in order; then known += product  (:224-225)
+            double t = J[0] * w01.x;
+            t += J[ncols] * w01.y;
+            t += J[2 * ncols] * w23.x;
+            t += J[3 * ncols] * w23.y;
+            t += J[4 * ncols] * w45.x;
+            t += J[5 * ncols] * w45.y;
+            acc = acc + t;
+        }
+        if (valid) {
+            if (staged) rows[sc * ncols + col] = acc;
+            else __stcs(a.out + row, acc);
+        }
+        __syncwarp();   // every lane is done with this stage
+        if (lane == 0 && sq + kGfStages < nstage) arm(sq + kGfStages);
+        if (++slot == kGfStages) {
+            slot = 0;
+            parity ^= 1u;
+        }
+    }
+    if (staged) {   // the warp's rows leave with one bulk store
+        ptx::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::bulk_s2g(a.out + row0, ptx::smem_addr(rows), rbytes);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read_all();
+        }
+    }
+}
 
 }  // namespace blfccm

@@ -152,10 +152,16 @@ def test_per_instance_facade_vs_reference_build(torch, ref):
 
 @pytest.mark.parametrize("p,m", [(2, 6), (3, 4), (1, 1)])
 def test_rls_sequences_vs_reference_build(torch, batch, ref, p, m):
-    """n independent estimators on the GPU, each following the SAME sequence as one reference
-    RecursiveLeastSquare object; both continue from their own state (no re-synchronisation), the
-    comparison scale is the magnitude of the operands (the covariance update cancels)."""
+    """n independent estimators on the GPU against one reference RecursiveLeastSquare object each,
+    two ways.  (i) STEP parity at the north-star tolerance: at every step the GPU starts from the
+    reference's own previous state, so the difference is one step's rounding; tolerance
+    max(1e-12, 128 eps cond(S)) on the operand-magnitude scale (tests/test_rls.py::_assert_step --
+    the reference inverts S by LU, the kernel factorises it, and P - K Y P cancels).  (ii) DRIFT:
+    a second set of estimators free-runs from its own state for all 25 steps; differences compound
+    with cond(S) per step, so that comparison is held to 1e-10 and is a stability check, not the
+    parity claim."""
     from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquareBatch
+    from test_rls import _assert_step
     rng = np.random.default_rng(10 * p + m)
     n, ns = 64, 25
     r, lam = rng.uniform(0.2, 1.5, m), 0.99
@@ -167,18 +173,29 @@ def test_rls_sequences_vs_reference_build(torch, batch, ref, p, m):
     P0[:, np.arange(p), np.arange(p)] = pd
     d_P = _dev(torch, P0.reshape(n, p * p).T)
     want = [ref.rls_run(r, lam, th0[i], pd[i], Y[i], z[i]) for i in range(n)]
+    worst_med = 0.0
     for s in range(ns):
-        rls.advance(_dev(torch, Y[:, s].reshape(n, m * p).T), _dev(torch, z[:, s].T), d_th, d_P)
+        th_prev = th0 if s == 0 else np.stack([want[i][0][s - 1] for i in range(n)])
+        P_prev = P0 if s == 0 else np.stack([want[i][1][s - 1] for i in range(n)])
+        th_ref = np.stack([want[i][0][s] for i in range(n)])
+        P_ref = np.stack([want[i][1][s] for i in range(n)])
+        d_Y, d_z = _dev(torch, Y[:, s].reshape(n, m * p).T), _dev(torch, z[:, s].T)
+        # (i) one step from the reference's previous state
+        s_th, s_P = _dev(torch, th_prev.T), _dev(torch, P_prev.reshape(n, p * p).T)
+        rls.advance(d_Y, d_z, s_th, s_P)
+        med = _assert_step(s_th.cpu().numpy().T, s_P.cpu().numpy().T.reshape(n, p, p), th_ref, P_ref,
+                           th_prev, P_prev, Y[:, s], z[:, s], r, lam, f"p={p} m={m} step {s}")
+        worst_med = max(worst_med, med)
+        # (ii) free-running
+        rls.advance(d_Y, d_z, d_th, d_P)
         th = d_th.cpu().numpy().T
         P = d_P.cpu().numpy().T.reshape(n, p, p)
         for i in range(n):
-            th_ref, P_ref = want[i][0][s], want[i][1][s]
-            P_prev = P0[i] if s == 0 else want[i][1][s - 1]
-            th_prev = th0[i] if s == 0 else want[i][0][s - 1]
-            scale_th = max(np.abs(th_ref).max(), np.abs(th_prev).max(), 1e-2)
-            scale_P = max(np.abs(P_prev).max(), np.abs(P_ref).max())
-            assert np.abs(th[i] - th_ref).max() <= 1e-10 * scale_th, (i, s)
-            assert np.abs(P[i] - P_ref).max() <= 1e-10 * scale_P, (i, s)
+            scale_th = max(np.abs(th_ref[i]).max(), np.abs(th_prev[i]).max(), 1e-2)
+            scale_P = max(np.abs(P_prev[i]).max(), np.abs(P_ref[i]).max())
+            assert np.abs(th[i] - th_ref[i]).max() <= 1e-10 * scale_th, (i, s)
+            assert np.abs(P[i] - P_ref[i]).max() <= 1e-10 * scale_P, (i, s)
+    assert worst_med <= 1e-13      # the typical estimator and step agree far below the bound
 
 
 @pytest.mark.parametrize("rho", [0.0, 2.0])

@@ -85,6 +85,35 @@ def test_euler_step_batch_vs_oracle(torch, batch, so, rho):
     assert rel(r.cpu().numpy().T, r_ref.T).max() <= TOL
 
 
+def test_rho_zero_skips_the_inverse_documented_deviation(torch, batch, so):
+    """The one documented behavioural deviation of the System rows (include/blf_ccm.h,
+    blf_sys_kinematics_*): with rho == 0 the backend does not form (R R^T)^-1 at all, so a SINGULAR
+    rotation matrix gives the finite rate -R.colwise().cross(w) where the reference's
+    0 * ((R R^T)^-1 - I) R is NaN (FloatingBaseSystemKinematics.cpp:62-66; pinned on the oracle side
+    by tests/test_sys_oracle.py::test_rho_zero_with_a_singular_rotation_is_nan_in_the_reference).
+    With rho != 0 a singular R is non-finite in both; for regular R both agree for every rho."""
+    from bipedal_locomotion_framework_b200.system import KinematicsBatch
+    kb = KinematicsBatch(0, batch.handle)
+    twist = np.array([0.1, -0.2, 0.3, 0.4, 0.5, -0.6])
+    singular = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [0.5, -1.0, 0.25]])
+    regular = np.array([[0.9, -0.1, 0.2], [0.1, 1.1, 0.0], [-0.2, 0.05, 0.95]])
+    R = np.stack([singular.reshape(9), regular.reshape(9)], axis=1)          # (9, 2) planes
+    tw = np.repeat(twist[:, None], 2, axis=1)
+    dT = 1e-2
+    for rho in (0.0, 3.0):
+        p, r = _dev(torch, np.zeros((3, 2))), _dev(torch, R)
+        kb.euler_step(rho, dT, _dev(torch, tw), p, r)
+        r = r.cpu().numpy()
+        _, r_ref = so.euler_step_batch_soa(rho, dT, tw, np.zeros((3, 2)), R)
+        assert rel(r[:, 1], r_ref[:, 1]) <= TOL                                  # regular: parity
+        if rho == 0.0:
+            assert np.isnan(r_ref[:, 0]).all()                                   # the reference's NaN
+            want = singular + dT * (-np.cross(singular.T, twist[3:]).T)
+            assert np.isfinite(r[:, 0]).all() and np.abs(r[:, 0] - want.reshape(9)).max() <= 1e-15
+        else:
+            assert not np.isfinite(r_ref[:, 0]).all() and not np.isfinite(r[:, 0]).all()
+
+
 def test_per_instance_facade_reference_property(torch):
     """IntegratorTest.cpp:80-126 through the Python mirror of the facade (every step on the GPU):
     identity start, constant twist; 200 integrate(0, dT) calls, then the closed form."""

@@ -222,6 +222,14 @@ def test_kinematics_dynamics_oracle_vs_reference_build(sys_oracle, ref):
         pd_o, rd_o = sys_oracle.kinematics_dynamics(rho, tw, R)
         pd_r, rd_r = ref.kin_dynamics(rho, tw, R)
         assert np.array_equal(pd_o, pd_r) and np.array_equal(rd_o, rd_r), f"state {i}"
+    # rho == 0 with a singular rotation: the reference's 0 * ((R R^T)^-1 - I) R is NaN
+    # (FloatingBaseSystemKinematics.cpp:62-66), and so is the oracle; the CUDA backend documents
+    # that it skips the inverse there (tests/test_gpu_sys.py pins that side)
+    tw = np.array([0.1, -0.2, 0.3, 0.4, 0.5, -0.6])
+    singular = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [0.5, -1.0, 0.25]])
+    _, rd_r = ref.kin_dynamics(0.0, tw, singular)
+    _, rd_o = sys_oracle.kinematics_dynamics(0.0, tw, singular)
+    assert np.isnan(rd_r).all() and np.isnan(np.asarray(rd_o)).all()
 
 
 @pytest.mark.parametrize("dt,t0,tf", [(0.01, 0.0, 0.1), (0.01, 0.0, 0.105), (0.003, 0.2, 0.25),

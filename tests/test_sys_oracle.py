@@ -101,6 +101,23 @@ def test_baumgarte_restores_orthonormality():
     assert np.abs(R @ R.T - np.eye(3)).max() < 1e-6
 
 
+def test_rho_zero_with_a_singular_rotation_is_nan_in_the_reference():
+    """FloatingBaseSystemKinematics.cpp:62-66 multiplies rho/2 into ((R R^T)^-1 - I) R even when rho
+    is 0: a singular R makes the inverse inf/NaN and 0 * inf = NaN poisons the rotation rate.  The
+    oracle (and the reference build, tests/test_reference_build.py) reproduce that; the CUDA backend
+    deliberately does not (include/blf_ccm.h, blf_sys_kinematics_*: with rho == 0 the inverse is
+    skipped) -- tests/test_gpu_sys.py pins the backend's side of this documented deviation.  For a
+    regular R, rho = 0 adds exact zeros and both agree."""
+    twist = np.array([0.1, -0.2, 0.3, 0.4, 0.5, -0.6])
+    singular = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [0.5, -1.0, 0.25]])   # rank 2
+    pd, rd = so.kinematics_dynamics(0.0, twist, singular.reshape(9))
+    assert np.array_equal(pd, twist[:3]) and np.isnan(rd).all()
+    regular = np.array([[0.9, -0.1, 0.2], [0.1, 1.1, 0.0], [-0.2, 0.05, 0.95]])
+    pd, rd = so.kinematics_dynamics(0.0, twist, regular.reshape(9))
+    want = -np.cross(regular.T, twist[3:]).T           # -R.colwise().cross(w)
+    assert np.isfinite(rd).all() and np.abs(rd.reshape(3, 3) - want).max() <= 1e-15
+
+
 def test_rollout_matches_80_digit_golden(g):
     nr, feet, H = (int(x) for x in g["ro_shape"])
     for nthreads in (1, 4):

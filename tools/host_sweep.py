@@ -23,12 +23,11 @@ tw, po, nu = pin(st["twists"]), pin(st["poses"]), pin(st["null_poses"])
 out = {"wrench": torch.empty((n, 6), dtype=torch.float64).pin_memory(),
        "autodyn": torch.empty((n, 6), dtype=torch.float64).pin_memory(),
        "ctrl": torch.empty((n, 36), dtype=torch.float64).pin_memory(), "regressor": None}
-b = ContinuousContactModelBatch(0)
-b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
 print(f"n = {n}, cores = {os.cpu_count()}, NOEXPAND = {os.environ.get('BLF_CCM_TUNE_HOST_NOEXPAND', '0')}")
+quick = "--quick" in sys.argv
 
 
-def rate(reps=6):
+def rate(b, reps=6):
     b.evaluate_host(tw, po, nu, None, FULL, out=out)
     best = 1e9
     for _ in range(reps):
@@ -38,12 +37,18 @@ def rate(reps=6):
     return n / best / 1e6, best * 1e3
 
 
-for chunk in (32768, 65536, 131072, 262144):
-    b.set_host_chunk(chunk)
-    for threads in (0, 1, 2, 4, 6, 8, 12, 16):
-        if threads > (os.cpu_count() or 1):
-            continue
-        b.set_host_threads(threads)
-        r, ms = rate()
-        print(f"chunk {chunk:7d}  threads {threads:2d} ({'dense download' if threads == 0 else 'compact + expand'}): "
-              f"{r:7.1f} M evals/s  {ms:7.2f} ms")
+# the stream / schedule knobs are read when a handle is created
+for up, down, ramp in ((1, 1, 0), (1, 1, 1), (2, 1, 1), (3, 1, 1), (2, 2, 1), (2, 1, 0)):
+    os.environ["BLF_CCM_TUNE_HOST_UP"], os.environ["BLF_CCM_TUNE_HOST_DOWN"] = str(up), str(down)
+    os.environ["BLF_CCM_TUNE_HOST_RAMP"] = str(ramp)
+    b = ContinuousContactModelBatch(0)
+    b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    for chunk in ((65536, 131072, 262144) if not quick else (131072,)):
+        b.set_host_chunk(chunk)
+        for threads in ((0, 2, 4, 6, 8) if not quick else (4,)):
+            b.set_host_threads(threads)
+            r, ms = rate(b)
+            print(f"up {up} down {down} ramp {ramp}  chunk {chunk:7d}  threads {threads:2d} "
+                  f"({'dense download' if threads == 0 else 'compact + expand'}): {r:7.1f} M evals/s  {ms:7.2f} ms",
+                  flush=True)
+    del b

@@ -154,22 +154,40 @@ def sys_only():
         del tws, pos, rot, null
         torch.cuda.empty_cache()
     # --- J^T wrench --------------------------------------------------------------------------------
-    for ns, cps, ncols in ((409600, 2, 29), (1 << 21, 2, 29), (1 << 20, 4, 38), (1 << 21, 1, 6),
-                           (1 << 21, 2, 6), (1 << 20, 2, 12)):
-        n = ns * cps
-        st = syn.make_states(min(n, 1 << 18), seed=49)
-        reps = (n + st["n"] - 1) // st["n"]
-        pl = torch.from_numpy(np.ascontiguousarray(np.tile(
-            syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]), (1, reps))[:, :n])).cuda()
-        Js = [rnd(n, 6, ncols) for _ in range(2)]
-        base = rnd(ns, ncols)
-        outs = [torch.empty_like(base) for _ in range(2)]
-        cls = [gf.prepare(cps, ncols, pl, Js[j], base, out=outs[j])[0] for j in range(2)]
-        ms = timeit(lambda i: cls[i % 2](), iters=50, warm=5)
-        per_contact = 200 + 48 * ncols + 16 * ncols / cps
-        row(f"J^T wrench systems={ns} contacts/system={cps} ncols={ncols}", ms, n, per_contact)
-        del Js, base, outs, cls, pl
-        torch.cuda.empty_cache()
+    gf_only()
+
+
+def gf_only():
+    """J^T wrench accumulation: wide Jacobians (lanes own columns) and narrow ones (lane groups own
+    whole systems, ccm_genforce_packed_kernel) beside the column-per-lane kernel they replace."""
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    rnd = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda") * 2 - 1
+    for no_pack in (0, 1):
+        b = make_batch(BLF_CCM_TUNE_NO_PACK=no_pack)
+        gf = GeneralizedForceBatch(b)
+        shapes = ((409600, 2, 29), (1 << 21, 2, 29), (1 << 20, 4, 38), (1 << 21, 1, 6), (1 << 21, 2, 6),
+                  (409600, 2, 6), (1 << 20, 2, 12), (409600, 2, 12), (1 << 20, 2, 16), (1 << 21, 2, 4),
+                  (1 << 19, 8, 6), (1 << 20, 4, 12))
+        for ns, cps, ncols in shapes:
+            if no_pack and ncols > 16:
+                continue
+            n = ns * cps
+            st = syn.make_states(min(n, 1 << 18), seed=49)
+            reps = (n + st["n"] - 1) // st["n"]
+            pl = torch.from_numpy(np.ascontiguousarray(np.tile(
+                syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]), (1, reps))[:, :n])).cuda()
+            nb = 2 if n * 48 * ncols > (256 << 20) else 3      # rotating sets: never L2-resident
+            Js = [rnd(n, 6, ncols) for _ in range(nb)]
+            base = rnd(ns, ncols)
+            outs = [torch.empty_like(base) for _ in range(nb)]
+            cls = [gf.prepare(cps, ncols, pl, Js[j], base, out=outs[j])[0] for j in range(nb)]
+            ms = timeit(lambda i: cls[i % nb](), iters=50, warm=5)
+            per_contact = 200 + 48 * ncols + 16 * ncols / cps
+            row(f"J^T wrench systems={ns} contacts/system={cps} ncols={ncols}"
+                f"{' [column-per-lane kernel forced]' if no_pack else ''}", ms, n, per_contact)
+            del Js, base, outs, cls, pl
+            torch.cuda.empty_cache()
+    os.environ.pop("BLF_CCM_TUNE_NO_PACK", None)
 
 
 def main():
@@ -177,6 +195,8 @@ def main():
         return rls_only()
     if "--sys-only" in sys.argv:
         return sys_only()
+    if "--gf-only" in sys.argv:
+        return gf_only()
     sizes = {"cfg3 819200": 2 * 4096 * 100, "8M": 1 << 23}
     NS = 3
     for label, n in sizes.items():
