@@ -61,6 +61,13 @@ struct KernelInfo {
     int blocks_per_sm = 0;
 };
 
+struct TensorMapEntry {
+    const double* ptr = nullptr;
+    int horizon = 0;
+    long long chains = 0;
+    CUtensorMap map;
+};
+
 struct blf_ccm_handle {
     unsigned magic = 0xB1FCC3A1u;
     int device = -1;
@@ -78,6 +85,10 @@ struct blf_ccm_handle {
     unsigned int* counter = nullptr;
     double* partials = nullptr;      // [n_rollouts][slots] per-(rollout, tile) cost partial sums
     size_t partials_bytes = 0;
+    std::vector<TensorMapEntry> tmaps;   // cached TMA descriptors of rollout twist planes
+    unsigned tmap_next = 0;
+    double* gen_work = nullptr;      // scratch of the general-size RLS kernel
+    size_t gen_bytes = 0;
     cudaEvent_t scratch_ev = nullptr;
     cudaStream_t scratch_stream = nullptr;   // stream of the last launch that used the scratch
     bool scratch_busy = false;
@@ -97,7 +108,7 @@ struct blf_ccm_handle {
     double* hbuf[kHostSlots] = {};
     long long hchunk = 0;      // contacts per chunk the slots are sized for
     size_t hbytes = 0;
-    long long host_chunk_pref = 65536;
+    long long host_chunk_pref = 131072;   // measured: profiles/r02_host_sweep.log
     // tuning overrides (environment, read once at create; 0 = automatic)
     int tune_cpt = 0;            // BLF_CCM_TUNE_CPT=2: use the 128-bit two-contacts-per-lane SoA kernel
     int tune_blocks_per_sm = 0;  // BLF_CCM_TUNE_BLOCKS_PER_SM>0: persistent grid with that many CTAs/SM
@@ -290,6 +301,7 @@ extern "C" int blf_ccm_destroy(blf_ccm_handle* h)
     if (h->block_best) cudaFree(h->block_best);
     if (h->counter) cudaFree(h->counter);
     if (h->partials) cudaFree(h->partials);
+    if (h->gen_work) cudaFree(h->gen_work);
     h->magic = 0;
     delete h;
     return BLF_CCM_OK;
@@ -1115,15 +1127,68 @@ static int rls_dispatch(int p, int m, blf_ccm_handle* h, const RlsArgs& a, cudaS
     }
 }
 
+// sizes / covariances the register kernels cover: 1..4 parameters, 1..6 measurements and
+// lambda * r[i] > 0 for every measurement (S symmetric positive definite, LDL^T without pivoting);
+// everything else the reference accepts goes to rls_advance_generic_kernel (partial-pivot LU)
+static bool rls_fast_path(int p, int m, double lambda, const double* cov)
+{
+    if (p > kRlsMaxP || m > kRlsMaxM) return false;
+    for (int i = 0; i < m; ++i)
+        if (!(lambda * cov[i] > 0.0)) return false;
+    return true;
+}
+
 static int rls_check_sizes(int p, int m, double lambda, const double* cov)
 {
-    if (p < 1 || p > kRlsMaxP) return fail(BLF_CCM_ERR_INVALID_ARG, "p = %d unsupported (1..4)", p);
-    if (m < 1 || m > kRlsMaxM) return fail(BLF_CCM_ERR_INVALID_ARG, "m = %d unsupported (1..6)", m);
+    if (p < 1 || p > 512) return fail(BLF_CCM_ERR_INVALID_ARG, "p = %d unsupported (1..512)", p);
+    if (m < 1 || m > 512) return fail(BLF_CCM_ERR_INVALID_ARG, "m = %d unsupported (1..512)", m);
     if (!cov) return fail(BLF_CCM_ERR_INVALID_ARG, "measurement covariance is NULL");
     if (!(lambda != 0.0)) return fail(BLF_CCM_ERR_INVALID_ARG, "lambda must be non-zero");
-    for (int i = 0; i < m; ++i)
-        if (!(cov[i] != 0.0))
-            return fail(BLF_CCM_ERR_INVALID_ARG, "measurement covariance %d is zero (singular R)", i);
+    return BLF_CCM_OK;
+}
+
+// the general kernel: scratch = [lambda r (m) | pointer table (SoA) | work], grown on demand
+static int rls_generic(blf_ccm_handle* h, long long n, int p, int m, const double* const* host_tabs,
+                       const double* dY, const double* dz, double* dtheta, double* dP,
+                       const double* host_cov, double lambda, cudaStream_t st)
+{
+    const size_t ntab = host_tabs ? size_t(m) * p + m + p + size_t(p) * p : 0;
+    const size_t head = (size_t(m) + ntab + 1) & ~size_t(1);           // doubles; pointers are 8 bytes too
+    const size_t need = (head + size_t(rls_gen_work_doubles(p, m)) * size_t(n)) * sizeof(double);
+    if (h->gen_bytes < need) {
+        if (h->gen_work) {
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaFree(h->gen_work));
+            h->gen_work = nullptr;
+            h->gen_bytes = 0;
+        }
+        CUDA_TRY(cudaMalloc(&h->gen_work, need));
+        h->gen_bytes = need;
+    }
+    std::vector<double> headbuf(head, 0.0);
+    for (int i = 0; i < m; ++i) headbuf[i] = lambda * host_cov[i];
+    if (host_tabs) memcpy(headbuf.data() + m, host_tabs, ntab * sizeof(double*));
+    // pageable source: the copy has left the host buffer when the call returns
+    CUDA_TRY(cudaMemcpyAsync(h->gen_work, headbuf.data(), head * sizeof(double), cudaMemcpyHostToDevice, st));
+    RlsGenArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tabs = host_tabs ? reinterpret_cast<const double* const*>(h->gen_work + m) : nullptr;
+    a.Y = dY;
+    a.z = dz;
+    a.theta = dtheta;
+    a.cov = dP;
+    a.lr = h->gen_work;
+    a.work = h->gen_work + head;
+    a.lambda = lambda;
+    a.n = n;
+    a.p = p;
+    a.m = m;
+    const int threads = 64;
+    const long long grid = (n + threads - 1) / threads;
+    if (grid > 0x7fffffffLL) return fail(BLF_CCM_ERR_INVALID_ARG, "n too large for one launch");
+    rls_advance_generic_kernel<<<static_cast<int>(grid), threads, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
     return BLF_CCM_OK;
 }
 
@@ -1140,12 +1205,24 @@ extern "C" int blf_rls_advance_batch(blf_ccm_handle* h, int64_t n, int p, int m,
     if (n == 0) return BLF_CCM_OK;
     if (!regressor_planes || !measurement_planes || !state_planes || !cov_planes)
         return fail(BLF_CCM_ERR_INVALID_ARG, "a plane-pointer array is NULL");
+    auto bad = [](const void* q) { return !q || !aligned8(q); };
+    if (!rls_fast_path(p, m, lambda, host_measurement_cov)) {
+        // any size / indefinite lambda R: the reference's own algorithm (pivoted LU)
+        std::vector<const double*> tabs;
+        for (int i = 0; i < m * p; ++i) tabs.push_back(regressor_planes[i]);
+        for (int i = 0; i < m; ++i) tabs.push_back(measurement_planes[i]);
+        for (int i = 0; i < p; ++i) tabs.push_back(state_planes[i]);
+        for (int i = 0; i < p * p; ++i) tabs.push_back(cov_planes[i]);
+        for (size_t i = 0; i < tabs.size(); ++i)
+            if (bad(tabs[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "plane %zu NULL or misaligned", i);
+        return rls_generic(h, n, p, m, tabs.data(), nullptr, nullptr, nullptr, nullptr, host_measurement_cov,
+                           lambda, static_cast<cudaStream_t>(stream));
+    }
     RlsArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n;
     a.lambda = lambda;
     for (int i = 0; i < m; ++i) a.w[i] = lambda * host_measurement_cov[i];
-    auto bad = [](const void* q) { return !q || !aligned8(q); };
     for (int i = 0; i < m * p; ++i) {
         if (bad(regressor_planes[i])) return fail(BLF_CCM_ERR_INVALID_ARG, "regressor_planes[%d] NULL or misaligned", i);
         a.Y[i] = regressor_planes[i];
@@ -1195,16 +1272,20 @@ extern "C" int blf_rls_advance_host(blf_ccm_handle* h, int64_t n, int p, int m, 
     CUDA_TRY(cudaMemcpyAsync(dz, z, size_t(n) * m * D, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dth, theta, size_t(n) * p * D, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dP, P, size_t(n) * p * p * D, cudaMemcpyHostToDevice, st));
-    RlsArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = n;
-    a.lambda = lambda;
-    for (int i = 0; i < m; ++i) a.w[i] = lambda * host_measurement_cov[i];
-    a.Y[0] = dY;
-    a.z[0] = dz;
-    a.theta[0] = dth;
-    a.cov[0] = dP;
-    if (int rc = rls_dispatch<true>(p, m, h, a, st)) return rc;
+    if (!rls_fast_path(p, m, lambda, host_measurement_cov)) {
+        if (int rc = rls_generic(h, n, p, m, nullptr, dY, dz, dth, dP, host_measurement_cov, lambda, st)) return rc;
+    } else {
+        RlsArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = n;
+        a.lambda = lambda;
+        for (int i = 0; i < m; ++i) a.w[i] = lambda * host_measurement_cov[i];
+        a.Y[0] = dY;
+        a.z[0] = dz;
+        a.theta[0] = dth;
+        a.cov[0] = dP;
+        if (int rc = rls_dispatch<true>(p, m, h, a, st)) return rc;
+    }
     CUDA_TRY(cudaMemcpyAsync(theta, dth, size_t(n) * p * D, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(P, dP, size_t(n) * p * p * D, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1222,6 +1303,9 @@ extern "C" int blf_ccm_rls_advance_contacts(blf_ccm_handle* h, int64_t n,
     CHECK_HANDLE(h);
     if (n < 0) return fail(BLF_CCM_ERR_INVALID_ARG, "n < 0");
     if (int rc = rls_check_sizes(2, 6, lambda, host_measurement_cov)) return rc;
+    if (!rls_fast_path(2, 6, lambda, host_measurement_cov))
+        return fail(BLF_CCM_ERR_INVALID_ARG, "the fused identification step needs lambda * measurement covariance > 0 "
+                                             "for all six wrench components (use blf_rls_advance_batch otherwise)");
     if (n == 0) return BLF_CCM_OK;
     if (!geometry_planes && !h->have_params)
         return fail(BLF_CCM_ERR_NOT_INITIALIZED,

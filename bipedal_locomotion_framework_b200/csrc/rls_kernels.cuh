@@ -250,6 +250,158 @@ rls_advance_pipe_kernel(const __grid_constant__ RlsArgs a, long long ntiles)
 }
 
 // Fused: contact state -> regressor (registers) -> RLS update of (spring, damper) per contact.
+// ------------------------------------------------------------------------------------------------
+// General sizes and general S: the fallback of the register kernels above.
+//
+// The reference takes any number of parameters and measurements and inverts S = lambda R + Y P Y^T
+// with Eigen's dynamic inverse(), i.e. an LU with partial pivoting -- it never requires S to be
+// positive definite (src/Estimators/src/RecursiveLeastSquare.cpp:118-130).  The register kernels
+// cover 1..4 x 1..6 and factorise S as LDL^T without pivoting, which presumes lambda R > 0.  This
+// kernel does what the reference does, for any p, m: one estimator per thread, work arrays in a
+// global scratch laid out [slot][estimator] (coalesced), the reference's association
+//   K = (P Y^T) S^-1,  theta += K (z - Y theta),  P = (P - (K Y) P) / lambda
+// and S^-1 by partial-pivot LU + n solves.  Not tuned: it exists so that nothing the reference
+// accepts is refused (a singular S gives inf/NaN, as the reference).
+// Arrays are array-of-structures (tabs == nullptr) or SoA planes through a device pointer table
+// tabs = [Y planes m*p | z planes m | theta planes p | cov planes p*p].
+// ------------------------------------------------------------------------------------------------
+struct RlsGenArgs {
+    const double* const* tabs;
+    const double* Y;
+    const double* z;
+    double* theta;
+    double* cov;
+    const double* lr;      // device, m entries: lambda * r[i]
+    double* work;          // rls_gen_work_doubles(p, m) * n doubles
+    double lambda;
+    long long n;
+    int p, m;
+};
+
+__host__ __device__ inline long long rls_gen_work_doubles(int p, int m)
+{
+    // YP m*p | LU m*m | Sinv m*m | PYt p*m | K p*m | innov m | y m | perm m | KY p*p | Pnew p*p
+    return 3LL * m * p + 2LL * m * m + 3LL * m + 2LL * p * p;
+}
+
+__global__ void __launch_bounds__(64)
+rls_advance_generic_kernel(const __grid_constant__ RlsGenArgs a)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int p = a.p, m = a.m;
+    const long long n = a.n;
+    const bool soa = a.tabs != nullptr;
+    auto Yel = [&](int r, int c) { return soa ? a.tabs[r * p + c][i] : a.Y[i * m * p + r * p + c]; };
+    auto zel = [&](int r) { return soa ? a.tabs[m * p + r][i] : a.z[i * m + r]; };
+    auto thp = [&](int r) -> double* {
+        return soa ? const_cast<double*>(a.tabs[m * p + m + r]) + i : a.theta + i * p + r;
+    };
+    auto Pp = [&](int r, int c) -> double* {
+        return soa ? const_cast<double*>(a.tabs[m * p + m + p + r * p + c]) + i : a.cov + i * p * p + r * p + c;
+    };
+    double* w = a.work + i;
+    auto W = [&](long long slot) -> double& { return w[slot * n]; };
+    const long long oYP = 0, oLU = oYP + 1LL * m * p, oSI = oLU + 1LL * m * m, oPY = oSI + 1LL * m * m,
+                    oK = oPY + 1LL * p * m, oIN = oK + 1LL * p * m, oY = oIN + m, oPM = oY + m,
+                    oKY = oPM + m, oPN = oKY + 1LL * p * p;
+
+    // YP = Y P ; S = lambda R + (Y P) Y^T
+    for (int r = 0; r < m; ++r)
+        for (int c = 0; c < p; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < p; ++k) acc = acc + Yel(r, k) * *Pp(k, c);
+            W(oYP + r * p + c) = acc;
+        }
+    for (int r = 0; r < m; ++r)
+        for (int c = 0; c < m; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < p; ++k) acc = acc + W(oYP + r * p + k) * Yel(c, k);
+            W(oLU + r * m + c) = (r == c ? a.lr[r] : 0.0) + acc;
+        }
+    // LU with partial pivoting, in place; perm as doubles
+    for (int r = 0; r < m; ++r) W(oPM + r) = r;
+    for (int k = 0; k < m; ++k) {
+        int piv = k;
+        double best = fabs(W(oLU + k * m + k));
+        for (int r = k + 1; r < m; ++r) {
+            const double v = fabs(W(oLU + r * m + k));
+            if (v > best) {
+                best = v;
+                piv = r;
+            }
+        }
+        if (piv != k) {
+            for (int c = 0; c < m; ++c) {
+                const double t = W(oLU + k * m + c);
+                W(oLU + k * m + c) = W(oLU + piv * m + c);
+                W(oLU + piv * m + c) = t;
+            }
+            const double t = W(oPM + k);
+            W(oPM + k) = W(oPM + piv);
+            W(oPM + piv) = t;
+        }
+        const double d = W(oLU + k * m + k);
+        for (int r = k + 1; r < m; ++r) {
+            const double l = W(oLU + r * m + k) / d;
+            W(oLU + r * m + k) = l;
+            for (int c = k + 1; c < m; ++c) W(oLU + r * m + c) = W(oLU + r * m + c) - l * W(oLU + k * m + c);
+        }
+    }
+    // Sinv: solve S x = e_c for every column
+    for (int c = 0; c < m; ++c) {
+        for (int r = 0; r < m; ++r) {
+            double acc = (static_cast<int>(W(oPM + r)) == c) ? 1.0 : 0.0;
+            for (int k = 0; k < r; ++k) acc = acc - W(oLU + r * m + k) * W(oY + k);
+            W(oY + r) = acc;
+        }
+        for (int r = m - 1; r >= 0; --r) {
+            double acc = W(oY + r);
+            for (int k = r + 1; k < m; ++k) acc = acc - W(oLU + r * m + k) * W(oSI + k * m + c);
+            W(oSI + r * m + c) = acc / W(oLU + r * m + r);
+        }
+    }
+    // K = (P Y^T) S^-1
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c < m; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < p; ++k) acc = acc + *Pp(r, k) * Yel(c, k);
+            W(oPY + r * m + c) = acc;
+        }
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c < m; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < m; ++k) acc = acc + W(oPY + r * m + k) * W(oSI + k * m + c);
+            W(oK + r * m + c) = acc;
+        }
+    // theta = theta + K (z - Y theta)
+    for (int r = 0; r < m; ++r) {
+        double acc = 0.0;
+        for (int k = 0; k < p; ++k) acc = acc + Yel(r, k) * *thp(k);
+        W(oIN + r) = zel(r) - acc;
+    }
+    for (int r = 0; r < p; ++r) {
+        double acc = 0.0;
+        for (int k = 0; k < m; ++k) acc = acc + W(oK + r * m + k) * W(oIN + k);
+        *thp(r) = *thp(r) + acc;
+    }
+    // P = (P - (K Y) P) / lambda
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c < p; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < m; ++k) acc = acc + W(oK + r * m + k) * Yel(k, c);
+            W(oKY + r * p + c) = acc;
+        }
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c < p; ++c) {
+            double acc = 0.0;
+            for (int k = 0; k < p; ++k) acc = acc + W(oKY + r * p + k) * *Pp(k, c);
+            W(oPN + r * p + c) = (*Pp(r, c) - acc) / a.lambda;
+        }
+    for (int r = 0; r < p; ++r)
+        for (int c = 0; c < p; ++c) *Pp(r, c) = W(oPN + r * p + c);
+}
+
 struct CcmRlsArgs {
     const double* in[30];
     const double* geom[2];     // length, width planes (HETG) else uniform

@@ -21,6 +21,8 @@
 // forming R R^T and inverting it with Eigen's general 3x3 formula.
 #pragma once
 
+#include <cuda.h>   // CUtensorMap (type only; the encoder is looked up at run time)
+
 #include "ccm_kernels.cuh"
 
 namespace blfccm {
@@ -34,23 +36,27 @@ struct Pose {
     V3 c0, c1, c2;  // columns of R
 };
 
-// d_j += rho/2 ((R R^T)^-1 R - R).col(j).  (R R^T)^-1 R = R^-T, and the columns of R^-T are the
-// cross products of R's columns over det R:  R^-T = [c1 x c2 | c2 x c0 | c0 x c1] / (c0 . (c1 x c2)).
-// Three cross products, one determinant and one division instead of forming R R^T, its adjugate
-// and a 3x3 product (about half the FP64 instructions of the first version, which matters: this
-// sits on the sequential chain of every rollout step).  Singular R gives inf/NaN, as the reference.
-__device__ __forceinline__ void kin_baumgarte_add(const Pose& s, double half_rho, V3& d0, V3& d1,
-                                                  V3& d2)
+// 1/x to the last bit or two: the hardware's reciprocal seed (MUFU.RCP64H, ~20 bits) and two Newton
+// steps.  An IEEE division costs 123 dependent cycles on B200 (tools/micro/fp64_lat.cu: DFMA 8.2,
+// division 131 with its DADD, this sequence 47), and it sits on the sequential chain of every
+// rollout step.  x = 0 gives NaN (inf from the seed, then 0 * inf), so a singular rotation still
+// poisons the result as in the reference.
+__device__ __forceinline__ double fast_rcp(double x)
 {
-    const V3 k0 = cross(s.c1, s.c2), k1 = cross(s.c2, s.c0), k2 = cross(s.c0, s.c1);
-    const double det = s.c0.x * k0.x + s.c0.y * k0.y + s.c0.z * k0.z;
-    const double g = half_rho / det;          // rho/2 / det R
-    // d_j += g * k_j - half_rho * c_j
-    d0 = d0 + (g * k0 - half_rho * s.c0);
-    d1 = d1 + (g * k1 - half_rho * s.c1);
-    d2 = d2 + (g * k2 - half_rho * s.c2);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
 }
 
+// Rates of FloatingBaseSystemKinematics::dynamics (FloatingBaseSystemKinematics.cpp:59-66):
+//   Rdot = -R.colwise().cross(w) + rho/2 ((R R^T)^-1 - I) R
+// column by column: Rdot.col(j) = w x c_j + rho/2 (k_j / det R - c_j), because (R R^T)^-1 R = R^-T and
+// the columns of R^-T are the cross products k_0 = c1 x c2, k_1 = c2 x c0, k_2 = c0 x c1 over
+// det R = c0 . k_0 -- three cross products, one determinant and one reciprocal instead of forming
+// R R^T, its adjugate and a 3x3 product.  Singular R gives NaN, as the reference.
 template <bool BAUM>
 __device__ __forceinline__ void kin_rates(const Pose& s, const V3& w, double half_rho, V3& d0,
                                           V3& d1, V3& d2)
@@ -58,38 +64,44 @@ __device__ __forceinline__ void kin_rates(const Pose& s, const V3& w, double hal
     d0 = cross(w, s.c0);
     d1 = cross(w, s.c1);
     d2 = cross(w, s.c2);
-    if constexpr (BAUM) kin_baumgarte_add(s, half_rho, d0, d1, d2);
+    if constexpr (BAUM) {
+        const V3 k0 = cross(s.c1, s.c2), k1 = cross(s.c2, s.c0), k2 = cross(s.c0, s.c1);
+        const double det = s.c0.x * k0.x + s.c0.y * k0.y + s.c0.z * k0.z;
+        const double g = half_rho * fast_rcp(det);          // rho/2 / det R
+        d0 = d0 + (g * k0 - half_rho * s.c0);
+        d1 = d1 + (g * k1 - half_rho * s.c1);
+        d2 = d2 + (g * k2 - half_rho * s.c2);
+    }
 }
 
-// x += dx * dT  (ForwardEuler.h:50)
-__device__ __forceinline__ void kin_apply(Pose& s, const V3& v, double dT, const V3& d0,
-                                          const V3& d1, const V3& d2)
-{
-    s.p = s.p + dT * v;
-    s.c0 = s.c0 + dT * d0;
-    s.c1 = s.c1 + dT * d1;
-    s.c2 = s.c2 + dT * d2;
-}
-
+// One ForwardEuler step x += dx * dT (ForwardEuler.h:50) of that system.  The Baumgarte step is
+// regrouped so that few operations depend on the reciprocal (it is the long pole of the chain):
+//   c_j' = c_j + dT (w x c_j + g k_j - rho/2 c_j) = (1 - dT rho/2) c_j + dT (w x c_j) + (dT g) k_j
+// i.e. everything but the last FMA per component is independent of 1/det.  75 FP64 instructions
+// per step instead of ~95, critical path k -> det -> 1/det -> dT g -> FMA (about 13 dependent
+// operations).  Every kernel integrates through this one function, so fused rollouts, the batched
+// Euler step and the per-instance integrate agree bit for bit with one another; against the oracle
+// (which follows Eigen's expression) the difference is a few ulp per step.
 template <bool BAUM>
 __device__ __forceinline__ void kin_euler_step(Pose& s, const V3& v, const V3& w, double half_rho,
                                                double dT)
 {
-    V3 d0, d1, d2;
-    kin_rates<BAUM>(s, w, half_rho, d0, d1, d2);
-    kin_apply(s, v, dT, d0, d1, d2);
-}
-
-// Same step when t1 = c0 x w and t2 = c1 x w are already known (the contact model computed them
-// for the same pose and twist): w x c0 = -t1, w x c1 = -t2 -- one cross product instead of three.
-template <bool BAUM>
-__device__ __forceinline__ void kin_euler_step_shared(Pose& s, const V3& v, const V3& w,
-                                                      const V3& t1, const V3& t2, double half_rho,
-                                                      double dT)
-{
-    V3 d0 = neg(t1), d1 = neg(t2), d2 = cross(w, s.c2);
-    if constexpr (BAUM) kin_baumgarte_add(s, half_rho, d0, d1, d2);
-    kin_apply(s, v, dT, d0, d1, d2);
+    s.p = s.p + dT * v;
+    const V3 x0 = cross(w, s.c0), x1 = cross(w, s.c1), x2 = cross(w, s.c2);
+    if constexpr (BAUM) {
+        const V3 k0 = cross(s.c1, s.c2), k1 = cross(s.c2, s.c0), k2 = cross(s.c0, s.c1);
+        const double det = s.c0.x * k0.x + s.c0.y * k0.y + s.c0.z * k0.z;
+        const double alpha = 1.0 - dT * half_rho;            // uniform: hoisted out of every loop
+        const double beta = (dT * half_rho) * fast_rcp(det);
+        const V3 y0 = alpha * s.c0 + dT * x0, y1 = alpha * s.c1 + dT * x1, y2 = alpha * s.c2 + dT * x2;
+        s.c0 = y0 + beta * k0;
+        s.c1 = y1 + beta * k1;
+        s.c2 = y2 + beta * k2;
+    } else {
+        s.c0 = s.c0 + dT * x0;
+        s.c1 = s.c1 + dT * x1;
+        s.c2 = s.c2 + dT * x2;
+    }
 }
 
 struct KinArgs {
@@ -212,6 +224,16 @@ struct RolloutArgs {
     int split;               // warps sharing one 32-chain tile (power of two, 1 = none)
     int t_base;              // global index of this launch's first step (time-chunked rollouts)
     int accumulate;          // chain_cost holds the cost of the steps before t_base: add to it
+    // ccm_rollout_ws3_kernel only: TMA descriptors of the six twist planes ([horizon][chains] doubles,
+    // box = kWs3BoxSteps x 32) and the fused reduction / arg-min / peer exchange
+    CUtensorMap twmap[6];
+    double* cost;            // [n_rollouts] or nullptr
+    CostIdx* block_best;     // gridDim.x entries (handle scratch)
+    unsigned int* counter;   // zero before launch; reset by the last CTA
+    CostIdx* best;
+    long long n_rollouts, index_base;
+    int feet;
+    P2pArgs p2p;             // nranks > 0: the last CTA also runs the peer exchange -> p2p.out
 };
 
 // Few chains (a sampling-MPC batch of configs[2] size is 8 192 chains = 256 warps for 592 warp
@@ -357,179 +379,12 @@ ccm_rollout_kernel(const __grid_constant__ RolloutArgs a)
 //
 // A sampling-MPC batch of configs[2] size has 8 192 chains: 256 warps for 592 warp schedulers, and
 // every warp walks 100 dependent steps -- latency, not throughput, sets the time.  Only the pose
-// integration is inherently sequential (~35 of the ~120 FP64 instructions of a step).  So a CTA of
-// four warps shares one 32-chain tile:
-//   warp 0 (producer)   reads the twists (cp.async ring), integrates the pose and PUBLISHES, per
-//                       step, what the contact model needs (v, w, p, e1, e2, R22: 16 doubles per
-//                       lane) into a shared-memory ring of kWsStages stages;
-//   warps 1..3          consumer k evaluates the steps t = k (mod 3): contact wrench + cost term.
-// Stages are handed over with mbarriers: full[s] (producer -> the one consumer of that step) and
-// empty[s] (that consumer -> producer).  Unlike `split` (every warp integrates everything) no work
-// is duplicated.  Each consumer keeps its own partial cost, chain_cost[chain*3 + k]; the reduction
-// kernel sums a rollout's feet*3 partials in index order (deterministic).
-// ------------------------------------------------------------------------------------------------
-
-constexpr int kWsConsumers = 3;
-constexpr int kWsStages = 9;                        // a multiple of kWsConsumers
-constexpr int kWsStageDoubles = 16 * kWarp;         // [16][32]
-constexpr int kWsSmemBytes = kRolloutRingBytes + kWsStages * kWsStageDoubles * 8 + 2 * kWsStages * 8 + 64;
-
-template <bool HET, bool BAUM>
-__global__ void __launch_bounds__(128)
-ccm_rollout_ws_kernel(const __grid_constant__ RolloutArgs a)
-{
-    constexpr int D = kRolloutDepth;
-    constexpr int S = kWsStages;
-    constexpr int C = kWsConsumers;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long wbase = static_cast<long long>(blockIdx.x) * kWarp;
-    const long long c = wbase + lane;
-    const bool on = c < a.chains;
-    const int H = a.horizon;
-
-    double* ring = reinterpret_cast<double*>(smem_raw);                      // producer's twist ring
-    double* stages = ring + D * 6 * kWarp;                                   // [S][16][32]
-    const uint32_t full0 = ptx::smem_addr(stages + S * kWsStageDoubles);     // S barriers
-    const uint32_t empty0 = full0 + 8 * S;                                   // S barriers
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(full0 + 8 * s, 1);
-            ptx::mbar_init(empty0 + 8 * s, 1);
-        }
-        ptx::fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (warp == 0) {
-        // ---------------- producer: twists -> pose trajectory -> stages --------------------------
-        // (kept lean: this warp's instruction stream IS the critical path of the kernel --
-        //  incremental pointers and stage indices, 128-bit shared-memory stores)
-        const uint32_t ring_s = ptx::smem_addr(ring) + static_cast<uint32_t>(lane) * 8u;
-        const double* src[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) src[j] = a.tw[j] + c;
-#pragma unroll
-        for (int t = 0; t < D; ++t) {
-            if (on && t < H) {
-                const uint32_t dst = ring_s + static_cast<uint32_t>(t * 6 * kWarp * 8);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, src[j] + static_cast<long long>(t) * a.chains);
-            }
-            ptx::cp_async_commit();
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) src[j] += static_cast<long long>(D) * a.chains;   // step t + D
-        Pose s{};
-        if (on) {
-            s.p = V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)};
-            s.c0 = V3{__ldg(a.rot0[0] + c), __ldg(a.rot0[3] + c), __ldg(a.rot0[6] + c)};
-            s.c1 = V3{__ldg(a.rot0[1] + c), __ldg(a.rot0[4] + c), __ldg(a.rot0[7] + c)};
-            s.c2 = V3{__ldg(a.rot0[2] + c), __ldg(a.rot0[5] + c), __ldg(a.rot0[8] + c)};
-        }
-        int st = 0;                 // stage of step t
-        uint32_t empty_parity = 0;  // completion of empty[st] to wait for: (t / S - 1) & 1
-        bool wrapped = false;
-        int slot = 0;               // twist ring slot of step t
-        for (int t = 0; t < H; ++t) {
-            ptx::cp_async_wait<D - 1>();
-            V3 v{}, w{};
-            const double* r = ring + slot * 6 * kWarp + lane;
-            if (on) {
-                v = V3{r[0], r[kWarp], r[2 * kWarp]};
-                w = V3{r[3 * kWarp], r[4 * kWarp], r[5 * kWarp]};
-            }
-            if (wrapped) ptx::mbar_wait(empty0 + 8 * st, empty_parity);   // stage consumed
-            double2* o = reinterpret_cast<double2*>(stages + st * kWsStageDoubles) + lane;
-            o[0 * kWarp] = make_double2(v.x, v.y);
-            o[1 * kWarp] = make_double2(v.z, w.x);
-            o[2 * kWarp] = make_double2(w.y, w.z);
-            o[3 * kWarp] = make_double2(s.p.x, s.p.y);
-            o[4 * kWarp] = make_double2(s.p.z, s.c0.x);
-            o[5 * kWarp] = make_double2(s.c0.y, s.c0.z);
-            o[6 * kWarp] = make_double2(s.c1.x, s.c1.y);
-            o[7 * kWarp] = make_double2(s.c1.z, s.c2.z);
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(full0 + 8 * st);
-            kin_euler_step<BAUM>(s, v, w, a.half_rho, a.dT);
-            // refill the twist slot just consumed with step t + D
-            if (on && t + D < H) {
-                const uint32_t dst = ring_s + static_cast<uint32_t>(slot * 6 * kWarp * 8);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) ptx::cp_async8(dst + j * kWarp * 8, src[j]);
-            }
-            ptx::cp_async_commit();
-#pragma unroll
-            for (int j = 0; j < 6; ++j) src[j] += a.chains;
-            slot = (slot + 1) & (D - 1);
-            if (++st == S) {
-                st = 0;
-                empty_parity = wrapped ? (empty_parity ^ 1u) : 0u;
-                wrapped = true;
-            }
-        }
-        if (on && a.write_final) {
-            a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
-            a.rot_out[0][c] = s.c0.x; a.rot_out[1][c] = s.c1.x; a.rot_out[2][c] = s.c2.x;
-            a.rot_out[3][c] = s.c0.y; a.rot_out[4][c] = s.c1.y; a.rot_out[5][c] = s.c2.y;
-            a.rot_out[6][c] = s.c0.z; a.rot_out[7][c] = s.c1.z; a.rot_out[8][c] = s.c2.z;
-        }
-        ptx::cp_async_wait<0>();
-    } else {
-        // ---------------- consumers: contact wrench + cost of the steps t = k (mod 3) ------------
-        const int k = warp - 1;
-        V3 p0{}, n1{}, n2{};
-        Prm q = a.uni;
-        if (on) {
-            p0 = V3{__ldg(a.nul[0] + c), __ldg(a.nul[1] + c), __ldg(a.nul[2] + c)};
-            n1 = V3{__ldg(a.nul[3] + c), __ldg(a.nul[6] + c), __ldg(a.nul[9] + c)};
-            n2 = V3{__ldg(a.nul[4] + c), __ldg(a.nul[7] + c), __ldg(a.nul[10] + c)};
-            if constexpr (HET)
-                q = make_prm(__ldg(a.prm[0] + c), __ldg(a.prm[1] + c), __ldg(a.prm[2] + c),
-                             __ldg(a.prm[3] + c));
-        }
-        double acc = 0.0;
-        int st = k;                 // stage of step t = k, k + 3, ... (C divides S)
-        uint32_t parity = 0;
-        for (int t = k; t < H; t += C) {
-            ptx::mbar_wait(full0 + 8 * st, parity);
-            const double2* in = reinterpret_cast<const double2*>(stages + st * kWsStageDoubles) + lane;
-            const double2 a0 = in[0 * kWarp], a1 = in[1 * kWarp], a2 = in[2 * kWarp], a3 = in[3 * kWarp];
-            const double2 a4 = in[4 * kWarp], a5 = in[5 * kWarp], a6 = in[6 * kWarp], a7 = in[7 * kWarp];
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(empty0 + 8 * st);   // the stage may be refilled
-            State x;
-            x.v = V3{a0.x, a0.y, a1.x};
-            x.w = V3{a1.y, a2.x, a2.y};
-            x.p = V3{a3.x, a3.y, a4.x};
-            x.e1 = V3{a4.y, a5.x, a5.y};
-            x.e2 = V3{a6.x, a6.y, a7.x};
-            x.R02 = 0.0; x.R12 = 0.0;
-            x.R22 = a7.y;
-            x.p0 = p0; x.n1 = n1; x.n2 = n2;
-            Result r;
-            eval_contact<M_WRENCH>(x, q, r);
-            if (on) {
-                const V3 df = r.force - V3{a.ref[0], a.ref[1], a.ref[2]};
-                const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
-                acc = acc + (a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
-                             a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
-            }
-            st += C;
-            if (st >= S) {
-                st -= S;
-                parity ^= 1u;
-            }
-        }
-        if (on) a.chain_cost[c * C + k] = acc;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Warp-specialised rollout, second form (round 2): the producer's instruction stream is the critical
-// path of a small batch (100 dependent steps whatever the batch size), so everything that is not
-// the pose recurrence leaves it:
+// integration is inherently sequential.  So a CTA shares one 32-chain tile: warp 0 (producer)
+// integrates the pose and publishes it per step into a shared-memory ring, C consumer warps
+// evaluate the contact wrench and the cost of the steps t = k (mod C); no work is duplicated (the
+// `split` form above lets every warp integrate everything).  The producer's instruction stream is
+// the critical path (100 dependent steps whatever the batch size), so everything that is not the
+// pose recurrence leaves it:
 //   * the twists of step t+1 are lifted out of the cp.async ring into registers while step t is
 //     integrated (the 29-cycle shared-memory latency is off the chain);
 //   * a stage holds only the pose (p, e1, e2, R22: 10 doubles per lane, five 128-bit stores); the
@@ -724,6 +579,272 @@ ccm_rollout_ws2_kernel(const __grid_constant__ RolloutArgs a)
             }
         }
         if (on) a.chain_cost[c * C + k] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Third form: the same producer / consumer split with the last avoidable work taken off the
+// producer and the second launch removed.
+//   * Twists arrive by TMA TENSOR copies (cp.async.bulk.tensor.2d, SASS UTMALDG): the six planes are
+//     [horizon][chains] tensors, one box = 8 steps x 32 chains (2 KB per plane), two boxes in
+//     flight; one elected lane issues six copies per EIGHT steps and the warp waits on one
+//     mbarrier per box.  The per-lane cp.async ring of the second form cost ~50 instructions per
+//     step on the critical warp (six 64-bit pointer increments, six LDGSTS, the commit/wait
+//     bookkeeping; ncu: 215 instructions and 774 cycles per step with the Baumgarte term).  Rows
+//     past the horizon and columns past the last chain are zero-filled by the hardware.
+//   * The step loop is unrolled over a box, so ring slots and shared-memory offsets are immediates.
+//   * The reduction is fused: consumers leave their partial costs in shared memory, warp 0 sums each
+//     rollout's feet*C partials in index order (the order of ccm_cost_reduce_kernel: bit-identical),
+//     arg-mins over the tile, and the last CTA to finish combines the CTAs' pairs and -- if enabled
+//     -- runs the NVLink peer exchange.  One launch per MPC step instead of two.
+// Needs: 32 % feet == 0 (no rollout straddles a tile), chains even and plane bases 16-byte aligned
+// (TMA global-stride rule); otherwise the second form + ccm_cost_reduce_kernel run.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kWs3BoxSteps = 8;
+constexpr int kWs3Boxes = 2;
+constexpr int kWs3BoxBytes = 6 * kWs3BoxSteps * kWarp * 8;   // 12 288 per box (six planes)
+
+template <int C>
+struct Ws3Cfg {
+    static constexpr int kStages = kWs2Groups * C;
+    static constexpr int kThreads = kWarp * (C + 1);
+    static constexpr int kBarBytes = 128;
+    static constexpr int kSmemBytes = kWs3Boxes * kWs3BoxBytes + kStages * kWs2StageDoubles * 8 + kBarBytes +
+                                      kWarp * C * 8;
+};
+
+namespace ptx {
+// 2-D tiled tensor copy global -> shared::cta, completion in bytes on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+}  // namespace ptx
+
+template <bool HET, bool BAUM, int C>
+__global__ void __launch_bounds__(kWarp * (C + 1))
+ccm_rollout_ws3_kernel(const __grid_constant__ RolloutArgs a)
+{
+    constexpr int S = Ws3Cfg<C>::kStages;
+    constexpr int NG = kWs2Groups;
+    constexpr int BS = kWs3BoxSteps;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wbase = static_cast<long long>(blockIdx.x) * kWarp;
+    const long long c = wbase + lane;
+    const bool on = c < a.chains;
+    const int H = a.horizon;
+
+    double* twbuf = reinterpret_cast<double*>(smem_raw);                              // [box][plane][step][lane]
+    double* stages = twbuf + kWs3Boxes * kWs3BoxBytes / 8;                            // [S][10][32]
+    const uint32_t bars = ptx::smem_addr(stages + S * kWs2StageDoubles);
+    const uint32_t twfull0 = bars;                 // kWs3Boxes barriers: a box has landed
+    const uint32_t full0 = bars + 8 * kWs3Boxes;   // NG barriers, 1 arrival: a stage group is written
+    const uint32_t empty0 = full0 + 8 * NG;        // NG barriers, C arrivals: a stage group is consumed
+    double* cst = stages + S * kWs2StageDoubles + Ws3Cfg<C>::kBarBytes / 8;           // [32][C] partial costs
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kWs3Boxes; ++b) ptx::mbar_init(twfull0 + 8 * b, 1);
+        for (int g = 0; g < NG; ++g) {
+            ptx::mbar_init(full0 + 8 * g, 1);
+            ptx::mbar_init(empty0 + 8 * g, C);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer: the pose recurrence and nothing else -------------------------
+        const int nbox = (H + BS - 1) / BS;
+        auto load_box = [&](int b) {   // lane 0: the six planes' box b into buffer b % kWs3Boxes
+            const int buf = b & (kWs3Boxes - 1);
+            const uint32_t bar = twfull0 + 8 * buf;
+            const uint32_t dst = ptx::smem_addr(twbuf) + buf * kWs3BoxBytes;
+            ptx::mbar_arrive_expect_tx(bar, kWs3BoxBytes);
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                ptx::tma_load_2d(dst + j * (BS * kWarp * 8), &a.twmap[j], static_cast<int>(wbase), b * BS, bar);
+        };
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < kWs3Boxes; ++b)
+                if (b < nbox) load_box(b);
+        }
+        Pose s{};
+        if (on) {
+            s.p = V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)};
+            s.c0 = V3{__ldg(a.rot0[0] + c), __ldg(a.rot0[3] + c), __ldg(a.rot0[6] + c)};
+            s.c1 = V3{__ldg(a.rot0[1] + c), __ldg(a.rot0[4] + c), __ldg(a.rot0[7] + c)};
+            s.c2 = V3{__ldg(a.rot0[2] + c), __ldg(a.rot0[5] + c), __ldg(a.rot0[8] + c)};
+        }
+        const double half_rho = a.half_rho, dT = a.dT;
+        int st = 0;                 // stage of step t
+        int gi = 0, g = 0;          // position inside the group, group slot
+        uint32_t empty_parity = 0;
+        bool wrapped = false;
+        uint32_t box_parity = 0;    // parity of the box buffers' current use (both buffers flip together)
+        for (int b = 0; b < nbox; ++b) {
+            const int buf = b & (kWs3Boxes - 1);
+            ptx::mbar_wait(twfull0 + 8 * buf, box_parity);
+            if (buf == kWs3Boxes - 1) box_parity ^= 1u;
+            const double* tw = twbuf + buf * (kWs3BoxBytes / 8) + lane;
+            const int steps = min(BS, H - b * BS);
+            V3 vn{tw[0], tw[BS * kWarp], tw[2 * BS * kWarp]};
+            V3 wn{tw[3 * BS * kWarp], tw[4 * BS * kWarp], tw[5 * BS * kWarp]};
+#pragma unroll
+            for (int q = 0; q < BS; ++q) {
+                if (q < steps) {
+                    const V3 v = vn, w = wn;
+                    if (q + 1 < BS) {   // next step's twist: in flight while this step is integrated
+                        const double* r = tw + (q + 1) * kWarp;
+                        vn = V3{r[0], r[BS * kWarp], r[2 * BS * kWarp]};
+                        wn = V3{r[3 * BS * kWarp], r[4 * BS * kWarp], r[5 * BS * kWarp]};
+                    }
+                    if (gi == 0 && wrapped) ptx::mbar_wait(empty0 + 8 * g, empty_parity);   // the group's stages are free
+                    double2* o = reinterpret_cast<double2*>(stages + st * kWs2StageDoubles) + lane;
+                    o[0 * kWarp] = make_double2(s.p.x, s.p.y);
+                    o[1 * kWarp] = make_double2(s.p.z, s.c0.x);
+                    o[2 * kWarp] = make_double2(s.c0.y, s.c0.z);
+                    o[3 * kWarp] = make_double2(s.c1.x, s.c1.y);
+                    o[4 * kWarp] = make_double2(s.c1.z, s.c2.z);
+                    kin_euler_step<BAUM>(s, v, w, half_rho, dT);
+                    if (++gi == C || b * BS + q == H - 1) {   // the group is complete: hand it over
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(full0 + 8 * g);
+                        gi = 0;
+                        if (++g == NG) {
+                            g = 0;
+                            empty_parity = wrapped ? (empty_parity ^ 1u) : 0u;
+                            wrapped = true;
+                        }
+                    }
+                    if (++st == S) st = 0;
+                }
+            }
+            // every lane holds the box's last twist in registers: the buffer may be refilled
+            __syncwarp();
+            if (lane == 0 && b + kWs3Boxes < nbox) {
+                ptx::fence_async_smem();
+                load_box(b + kWs3Boxes);
+            }
+        }
+        if (on && a.write_final) {
+            a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
+            a.rot_out[0][c] = s.c0.x; a.rot_out[1][c] = s.c1.x; a.rot_out[2][c] = s.c2.x;
+            a.rot_out[3][c] = s.c0.y; a.rot_out[4][c] = s.c1.y; a.rot_out[5][c] = s.c2.y;
+            a.rot_out[6][c] = s.c0.z; a.rot_out[7][c] = s.c1.z; a.rot_out[8][c] = s.c2.z;
+        }
+    } else {
+        // ---------------- consumer k: contact wrench + cost of the steps g*C + k -----------------
+        const int k = warp - 1;
+        V3 p0{}, n1{}, n2{};
+        Prm q = a.uni;
+        if (on) {
+            p0 = V3{__ldg(a.nul[0] + c), __ldg(a.nul[1] + c), __ldg(a.nul[2] + c)};
+            n1 = V3{__ldg(a.nul[3] + c), __ldg(a.nul[6] + c), __ldg(a.nul[9] + c)};
+            n2 = V3{__ldg(a.nul[4] + c), __ldg(a.nul[7] + c), __ldg(a.nul[10] + c)};
+            if constexpr (HET)
+                q = make_prm(__ldg(a.prm[0] + c), __ldg(a.prm[1] + c), __ldg(a.prm[2] + c),
+                             __ldg(a.prm[3] + c));
+        }
+        // the twists of this consumer's own steps come straight from global memory, one step ahead
+        const long long tstride = static_cast<long long>(C) * a.chains;
+        long long ti = static_cast<long long>(k) * a.chains + c;
+        V3 vn{}, wn{};
+        if (on && k < H) {
+            vn = V3{__ldg(a.tw[0] + ti), __ldg(a.tw[1] + ti), __ldg(a.tw[2] + ti)};
+            wn = V3{__ldg(a.tw[3] + ti), __ldg(a.tw[4] + ti), __ldg(a.tw[5] + ti)};
+        }
+        double acc = 0.0;
+        int g = 0;
+        uint32_t parity = 0;
+        const double2* stage_k = reinterpret_cast<const double2*>(stages + k * kWs2StageDoubles) + lane;
+        for (int t = k; t < H; t += C) {
+            State x;
+            x.v = vn;
+            x.w = wn;
+            ti += tstride;
+            if (on && t + C < H) {
+                vn = V3{__ldg(a.tw[0] + ti), __ldg(a.tw[1] + ti), __ldg(a.tw[2] + ti)};
+                wn = V3{__ldg(a.tw[3] + ti), __ldg(a.tw[4] + ti), __ldg(a.tw[5] + ti)};
+            }
+            ptx::mbar_wait(full0 + 8 * g, parity);
+            const double2* in = stage_k + g * (C * kWs2StageDoubles / 2);
+            const double2 a0 = in[0 * kWarp], a1 = in[1 * kWarp], a2 = in[2 * kWarp], a3 = in[3 * kWarp],
+                          a4 = in[4 * kWarp];
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty0 + 8 * g);   // one of the C arrivals that free the group
+            x.p = V3{a0.x, a0.y, a1.x};
+            x.e1 = V3{a1.y, a2.x, a2.y};
+            x.e2 = V3{a3.x, a3.y, a4.x};
+            x.R02 = 0.0; x.R12 = 0.0;
+            x.R22 = a4.y;
+            x.p0 = p0; x.n1 = n1; x.n2 = n2;
+            Result r;
+            eval_contact<M_WRENCH>(x, q, r);
+            if (on) {
+                const V3 df = r.force - V3{a.ref[0], a.ref[1], a.ref[2]};
+                const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
+                acc = acc + (a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
+                             a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
+            }
+            if (++g == NG) {
+                g = 0;
+                parity ^= 1u;
+            }
+        }
+        cst[lane * C + k] = acc;    // chains past the end: 0, never read
+    }
+
+    // ---------------- fused reduction: rollout costs of this tile, arg-min, last CTA combines -----
+    __syncthreads();
+    if (warp != 0) return;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    CostIdx mine{inf, 0x7fffffffffffffffLL};
+    {
+        const int feet = a.feet;
+        const long long ro = wbase / feet + lane;          // 32 % feet == 0: tiles hold whole rollouts
+        if (lane < kWarp / feet && ro < a.n_rollouts) {
+            const double* p = cst + lane * feet * C;
+            double sum = 0.0;
+            for (int j = 0; j < feet * C; ++j) sum += p[j];
+            if (a.cost) a.cost[ro] = sum;
+            mine.cost = sum;
+            mine.idx = a.index_base + ro;
+            if (!(sum == sum)) mine = CostIdx{inf, 0x7fffffffffffffffLL};   // NaN never wins
+        }
+    }
+    mine = warp_best(mine);
+    if (lane == 0) {
+        a.block_best[blockIdx.x] = mine;
+        __threadfence();
+        const unsigned int done = atomicAdd(a.counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncwarp();
+    if (!s_last) return;
+    __threadfence();
+    CostIdx b{inf, 0x7fffffffffffffffLL};
+    for (unsigned int j = lane; j < gridDim.x; j += kWarp) {
+        CostIdx cand;
+        cand.cost = *reinterpret_cast<volatile double*>(&a.block_best[j].cost);
+        cand.idx = *reinterpret_cast<volatile long long*>(&a.block_best[j].idx);
+        if (better(cand.cost, cand.idx, b.cost, b.idx)) b = cand;
+    }
+    b = warp_best(b);
+    if (b.idx == 0x7fffffffffffffffLL) b.idx = -1;  // nothing comparable (empty / all NaN)
+    if (lane == 0) {
+        *a.best = b;
+        *a.counter = 0u;
+    }
+    if (a.p2p.nranks > 0) {   // fused collective: this rank's pair goes straight to the peers' mailboxes
+        const CostIdx gbest = p2p_exchange_warp(a.p2p, b, lane);
+        if (lane == 0) *a.p2p.out = gbest;
     }
 }
 

@@ -145,13 +145,14 @@ BLF_CCM_API int blf_ccm_eval_batch_host(blf_ccm_handle* h, int64_t n, const doub
                                         double* wrench, double* autodyn, double* ctrl,
                                         double* regressor);
 
-/* Contacts per chunk of the blf_ccm_eval_batch_host pipeline (default 65536, measured best on B200 + PCIe Gen5; tuning knob). */
+/* Largest chunk (contacts) of the blf_ccm_eval_batch_host pipeline (default 131072, measured best on B200 + PCIe Gen5;
+ * the schedule ramps chunk/4, chunk/2, chunk ... chunk, chunk/2, chunk/4; tuning knob). */
 BLF_CCM_API int blf_ccm_set_host_chunk(blf_ccm_handle* h, int64_t contacts);
 
 /* blf_ccm_eval_batch_host moves the control matrix over PCIe in compact form (its 7 distinct values,
  * 64 instead of 288 bytes per contact) and `threads` host worker threads of the library expand it
  * into the caller's dense Matrix6x6 array, structural zeros +0.0, bit-identical to the device
- * layout.  -1 (default) = min(8, cores/2) (cores divided by LOCAL_WORLD_SIZE when a launcher sets
+ * layout.  -1 (default) = min(4, cores/2) (cores divided by LOCAL_WORLD_SIZE when a launcher sets
  * it); 0 = download the dense array instead (no host threads).  Environment override at create:
  * BLF_CCM_HOST_THREADS. */
 BLF_CCM_API int blf_ccm_set_host_threads(blf_ccm_handle* h, int threads);
@@ -227,10 +228,15 @@ BLF_CCM_API int blf_ccm_p2p_mailbox_destroy(blf_ccm_handle* h);
  * Batched Estimators::RecursiveLeastSquare::advance (reference:
  * src/Estimators/src/RecursiveLeastSquare.cpp:96-133), n independent estimators, one step each:
  *   K = P Y^T (lambda R + Y P Y^T)^-1 ; theta += K (z - Y theta) ; P = (P - K Y P) / lambda
- * p parameters (1..4), m measurements (1..6).  SoA device planes of n doubles:
- * regressor_planes[m*p] (row-major m x p index), measurement_planes[m], state_planes[p] (in/out),
- * cov_planes[p*p] (row-major, in/out).  host_measurement_cov[m] is the diagonal of R (the reference
- * assumes uncorrelated measurements, RecursiveLeastSquare.cpp:38-50).
+ * p parameters, m measurements (1..512 each, as the reference takes any size).  SoA device planes
+ * of n doubles: regressor_planes[m*p] (row-major m x p index), measurement_planes[m],
+ * state_planes[p] (in/out), cov_planes[p*p] (row-major, in/out).  host_measurement_cov[m] is the
+ * diagonal of R (the reference assumes uncorrelated measurements, RecursiveLeastSquare.cpp:38-50).
+ * Two code paths, chosen per call: p <= 4, m <= 6 and lambda * R > 0 (S symmetric positive
+ * definite) run in registers with an LDL^T factorisation at the HBM roofline; any other size, or a
+ * zero / negative lambda * R entry, runs the reference's own algorithm -- inverse of S by LU with
+ * partial pivoting -- in a general kernel with global scratch (a singular S gives inf/NaN, as the
+ * reference).
  */
 BLF_CCM_API int blf_rls_advance_batch(blf_ccm_handle* h, int64_t n, int p, int m,
                                       const double* const* regressor_planes,

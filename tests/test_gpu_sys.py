@@ -686,11 +686,17 @@ def test_non_finite_inputs_stay_local_and_never_win_the_argmin(torch, batch, so)
     assert batch.decode_best(allnan["best"])[1] == -1
 
 
+@pytest.mark.parametrize("variant", [13, 15, 17, 3, 7])
 @pytest.mark.parametrize("het,rho,nr,feet,H", [(True, 3.0, 100, 2, 31), (False, 0.0, 33, 1, 2),
-                                               (True, 0.0, 10, 3, 10), (False, 0.5, 700, 2, 64)])
-def test_rollout_warp_specialised_variant_vs_oracle(torch, so, het, rho, nr, feet, H):
-    """ccm_rollout_ws_kernel (producer + three consumers, mbarrier hand-over) forced for every
-    template instance, incl. horizons shorter than the stage ring and ragged tiles."""
+                                               (True, 0.0, 10, 3, 10), (False, 0.5, 700, 2, 64),
+                                               (False, 0.01, 4096, 2, 100), (False, 2.0, 37, 4, 17),
+                                               (True, 0.01, 8, 2, 8), (False, 0.0, 5, 2, 1)])
+def test_rollout_warp_specialised_variant_vs_oracle(torch, so, variant, het, rho, nr, feet, H):
+    """The warp-specialised rollout kernels forced for every template instance, incl. horizons
+    shorter than a TMA box / the stage ring, ragged tiles, an odd number of chains and a foot count
+    that does not divide 32 (where the third form must hand over to the second).  variant 13/15/17:
+    ccm_rollout_ws3_kernel (TMA tensor copies for the twists, fused reduction: ONE launch) with 3/5/7
+    consumer warps; 3/7: ccm_rollout_ws2_kernel + ccm_cost_reduce_kernel (two launches)."""
     from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
     from bipedal_locomotion_framework_b200.system import RolloutBatch
     chains = nr * feet
@@ -703,7 +709,7 @@ def test_rollout_warp_specialised_variant_vs_oracle(torch, so, het, rho, nr, fee
     ref_w, wts = np.array([0.0, 0.0, 30.0, 0.1, -0.1, 0.0]), np.array([1.0, 25.0])
     ref = so.rollout(nr, feet, H, 0.01, rho, tw, pos0, rot0, null, param_planes=prm,
                      uniform=syn.REFERENCE_TEST_PARAMS, mask=0, wrench_ref=ref_w, weights=wts)
-    os.environ["BLF_CCM_TUNE_ROLLOUT_WS"] = "1"
+    os.environ["BLF_CCM_TUNE_ROLLOUT_WS"] = str(variant)
     try:
         b = ContinuousContactModelBatch(0)
     finally:
@@ -713,7 +719,8 @@ def test_rollout_warp_specialised_variant_vs_oracle(torch, so, het, rho, nr, fee
     out = RolloutBatch(b).run(nr, feet, H, 0.01, rho, _dev(torch, tw), _dev(torch, pos0),
                               _dev(torch, rot0), _dev(torch, null), ref_w, wts,
                               param_planes=_dev(torch, prm), mask=0, want_final=True)
-    assert b.handle.launch_count - launches == 2
+    third_form = variant > 10 and 32 % feet == 0 and chains % 2 == 0
+    assert b.handle.launch_count - launches == (1 if third_form else 2)
     cost = out["cost"].cpu().numpy()
     assert np.all(rel(cost[:, None], ref["cost"][:, None]) <= TOL)
     assert rel(out["final_pos"].cpu().numpy().T, ref["pos"].T).max() <= TOL
@@ -724,3 +731,8 @@ def test_rollout_warp_specialised_variant_vs_oracle(torch, so, het, rho, nr, fee
                                _dev(torch, rot0), _dev(torch, null), ref_w, wts,
                                param_planes=_dev(torch, prm), mask=0)
     assert np.array_equal(out2["cost"].cpu().numpy(), cost)     # deterministic
+    # index_base and a NULL cost array through the fused reduction
+    out3 = RolloutBatch(b).run(nr, feet, H, 0.01, rho, _dev(torch, tw), _dev(torch, pos0),
+                               _dev(torch, rot0), _dev(torch, null), ref_w, wts,
+                               param_planes=_dev(torch, prm), mask=0, index_base=1000, want_cost=False)
+    assert b.decode_best(out3["best"]) == (c, idx + 1000)

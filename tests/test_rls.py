@@ -201,6 +201,77 @@ def test_rls_batch_sizes_against_oracle(torch, batch, oracle, p, m):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("p,m,negative", [(5, 3, False), (8, 8, False), (6, 7, False), (2, 8, False),
+                                          (2, 6, True), (4, 4, True), (3, 1, True)])
+@pytest.mark.parametrize("layout", ["soa", "host"])
+def test_rls_general_sizes_and_indefinite_covariance_against_oracle(torch, batch, oracle, p, m, negative, layout):
+    """What the reference accepts and the register kernels do not cover -- more than 4 parameters
+    or 6 measurements, or a lambda*R that is not positive (S not positive definite) -- runs the
+    reference's own algorithm (LU with partial pivoting) in rls_advance_generic_kernel."""
+    from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquareBatch
+    import ctypes as C
+    from bipedal_locomotion_framework_b200 import _capi
+    rng = np.random.default_rng(1000 * p + 10 * m + negative)
+    n = 1025
+    r = rng.uniform(0.1, 1.0, m)
+    if negative:
+        r[rng.integers(0, m)] *= -1.0           # an indefinite measurement covariance entry
+    lam = 0.97
+    theta = rng.normal(0, 1, (n, p))
+    A = rng.normal(0, 1, (n, p, p))
+    P = A @ A.transpose(0, 2, 1) + 0.5 * np.eye(p)
+    for step in range(3):
+        Y = rng.normal(0, 1, (n, m, p))
+        z = rng.normal(0, 1, (n, m))
+        theta_ref, P_ref = oracle.rls_advance_batch(Y, z, r, lam, theta, P)
+        if layout == "soa":
+            d_theta = torch.from_numpy(np.ascontiguousarray(theta.T)).cuda()
+            d_P = torch.from_numpy(np.ascontiguousarray(P.reshape(n, p * p).T)).cuda()
+            RecursiveLeastSquareBatch(batch, r, lam).advance(
+                torch.from_numpy(np.ascontiguousarray(Y.reshape(n, m * p).T)).cuda(),
+                torch.from_numpy(np.ascontiguousarray(z.T)).cuda(), d_theta, d_P)
+            got_t, got_P = d_theta.cpu().numpy().T, d_P.cpu().numpy().T.reshape(n, p, p)
+        else:
+            got_t, got_P = theta.copy(), np.ascontiguousarray(P).copy()
+            ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+            Yc, zc, rc_ = np.ascontiguousarray(Y), np.ascontiguousarray(z), np.ascontiguousarray(r)
+            _capi.check(_capi.lib().blf_rls_advance_host(batch.handle.ptr, n, p, m, ptr(Yc), ptr(zc), ptr(rc_),
+                                                         lam, ptr(got_t), ptr(got_P)))
+        # same algorithm, same order of operations as the oracle: agreement far below the bound
+        _assert_step(got_t, got_P, theta_ref, P_ref, theta, P, Y, z, r, lam, f"p={p} m={m} step {step} {layout}")
+        theta, P = theta_ref, P_ref
+
+
+@pytest.mark.gpu
+def test_rls_sizes_beyond_the_oracle_against_numpy(torch, batch):
+    """p = 12 parameters, m = 10 measurements through the per-instance facade (the reference takes
+    dynamic sizes): compared with a numpy restatement of RecursiveLeastSquare.cpp:118-130."""
+    from bipedal_locomotion_framework_b200.estimators import RecursiveLeastSquare
+    rng = np.random.default_rng(5)
+    p, m, lam = 12, 10, 0.99
+    r = rng.uniform(0.2, 1.0, m)
+    est = RecursiveLeastSquare()
+    assert est.initialize(_handler(lam=lam, measurement_covariance=list(r), state=[0.0] * p,
+                                   state_covariance=[4.0] * p))
+    cur = {}
+    est.setRegressorFunction(lambda: cur["Y"])
+    theta, P = np.zeros(p), 4.0 * np.eye(p)
+    truth = rng.normal(size=p)
+    for _ in range(40):
+        Y = rng.normal(size=(m, p))
+        z = Y @ truth + 1e-3 * rng.normal(size=m)
+        cur["Y"] = Y
+        est.setMeasurements(z)
+        assert est.advance()
+        K = P @ Y.T @ np.linalg.inv(lam * np.diag(r) + Y @ P @ Y.T)
+        theta = theta + K @ (z - Y @ theta)
+        P = (P - K @ Y @ P) / lam
+        assert np.abs(est.parametersExpectedValue() - theta).max() <= 1e-9 * max(1.0, np.abs(theta).max())
+        assert np.abs(est.parametersCovarianceMatrix() - P).max() <= 1e-9 * np.abs(P).max()
+    assert np.abs(est.parametersExpectedValue() - truth).max() < 1e-2
+
+
+@pytest.mark.gpu
 def test_fused_contact_identification(torch, batch, oracle):
     """blf_ccm_rls_advance_contacts == regressor kernel + blf_rls_advance_batch (bit for bit), and
     agrees with the oracle chain regressor -> advance; over many steps it recovers each contact's

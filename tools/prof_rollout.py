@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A few fused-rollout steps of ONE kernel variant at the sampling-MPC size, for ncu:
-   BLF_CCM_TUNE_ROLLOUT_WS=3 python tools/prof_rollout.py [rho] [samples]"""
+   BLF_CCM_TUNE_ROLLOUT_WS=13 python tools/prof_rollout.py [rho] [samples]"""
 import os
 import sys
 

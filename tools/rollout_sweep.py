@@ -36,9 +36,10 @@ def timeit(fn, iters=200, warm=20):
 VARIANTS = [("auto", {}), ("split 1", {"BLF_CCM_TUNE_ROLLOUT_SPLIT": 1, "BLF_CCM_TUNE_ROLLOUT_WS": 2}),
             ("split 2", {"BLF_CCM_TUNE_ROLLOUT_SPLIT": 2, "BLF_CCM_TUNE_ROLLOUT_WS": 2}),
             ("split 4", {"BLF_CCM_TUNE_ROLLOUT_SPLIT": 4, "BLF_CCM_TUNE_ROLLOUT_WS": 2}),
-            ("ws (3 consumers, per-step hand-over)", {"BLF_CCM_TUNE_ROLLOUT_WS": 1}),
-            ("ws2 C=3", {"BLF_CCM_TUNE_ROLLOUT_WS": 3}), ("ws2 C=5", {"BLF_CCM_TUNE_ROLLOUT_WS": 5}),
-            ("ws2 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 7})]
+            ("ws2 C=3 (cp.async ring, 2 launches)", {"BLF_CCM_TUNE_ROLLOUT_WS": 3}),
+            ("ws2 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 7}),
+            ("ws3 C=3 (TMA twists, fused reduction)", {"BLF_CCM_TUNE_ROLLOUT_WS": 13}),
+            ("ws3 C=5", {"BLF_CCM_TUNE_ROLLOUT_WS": 15}), ("ws3 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 17})]
 
 for samples in (4096, 16384, 65536):
     chains = FEET * samples

@@ -141,7 +141,7 @@ def sys_only():
                     row(f"split={split} rho={rho} out_mask={mask}", ms, n, bytes_per)
                     del cls
         os.environ.pop("BLF_CCM_TUNE_ROLLOUT_SPLIT", None)
-        for ws, label in ((1, "warp-specialised (1 producer + 3 consumers)"), (2, "plain / split (auto)")):
+        for ws, label in ((1, "warp-specialised, third form (TMA twists, fused reduction)"), (2, "plain / split (auto)")):
             bs = make_batch(BLF_CCM_TUNE_ROLLOUT_WS=ws)
             rbs = RolloutBatch(bs)
             for rho in (0.0, 0.01, 2.0):
