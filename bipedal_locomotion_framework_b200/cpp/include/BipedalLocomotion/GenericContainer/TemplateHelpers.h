@@ -1,9 +1,8 @@
 /**
  * @file TemplateHelpers.h
  * Present so that code including the reference's header of the same name compiles against this
- * build; the metaprogramming helpers of the reference
- * (src/GenericContainer/include/BipedalLocomotion/GenericContainer/TemplateHelpers.h) serve its
- * GenericContainer::Vector, which this build does not carry.
+ * build: the traits GenericContainer::Vector needs (is_vector, is_vector_constructible and the
+ * data()/size()/resize() detectors) live in Vector.h here.
  */
 #ifndef BIPEDAL_LOCOMOTION_TEMPLATEHELPERS_H
 #define BIPEDAL_LOCOMOTION_TEMPLATEHELPERS_H

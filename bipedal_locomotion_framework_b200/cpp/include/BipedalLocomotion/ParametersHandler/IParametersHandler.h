@@ -4,9 +4,10 @@
  *
  * Mirrors the public surface of the reference interface
  * (src/ParametersHandler/include/BipedalLocomotion/ParametersHandler/IParametersHandler.h:26-249):
- * same method names, argument meaning and bool-return error convention.  Vector parameters are
- * carried as std::vector<T> (the reference routes them through GenericContainer::Vector, a host
- * utility that is outside this build's scope) and keep the reference's resize contract: by default
+ * same method names, argument meaning and bool-return error convention.  Vector parameters can be
+ * read into / set from std::vector<T> directly and, as in the reference, from ANY container a
+ * GenericContainer::Vector can view (std::array, iDynTree::VectorDynSize, Eigen vectors, plain
+ * arrays: the templates below).  The reference's resize contract holds for all of them: by default
  * (VectorResizeMode::Fixed) the destination must already have the size of the stored list, pass
  * VectorResizeMode::Resizable to have it resized (IParametersHandler.h:129-139,
  * StdImplementation.tpp:62-85).  std::vector<bool> is always resized, as upstream.
@@ -14,8 +15,10 @@
 #ifndef BIPEDAL_LOCOMOTION_PARAMETERS_HANDLER_IPARAMETERS_HANDLER_H
 #define BIPEDAL_LOCOMOTION_PARAMETERS_HANDLER_IPARAMETERS_HANDLER_H
 
+#include <iterator>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <BipedalLocomotion/GenericContainer/Vector.h>
@@ -27,6 +30,13 @@ namespace ParametersHandler
 
 class IParametersHandler
 {
+    template <typename T> struct is_std_vector : std::false_type
+    {
+    };
+    template <typename T, typename A> struct is_std_vector<std::vector<T, A>> : std::true_type
+    {
+    };
+
 public:
     using unique_ptr = std::unique_ptr<IParametersHandler>;
     using shared_ptr = std::shared_ptr<IParametersHandler>;
@@ -44,6 +54,38 @@ public:
                               GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const = 0;
     virtual bool getParameter(const std::string& parameterName, std::vector<std::string>& parameter,
                               GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const = 0;
+
+    /** Vector parameters through a generic view (any element storage; see the template below). */
+    virtual bool getParameter(const std::string& parameterName, GenericContainer::Vector<int>& parameter) const = 0;
+    virtual bool getParameter(const std::string& parameterName, GenericContainer::Vector<double>& parameter) const = 0;
+    virtual bool getParameter(const std::string& parameterName, GenericContainer::Vector<std::string>& parameter) const = 0;
+
+    /** Get a vector parameter into any container a GenericContainer::Vector can view (same
+     * template as the reference's, IParametersHandler.h:121-139). */
+    template <class Container,
+              typename = std::enable_if_t<!GenericContainer::is_vector<Container>::value
+                                          && !is_std_vector<Container>::value
+                                          && !std::is_same<Container, std::string>::value
+                                          && GenericContainer::is_vector_constructible<Container>::value>>
+    bool getParameter(const std::string& parameterName, Container& parameter,
+                      GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const
+    {
+        auto view = GenericContainer::make_vector(parameter, mode);
+        return this->getParameter(parameterName, view);
+    }
+
+    /** Set a vector parameter from any such container (stored as std::vector<T>). */
+    template <class Container,
+              typename = std::enable_if_t<!is_std_vector<Container>::value
+                                          && !std::is_same<Container, std::string>::value
+                                          && !std::is_convertible<Container, const char*>::value
+                                          && (GenericContainer::is_vector<Container>::value
+                                              || GenericContainer::is_vector_constructible<Container>::value)>>
+    void setParameter(const std::string& parameterName, const Container& parameter)
+    {
+        using T = std::remove_cv_t<std::remove_reference_t<decltype(*std::begin(parameter))>>;
+        this->setParameter(parameterName, std::vector<T>(std::begin(parameter), std::end(parameter)));
+    }
 
     virtual void setParameter(const std::string& parameterName, const int& parameter) = 0;
     virtual void setParameter(const std::string& parameterName, const double& parameter) = 0;

@@ -66,7 +66,26 @@ class StdImplementation : public IParametersHandler
         return true;
     }
 
+    /** The same contract through a generic view: the view resizes its owner when it may. */
+    template <typename T>
+    bool getViewPrivate(const std::string& parameterName, GenericContainer::Vector<T>& parameter) const
+    {
+        std::vector<T> stored;
+        if (!getParameterPrivate(parameterName, stored)) return false;
+        const auto want = static_cast<typename GenericContainer::Vector<T>::index_type>(stored.size());
+        if (parameter.size() != want && !parameter.resizeVector(want))
+        {
+            std::cerr << "[StdImplementation::getParameterPrivate] Unable to resize the vector. List size: "
+                      << stored.size() << ". Vector size: " << parameter.size() << std::endl;
+            return false;
+        }
+        for (std::size_t i = 0; i < stored.size(); ++i) parameter[static_cast<std::ptrdiff_t>(i)] = stored[i];
+        return true;
+    }
+
 public:
+    using IParametersHandler::getParameter;   // the container templates of the interface
+    using IParametersHandler::setParameter;
     // unique_ptr / shared_ptr / weak_ptr are the ones inherited from IParametersHandler (pointers to
     // the INTERFACE), as upstream: `StdImplementation::shared_ptr g = h->getGroup("x").lock();`
 
@@ -92,6 +111,13 @@ public:
                       GenericContainer::VectorResizeMode mode = GenericContainer::VectorResizeMode::Fixed) const final
     {
         return getVectorPrivate(n, p, mode);
+    }
+
+    bool getParameter(const std::string& n, GenericContainer::Vector<int>& p) const final { return getViewPrivate(n, p); }
+    bool getParameter(const std::string& n, GenericContainer::Vector<double>& p) const final { return getViewPrivate(n, p); }
+    bool getParameter(const std::string& n, GenericContainer::Vector<std::string>& p) const final
+    {
+        return getViewPrivate(n, p);
     }
 
     void setParameter(const std::string& n, const int& p) final { m_map[n] = p; }

@@ -11,8 +11,11 @@
 #endif
 
 #include <any>
+#include <array>
 #include <iostream>
 #include <unordered_map>
+
+#include <iDynTree/Core/VectorDynSize.h>
 
 #include <BipedalLocomotion/ParametersHandler/IniFile.h>
 #include <BipedalLocomotion/ParametersHandler/StdImplementation.h>
@@ -63,6 +66,47 @@ TEST_CASE("Get parameters")
         std::vector<int> sized(8, 0);
         REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", sized));
         REQUIRE(sized == element);
+    }
+
+    SECTION("Get Vector into any container a GenericContainer::Vector can view")
+    {
+        using BipedalLocomotion::GenericContainer::VectorResizeMode;
+        namespace GC = BipedalLocomotion::GenericContainer;
+        parameterHandler->setParameter("gains", std::vector<double>{1.5, -2.0, 0.25});
+        // fixed-size destinations: std::array and a plain array of the right size succeed, a wrong size fails
+        std::array<double, 3> arr{};
+        REQUIRE(parameterHandler->getParameter("gains", arr));
+        REQUIRE((arr[0] == 1.5 && arr[1] == -2.0 && arr[2] == 0.25));
+        std::array<double, 4> wrong{};
+        REQUIRE_FALSE(parameterHandler->getParameter("gains", wrong));
+        REQUIRE_FALSE(parameterHandler->getParameter("gains", wrong, VectorResizeMode::Resizable)); // cannot resize
+        double plain[3] = {0, 0, 0};
+        REQUIRE(parameterHandler->getParameter("gains", plain));
+        REQUIRE(plain[2] == 0.25);
+        // iDynTree::VectorDynSize: resized on request, as reference user code expects
+        iDynTree::VectorDynSize dyn;
+        REQUIRE_FALSE(parameterHandler->getParameter("gains", dyn));
+        REQUIRE(parameterHandler->getParameter("gains", dyn, VectorResizeMode::Resizable));
+        REQUIRE((dyn.size() == 3 && dyn(1) == -2.0));
+        // the view itself, and strict typing through it
+        std::vector<double> owner(3);
+        auto view = GC::make_vector(owner);
+        REQUIRE(parameterHandler->getParameter("gains", view));
+        REQUIRE(owner[0] == 1.5);
+        std::array<int, 3> ints{};
+        REQUIRE_FALSE(parameterHandler->getParameter("gains", ints));          // stored as double
+        std::array<int, 8> fib{};
+        REQUIRE(parameterHandler->getParameter("Fibonacci Numbers", fib));
+        REQUIRE(fib[7] == 21);
+        // set from a non-std::vector container
+        parameterHandler->setParameter("from_array", arr);
+        std::vector<double> back;
+        REQUIRE(parameterHandler->getParameter("from_array", back, VectorResizeMode::Resizable));
+        REQUIRE(back == std::vector<double>{1.5, -2.0, 0.25});
+        static_assert(GC::is_vector<GC::Vector<double>>::value && !GC::is_vector<std::vector<double>>::value, "traits");
+        static_assert(GC::is_vector_constructible<std::array<double, 3>>::value
+                          && !GC::is_vector_constructible<std::string>::value && !GC::is_vector_constructible<double>::value,
+                      "traits");
     }
 
     SECTION("Strict typing and missing keys")
