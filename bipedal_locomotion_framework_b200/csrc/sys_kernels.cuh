@@ -82,26 +82,46 @@ __device__ __forceinline__ void kin_rates(const Pose& s, const V3& w, double hal
 // operations).  Every kernel integrates through this one function, so fused rollouts, the batched
 // Euler step and the per-instance integrate agree bit for bit with one another; against the oracle
 // (which follows Eigen's expression) the difference is a few ulp per step.
+// One component of a rotation column's update, with the contraction spelled out so that every
+// kernel rounds it the same way:  c' = beta k + (dT x + alpha c)   [ c' = dT x + c  without Baumgarte ]
+template <bool BAUM>
+__device__ __forceinline__ double kin_col_step(double c, double x, double k, double alpha, double beta, double dT)
+{
+    if constexpr (BAUM) return fma(beta, k, fma(dT, x, __dmul_rn(alpha, c)));
+    else return fma(dT, x, c);
+}
+
+template <bool BAUM>
+__device__ __forceinline__ V3 kin_col_step(const V3& c, const V3& x, const V3& k, double alpha, double beta, double dT)
+{
+    return V3{kin_col_step<BAUM>(c.x, x.x, k.x, alpha, beta, dT), kin_col_step<BAUM>(c.y, x.y, k.y, alpha, beta, dT),
+              kin_col_step<BAUM>(c.z, x.z, k.z, alpha, beta, dT)};
+}
+
+// the two uniform factors of the regrouped Baumgarte step, rounded the same way wherever they are formed
+__device__ __forceinline__ double kin_dthr(double dT, double half_rho) { return __dmul_rn(dT, half_rho); }
+__device__ __forceinline__ double kin_alpha(double dT, double half_rho) { return __dsub_rn(1.0, __dmul_rn(dT, half_rho)); }
+
+__device__ __forceinline__ double dot3(const V3& a, const V3& b) { return fma(a.z, b.z, fma(a.y, b.y, __dmul_rn(a.x, b.x))); }
+
 template <bool BAUM>
 __device__ __forceinline__ void kin_euler_step(Pose& s, const V3& v, const V3& w, double half_rho,
                                                double dT)
 {
-    s.p = s.p + dT * v;
+    s.p = V3{fma(dT, v.x, s.p.x), fma(dT, v.y, s.p.y), fma(dT, v.z, s.p.z)};
     const V3 x0 = cross(w, s.c0), x1 = cross(w, s.c1), x2 = cross(w, s.c2);
+    V3 k0{}, k1{}, k2{};
+    double alpha = 1.0, beta = 0.0;
     if constexpr (BAUM) {
-        const V3 k0 = cross(s.c1, s.c2), k1 = cross(s.c2, s.c0), k2 = cross(s.c0, s.c1);
-        const double det = s.c0.x * k0.x + s.c0.y * k0.y + s.c0.z * k0.z;
-        const double alpha = 1.0 - dT * half_rho;            // uniform: hoisted out of every loop
-        const double beta = (dT * half_rho) * fast_rcp(det);
-        const V3 y0 = alpha * s.c0 + dT * x0, y1 = alpha * s.c1 + dT * x1, y2 = alpha * s.c2 + dT * x2;
-        s.c0 = y0 + beta * k0;
-        s.c1 = y1 + beta * k1;
-        s.c2 = y2 + beta * k2;
-    } else {
-        s.c0 = s.c0 + dT * x0;
-        s.c1 = s.c1 + dT * x1;
-        s.c2 = s.c2 + dT * x2;
+        k0 = cross(s.c1, s.c2);
+        k1 = cross(s.c2, s.c0);
+        k2 = cross(s.c0, s.c1);
+        alpha = kin_alpha(dT, half_rho);                     // uniform: hoisted out of every loop
+        beta = __dmul_rn(kin_dthr(dT, half_rho), fast_rcp(dot3(s.c0, k0)));   // dT rho/2 / det R
     }
+    s.c0 = kin_col_step<BAUM>(s.c0, x0, k0, alpha, beta, dT);
+    s.c1 = kin_col_step<BAUM>(s.c1, x1, k1, alpha, beta, dT);
+    s.c2 = kin_col_step<BAUM>(s.c2, x2, k2, alpha, beta, dT);
 }
 
 struct KinArgs {
@@ -844,6 +864,292 @@ ccm_rollout_ws3_kernel(const __grid_constant__ RolloutArgs a)
     }
     if (a.p2p.nranks > 0) {   // fused collective: this rank's pair goes straight to the peers' mailboxes
         const CostIdx gbest = p2p_exchange_warp(a.p2p, b, lane);
+        if (lane == 0) *a.p2p.out = gbest;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fourth form: the pose recurrence itself is spread over LANES.
+//
+// ncu on the second form showed what bounds a small batch: the lone producer warp issues one
+// instruction every ~3.6 cycles (a single warp per scheduler: every dependent or same-pipe
+// instruction waits), so the per-step time is its instruction count -- 215 instructions, 774 cycles
+// with the Baumgarte term.  The third form cut that to ~117.  Here FOUR lanes share a chain: lanes
+// 0-2 own one column of R each, lane 3 owns the position; the columns' updates are independent
+// given w (three lanes do in parallel what one lane did in sequence), and the Baumgarte term,
+// which couples the columns, gets the two other columns by warp shuffles (k_j = c_{j+1} x c_{j+2}
+// is cyclic, so every lane runs the same code) and dT rho/2 / det R from lane 0 (the one value
+// every other kernel uses, so results stay bit-identical to them).  A 32-chain tile now has four
+// producer warps of 8 chains; per lane and step ~9 (rho = 0) or ~30 (rho != 0) FP64 instructions
+// instead of 30 / 75.  Twists by TMA tensor copies, stage hand-over in groups, C consumer warps
+// and the fused reduction exactly as in the third form.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kWs4Producers = 4;
+constexpr int kWs4StageDoubles = 16 * kWarp;   // 8 double2 slots x 32 chains: p.xy p.z_ c0.xy c0.z_ c1.xy c1.z_ c2.xy c2.z_
+
+template <int C>
+struct Ws4Cfg {
+    static constexpr int kStages = kWs2Groups * C;
+    static constexpr int kThreads = kWarp * (kWs4Producers + C);
+    static constexpr int kBarBytes = 128;
+    static constexpr int kSmemBytes = kWs3Boxes * kWs3BoxBytes + kStages * kWs4StageDoubles * 8 + kBarBytes +
+                                      kWarp * C * 8;
+};
+
+__device__ __forceinline__ V3 shfl3(const V3& a, int src)
+{
+    return V3{__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src),
+              __shfl_sync(0xffffffffu, a.z, src)};
+}
+
+template <bool HET, bool BAUM, int C>
+__global__ void __launch_bounds__(kWarp * (kWs4Producers + C))
+ccm_rollout_ws4_kernel(const __grid_constant__ RolloutArgs a)
+{
+    constexpr int NP = kWs4Producers;
+    constexpr int S = Ws4Cfg<C>::kStages;
+    constexpr int NG = kWs2Groups;
+    constexpr int BS = kWs3BoxSteps;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wbase = static_cast<long long>(blockIdx.x) * kWarp;
+    const int H = a.horizon;
+
+    double* twbuf = reinterpret_cast<double*>(smem_raw);                              // [box][plane][step][chain]
+    double* stages = twbuf + kWs3Boxes * kWs3BoxBytes / 8;                            // [S][8 slots][32] double2
+    const uint32_t bars = ptx::smem_addr(stages + S * kWs4StageDoubles);
+    const uint32_t twfull0 = bars;                        // a box has landed (TMA bytes)
+    const uint32_t twempty0 = twfull0 + 8 * kWs3Boxes;    // NP arrivals: every producer warp has read the box
+    const uint32_t full0 = twempty0 + 8 * kWs3Boxes;      // NP arrivals: a stage group is written
+    const uint32_t empty0 = full0 + 8 * NG;               // C arrivals: a stage group is consumed
+    double* cst = stages + S * kWs4StageDoubles + Ws4Cfg<C>::kBarBytes / 8;           // [32][C] partial costs
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kWs3Boxes; ++b) {
+            ptx::mbar_init(twfull0 + 8 * b, 1);
+            ptx::mbar_init(twempty0 + 8 * b, NP);
+        }
+        for (int g = 0; g < NG; ++g) {
+            ptx::mbar_init(full0 + 8 * g, NP);
+            ptx::mbar_init(empty0 + 8 * g, C);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp < NP) {
+        // ---------------- producers: lane = 4 * (chain in warp) + part; part 0-2 = column of R, 3 = position
+        const int part = lane & 3;
+        const int ct = warp * 8 + (lane >> 2);            // chain inside the tile
+        const long long c = wbase + ct;
+        const bool on = c < a.chains;
+        const bool is_p = part == 3;
+        const int nbox = (H + BS - 1) / BS;
+        auto load_box = [&](int b) {   // one thread: the six planes' box b into buffer b % kWs3Boxes
+            const int buf = b & (kWs3Boxes - 1);
+            const uint32_t bar = twfull0 + 8 * buf;
+            const uint32_t dst = ptx::smem_addr(twbuf) + buf * kWs3BoxBytes;
+            ptx::mbar_arrive_expect_tx(bar, kWs3BoxBytes);
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                ptx::tma_load_2d(dst + j * (BS * kWarp * 8), &a.twmap[j], static_cast<int>(wbase), b * BS, bar);
+        };
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int b = 0; b < kWs3Boxes; ++b)
+                if (b < nbox) load_box(b);
+        }
+        // this lane's state vector: a column of R (row-major planes part, 3 + part, 6 + part) or the position
+        V3 x{};
+        if (on) {
+            x = is_p ? V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)}
+                     : V3{__ldg(a.rot0[part] + c), __ldg(a.rot0[3 + part] + c), __ldg(a.rot0[6 + part] + c)};
+        }
+        // the twist half this lane needs: angular (planes 3-5) for a column, linear (0-2) for the position
+        const double* twl = twbuf + (is_p ? 0 : 3) * BS * kWarp + ct;
+        // the two other columns, cyclically: part j gets c_{j+1} and c_{j+2}; the position lane reads itself
+        const int lb = lane & ~3;
+        const int srcA = is_p ? lane : lb + (part + 1) % 3, srcB = is_p ? lane : lb + (part + 2) % 3;
+        const double dT = a.dT;
+        const double alpha = is_p ? 1.0 : kin_alpha(dT, a.half_rho);
+        const double dthr = kin_dthr(dT, a.half_rho);
+        // stage slots of this lane's vector: p -> 0,1; column j -> 2 + 2j, 3 + 2j
+        const int slot0 = is_p ? 0 : 2 + 2 * part;
+        int st = 0;
+        int gi = 0, g = 0;
+        uint32_t empty_parity = 0;
+        bool wrapped = false;
+        uint32_t box_parity = 0;
+        for (int b = 0; b < nbox; ++b) {
+            const int buf = b & (kWs3Boxes - 1);
+            ptx::mbar_wait(twfull0 + 8 * buf, box_parity);
+            const double* tw = twl + buf * (kWs3BoxBytes / 8);
+            const int steps = min(BS, H - b * BS);
+            V3 un{tw[0], tw[BS * kWarp], tw[2 * BS * kWarp]};
+#pragma unroll
+            for (int q = 0; q < BS; ++q) {
+                if (q < steps) {
+                    const V3 u = un;
+                    if (q + 1 < BS) {   // next step's twist: in flight while this step is integrated
+                        const double* r = tw + (q + 1) * kWarp;
+                        un = V3{r[0], r[BS * kWarp], r[2 * BS * kWarp]};
+                    }
+                    if (gi == 0 && wrapped) ptx::mbar_wait(empty0 + 8 * g, empty_parity);   // the group's stages are free
+                    double2* o = reinterpret_cast<double2*>(stages + st * kWs4StageDoubles) + slot0 * kWarp + ct;
+                    o[0] = make_double2(x.x, x.y);
+                    o[kWarp] = make_double2(x.z, 0.0);
+                    // ---- one ForwardEuler step of this lane's vector (kin_euler_step, one column per lane)
+                    V3 k{};
+                    double beta = 0.0;
+                    if constexpr (BAUM) {
+                        const V3 ca = shfl3(x, srcA), cb = shfl3(x, srcB);
+                        k = cross(ca, cb);                                  // position lane: p x p = 0
+                        const double bl = __dmul_rn(dthr, fast_rcp(dot3(x, k)));   // part 0: dT rho/2 / (c0 . (c1 x c2))
+                        beta = __shfl_sync(0xffffffffu, bl, lb);            // every kernel uses THAT determinant
+                        if (is_p) beta = 0.0;
+                    }
+                    const V3 xc = cross(u, x);                              // w x c_j
+                    const V3 rate = is_p ? u : xc;                          // the position integrates v itself
+                    x = kin_col_step<BAUM>(x, rate, k, alpha, beta, dT);
+                    if (++gi == C || b * BS + q == H - 1) {   // the group is complete: hand it over
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(full0 + 8 * g);
+                        gi = 0;
+                        if (++g == NG) {
+                            g = 0;
+                            empty_parity = wrapped ? (empty_parity ^ 1u) : 0u;
+                            wrapped = true;
+                        }
+                    }
+                    if (++st == S) st = 0;
+                }
+            }
+            // this warp holds the box's last twist in registers: release the buffer; thread 0 refills it
+            // once all four producer warps have
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(twempty0 + 8 * buf);
+            if (threadIdx.x == 0 && b + kWs3Boxes < nbox) {
+                ptx::mbar_wait(twempty0 + 8 * buf, box_parity);
+                ptx::fence_async_smem();
+                load_box(b + kWs3Boxes);
+            }
+            if (buf == kWs3Boxes - 1) box_parity ^= 1u;
+        }
+        if (on && a.write_final) {
+            if (is_p) {
+                a.pos_out[0][c] = x.x; a.pos_out[1][c] = x.y; a.pos_out[2][c] = x.z;
+            } else {
+                a.rot_out[part][c] = x.x; a.rot_out[3 + part][c] = x.y; a.rot_out[6 + part][c] = x.z;
+            }
+        }
+    } else {
+        // ---------------- consumer k: contact wrench + cost of the steps g*C + k -----------------
+        const long long c = wbase + lane;
+        const bool on = c < a.chains;
+        const int k = warp - NP;
+        V3 p0{}, n1{}, n2{};
+        Prm q = a.uni;
+        if (on) {
+            p0 = V3{__ldg(a.nul[0] + c), __ldg(a.nul[1] + c), __ldg(a.nul[2] + c)};
+            n1 = V3{__ldg(a.nul[3] + c), __ldg(a.nul[6] + c), __ldg(a.nul[9] + c)};
+            n2 = V3{__ldg(a.nul[4] + c), __ldg(a.nul[7] + c), __ldg(a.nul[10] + c)};
+            if constexpr (HET)
+                q = make_prm(__ldg(a.prm[0] + c), __ldg(a.prm[1] + c), __ldg(a.prm[2] + c),
+                             __ldg(a.prm[3] + c));
+        }
+        const long long tstride = static_cast<long long>(C) * a.chains;
+        long long ti = static_cast<long long>(k) * a.chains + c;
+        V3 vn{}, wn{};
+        if (on && k < H) {
+            vn = V3{__ldg(a.tw[0] + ti), __ldg(a.tw[1] + ti), __ldg(a.tw[2] + ti)};
+            wn = V3{__ldg(a.tw[3] + ti), __ldg(a.tw[4] + ti), __ldg(a.tw[5] + ti)};
+        }
+        double acc = 0.0;
+        int g = 0;
+        uint32_t parity = 0;
+        const double2* stage_k = reinterpret_cast<const double2*>(stages + k * kWs4StageDoubles) + lane;
+        for (int t = k; t < H; t += C) {
+            State x;
+            x.v = vn;
+            x.w = wn;
+            ti += tstride;
+            if (on && t + C < H) {
+                vn = V3{__ldg(a.tw[0] + ti), __ldg(a.tw[1] + ti), __ldg(a.tw[2] + ti)};
+                wn = V3{__ldg(a.tw[3] + ti), __ldg(a.tw[4] + ti), __ldg(a.tw[5] + ti)};
+            }
+            ptx::mbar_wait(full0 + 8 * g, parity);
+            const double2* in = stage_k + g * (C * kWs4StageDoubles / 2);
+            const double2 a0 = in[0 * kWarp], a1 = in[1 * kWarp], a2 = in[2 * kWarp], a3 = in[3 * kWarp],
+                          a4 = in[4 * kWarp], a5 = in[5 * kWarp], a7 = in[7 * kWarp];
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty0 + 8 * g);   // one of the C arrivals that free the group
+            x.p = V3{a0.x, a0.y, a1.x};
+            x.e1 = V3{a2.x, a2.y, a3.x};
+            x.e2 = V3{a4.x, a4.y, a5.x};
+            x.R02 = 0.0; x.R12 = 0.0;
+            x.R22 = a7.x;
+            x.p0 = p0; x.n1 = n1; x.n2 = n2;
+            Result r;
+            eval_contact<M_WRENCH>(x, q, r);
+            if (on) {
+                const V3 df = r.force - V3{a.ref[0], a.ref[1], a.ref[2]};
+                const V3 dt = r.torque - V3{a.ref[3], a.ref[4], a.ref[5]};
+                acc = acc + (a.wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
+                             a.wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
+            }
+            if (++g == NG) {
+                g = 0;
+                parity ^= 1u;
+            }
+        }
+        cst[lane * C + k] = acc;    // chains past the end: 0, never read
+    }
+
+    // ---------------- fused reduction (as in the third form) ----------------------------------------
+    __syncthreads();
+    if (warp != 0) return;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    CostIdx mine{inf, 0x7fffffffffffffffLL};
+    {
+        const int feet = a.feet;
+        const long long ro = wbase / feet + lane;          // 32 % feet == 0: tiles hold whole rollouts
+        if (lane < kWarp / feet && ro < a.n_rollouts) {
+            const double* p = cst + lane * feet * C;
+            double sum = 0.0;
+            for (int j = 0; j < feet * C; ++j) sum += p[j];
+            if (a.cost) a.cost[ro] = sum;
+            mine.cost = sum;
+            mine.idx = a.index_base + ro;
+            if (!(sum == sum)) mine = CostIdx{inf, 0x7fffffffffffffffLL};   // NaN never wins
+        }
+    }
+    mine = warp_best(mine);
+    if (lane == 0) {
+        a.block_best[blockIdx.x] = mine;
+        __threadfence();
+        const unsigned int done = atomicAdd(a.counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncwarp();
+    if (!s_last) return;
+    __threadfence();
+    CostIdx bb{inf, 0x7fffffffffffffffLL};
+    for (unsigned int j = lane; j < gridDim.x; j += kWarp) {
+        CostIdx cand;
+        cand.cost = *reinterpret_cast<volatile double*>(&a.block_best[j].cost);
+        cand.idx = *reinterpret_cast<volatile long long*>(&a.block_best[j].idx);
+        if (better(cand.cost, cand.idx, bb.cost, bb.idx)) bb = cand;
+    }
+    bb = warp_best(bb);
+    if (bb.idx == 0x7fffffffffffffffLL) bb.idx = -1;  // nothing comparable (empty / all NaN)
+    if (lane == 0) {
+        *a.best = bb;
+        *a.counter = 0u;
+    }
+    if (a.p2p.nranks > 0) {   // fused collective: this rank's pair goes straight to the peers' mailboxes
+        const CostIdx gbest = p2p_exchange_warp(a.p2p, bb, lane);
         if (lane == 0) *a.p2p.out = gbest;
     }
 }

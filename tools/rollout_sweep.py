@@ -39,9 +39,11 @@ VARIANTS = [("auto", {}), ("split 1", {"BLF_CCM_TUNE_ROLLOUT_SPLIT": 1, "BLF_CCM
             ("ws2 C=3 (cp.async ring, 2 launches)", {"BLF_CCM_TUNE_ROLLOUT_WS": 3}),
             ("ws2 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 7}),
             ("ws3 C=3 (TMA twists, fused reduction)", {"BLF_CCM_TUNE_ROLLOUT_WS": 13}),
-            ("ws3 C=5", {"BLF_CCM_TUNE_ROLLOUT_WS": 15}), ("ws3 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 17})]
+            ("ws3 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 17}),
+            ("ws4 C=3 (4 lanes per chain, TMA, fused reduction)", {"BLF_CCM_TUNE_ROLLOUT_WS": 23}),
+            ("ws4 C=5", {"BLF_CCM_TUNE_ROLLOUT_WS": 25}), ("ws4 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 27})]
 
-for samples in (4096, 16384, 65536):
+for samples in (4096, 1024, 16384, 65536):
     chains = FEET * samples
     n = chains * H
     st = syn.make_states(min(n, 1 << 20), seed=45)
@@ -67,6 +69,6 @@ for samples in (4096, 16384, 65536):
             if base_cost is None:
                 base_cost = cost
             err = float(np.max(np.abs(cost - base_cost) / np.maximum(np.abs(base_cost), 1e-300)))
-            print(f"  {name:40s} {ms*1e3:8.1f} us/step  {n/ms/1e6:8.2f} G evals/s  argmin {best[1]:6d}  "
+            print(f"  {name:52s} {ms*1e3:8.1f} us/step  {n/ms/1e6:8.2f} G evals/s  argmin {best[1]:6d}  "
                   f"max cost dev vs first variant {err:.1e}", flush=True)
             del b, rb, calls, sets
