@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost a pointer test unless a profiler is attached
 
 #include <algorithm>
 #include <atomic>
@@ -163,8 +164,18 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
+// One NVTX range per C-ABI call, named after the entry point (nsys / ncu --nvtx show the host side
+// of every call: argument checks, launches, and for the _host entry points the whole pipeline).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 #define CHECK_HANDLE(h)                                                        \
     if (!valid(h)) return fail(BLF_CCM_ERR_INVALID_HANDLE, "invalid handle"); \
+    NvtxRange nvtx_range_(__func__);                                           \
     DeviceGuard dev_guard_((h)->device);                                       \
     if (dev_guard_.err != cudaSuccess)                                         \
     return fail(BLF_CCM_ERR_CUDA, "cudaSetDevice(%d): %s", (h)->device, cudaGetErrorString(dev_guard_.err))
