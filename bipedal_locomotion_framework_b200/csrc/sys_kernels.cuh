@@ -1155,6 +1155,316 @@ ccm_rollout_ws4_kernel(const __grid_constant__ RolloutArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fifth form: the hand-over unit is a BOX of eight steps, the producer's step loop is straight-line
+// code, and nothing but the pose recurrence is left on the producer warp.
+//
+// ncu on the third form (profiles/r02_ncu_rollout_ws3_details.txt): the lone producer warp issues
+// one instruction every 3.2 cycles -- 124 instructions and 391 cycles per step with the Baumgarte
+// term.  The recurrence alone, timed in isolation (tools/micro/kin_step_lat.cu), takes 191 cycles
+// per step (75 FP64 instructions at 2.3 issue cycles each, chain k -> det -> 1/det -> beta -> FMA
+// ~105 cycles): half of the producer's time was control -- per step five branches, seven integer
+// compares, fourteen register moves rotating the prefetched twist, a try_wait and an arrive every
+// third step; per box an elected lane issuing six TMA copies while 31 lanes wait.  A single warp
+// has nothing else to issue while a branch resolves or an mbarrier answers (~90 cycles).  Here
+//   * a pose stage group IS a twist box: eight steps.  The producer waits and signals once per box;
+//     the eight steps in between are one basic block with immediate shared-memory offsets; only the
+//     last, partial box runs a rolled loop;
+//   * the barriers of box b + 1 are TESTED (mbarrier.test_wait, non-blocking) in the middle of box
+//     b, so their latency overlaps the arithmetic and the box border costs no wait in the steady
+//     state; a blocking wait runs only when a test said "not yet";
+//   * a LOADER warp (one lane) owns the TMA descriptors: it waits for the consumers to release a
+//     twist slot and issues the six tensor copies, up to four boxes ahead of the producer;
+//   * consumers read the twists of their steps from the SAME box in shared memory (six LDS) instead
+//     of global memory (the third form spends ~45 integer instructions per step on six 64-bit
+//     plane pointers); every consumer owns a fixed range of the eight steps of a box;
+//   * warp roles follow the scheduler map measured in tools/micro/fp64_lat.cu and warp_slots.cu
+//     (see Ws5Cfg): the producer shares its FP64 pipe with the idle loader and, when two CTAs share
+//     an SM, with the lightest consumer of the other tile;
+//   * two rings: four twist boxes (released by the consumers) and three pose groups.
+// Reduction, arg-min and peer exchange are fused as in the third form.  Same preconditions.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kWs5TwSlots = 4;
+constexpr int kWs5PoseSlots = 3;
+constexpr int kWs5PoseBytes = kWs3BoxSteps * kWs2StageDoubles * 8;   // 20 480: eight stages of (p, e1, e2, R22) x 32 lanes
+
+// Warp roles.  Warp w of a CTA runs on sub-partition (w + r) mod 4, and when two CTAs share an SM the
+// second one's r is the first one's + 1 (tools/micro/warp_slots.cu: warp ids 0 1 2 3 4 5 6 7 and
+// 9 10 11 8 13 14 15 12), so warp i of one CTA shares a scheduler with warp i + 1 of the other:
+// warps 1 and 3 sit beside the OTHER tile's producer.  Layouts (steps of every eight-step box):
+//   0: five warps;  producer 0, loader 4, consumers 1 2 3 take steps 0-2 3-5 6-7
+//   1: eight warps; producer 0, loader 4, consumers 2 6 1 3 take steps 0-2 3-5 6 7 (the two warps
+//      that share a scheduler with a producer get one step each), warps 5 7 idle
+//   2: eight warps; consumers 2 6 1 3 take two steps each
+struct Ws5Role {
+    int k;       // consumer index (column of the partial-cost table), -1: none
+    int first;   // first step of the box
+    int count;
+};
+
+template <int LAYOUT>
+struct Ws5Cfg {
+    static constexpr int kConsumers = LAYOUT == 0 ? 3 : 4;
+    static constexpr int kWarps = LAYOUT == 0 ? 5 : 8;
+    static constexpr int kThreads = kWarp * kWarps;
+    static constexpr int kBarBytes = 128;
+    static constexpr int kSmemBytes = kWs5TwSlots * kWs3BoxBytes + kWs5PoseSlots * kWs5PoseBytes + kBarBytes +
+                                      kWarp * kConsumers * 8;
+    __device__ static Ws5Role role(int warp)
+    {
+        if (LAYOUT == 0) {
+            if (warp >= 1 && warp <= 3) return Ws5Role{warp - 1, 3 * (warp - 1), warp == 3 ? 2 : 3};
+            return Ws5Role{-1, 0, 0};
+        }
+        const bool weighted = LAYOUT == 1;
+        switch (warp) {
+        case 2: return weighted ? Ws5Role{0, 0, 3} : Ws5Role{0, 0, 2};
+        case 6: return weighted ? Ws5Role{1, 3, 3} : Ws5Role{1, 2, 2};
+        case 1: return weighted ? Ws5Role{2, 6, 1} : Ws5Role{2, 4, 2};
+        case 3: return weighted ? Ws5Role{3, 7, 1} : Ws5Role{3, 6, 2};
+        default: return Ws5Role{-1, 0, 0};
+        }
+    }
+};
+
+// Rollout costs of one 32-chain tile from the consumers' partial sums (cst[lane][parts], summed in
+// index order like ccm_cost_reduce_kernel), arg-min over the tile, and -- in the last CTA to get
+// here -- over the grid, plus the fused peer exchange.  Called by warp 0 after a __syncthreads().
+__device__ __forceinline__ void rollout_tile_reduce(const RolloutArgs& a, const double* cst, int parts,
+                                                    long long wbase, int lane, bool* s_last)
+{
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    CostIdx mine{inf, 0x7fffffffffffffffLL};
+    {
+        const int feet = a.feet;
+        const long long ro = wbase / feet + lane;          // 32 % feet == 0: tiles hold whole rollouts
+        if (lane < kWarp / feet && ro < a.n_rollouts) {
+            const double* p = cst + lane * feet * parts;
+            double sum = 0.0;
+            for (int j = 0; j < feet * parts; ++j) sum += p[j];
+            if (a.cost) a.cost[ro] = sum;
+            mine.cost = sum;
+            mine.idx = a.index_base + ro;
+            if (!(sum == sum)) mine = CostIdx{inf, 0x7fffffffffffffffLL};   // NaN never wins
+        }
+    }
+    mine = warp_best(mine);
+    if (lane == 0) {
+        a.block_best[blockIdx.x] = mine;
+        __threadfence();
+        const unsigned int done = atomicAdd(a.counter, 1u);
+        *s_last = (done == gridDim.x - 1);
+    }
+    __syncwarp();
+    if (!*s_last) return;
+    __threadfence();
+    CostIdx b{inf, 0x7fffffffffffffffLL};
+    for (unsigned int j = lane; j < gridDim.x; j += kWarp) {
+        CostIdx cand;
+        cand.cost = *reinterpret_cast<volatile double*>(&a.block_best[j].cost);
+        cand.idx = *reinterpret_cast<volatile long long*>(&a.block_best[j].idx);
+        if (better(cand.cost, cand.idx, b.cost, b.idx)) b = cand;
+    }
+    b = warp_best(b);
+    if (b.idx == 0x7fffffffffffffffLL) b.idx = -1;  // nothing comparable (empty / all NaN)
+    if (lane == 0) {
+        *a.best = b;
+        *a.counter = 0u;
+    }
+    if (a.p2p.nranks > 0) {   // fused collective: this rank's pair goes straight to the peers' mailboxes
+        const CostIdx gbest = p2p_exchange_warp(a.p2p, b, lane);
+        if (lane == 0) *a.p2p.out = gbest;
+    }
+}
+
+template <bool HET, bool BAUM, int LAYOUT>
+__global__ void __launch_bounds__(Ws5Cfg<LAYOUT>::kThreads)
+ccm_rollout_ws5_kernel(const __grid_constant__ RolloutArgs a)
+{
+    using Cfg = Ws5Cfg<LAYOUT>;
+    constexpr int C = Cfg::kConsumers;
+    constexpr int BS = kWs3BoxSteps;
+    constexpr int NT = kWs5TwSlots, NP = kWs5PoseSlots;
+    constexpr int PL = BS * kWarp;                       // doubles per twist plane of a box
+    constexpr int kLoaderWarp = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long wbase = static_cast<long long>(blockIdx.x) * kWarp;
+    const long long c = wbase + lane;
+    const bool on = c < a.chains;
+    const int H = a.horizon;
+    const int nbox = (H + BS - 1) / BS;
+
+    double* twbuf = reinterpret_cast<double*>(smem_raw);                       // [NT][plane][step][lane]
+    double* poses = twbuf + NT * kWs3BoxBytes / 8;                             // [NP][step][5 double2][lane]
+    const uint32_t bars = ptx::smem_addr(poses + NP * kWs5PoseBytes / 8);
+    const uint32_t twfull0 = bars;                    // NT barriers: a twist box has landed (TMA bytes)
+    const uint32_t twempty0 = twfull0 + 8 * NT;       // NT barriers, C arrivals: the consumers have read it
+    const uint32_t full0 = twempty0 + 8 * NT;         // NP barriers, 1 arrival: a pose group is written
+    const uint32_t empty0 = full0 + 8 * NP;           // NP barriers, C arrivals: a pose group is consumed
+    double* cst = poses + NP * kWs5PoseBytes / 8 + Cfg::kBarBytes / 8;         // [32][C] partial costs
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NT; ++i) {
+            ptx::mbar_init(twfull0 + 8 * i, 1);
+            ptx::mbar_init(twempty0 + 8 * i, C);
+        }
+        for (int i = 0; i < NP; ++i) {
+            ptx::mbar_init(full0 + 8 * i, 1);
+            ptx::mbar_init(empty0 + 8 * i, C);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kLoaderWarp) {
+        // ---------------- loader: twist boxes by TMA, as far ahead as the ring allows -------------
+        if (lane == 0) {
+            for (int b = 0; b < nbox; ++b) {
+                const int slot = b & (NT - 1);
+                if (b >= NT) {   // the slot held box b - NT: every consumer must have read it
+                    ptx::mbar_wait(twempty0 + 8 * slot, ((b - NT) / NT) & 1);
+                    ptx::fence_async_smem();
+                }
+                const uint32_t bar = twfull0 + 8 * slot;
+                const uint32_t dst = ptx::smem_addr(twbuf) + slot * kWs3BoxBytes;
+                ptx::mbar_arrive_expect_tx(bar, kWs3BoxBytes);
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    ptx::tma_load_2d(dst + j * (PL * 8), &a.twmap[j], static_cast<int>(wbase), b * BS, bar);
+            }
+        }
+    } else if (warp == 0) {
+        // ---------------- producer: the pose recurrence, one basic block per box ------------------
+        Pose s{};
+        if (on) {
+            s.p = V3{__ldg(a.pos0[0] + c), __ldg(a.pos0[1] + c), __ldg(a.pos0[2] + c)};
+            s.c0 = V3{__ldg(a.rot0[0] + c), __ldg(a.rot0[3] + c), __ldg(a.rot0[6] + c)};
+            s.c1 = V3{__ldg(a.rot0[1] + c), __ldg(a.rot0[4] + c), __ldg(a.rot0[7] + c)};
+            s.c2 = V3{__ldg(a.rot0[2] + c), __ldg(a.rot0[5] + c), __ldg(a.rot0[8] + c)};
+        }
+        const double half_rho = a.half_rho, dT = a.dT;
+        auto step = [&](const double* tw, double2* o, int q) {   // publish the pose of step q, then integrate it
+            const double* r = tw + q * kWarp;
+            const V3 v{r[0], r[PL], r[2 * PL]};
+            const V3 w{r[3 * PL], r[4 * PL], r[5 * PL]};
+            double2* oq = o + q * (5 * kWarp);
+            oq[0 * kWarp] = make_double2(s.p.x, s.p.y);
+            oq[1 * kWarp] = make_double2(s.p.z, s.c0.x);
+            oq[2 * kWarp] = make_double2(s.c0.y, s.c0.z);
+            oq[3 * kWarp] = make_double2(s.c1.x, s.c1.y);
+            oq[4 * kWarp] = make_double2(s.c1.z, s.c2.z);
+            kin_euler_step<BAUM>(s, v, w, half_rho, dT);
+        };
+        int ps = 0;                        // pose slot of box b (b mod NP)
+        uint32_t pose_use = 0;             // b div NP
+        bool tw_ready = false, pose_free = true;   // what the tests issued during the previous box found
+        for (int b = 0; b < nbox; ++b) {
+            const int ts = b & (NT - 1);
+            if (!tw_ready) ptx::mbar_wait(twfull0 + 8 * ts, (b / NT) & 1);
+            if (!pose_free) ptx::mbar_wait(empty0 + 8 * ps, (pose_use - 1) & 1);   // pose group of box b - NP consumed
+            const double* tw = twbuf + ts * (kWs3BoxBytes / 8) + lane;
+            double2* o = reinterpret_cast<double2*>(poses + ps * (kWs5PoseBytes / 8)) + lane;
+            // the next box's barriers, tested while this box is integrated
+            const int nps = ps + 1 == NP ? 0 : ps + 1;
+            const uint32_t nuse = ps + 1 == NP ? pose_use + 1 : pose_use;
+            auto test_next = [&]() {
+                tw_ready = ptx::mbar_test(twfull0 + 8 * ((b + 1) & (NT - 1)), ((b + 1) / NT) & 1);
+                pose_free = (b + 1 < NP) || ptx::mbar_test(empty0 + 8 * nps, (nuse - 1) & 1);
+            };
+            if ((b + 1) * BS <= H) {
+#pragma unroll
+                for (int q = 0; q < BS; ++q) {
+                    if (q == BS - 3) test_next();
+                    step(tw, o, q);
+                }
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < H - b * BS; ++q) step(tw, o, q);
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(full0 + 8 * ps);
+            ps = nps;
+            pose_use = nuse;
+        }
+        if (on && a.write_final) {
+            a.pos_out[0][c] = s.p.x; a.pos_out[1][c] = s.p.y; a.pos_out[2][c] = s.p.z;
+            a.rot_out[0][c] = s.c0.x; a.rot_out[1][c] = s.c1.x; a.rot_out[2][c] = s.c2.x;
+            a.rot_out[3][c] = s.c0.y; a.rot_out[4][c] = s.c1.y; a.rot_out[5][c] = s.c2.y;
+            a.rot_out[6][c] = s.c0.z; a.rot_out[7][c] = s.c1.z; a.rot_out[8][c] = s.c2.z;
+        }
+    } else if (Cfg::role(warp).k >= 0) {
+        // ---------------- consumer: contact wrench + cost of its steps of every box ---------------
+        const Ws5Role role = Cfg::role(warp);
+        const int k = role.k;
+        V3 p0{}, n1{}, n2{};
+        Prm q = a.uni;
+        if (on) {
+            p0 = V3{__ldg(a.nul[0] + c), __ldg(a.nul[1] + c), __ldg(a.nul[2] + c)};
+            n1 = V3{__ldg(a.nul[3] + c), __ldg(a.nul[6] + c), __ldg(a.nul[9] + c)};
+            n2 = V3{__ldg(a.nul[4] + c), __ldg(a.nul[7] + c), __ldg(a.nul[10] + c)};
+            if constexpr (HET)
+                q = make_prm(__ldg(a.prm[0] + c), __ldg(a.prm[1] + c), __ldg(a.prm[2] + c),
+                             __ldg(a.prm[3] + c));
+        }
+        const V3 fref{a.ref[0], a.ref[1], a.ref[2]}, tref{a.ref[3], a.ref[4], a.ref[5]};
+        const double wf = a.wf, wt = a.wt;
+        double acc = 0.0;
+        int ps = 0;
+        uint32_t pose_use = 0;
+        for (int b = 0; b < nbox; ++b) {
+            const int ts = b & (NT - 1);
+            ptx::mbar_wait(full0 + 8 * ps, pose_use & 1);
+            ptx::mbar_wait(twfull0 + 8 * ts, (b / NT) & 1);   // landed long ago; makes the TMA's writes visible to this warp
+            const double* tw = twbuf + ts * (kWs3BoxBytes / 8) + lane;
+            const double2* in = reinterpret_cast<const double2*>(poses + ps * (kWs5PoseBytes / 8)) + lane;
+            const int steps = min(BS, H - b * BS);
+            const int last = min(role.first + role.count, steps);
+#pragma unroll 1
+            for (int s = role.first; s < last; ++s) {
+                {
+                    const double* r = tw + s * kWarp;
+                    const double2* is = in + s * (5 * kWarp);
+                    const double2 a0 = is[0 * kWarp], a1 = is[1 * kWarp], a2 = is[2 * kWarp], a3 = is[3 * kWarp],
+                                  a4 = is[4 * kWarp];
+                    State x;
+                    x.v = V3{r[0], r[PL], r[2 * PL]};
+                    x.w = V3{r[3 * PL], r[4 * PL], r[5 * PL]};
+                    x.p = V3{a0.x, a0.y, a1.x};
+                    x.e1 = V3{a1.y, a2.x, a2.y};
+                    x.e2 = V3{a3.x, a3.y, a4.x};
+                    x.R02 = 0.0; x.R12 = 0.0;
+                    x.R22 = a4.y;
+                    x.p0 = p0; x.n1 = n1; x.n2 = n2;
+                    Result res;
+                    eval_contact<M_WRENCH>(x, q, res);
+                    if (on) {
+                        const V3 df = res.force - fref;
+                        const V3 dt = res.torque - tref;
+                        acc = acc + (wf * (df.x * df.x + df.y * df.y + df.z * df.z) +
+                                     wt * (dt.x * dt.x + dt.y * dt.y + dt.z * dt.z));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {   // this warp's share of the C arrivals that free the box and the group
+                ptx::mbar_arrive(empty0 + 8 * ps);
+                ptx::mbar_arrive(twempty0 + 8 * ts);
+            }
+            if (++ps == NP) {
+                ps = 0;
+                ++pose_use;
+            }
+        }
+        cst[lane * C + k] = acc;    // chains past the end: 0, never read
+    }
+
+    __syncthreads();
+    if (warp == 0) rollout_tile_reduce(a, cst, C, wbase, lane, &s_last);
+}
+
+// ------------------------------------------------------------------------------------------------
 // J^T * wrench accumulation
 // ------------------------------------------------------------------------------------------------
 

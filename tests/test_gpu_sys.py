@@ -686,7 +686,7 @@ def test_non_finite_inputs_stay_local_and_never_win_the_argmin(torch, batch, so)
     assert batch.decode_best(allnan["best"])[1] == -1
 
 
-@pytest.mark.parametrize("variant", [23, 25, 27, 13, 17, 3, 7])
+@pytest.mark.parametrize("variant", [33, 34, 35, 23, 25, 27, 13, 17, 3, 7])
 @pytest.mark.parametrize("het,rho,nr,feet,H", [(True, 3.0, 100, 2, 31), (False, 0.0, 33, 1, 2),
                                                (True, 0.0, 10, 3, 10), (False, 0.5, 700, 2, 64),
                                                (False, 0.01, 4096, 2, 100), (False, 2.0, 37, 4, 17),
@@ -694,7 +694,9 @@ def test_non_finite_inputs_stay_local_and_never_win_the_argmin(torch, batch, so)
 def test_rollout_warp_specialised_variant_vs_oracle(torch, so, variant, het, rho, nr, feet, H):
     """The warp-specialised rollout kernels forced for every template instance, incl. horizons
     shorter than a TMA box / the stage ring, ragged tiles, an odd number of chains and a foot count
-    that does not divide 32 (where the TMA forms must hand over to the second).  variant 23/25/27:
+    that does not divide 32 (where the TMA forms must hand over to the second).  variant 33/34/35:
+    ccm_rollout_ws5_kernel (hand-over per eight-step box, straight-line producer, consumers read the
+    twists from the TMA box; warp layout 0/1/2 of Ws5Cfg: 3 or 4 consumer warps and a TMA loader warp; ONE launch); 23/25/27:
     ccm_rollout_ws4_kernel (four lanes per chain, TMA twists, fused reduction: ONE launch) with 3/5/7
     consumer warps; 13/17: ccm_rollout_ws3_kernel (one lane per chain, otherwise the same); 3/7:
     ccm_rollout_ws2_kernel + ccm_cost_reduce_kernel (two launches)."""

@@ -41,7 +41,12 @@ VARIANTS = [("auto", {}), ("split 1", {"BLF_CCM_TUNE_ROLLOUT_SPLIT": 1, "BLF_CCM
             ("ws3 C=3 (TMA twists, fused reduction)", {"BLF_CCM_TUNE_ROLLOUT_WS": 13}),
             ("ws3 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 17}),
             ("ws4 C=3 (4 lanes per chain, TMA, fused reduction)", {"BLF_CCM_TUNE_ROLLOUT_WS": 23}),
-            ("ws4 C=5", {"BLF_CCM_TUNE_ROLLOUT_WS": 25}), ("ws4 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 27})]
+            ("ws4 C=5", {"BLF_CCM_TUNE_ROLLOUT_WS": 25}), ("ws4 C=7", {"BLF_CCM_TUNE_ROLLOUT_WS": 27}),
+            ("ws5 layout 0 (box hand-over, loader warp, 3 consumers)", {"BLF_CCM_TUNE_ROLLOUT_WS": 33}),
+            ("ws5 layout 1 (4 consumers, steps 3/3/1/1)", {"BLF_CCM_TUNE_ROLLOUT_WS": 34}), ("ws5 layout 2 (4 consumers, steps 2/2/2/2)", {"BLF_CCM_TUNE_ROLLOUT_WS": 35})]
+if os.environ.get("SWEEP_ONLY"):   # e.g. SWEEP_ONLY=auto,ws3,ws5
+    keep = os.environ["SWEEP_ONLY"].split(",")
+    VARIANTS = [v for v in VARIANTS if any(v[0].startswith(k) for k in keep)]
 
 for samples in (4096, 1024, 16384, 65536):
     chains = FEET * samples
