@@ -643,6 +643,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, int c
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// bring a tensor map (kernel parameter) into the descriptor cache ahead of its first use
+__device__ __forceinline__ void prefetch_tensormap(const void* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 }  // namespace ptx
 
 template <bool HET, bool BAUM, int C>
@@ -1316,6 +1321,12 @@ ccm_rollout_ws5_kernel(const __grid_constant__ RolloutArgs a)
         }
         ptx::fence_mbar_init();
     }
+    if (warp == kLoaderWarp && lane < 6) ptx::prefetch_tensormap(&a.twmap[lane]);   // parameters: safe before the wait
+    // Programmatic dependent launch, LATE form: this grid's CTAs may become resident while the
+    // previous kernel of the stream drains (its CTAs signal after their step loops, below), but
+    // nothing global is touched before that kernel has completed.  Signalling at the START (as the
+    // streaming kernels do) parks the next launch's CTAs beside a latency-bound kernel and slows it.
+    ptx::grid_dep_wait();
     __syncthreads();
 
     if (warp == kLoaderWarp) {
@@ -1460,6 +1471,7 @@ ccm_rollout_ws5_kernel(const __grid_constant__ RolloutArgs a)
         cst[lane * C + k] = acc;    // chains past the end: 0, never read
     }
 
+    ptx::grid_dep_launch_dependents();   // the next launch may take the slots this CTA is about to free
     __syncthreads();
     if (warp == 0) rollout_tile_reduce(a, cst, C, wbase, lane, &s_last);
 }
