@@ -873,6 +873,13 @@ def run_ours(args):
                 pv, ppasses, _, _, pwhat = cpu_reference_pass(st, cores, 2.0, prefer_reference=False)
                 cb["port_value"] = pv
                 cb["port_sample"] = f"best of {ppasses} passes, {pwhat}"
+            # the same path on ONE thread beside the all-cores figure
+            n1 = N_MPC // 8
+            st1 = {k: (v[:n1] if hasattr(v, "shape") and v.shape[:1] == (N_MPC,) else v) for k, v in st.items()}
+            st1["n"] = n1
+            v1, p1, _, _, _ = cpu_reference_pass(st1, 1, min_seconds=1.0)
+            cb["single_thread_value"] = v1
+            cb["single_thread_sample"] = f"best of {p1} passes over the first {n1} states of that sample, 1 thread"
             line["cpu_baseline"] = cb
     if cx.rank == 0:
         emit(line)
