@@ -1181,12 +1181,16 @@ ccm_rollout_ws4_kernel(const __grid_constant__ RolloutArgs a)
 //     twist slot and issues the six tensor copies, up to four boxes ahead of the producer;
 //   * consumers read the twists of their steps from the SAME box in shared memory (six LDS) instead
 //     of global memory (the third form spends ~45 integer instructions per step on six 64-bit
-//     plane pointers); every consumer owns a fixed range of the eight steps of a box;
+//     plane pointers); every consumer owns a fixed range of the eight steps of a box (the last box
+//     of the horizon is dealt round the consumers step by step: nothing follows to hide a long tail);
 //   * warp roles follow the scheduler map measured in tools/micro/fp64_lat.cu and warp_slots.cu
 //     (see Ws5Cfg): the producer shares its FP64 pipe with the idle loader and, when two CTAs share
 //     an SM, with the lightest consumer of the other tile;
 //   * two rings: four twist boxes (released by the consumers) and three pose groups.
+//   * programmatic dependent launch in its LATE form (signal after the step loops, wait before the
+//     first global access), so the next launch's latency and prologue overlap this one's tail.
 // Reduction, arg-min and peer exchange are fused as in the third form.  Same preconditions.
+// Measured (profiles/r02_rollout_*.log): 30.8 -> 21.1 us per 4096 x 2 x 100 step with rho = 0.01.
 // ------------------------------------------------------------------------------------------------
 
 constexpr int kWs5TwSlots = 4;
@@ -1431,9 +1435,15 @@ ccm_rollout_ws5_kernel(const __grid_constant__ RolloutArgs a)
             const double* tw = twbuf + ts * (kWs3BoxBytes / 8) + lane;
             const double2* in = reinterpret_cast<const double2*>(poses + ps * (kWs5PoseBytes / 8)) + lane;
             const int steps = min(BS, H - b * BS);
-            const int last = min(role.first + role.count, steps);
+            // The last box has nothing behind it to hide an uneven split: its steps go round the
+            // consumers one by one, so the tail after the producer's last step is ceil(steps / C)
+            // evaluations long instead of role.count.
+            const bool tail = b == nbox - 1;
+            const int first = tail ? k : role.first;
+            const int last = tail ? steps : min(role.first + role.count, steps);
+            const int stride = tail ? C : 1;
 #pragma unroll 1
-            for (int s = role.first; s < last; ++s) {
+            for (int s = first; s < last; s += stride) {
                 {
                     const double* r = tw + s * kWarp;
                     const double2* is = in + s * (5 * kWarp);

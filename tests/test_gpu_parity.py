@@ -589,9 +589,15 @@ def test_config5_full_size_256m_properties(torch, batch, oracle):
     n_rollouts, rl = 1 << 20, 256
     n = n_rollouts * rl
     dev = torch.device("cuda", 0)
-    planes, _ = syn.make_planes_torch(n, dev, seed=46)
     ref_wrench, weights = [0.0, 0.0, 30.0, 0.0, 0.0, 0.0], [1.0, 10.0]
-    out, cost, best = batch.rollout_cost_argmin(planes, rl, ref_wrench, weights, None, mask=FULL)
+    try:
+        planes, _ = syn.make_planes_torch(n, dev, seed=46)
+        out, cost, best = batch.rollout_cost_argmin(planes, rl, ref_wrench, weights, None, mask=FULL)
+    except torch.cuda.OutOfMemoryError as e:   # another process took memory after the check above
+        planes = out = None
+        gc.collect()
+        torch.cuda.empty_cache()
+        pytest.skip(f"161 GB working set does not fit beside what else is on the device: {e}")
     torch.cuda.synchronize()
     # (i) oracle parity: every 4099th state (65 489 states), then the first and the last 2^20
     for what, idx in (("strided", torch.arange(0, n, 4099, device=dev)),
@@ -631,6 +637,9 @@ def test_config5_full_size_256m_properties(torch, batch, oracle):
         assert bool(torch.isfinite(p).all())
     for p in out["autodyn"]:
         assert bool(torch.isfinite(p).all())
+    del planes, out, cost, best, bits
+    gc.collect()
+    torch.cuda.empty_cache()   # hand the 161 GB back before the next test
 
 
 @pytest.mark.parametrize("n", [2, 33, 4097, 65536, 65537, 200003])
