@@ -118,6 +118,7 @@ struct blf_ccm_handle {
     int tune_rollout_ws = 0;     // BLF_CCM_TUNE_ROLLOUT_WS: 1 force / 2 forbid the warp-specialised rollout
     int tune_no_pack = 0;        // BLF_CCM_TUNE_NO_PACK=1: J^T wrench for narrow Jacobians with the column-per-lane kernel
     int tune_no_rows = 0;        // BLF_CCM_TUNE_NO_ROWS=1: J^T wrench without base/out row staging
+    int tune_gf_stages = 0;      // BLF_CCM_TUNE_GF_STAGES=4: lane-packed J^T wrench with the four-stage ring (default two: twice the warps per SM)
     int tune_no_pdl = 0;         // BLF_CCM_TUNE_NO_PDL=1: plain launches (no programmatic dependent launch)
     int tune_rollout_chunk_mb = 0;  // BLF_CCM_TUNE_ROLLOUT_CHUNK_MB: twist bytes per time chunk of the host rollout (default 8)
     int tune_host_up = 0, tune_host_down = 0;   // BLF_CCM_TUNE_HOST_UP / _DOWN: copy streams per direction of the host evaluation
@@ -231,6 +232,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_rls_pipe = env_int("BLF_CCM_TUNE_RLS_PIPE");
     h->tune_rollout_chunk_mb = env_int("BLF_CCM_TUNE_ROLLOUT_CHUNK_MB");
     h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
+    h->tune_gf_stages = env_int("BLF_CCM_TUNE_GF_STAGES");
     h->tune_no_pack = env_int("BLF_CCM_TUNE_NO_PACK");
     h->tune_rollout_ws = env_int("BLF_CCM_TUNE_ROLLOUT_WS");
     if (const char* v = getenv("BLF_CCM_HOST_THREADS")) h->host_threads = atoi(v);

@@ -1725,10 +1725,12 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
 // because no sum crosses a group.  A ring stage holds the Jacobians of G consecutive systems
 // (G * cps contacts, contiguous in memory): one mbarrier wait + one re-arm per G systems.  The
 // instruction stream per iteration is the one of the kernel above, but it now covers G contacts.
+// NST = ring stages per warp: 2 by default (twice the warps per SM of a four-stage ring, measured
+// 84 -> 107 % of HBM at 6 columns), 4 with BLF_CCM_TUNE_GF_STAGES=4.
 // (A first lane-packed attempt in round 1 split the CONTACTS of one system over the groups and
 // needed ordered shuffles; it gained nothing and was removed.)
 // ------------------------------------------------------------------------------------------------
-template <bool HET, int NCP>
+template <bool HET, int NCP, int NST>
 __global__ void __launch_bounds__(128)
 ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
 {
@@ -1747,31 +1749,31 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
     const int jd = 6 * ncols;
     const int nstage = (nsys + G - 1) / G;     // G systems per stage
 
-    const int per_warp = kGfStages * stage_bytes + kWarp * 48 + 128 + a.row_bytes;
+    const int per_warp = NST * stage_bytes + kWarp * 48 + 128 + a.row_bytes;
     unsigned char* ws = smem_raw + static_cast<size_t>(warp) * per_warp;
-    double* wsm = reinterpret_cast<double*>(ws + kGfStages * stage_bytes);
-    const uint32_t bar0 = ptx::smem_addr(ws + kGfStages * stage_bytes + kWarp * 48);
-    const uint32_t rbar = bar0 + 8 * kGfStages;
-    double* rows = reinterpret_cast<double*>(ws + kGfStages * stage_bytes + kWarp * 48 + 128);
+    double* wsm = reinterpret_cast<double*>(ws + NST * stage_bytes);
+    const uint32_t bar0 = ptx::smem_addr(ws + NST * stage_bytes + kWarp * 48);
+    const uint32_t rbar = bar0 + 8 * NST;
+    double* rows = reinterpret_cast<double*>(ws + NST * stage_bytes + kWarp * 48 + 128);
     const uint32_t stage0 = ptx::smem_addr(ws);
     const double* jac0 = a.jac + c0 * jd;
     const long long row0 = sys0 * ncols;
     const uint32_t rbytes = static_cast<uint32_t>(nsys) * ncols * 8u;
     const bool staged = a.row_bytes > 0 && ((row0 | (static_cast<long long>(nsys) * ncols)) & 1) == 0;
 
-    auto arm = [&](int q) {   // lane 0: the Jacobians of systems q*G .. q*G+G-1 into ring slot q % kGfStages
+    auto arm = [&](int q) {   // lane 0: the Jacobians of systems q*G .. q*G+G-1 into ring slot q % NST
         const int first = q * G * cps;
         const uint32_t bytes = static_cast<uint32_t>(min(G * cps, ncont - first)) * jd * 8u;
-        const uint32_t bar = bar0 + 8 * (q & (kGfStages - 1));
+        const uint32_t bar = bar0 + 8 * (q & (NST - 1));
         ptx::mbar_arrive_expect_tx(bar, bytes);
-        ptx::bulk_g2s(stage0 + (q & (kGfStages - 1)) * stage_bytes, jac0 + static_cast<long long>(first) * jd,
+        ptx::bulk_g2s(stage0 + (q & (NST - 1)) * stage_bytes, jac0 + static_cast<long long>(first) * jd,
                       bytes, bar);
     };
 
     ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s <= kGfStages; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s <= NST; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
         ptx::fence_mbar_init();
     }
     ptx::grid_dep_wait();
@@ -1781,7 +1783,7 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
             ptx::bulk_g2s(ptx::smem_addr(rows), a.base + row0, rbytes, rbar);
         }
 #pragma unroll
-        for (int q = 0; q < kGfStages; ++q)
+        for (int q = 0; q < NST; ++q)
             if (q < nstage) arm(q);
     }
     __syncwarp();
@@ -1858,8 +1860,8 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
             else __stcs(a.out + row, acc);
         }
         __syncwarp();   // every lane is done with this stage
-        if (lane == 0 && sq + kGfStages < nstage) arm(sq + kGfStages);
-        if (++slot == kGfStages) {
+        if (lane == 0 && sq + NST < nstage) arm(sq + NST);
+        if (++slot == NST) {
             slot = 0;
             parity ^= 1u;
         }

@@ -6,7 +6,7 @@ WL=${@:-rollout_small rollout_large rollout_large_rho rollout_full genforce genf
 O=gpurun_out/$TAG
 mkdir -p $O
 for W in $WL; do
-  case $W in rollout_small) K=ccm_rollout;; rollout*) K=ccm_rollout_kernel;; genforce*) K=ccm_genforce_kernel;; *) K=sys_kin_euler_kernel;; esac
+  case $W in rollout_small) K=ccm_rollout;; rollout*) K=ccm_rollout_kernel;; genforce_6x2|genforce_12x2|genforce_narrow) K=ccm_genforce_packed_kernel;; genforce*) K=ccm_genforce_kernel;; *) K=sys_kin_euler_kernel;; esac
   python tools/prof_sys.py $W > $O/plain_$W.log 2>&1 && \
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o $O/$W python tools/prof_sys.py $W > $O/ncu_$W.log 2>&1
   tail -1 $O/ncu_$W.log

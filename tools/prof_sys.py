@@ -2,7 +2,7 @@
 """Launch a few iterations of one System-row kernel, for ncu (development aid, not the bench).
 
   python tools/prof_sys.py rollout_small | rollout_large | rollout_large_rho | rollout_full |
-                           genforce | genforce_small | euler
+                           genforce | genforce_small | genforce_narrow | genforce_6x2 | genforce_12x2 | euler
 """
 import os
 import sys
@@ -38,7 +38,8 @@ def main():
         call, out = RolloutBatch(b).prepare(nr, feet, H, 0.01, rho, tw, pos, rot, null,
                                             [0, 0, 30., 0, 0, 0], [1., 10.], mask=mask)
     elif what.startswith("genforce"):
-        ns, cps, ncols = {"genforce_small": (409600, 2, 29), "genforce_narrow": (1 << 21, 1, 6)}.get(
+        ns, cps, ncols = {"genforce_small": (409600, 2, 29), "genforce_narrow": (1 << 21, 1, 6),
+                          "genforce_6x2": (1 << 21, 2, 6), "genforce_12x2": (1 << 20, 2, 12)}.get(
             what, (1 << 21, 2, 29))
         n = ns * cps
         st = syn.make_states(min(n, 1 << 17), seed=49)

@@ -162,14 +162,14 @@ def gf_only():
     whole systems, ccm_genforce_packed_kernel) beside the column-per-lane kernel they replace."""
     from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
     rnd = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda") * 2 - 1
-    for no_pack in (0, 1):
-        b = make_batch(BLF_CCM_TUNE_NO_PACK=no_pack)
+    for no_pack, stages in ((0, 0), (0, 4), (1, 0)):
+        b = make_batch(BLF_CCM_TUNE_NO_PACK=no_pack, BLF_CCM_TUNE_GF_STAGES=stages)
         gf = GeneralizedForceBatch(b)
         shapes = ((409600, 2, 29), (1 << 21, 2, 29), (1 << 20, 4, 38), (1 << 21, 1, 6), (1 << 21, 2, 6),
                   (409600, 2, 6), (1 << 20, 2, 12), (409600, 2, 12), (1 << 20, 2, 16), (1 << 21, 2, 4),
                   (1 << 19, 8, 6), (1 << 20, 4, 12))
         for ns, cps, ncols in shapes:
-            if no_pack and ncols > 16:
+            if (no_pack or stages) and ncols > 16:
                 continue
             n = ns * cps
             st = syn.make_states(min(n, 1 << 18), seed=49)
@@ -184,10 +184,12 @@ def gf_only():
             ms = timeit(lambda i: cls[i % nb](), iters=50, warm=5)
             per_contact = 200 + 48 * ncols + 16 * ncols / cps
             row(f"J^T wrench systems={ns} contacts/system={cps} ncols={ncols}"
-                f"{' [column-per-lane kernel forced]' if no_pack else ''}", ms, n, per_contact)
+                f"{' [column-per-lane kernel forced]' if no_pack else ''}{' [four-stage ring]' if stages else ''}",
+                ms, n, per_contact)
             del Js, base, outs, cls, pl
             torch.cuda.empty_cache()
     os.environ.pop("BLF_CCM_TUNE_NO_PACK", None)
+    os.environ.pop("BLF_CCM_TUNE_GF_STAGES", None)
 
 
 def main():
