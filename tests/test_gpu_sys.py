@@ -734,6 +734,19 @@ def test_rollout_warp_specialised_variant_vs_oracle(torch, so, variant, het, rho
                                _dev(torch, rot0), _dev(torch, null), ref_w, wts,
                                param_planes=_dev(torch, prm), mask=0)
     assert np.array_equal(out2["cost"].cpu().numpy(), cost)     # deterministic
+    # every kernel form integrates through the same kin_euler_step: the final poses are bit-identical
+    # to the plain one-lane-per-chain kernel (the costs differ in the last bits: other summation order)
+    os.environ["BLF_CCM_TUNE_ROLLOUT_WS"] = "2"
+    try:
+        bp = ContinuousContactModelBatch(0)
+    finally:
+        os.environ.pop("BLF_CCM_TUNE_ROLLOUT_WS", None)
+    bp.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    plain = RolloutBatch(bp).run(nr, feet, H, 0.01, rho, _dev(torch, tw), _dev(torch, pos0),
+                                 _dev(torch, rot0), _dev(torch, null), ref_w, wts,
+                                 param_planes=_dev(torch, prm), mask=0, want_final=True)
+    assert torch.equal(plain["final_pos"], out["final_pos"]) and torch.equal(plain["final_rot"], out["final_rot"])
+    assert np.all(rel(plain["cost"].cpu().numpy()[:, None], cost[:, None]) <= 1e-13)
     # index_base and a NULL cost array through the fused reduction
     out3 = RolloutBatch(b).run(nr, feet, H, 0.01, rho, _dev(torch, tw), _dev(torch, pos0),
                                _dev(torch, rot0), _dev(torch, null), ref_w, wts,
