@@ -7,7 +7,7 @@ mkdir -p $O
 nvidia-smi --query-gpu=index,name,clocks.max.sm --format=csv > $O/gpus.csv 2>&1
 nvidia-smi topo -m > $O/topo.txt 2>&1
 nproc > $O/nproc.txt; lscpu | grep -E "Model name|Socket|NUMA|^CPU\(s\)" >> $O/nproc.txt
-timeout 600 python -m pytest tests/test_gpu_p2p.py tests/test_gpu_parity.py -m gpu -q -x -k "p2p or restore" > $O/pytest_p2p.log 2>&1; echo "pytest exit $?" >> $O/pytest_p2p.log
+timeout 900 python -m pytest tests/test_gpu_p2p.py tests/test_gpu_parity.py tests/test_gpu_sys.py -m gpu -q -x -k "p2p or restore or warp_specialised" > $O/pytest_p2p.log 2>&1; echo "pytest exit $?" >> $O/pytest_p2p.log
 tail -4 $O/pytest_p2p.log
 for n in $NS; do
   out=$O/bench_n$n
