@@ -45,16 +45,35 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     if not force and _newer(CUDA_LIB, cuda_sources()):
         return CUDA_LIB
-    # one CUDA translation unit + the host-only expansion helper (plain C++, passed through to g++)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", CUDA_LIB, os.path.join(_HERE, "csrc", "ccm_capi.cu"),
-           os.path.join(_HERE, "csrc", "host_expand.cpp"), "-lcudart", "-ldl", "-lpthread"]
+    # two CUDA translation units compiled side by side (ccm_capi.cu: C ABI + contact / estimator /
+    # system kernels; dyn_kernels.cu: the unrolled mass-matrix solves) + the host-only expansion
+    # helper (plain C++, passed through to g++); one device link-free shared library
+    from concurrent.futures import ThreadPoolExecutor
+
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    units = ["ccm_capi.cu", "dyn_kernels.cu", "host_expand.cpp"]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(name: str) -> tuple[str, str]:
+        obj = os.path.join(obj_dir, name.rsplit(".", 1)[0] + ".o")
+        cmd = [_nvcc(), *compile_flags, "-c", "-o", obj, os.path.join(_HERE, "csrc", name)]
+        if verbose and name.endswith(".cu"):
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on " + name + ":\n" + r.stdout)
+        return obj, r.stdout
+
+    with ThreadPoolExecutor(max_workers=len(units)) as ex:
+        results = list(ex.map(compile_one, units))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+        for _, out in results:
+            print(out)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", CUDA_LIB, *[o for o, _ in results], "-lcudart", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout)
-    if verbose:
-        print(r.stdout)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout)
     return CUDA_LIB
 
 

@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "ccm_kernels.cuh"
+#include "dyn_kernels.h"
 #include "host_expand.h"
 #include "rls_kernels.cuh"
 #include "sys_kernels.cuh"
@@ -124,6 +125,7 @@ struct blf_ccm_handle {
     int tune_host_up = 0, tune_host_down = 0;   // BLF_CCM_TUNE_HOST_UP / _DOWN: copy streams per direction of the host evaluation
     int tune_host_ramp = 1;      // BLF_CCM_TUNE_HOST_RAMP=0: equal chunks instead of the ramped schedule
     int tune_host_noexpand = 0;  // BLF_CCM_TUNE_HOST_NOEXPAND=1: measurement aid, the workers skip the expansion (results WRONG)
+    int tune_llt_general = 0;    // BLF_CCM_TUNE_LLT_GENERAL=1: mass-matrix solve with the block-level kernel whatever the size
     int tune_rls_pipe = 0;       // BLF_CCM_TUNE_RLS_PIPE=1: the plain one-estimator-per-thread RLS kernel instead of the pipelined one
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
@@ -230,6 +232,7 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->tune_host_down = env_int("BLF_CCM_TUNE_HOST_DOWN");
     if (const char* v = getenv("BLF_CCM_TUNE_HOST_RAMP")) h->tune_host_ramp = atoi(v);
     h->tune_rls_pipe = env_int("BLF_CCM_TUNE_RLS_PIPE");
+    h->tune_llt_general = env_int("BLF_CCM_TUNE_LLT_GENERAL");
     h->tune_rollout_chunk_mb = env_int("BLF_CCM_TUNE_ROLLOUT_CHUNK_MB");
     h->tune_no_rows = env_int("BLF_CCM_TUNE_NO_ROWS");
     h->tune_gf_stages = env_int("BLF_CCM_TUNE_GF_STAGES");

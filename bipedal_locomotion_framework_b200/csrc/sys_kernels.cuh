@@ -1510,6 +1510,8 @@ struct GenForceArgs {
     int cps_stage;         // consecutive contacts per ring stage (about 2 KB of Jacobians)
     int stage_bytes;       // per-stage shared-memory bytes (cps_stage*48*ncols rounded up to 128)
     int row_bytes;         // > 0: per-warp shared-memory bytes for the warp's base / out rows
+    int base_negate;       // != 0: start from -base (the reference starts from the negated bias forces,
+                           // FloatingBaseSystemDynamics.cpp:191-196); the sign flip is exact
 };
 
 // NCH = ceil(ncols / 32): column chunks a lane owns (compile-time so dead chunks cost nothing);
@@ -1654,6 +1656,7 @@ ccm_genforce_kernel(const __grid_constant__ GenForceArgs a)
                 for (int ch = 0; ch < NCH; ++ch) {
                     if (staged) acc[ch] = (mine[ch] && a.base) ? rows[sys * ncols + lane + ch * kWarp] : 0.0;
                     else acc[ch] = (mine[ch] && a.base) ? __ldcs(a.base + row + ch * kWarp) : 0.0;
+                    if (a.base_negate) acc[ch] = -acc[ch];
                 }
             }
             const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
@@ -1844,6 +1847,7 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
         const long long row = (sys0 + sc) * ncols + col;
         double acc = 0.0;
         if (valid && a.base) acc = staged ? rows[sc * ncols + col] : __ldcs(a.base + row);
+        if (a.base_negate) acc = -acc;
         for (int j = 0; j < cps; ++j, J += jd, wv += 3) {
             const double2 w01 = wv[0], w23 = wv[1], w45 = wv[2];
             // (J^T w)[col], rows in order; then known += product  (:224-225)

@@ -238,3 +238,21 @@ def sample_states_from_planes(planes, prm, idx) -> dict:
     if prm is not None:
         out["params"] = np.ascontiguousarray(torch.stack([q[idx].cpu() for q in prm], dim=1).numpy())
     return out
+
+
+def make_mass_matrices(n_systems: int, ncols: int, seed: int = 7, spread: float = 1.0) -> np.ndarray:
+    """Seeded symmetric positive definite (n_systems, ncols, ncols) matrices shaped like free-floating
+    mass matrices: M = D (A A^T / ncols + I/2) D, A ~ U(-1,1), D = diag(10^U(-spread, spread)) -- the
+    diagonal scaling spreads the "inertias" over 2*spread decades (a humanoid's span kg to 1e-3 kg m^2),
+    so the condition number grows like 100^spread; spread = 0 is benign (cond < 4).  Exactly
+    symmetric (both triangles hold the same bits)."""
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-1.0, 1.0, (n_systems, ncols, ncols))
+    M = A @ A.transpose(0, 2, 1) / ncols
+    idx = np.arange(ncols)
+    M[:, idx, idx] += 0.5
+    if spread > 0:
+        d = 10.0 ** rng.uniform(-spread, spread, (n_systems, ncols))
+        M = M * d[:, :, None] * d[:, None, :]
+    lo = np.tril(M)
+    return lo + np.tril(M, -1).transpose(0, 2, 1)

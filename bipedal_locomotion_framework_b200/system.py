@@ -288,3 +288,75 @@ class GeneralizedForceBatch:
         call, out, wrench = self.prepare(*args, **kw)
         call()
         return (out, wrench) if wrench is not None else out
+
+
+class FloatingBaseDynamicsBatch:
+    """FloatingBaseDynamicalSystem::dynamics from the bias forces on, batched on one GPU
+    (reference: src/System/src/FloatingBaseSystemDynamics.cpp:188-248); the rigid-body quantities
+    (mass matrices, bias forces, frame Jacobians) are the caller's.
+
+    solve():         acc = (mass + regularization).llt().solve(known [+ joint torques])
+                     (blf_sys_mass_matrix_solve)
+    acceleration():  known = -bias + sum_c J_c^T wrench_c, then the same solve
+                     (blf_sys_floating_base_acceleration)
+    """
+
+    def __init__(self, batch: ContinuousContactModelBatch):
+        self._b = batch
+        self._torch = batch._torch
+        self.device = batch.device
+
+    def prepare_solve(self, mass, known, joint_torques=None, regularization=None, out=None):
+        """mass (n,nc,nc), known (n,nc), joint_torques (n,nc-6) or None, regularization (nc,nc)
+        or None: CUDA float64 tensors.  out may be `known` itself (in place)."""
+        t = self._torch
+        ns, nc = int(known.shape[0]), int(known.shape[1])
+        assert tuple(mass.shape) == (ns, nc, nc) and mass.is_contiguous() and known.is_contiguous()
+        out = out if out is not None else t.empty((ns, nc), dtype=t.float64, device=self.device)
+        dp = lambda x: x.data_ptr() if x is not None else None
+        args = (self._b.handle.ptr, ns, nc, dp(mass), dp(regularization), dp(known), dp(joint_torques),
+                dp(out), self._b._stream())
+        fn = _capi.lib().blf_sys_mass_matrix_solve
+        keep = (mass, known, joint_torques, regularization, out)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call, out
+
+    def solve(self, *args, **kw):
+        call, out = self.prepare_solve(*args, **kw)
+        call()
+        return out
+
+    def prepare_acceleration(self, contacts_per_system, planes, jacobians, bias, mass,
+                             joint_torques=None, regularization=None, param_planes=None, out=None,
+                             want_wrench: bool = False):
+        """planes (30,n) contact states; jacobians (n,6,nc); bias (n_systems,nc) = generalized bias
+        forces [base wrench; joint torques]; mass (n_systems,nc,nc)."""
+        t = self._torch
+        n = self._b._num_contacts(planes)
+        assert n % contacts_per_system == 0
+        ns, nc = n // contacts_per_system, int(bias.shape[1])
+        assert tuple(mass.shape) == (ns, nc, nc) and int(bias.shape[0]) == ns
+        out = out if out is not None else t.empty((ns, nc), dtype=t.float64, device=self.device)
+        wrench = t.empty((6, n), dtype=t.float64, device=self.device) if want_wrench else None
+        pp = ContinuousContactModelBatch._plane_ptrs
+        dp = lambda x: x.data_ptr() if x is not None else None
+        args = (self._b.handle.ptr, ns, int(contacts_per_system), nc, pp(planes, 30), pp(param_planes, 4),
+                dp(jacobians), dp(bias), dp(joint_torques), dp(mass), dp(regularization), dp(out),
+                pp(wrench, 6), self._b._stream())
+        fn = _capi.lib().blf_sys_floating_base_acceleration
+        keep = (planes, jacobians, bias, mass, joint_torques, regularization, param_planes, out, wrench)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call, out, wrench
+
+    def acceleration(self, *args, **kw):
+        call, out, wrench = self.prepare_acceleration(*args, **kw)
+        call()
+        return (out, wrench) if wrench is not None else out

@@ -101,7 +101,9 @@ typedef struct {
 enum {
     BLF_CCM_PATH_NONE = 0,
     BLF_CCM_PATH_BULK = 1,    /* bulk-copy (TMA) staging in use: every staged buffer 16-byte aligned */
-    BLF_CCM_PATH_DIRECT64 = 2 /* a staged buffer is only 8-byte aligned: direct 64-bit accesses     */
+    BLF_CCM_PATH_DIRECT64 = 2,/* a staged buffer is only 8-byte aligned: direct 64-bit accesses     */
+    BLF_CCM_PATH_LLT_WARP = 3,/* mass-matrix solve: warp-level kernel (ncols <= 31)                 */
+    BLF_CCM_PATH_LLT_BLOCK = 4/* mass-matrix solve: block-level kernel (ncols 32..128)              */
 };
 
 BLF_CCM_API const char* blf_ccm_version(void);
@@ -365,6 +367,43 @@ BLF_CCM_API int blf_ccm_generalized_force_soa(blf_ccm_handle* h, int64_t n_syste
                                               const double* jacobians, const double* base,
                                               double* out, double* const* wrench_planes,
                                               void* stream);
+
+/*
+ * Last step of FloatingBaseDynamicalSystem::dynamics
+ * (src/System/src/FloatingBaseSystemDynamics.cpp:226-248), n_systems independent systems of
+ * ncols = 6 + actuated DoFs unknowns:
+ *   rhs[s] = known[s];  rhs[s][6 ..] += joint_torques[s]                               (:226-227)
+ *   acc[s] = (mass[s] + regularization).llt().solve(rhs[s])                            (:235-243)
+ * mass: n_systems*ncols*ncols doubles, row-major per system (iDynTree::MatrixDynSize as
+ * getFreeFloatingMassMatrix fills it); like Eigen's LLT only the LOWER triangle is read.
+ * regularization: ncols*ncols row-major DEVICE array shared by all systems (what
+ * setMassMatrixRegularization stores, :72-95) or NULL.  known, acc: n_systems*ncols (acc may alias
+ * known); joint_torques: n_systems*(ncols-6) or NULL.  ncols 1..128: up to 31 a warp-level kernel
+ * (rows in registers), above a block-level one (blf_ccm_last_path tells which).  A matrix that is
+ * not positive definite yields NaN for that system (the reference's Eigen stops factorising and
+ * solves with the partial factor: meaningless numbers, no error there either).
+ */
+BLF_CCM_API int blf_sys_mass_matrix_solve(blf_ccm_handle* h, int64_t n_systems, int ncols,
+                                          const double* mass, const double* regularization,
+                                          const double* known, const double* joint_torques,
+                                          double* acc, void* stream);
+
+/*
+ * FloatingBaseDynamicalSystem::dynamics from the bias forces on (:188-248), the rigid-body
+ * quantities (mass matrix, bias forces, frame Jacobians, frame poses/twists: iDynTree
+ * KinDynComputations in the reference) supplied by the caller:
+ *   known = -bias_forces + sum_c J_c^T wrench_c ;  known[6 ..] += joint_torques ;
+ *   acc   = (mass + regularization).llt().solve(known)         = [base acc (6); joint acc]
+ * Arguments as blf_ccm_generalized_force_soa (in_planes, param_planes, jacobians, wrench_planes)
+ * and blf_sys_mass_matrix_solve (mass, regularization, joint_torques); bias_forces =
+ * n_systems*ncols, [base wrench (6); joint torques] of generalizedBiasForces; ncols >= 6.
+ * Two launches on `stream` (J^T wrench accumulation into acc, then the solve in place).
+ */
+BLF_CCM_API int blf_sys_floating_base_acceleration(
+    blf_ccm_handle* h, int64_t n_systems, int contacts_per_system, int ncols,
+    const double* const* in_planes, const double* const* param_planes, const double* jacobians,
+    const double* bias_forces, const double* joint_torques, const double* mass,
+    const double* regularization, double* acc, double* const* wrench_planes, void* stream);
 
 /*
  * Device / pinned-host memory and stream helpers, so that host code above this ABI (the C++17

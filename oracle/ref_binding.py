@@ -91,6 +91,7 @@ def lib():
         L.blf_ref_kin_integrate.argtypes = [d, d, d, d, vp, vp, vp, i, vp, vp]
         L.blf_ref_rollout.argtypes = [sz, i, d, d, vp, vp, vp, vp, vp, C.c_uint, vp, vp, vp, i]
         L.blf_ref_generalized_force.argtypes = [sz, i, i] + [vp] * 9 + [i]
+        L.blf_ref_floating_base_dynamics.argtypes = [sz, i, i] + [vp] * 12 + [i]
         _lib = L
     return _lib
 
@@ -281,6 +282,39 @@ def generalized_force(contacts_per_system, ncols, twists, poses, null_poses, jac
     rc = lib().blf_ref_generalized_force(ns, int(contacts_per_system), int(ncols), _ptr(twists), _ptr(poses),
                                          _ptr(null_poses), _ptr(pr), _ptr(uni), _ptr(J), _ptr(b), _ptr(out),
                                          _ptr(wr), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"reference FloatingBaseDynamicalSystem failed (rc={rc})")
+    return (out, wr) if want_wrench else out
+
+
+def floating_base_dynamics(contacts_per_system, twists, poses, null_poses, jacobians, bias, mass,
+                           joint_torques=None, reg=None, params=None, uniform=None, want_wrench=False,
+                           nthreads=1):
+    """The whole of FloatingBaseDynamicalSystem::dynamics from the bias forces on, run from the
+    reference's own source over the KinDynComputations test double loaded with the given mass
+    matrices (n_systems, nc, nc), bias forces (n_systems, nc) and contact frames; reg (nc, nc)
+    goes through setMassMatrixRegularization.  Returns [base acc; joint acc] (n_systems, nc)."""
+    twists, poses, null_poses = _f64(twists), _f64(poses), _f64(null_poses)
+    n = twists.shape[0]
+    assert n % contacts_per_system == 0
+    ns = n // contacts_per_system
+    b = _f64(bias)
+    ncols = b.shape[1]
+    assert b.shape[0] == ns
+    J = _f64(jacobians)
+    assert J.size == n * 6 * ncols
+    M = _f64(mass)
+    assert M.shape == (ns, ncols, ncols)
+    tau = None if joint_torques is None else _f64(joint_torques).reshape(ns, ncols - 6)
+    rg = None if reg is None else _f64(reg).reshape(ncols, ncols)
+    pr = None if params is None else _f64(params).reshape(n, 4)
+    uni = np.asarray(uniform if uniform is not None else (0, 0, 0, 0), dtype=np.float64)
+    out = np.empty((ns, ncols))
+    wr = np.empty((n, 6)) if want_wrench else None
+    rc = lib().blf_ref_floating_base_dynamics(ns, int(contacts_per_system), int(ncols), _ptr(twists),
+                                              _ptr(poses), _ptr(null_poses), _ptr(pr), _ptr(uni), _ptr(J),
+                                              _ptr(b), _ptr(tau), _ptr(M), _ptr(rg), _ptr(out), _ptr(wr),
+                                              int(nthreads))
     if rc != 0:
         raise RuntimeError(f"reference FloatingBaseDynamicalSystem failed (rc={rc})")
     return (out, wr) if want_wrench else out

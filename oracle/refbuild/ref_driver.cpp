@@ -439,10 +439,13 @@ int blf_ref_rollout(std::size_t chains, int horizon, double dT, double rho, cons
 // = base + sum_c J_c^T * wrench_c in the reference's own order.  Argument meaning as
 // oracle/sys_oracle.h::syso_generalized_force, AoS: twists n*6, poses n*12, null_poses n*12 with
 // n = n_systems*contacts_per_system; jacobians n*6*ncols; base / out n_systems*ncols; wrench n*6 or NULL.
-int blf_ref_generalized_force(std::size_t n_systems, int contacts_per_system, int ncols, const double* twists,
-                              const double* poses, const double* null_poses, const double* params,
-                              const double uniform[4], const double* jacobians, const double* base, double* out,
-                              double* wrench, int nthreads)
+// The same routine, given mass matrices / joint torques / a regularisation term and the bias forces
+// themselves (base_is_bias), runs the whole of dynamics() for blf_ref_floating_base_dynamics below.
+static int dynamicsOverTestDouble(std::size_t n_systems, int contacts_per_system, int ncols, const double* twists,
+                                  const double* poses, const double* null_poses, const double* params,
+                                  const double uniform[4], const double* jacobians, const double* base,
+                                  bool base_is_bias, const double* joint_torques, const double* mass_matrices,
+                                  const double* regularization, double* out, double* wrench, int nthreads)
 {
     if (ncols < 6 || contacts_per_system < 1) return -3;
     return runPartitioned(n_systems, nthreads, [=](std::size_t b, std::size_t e, int* status) {
@@ -452,13 +455,16 @@ int blf_ref_generalized_force(std::size_t n_systems, int contacts_per_system, in
             auto kinDyn = std::make_shared<iDynTree::KinDynComputations>();
             kinDyn->standinSetModel(dofs);
             iDynTree::MatrixDynSize mass(nc, nc);
-            for (std::size_t i = 0; i < nc; ++i)
-                mass(i, i) = 1.0;
+            if (mass_matrices)
+                std::memcpy(mass.data(), mass_matrices + s * nc * nc, sizeof(double) * nc * nc);
+            else
+                for (std::size_t i = 0; i < nc; ++i)
+                    mass(i, i) = 1.0;
             kinDyn->standinSetMassMatrix(mass);
             iDynTree::FreeFloatingGeneralizedTorques h(kinDyn->model());
             for (std::size_t q = 0; q < nc; ++q)
             {
-                const double v = base ? -base[s * nc + q] : -0.0;
+                const double v = base ? (base_is_bias ? base[s * nc + q] : -base[s * nc + q]) : -0.0;
                 if (q < 6)
                     h.baseWrench()(static_cast<unsigned>(q)) = v;
                 else
@@ -501,8 +507,26 @@ int blf_ref_generalized_force(std::size_t n_systems, int contacts_per_system, in
             basePosition.setZero();
             Eigen::Matrix3d baseOrientation;
             baseOrientation.setIdentity();
+            Eigen::VectorXd torques(nd);
+            torques.setZero();
+            if (joint_torques)
+                for (Eigen::Index q = 0; q < nd; ++q)
+                    torques(q) = joint_torques[s * dofs + std::size_t(q)];
+            if (regularization)
+            {
+                const Eigen::Index ncI = Eigen::Index(nc);
+                Eigen::MatrixXd reg(ncI, ncI);
+                for (std::size_t i = 0; i < nc; ++i)
+                    for (std::size_t k = 0; k < nc; ++k)
+                        reg(Eigen::Index(i), Eigen::Index(k)) = regularization[i * nc + k];
+                if (!system.setMassMatrixRegularization(reg))
+                {
+                    *status = -1;
+                    return;
+                }
+            }
             if (!system.setState({baseVelocity, zeros, basePosition, baseOrientation, zeros})
-                || !system.setControlInput({zeros, contacts}))
+                || !system.setControlInput({torques, contacts}))
             {
                 *status = -1;
                 return;
@@ -523,6 +547,34 @@ int blf_ref_generalized_force(std::size_t n_systems, int contacts_per_system, in
                         wrench[6 * (s * cps + c) + k] = models[c]->getContactWrench()(k);
         }
     });
+}
+
+int blf_ref_generalized_force(std::size_t n_systems, int contacts_per_system, int ncols, const double* twists,
+                              const double* poses, const double* null_poses, const double* params,
+                              const double uniform[4], const double* jacobians, const double* base, double* out,
+                              double* wrench, int nthreads)
+{
+    return dynamicsOverTestDouble(n_systems, contacts_per_system, ncols, twists, poses, null_poses, params,
+                                  uniform, jacobians, base, false, nullptr, nullptr, nullptr, out, wrench,
+                                  nthreads);
+}
+
+// FloatingBaseDynamicalSystem::dynamics from the bias forces on (FloatingBaseSystemDynamics.cpp:188-248),
+// run from the reference's own source: the test double is loaded per system with the given mass matrix
+// (ncols x ncols row-major), generalized bias forces h (ncols: base wrench, joint torques) and the
+// contact frames as above; joint_torques (n_systems*(ncols-6)) or NULL = zeros; regularization
+// (ncols x ncols row-major, through setMassMatrixRegularization) or NULL.
+// out = [baseAcceleration; jointAcceleration] = (M + reg).llt().solve(-h + sum J^T wrench + [0; tau]).
+int blf_ref_floating_base_dynamics(std::size_t n_systems, int contacts_per_system, int ncols, const double* twists,
+                                   const double* poses, const double* null_poses, const double* params,
+                                   const double uniform[4], const double* jacobians, const double* bias_forces,
+                                   const double* joint_torques, const double* mass_matrices,
+                                   const double* regularization, double* out, double* wrench, int nthreads)
+{
+    if (!bias_forces || !mass_matrices) return -3;
+    return dynamicsOverTestDouble(n_systems, contacts_per_system, ncols, twists, poses, null_poses, params,
+                                  uniform, jacobians, bias_forces, true, joint_torques, mass_matrices,
+                                  regularization, out, wrench, nthreads);
 }
 
 } // extern "C"

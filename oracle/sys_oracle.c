@@ -176,6 +176,13 @@ struct job {
     const double* jacobians;
     const double* base;
     double* out;
+    int base_negate;
+    /* mass-matrix solve */
+    const double* mass;
+    const double* reg;
+    const double* known;
+    const double* tau;
+    double* acc;
 };
 
 static void* trampoline(void* arg)
@@ -344,6 +351,8 @@ static void genforce_range(const job_t* j, size_t begin, size_t end)
         double* o = j->out + s * (size_t)nc;
         /* m_knownCoefficent starts from the bias terms (:191-196) */
         for (int q = 0; q < nc; ++q) o[q] = j->base ? j->base[s * (size_t)nc + (size_t)q] : 0.0;
+        if (j->base_negate)   /* head = -baseWrench, tail = -jointTorques of the bias forces */
+            for (int q = 0; q < nc; ++q) o[q] = -o[q];
         for (int c = 0; c < j->cps; ++c) {               /* for (contactWrench : contactWrenches) */
             const size_t i = s * (size_t)j->cps + (size_t)c;
             const double* const* P = j->in_planes;
@@ -392,4 +401,93 @@ void syso_generalized_force(size_t n_systems, int contacts_per_system, int ncols
     j.out = out;
     j.wrench_planes = wrench_planes;
     parallel_for(&j, n_systems, nthreads);
+}
+
+/* ---- (M + reg).llt().solve(known) ------------------------------------------------------------ */
+
+void syso_llt_solve_one(int nc, const double* mass, const double* reg, const double* rhs,
+                        double* x, double* work)
+{
+    /* work = the matrix LLT factorises: M, or the evaluated sum M + reg (:236-239) */
+    double* L = work;
+    for (int i = 0; i < nc * nc; ++i) L[i] = reg ? mass[i] + reg[i] : mass[i];
+    /* lower Cholesky, column by column; only the lower triangle is read */
+    for (int j = 0; j < nc; ++j) {
+        double d = L[j * nc + j];
+        for (int k = 0; k < j; ++k) d = d - L[j * nc + k] * L[j * nc + k];
+        const double ljj = sqrt(d);
+        L[j * nc + j] = ljj;
+        for (int i = j + 1; i < nc; ++i) {
+            double t = L[i * nc + j];
+            for (int k = 0; k < j; ++k) t = t - L[i * nc + k] * L[j * nc + k];
+            L[i * nc + j] = t / ljj;
+        }
+    }
+    for (int i = 0; i < nc; ++i) {                 /* L y = b */
+        double t = rhs[i];
+        for (int k = 0; k < i; ++k) t = t - L[i * nc + k] * x[k];
+        x[i] = t / L[i * nc + i];
+    }
+    for (int i = nc - 1; i >= 0; --i) {            /* L^T x = y */
+        double t = x[i];
+        for (int k = i + 1; k < nc; ++k) t = t - L[k * nc + i] * x[k];
+        x[i] = t / L[i * nc + i];
+    }
+}
+
+static void llt_range(const job_t* j, size_t begin, size_t end)
+{
+    const int nc = j->ncols;
+    double* work = (double*)malloc(sizeof(double) * ((size_t)nc * (size_t)nc + 2u * (size_t)nc));
+    double* rhs = work + (size_t)nc * (size_t)nc;
+    double* x = rhs + nc;
+    for (size_t s = begin; s < end; ++s) {
+        for (int q = 0; q < nc; ++q) rhs[q] = j->known[s * (size_t)nc + (size_t)q];
+        if (j->tau)   /* m_knownCoefficent.tail(m_actuatedDoFs) += jointTorques  (:226-227) */
+            for (int q = 6; q < nc; ++q) rhs[q] = rhs[q] + j->tau[s * (size_t)(nc - 6) + (size_t)(q - 6)];
+        syso_llt_solve_one(nc, j->mass + s * (size_t)nc * (size_t)nc, j->reg, rhs, x, work);
+        for (int q = 0; q < nc; ++q) j->acc[s * (size_t)nc + (size_t)q] = x[q];
+    }
+    free(work);
+}
+
+void syso_mass_matrix_solve(size_t n_systems, int ncols, const double* mass, const double* reg,
+                            const double* known, const double* joint_torques, double* acc,
+                            int nthreads)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.fn = llt_range;
+    j.ncols = ncols;
+    j.mass = mass;
+    j.reg = reg;
+    j.known = known;
+    j.tau = joint_torques;
+    j.acc = acc;
+    parallel_for(&j, n_systems, nthreads);
+}
+
+void syso_floating_base_acceleration(size_t n_systems, int contacts_per_system, int ncols,
+                                     const double* const* in_planes,
+                                     const double* const* param_planes, const double uniform[4],
+                                     const double* jacobians, const double* bias_forces,
+                                     const double* joint_torques, const double* mass,
+                                     const double* reg, double* acc, double* const* wrench_planes,
+                                     int nthreads)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.fn = genforce_range;
+    j.cps = contacts_per_system;
+    j.ncols = ncols;
+    j.in_planes = in_planes;
+    j.param_planes = param_planes;
+    j.uniform = param_planes ? NULL : uniform;
+    j.jacobians = jacobians;
+    j.base = bias_forces;
+    j.base_negate = 1;
+    j.out = acc;
+    j.wrench_planes = wrench_planes;
+    parallel_for(&j, n_systems, nthreads);
+    syso_mass_matrix_solve(n_systems, ncols, mass, reg, acc, joint_torques, acc, nthreads);
 }

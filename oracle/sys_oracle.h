@@ -27,6 +27,7 @@
  *   src/System/include/BipedalLocomotion/System/ForwardEuler.tpp:19-49 oneStepIntegration
  *   src/System/include/BipedalLocomotion/System/FixedStepIntegrator.tpp:19-76  integrate()
  *   src/System/src/FloatingBaseSystemDynamics.cpp:199-226              known += J^T * wrench
+ *   src/System/src/FloatingBaseSystemDynamics.cpp:188-196, 226-248     -bias, += torques, llt().solve
  *
  * Third-party semantics relied on (Eigen >= 3.2.92, not vendored; [from memory]):
  *   a.cross(b) = (a1 b2 - a2 b1, a2 b0 - a0 b2, a0 b1 - a1 b0);  M.colwise().cross(w) applies it
@@ -107,6 +108,39 @@ void syso_generalized_force(size_t n_systems, int contacts_per_system, int ncols
                             const double* const* in_planes, const double* const* param_planes,
                             const double uniform[4], const double* jacobians, const double* base,
                             double* out, double* const* wrench_planes, int nthreads);
+
+/*
+ * FloatingBaseDynamicalSystem::dynamics, last step (:226-243):
+ *   rhs = known;  rhs.tail(ncols - 6) += joint_torques;  acc = (mass [+ reg]).llt().solve(rhs)
+ * Eigen's LLT (third party, >= 3.2.92, not vendored) restated from its published algorithm: the
+ * lower Cholesky factor L of the LOWER triangle of A (column by column: d = A_jj - sum_k L_jk^2,
+ * L_jj = sqrt(d), L_ij = (A_ij - sum_k L_ik L_jk) / L_jj, k ascending), then L y = b and L^T x = y by
+ * substitution, one rounding per operation.  Eigen's own kernels sum the same products in a
+ * vectorised / blocked order, so agreement with an Eigen binary is to rounding, scaled by the
+ * conditioning of A -- not bit for bit; agreement with oracle/_ref (the reference's dynamics()
+ * compiled over the stand-in Eigen, which evaluates LLT in exactly this order) IS bit for bit
+ * (tests/test_reference_build.py).  A matrix that is not positive definite gives NaN here (sqrt of
+ * a negative number); Eigen stops factorising at that column and solves with the partial factor.
+ * mass: n_systems*ncols*ncols row-major; reg: ncols*ncols or NULL; known, acc: n_systems*ncols
+ * (may alias); joint_torques: n_systems*(ncols-6) or NULL.
+ */
+void syso_mass_matrix_solve(size_t n_systems, int ncols, const double* mass, const double* reg,
+                            const double* known, const double* joint_torques, double* acc,
+                            int nthreads);
+
+/* one system; work: ncols*ncols doubles of scratch */
+void syso_llt_solve_one(int nc, const double* mass, const double* reg, const double* rhs, double* x,
+                        double* work);
+
+/* dynamics() from the bias forces on (:188-248): known = -bias_forces + sum_c J_c^T wrench_c
+ * (syso_generalized_force with the negated bias as base), then syso_mass_matrix_solve in place. */
+void syso_floating_base_acceleration(size_t n_systems, int contacts_per_system, int ncols,
+                                     const double* const* in_planes,
+                                     const double* const* param_planes, const double uniform[4],
+                                     const double* jacobians, const double* bias_forces,
+                                     const double* joint_torques, const double* mass,
+                                     const double* reg, double* acc, double* const* wrench_planes,
+                                     int nthreads);
 
 #ifdef __cplusplus
 }

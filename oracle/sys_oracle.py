@@ -31,6 +31,9 @@ def lib():
         L.syso_rollout.argtypes = [sz, ci, ci, dbl, dbl, vp, vp, vp, vp, vp, vp, C.c_uint, vp, vp,
                                    vp, vp, vp, vp, vp, ci]
         L.syso_generalized_force.argtypes = [sz, ci, ci, vp, vp, vp, vp, vp, vp, vp, ci]
+        L.syso_mass_matrix_solve.argtypes = [sz, ci, vp, vp, vp, vp, vp, ci]
+        L.syso_floating_base_acceleration.argtypes = [sz, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                      vp, ci]
         _configured = True
     return L
 
@@ -150,3 +153,45 @@ def generalized_force(contacts_per_system, ncols, in_planes, jacobians, base=Non
                                  _planes(pr), _ptr(uni), _ptr(J), _ptr(b), _ptr(out), _planes(wr),
                                  int(nthreads))
     return (out, wr) if want_wrench else out
+
+
+def mass_matrix_solve(mass, known, joint_torques=None, reg=None, nthreads=1):
+    """acc[s] = (mass[s] + reg).llt().solve(known[s] (+ joint torques on the tail)).
+    mass (n, nc, nc), known (n, nc), joint_torques (n, nc-6) or None, reg (nc, nc) or None."""
+    M = np.ascontiguousarray(mass, dtype=np.float64)
+    k = np.ascontiguousarray(known, dtype=np.float64)
+    ns, nc = k.shape
+    assert M.shape == (ns, nc, nc)
+    tau = None if joint_torques is None else np.ascontiguousarray(joint_torques, dtype=np.float64)
+    rg = None if reg is None else np.ascontiguousarray(reg, dtype=np.float64)
+    acc = np.empty((ns, nc))
+    lib().syso_mass_matrix_solve(ns, int(nc), _ptr(M), _ptr(rg), _ptr(k), _ptr(tau), _ptr(acc),
+                                 int(nthreads))
+    return acc
+
+
+def floating_base_acceleration(contacts_per_system, in_planes, jacobians, bias, mass,
+                               joint_torques=None, reg=None, param_planes=None, uniform=None,
+                               want_wrench=False, nthreads=1):
+    """dynamics() from the bias forces on: (mass + reg).llt().solve(-bias + sum J^T wrench (+ tau))."""
+    planes = in_planes
+    n = (planes.shape[1] if not isinstance(planes, (list, tuple))
+         else next(p for p in planes if p is not None).shape[0])
+    assert n % contacts_per_system == 0
+    ns = n // contacts_per_system
+    b = np.ascontiguousarray(bias, dtype=np.float64)
+    nc = b.shape[1]
+    J = np.ascontiguousarray(jacobians, dtype=np.float64)
+    assert J.size == n * 6 * nc
+    M = np.ascontiguousarray(mass, dtype=np.float64)
+    assert M.shape == (ns, nc, nc)
+    tau = None if joint_torques is None else np.ascontiguousarray(joint_torques, dtype=np.float64)
+    rg = None if reg is None else np.ascontiguousarray(reg, dtype=np.float64)
+    pr = None if param_planes is None else np.ascontiguousarray(param_planes, dtype=np.float64)
+    uni = np.asarray(uniform if uniform is not None else (0, 0, 0, 0), dtype=np.float64)
+    acc = np.empty((ns, nc))
+    wr = np.empty((6, n)) if want_wrench else None
+    lib().syso_floating_base_acceleration(ns, int(contacts_per_system), int(nc), _planes(planes),
+                                          _planes(pr), _ptr(uni), _ptr(J), _ptr(b), _ptr(tau), _ptr(M),
+                                          _ptr(rg), _ptr(acc), _planes(wr), int(nthreads))
+    return (acc, wr) if want_wrench else acc

@@ -47,3 +47,14 @@ def assert_ctrl_structure(ctrl):
     z = c[:, CTRL_STRUCTURAL_ZERO]
     assert np.all(z == 0.0) and not np.signbit(z).any(), "structural zero is not +0.0"
     assert np.array_equal(c[:, 0], c[:, 7]) and np.array_equal(c[:, 0], c[:, 14])
+
+
+EPS = 2.0 ** -52
+
+
+def llt_tolerance(nc, cond):
+    """Tolerance for a Cholesky solve of an nc x nc system with condition number `cond`: the flat
+    north_star 1e-12 where the conditioning allows it, else the forward-error bound of any
+    floating-point LLT, c n eps cond(A) (Higham, Accuracy and Stability of Numerical Algorithms,
+    thm 10.4 + 7.2) -- the reference's own Eigen LLT is only that close to the exact solution."""
+    return np.maximum(TOL, 4.0 * nc * EPS * np.asarray(cond))

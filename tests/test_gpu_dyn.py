@@ -1,0 +1,296 @@
+"""GPU parity tests for the end of FloatingBaseDynamicalSystem::dynamics
+(src/System/src/FloatingBaseSystemDynamics.cpp:188-248 of the reference): the batched mass-matrix
+solve (M + reg).llt().solve(known + torques) and the whole step from the bias forces on -- the CUDA
+path through the C ABI against the CPU oracle on the same bits, the exact-rational golden fixture and
+the reference's own source run over the KinDynComputations test double (oracle/_ref).
+Tolerance: 1e-12 norm-wise relative per system (north_star) where the matrix's conditioning allows
+it, c n eps cond(A) otherwise (parity.llt_tolerance)."""
+import os
+
+import numpy as np
+import pytest
+
+from bipedal_locomotion_framework_b200 import synthetic as syn
+from parity import TOL, assert_parity, llt_tolerance
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NTHREADS = max(1, (os.cpu_count() or 1))
+PATH_LLT_WARP, PATH_LLT_BLOCK = 3, 4
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def batch(torch):
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    b = ContinuousContactModelBatch(0)
+    b.set_uniform_params(*syn.REFERENCE_TEST_PARAMS)
+    return b
+
+
+@pytest.fixture(scope="module")
+def dyn(batch):
+    from bipedal_locomotion_framework_b200.system import FloatingBaseDynamicsBatch
+    return FloatingBaseDynamicsBatch(batch)
+
+
+@pytest.fixture(scope="module")
+def so(oracle):
+    from oracle import sys_oracle
+    return sys_oracle
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_binding
+    # the prebuilt oracle/_ref travels with the snapshot; without it these tests cannot claim anything
+    assert ref_binding.available(), "oracle/_ref/libblf_reference.so was not shipped to the GPU box"
+    return ref_binding
+
+
+@pytest.fixture(scope="module")
+def gd():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "dyn_exact_golden.npz")))
+
+
+def _dev(torch, a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(got, ref):
+    num = np.abs(np.asarray(got) - ref).max(axis=-1)
+    den = np.maximum(np.abs(ref).max(axis=-1), 1e-300)
+    return np.where(num == 0, 0.0, num / den)
+
+
+def _last_path(batch):
+    from bipedal_locomotion_framework_b200 import _capi
+    return _capi.lib().blf_ccm_last_path(batch.handle.ptr)
+
+
+def _case(nc, ns, seed, spread=0.0, with_tau=True, with_reg=False):
+    rng = np.random.default_rng(seed)
+    M = syn.make_mass_matrices(ns, nc, seed=seed + 1, spread=spread)
+    known = rng.normal(size=(ns, nc)) * 30.0
+    tau = rng.normal(size=(ns, nc - 6)) * 5.0 if (with_tau and nc > 6) else None
+    reg = None
+    if with_reg:
+        reg = np.diag(10.0 ** rng.uniform(-4, -2, nc))
+        reg[nc - 1, 0] = reg[0, nc - 1] = 1e-3
+    return M, known, tau, reg
+
+
+# --- the solve -------------------------------------------------------------------------------------
+
+def test_mass_matrix_solve_matches_exact_rationals(torch, dyn, gd):
+    """oracle/exact_golden_dyn.py: the solution is rational in the inputs, evaluated exactly."""
+    for tag in gd["tags"]:
+        M, known, acc, cond = (gd[f"{tag}_{k}"] for k in ("M", "known", "acc", "cond"))
+        tau, reg = gd.get(f"{tag}_tau"), gd.get(f"{tag}_reg")
+        x = dyn.solve(_dev(torch, M), _dev(torch, known), _dev(torch, tau), _dev(torch, reg)).cpu().numpy()
+        err = rel(x, acc)
+        assert (err <= llt_tolerance(known.shape[1], cond)).all(), (tag, err.max())
+        easy = cond < 100
+        if easy.any():
+            assert err[easy].max() <= TOL, (tag, err[easy].max())
+
+
+@pytest.mark.parametrize("nc", list(range(1, 41)) + [64, 100, 128])
+def test_mass_matrix_solve_vs_oracle_every_size(torch, batch, dyn, so, nc):
+    """Every size class of the warp-level kernel (nc <= 31) and the block-level kernel above, a
+    system count that fills no warp or CTA evenly; benign conditioning (cond < 4): flat 1e-12."""
+    ns = 1003 if nc <= 40 else 37
+    M, known, tau, reg = _case(nc, ns, 500 + nc, with_reg=bool(nc % 2))
+    want = so.mass_matrix_solve(M, known, tau, reg, nthreads=NTHREADS)
+    x = dyn.solve(_dev(torch, M), _dev(torch, known), _dev(torch, tau), _dev(torch, reg)).cpu().numpy()
+    assert _last_path(batch) == (PATH_LLT_WARP if nc <= 31 else PATH_LLT_BLOCK)
+    assert np.isfinite(x).all()
+    err = rel(x, want)
+    assert err.max() <= TOL, (int(np.argmax(err)), err.max())
+
+
+def test_warp_and_block_kernels_agree_bit_for_bit(torch, dyn):
+    """Same operations in the same order: the block-level kernel (forced on a second handle through
+    BLF_CCM_TUNE_LLT_GENERAL, read when a handle is created) reproduces the warp-level one."""
+    from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+    from bipedal_locomotion_framework_b200.system import FloatingBaseDynamicsBatch
+    os.environ["BLF_CCM_TUNE_LLT_GENERAL"] = "1"
+    try:
+        b2 = ContinuousContactModelBatch(0)
+    finally:
+        os.environ.pop("BLF_CCM_TUNE_LLT_GENERAL", None)
+    gen = FloatingBaseDynamicsBatch(b2)
+    for nc in (1, 3, 6, 7, 8, 12, 15, 16, 23, 29, 31):
+        M, known, tau, reg = _case(nc, 301, 900 + nc, spread=1.0, with_reg=nc in (7, 29))
+        args = [_dev(torch, a) for a in (M, known, tau, reg)]
+        fast = dyn.solve(*args).cpu().numpy()
+        assert _last_path(dyn._b) == PATH_LLT_WARP
+        slow = gen.solve(*args).cpu().numpy()
+        assert _last_path(b2) == PATH_LLT_BLOCK
+        assert np.array_equal(fast, slow), nc
+
+
+def test_mass_matrix_solve_in_place_and_stream(torch, dyn):
+    """acc may alias known; the launch runs on the caller's current stream."""
+    M, known, tau, _ = _case(29, 4097, 77)
+    dM, dk, dt = (_dev(torch, a) for a in (M, known, tau))
+    ref = dyn.solve(dM, dk, dt).clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        buf = dk.clone()
+        out = dyn.solve(dM, buf, dt, out=buf)
+    s.synchronize()
+    assert out.data_ptr() == buf.data_ptr() and torch.equal(buf, ref)
+
+
+def test_mass_matrix_solve_reads_only_the_lower_triangle(torch, dyn):
+    M, known, tau, reg = _case(29, 513, 31, with_reg=True)
+    x0 = dyn.solve(_dev(torch, M), _dev(torch, known), _dev(torch, tau), _dev(torch, reg))
+    iu = np.triu_indices(29, 1)
+    M2, reg2 = M.copy(), reg.copy()
+    M2[:, iu[0], iu[1]] = np.nan
+    reg2[iu] = np.nan
+    x1 = dyn.solve(_dev(torch, M2), _dev(torch, known), _dev(torch, tau), _dev(torch, reg2))
+    assert torch.equal(x0, x1)
+
+
+@pytest.mark.parametrize("nc,spread", [(29, 1.5), (12, 2.0), (38, 1.0)])
+def test_mass_matrix_solve_ill_conditioned(torch, dyn, so, nc, spread):
+    """Inertias spread over 2-4 decades (cond up to ~1e8): forward error against the oracle within
+    the bound both factorisations obey, and the backward error -- the residual -- at rounding level."""
+    ns = 2001
+    M, known, tau, _ = _case(nc, ns, 40 + nc, spread=spread)
+    want = so.mass_matrix_solve(M, known, tau, nthreads=NTHREADS)
+    x = dyn.solve(_dev(torch, M), _dev(torch, known), _dev(torch, tau)).cpu().numpy()
+    cond = np.linalg.cond(M, np.inf)
+    assert (rel(x, want) <= 2 * llt_tolerance(nc, cond)).all()
+    rhs = known.copy()
+    if tau is not None:
+        rhs[:, 6:] += tau
+    res = np.abs(np.einsum("sij,sj->si", M, x) - rhs).max(axis=1)
+    scale = np.abs(M).sum(axis=2).max(axis=1) * np.abs(x).max(axis=1) + np.abs(rhs).max(axis=1)
+    assert (res <= 8 * nc * 2.0 ** -52 * scale).all()
+
+
+def test_not_positive_definite_gives_nan_for_that_system_only(torch, dyn, so):
+    M, known, tau, _ = _case(12, 200, 9)
+    M[17] = -M[17]
+    M[101, 5, 5] = -1.0
+    x = dyn.solve(_dev(torch, M), _dev(torch, known), _dev(torch, tau)).cpu().numpy()
+    bad = np.isnan(x).any(axis=1)
+    assert bad[17] and bad[101] and bad.sum() == 2
+    want = so.mass_matrix_solve(M, known, tau)
+    assert np.array_equal(np.isnan(want).any(axis=1), bad)      # the oracle: NaN for the same systems
+    assert rel(x[~bad], want[~bad]).max() <= TOL
+
+
+def test_mass_matrix_solve_rejects_bad_arguments(torch, batch, dyn):
+    from bipedal_locomotion_framework_b200 import _capi
+    L, h = _capi.lib(), batch.handle.ptr
+    M, known, tau, _ = _case(8, 4, 1)
+    dM, dk, dt = (_dev(torch, a) for a in (M, known, tau))
+    out = torch.empty_like(dk)
+    ok = lambda *a: L.blf_sys_mass_matrix_solve(h, *a)
+    assert ok(4, 8, dM.data_ptr(), None, dk.data_ptr(), dt.data_ptr(), out.data_ptr(), None) == 0
+    assert ok(0, 8, None, None, None, None, None, None) == 0                       # empty batch
+    assert ok(-1, 8, dM.data_ptr(), None, dk.data_ptr(), None, out.data_ptr(), None) != 0
+    assert ok(4, 0, dM.data_ptr(), None, dk.data_ptr(), None, out.data_ptr(), None) != 0
+    assert ok(4, 129, dM.data_ptr(), None, dk.data_ptr(), None, out.data_ptr(), None) != 0
+    assert ok(4, 8, None, None, dk.data_ptr(), None, out.data_ptr(), None) != 0
+    assert ok(4, 8, dM.data_ptr() + 4, None, dk.data_ptr(), None, out.data_ptr(), None) != 0
+    assert ok(4, 6, dM.data_ptr(), None, dk.data_ptr(), dt.data_ptr(), out.data_ptr(), None) != 0  # torques, no joints
+    assert b"joint" in L.blf_ccm_last_error()
+
+
+# --- the whole step: -bias + sum J^T wrench + torques, then the solve -------------------------------
+
+def _acc_tolerance(M, x_ref, mag_rhs):
+    """|dx| <= |M^-1| |d rhs| + LLT error: the right-hand side is a cancelling sum known only to
+    1e-12 of the magnitude of its terms."""
+    nc = M.shape[1]
+    inv_norm = np.abs(np.linalg.inv(M)).sum(axis=2).max(axis=1)
+    cond = inv_norm * np.abs(M).sum(axis=2).max(axis=1)
+    return TOL * inv_norm * mag_rhs + llt_tolerance(nc, cond) * np.abs(x_ref).max(axis=1)
+
+
+@pytest.mark.parametrize("cps,ncols,het,with_reg,spread", [
+    (2, 29, False, False, 0.0), (2, 29, True, True, 1.0), (1, 6, False, False, 0.5),
+    (4, 38, True, True, 0.5), (3, 12, False, True, 0.0)])
+def test_floating_base_acceleration_vs_reference_build(torch, batch, dyn, ref, cps, ncols, het, with_reg, spread):
+    """blf_sys_floating_base_acceleration against FloatingBaseDynamicalSystem::dynamics run from the
+    reference's own FloatingBaseSystemDynamics.cpp over the KinDynComputations test double (mass
+    matrices, bias forces, Jacobians and frame states injected; regularisation through
+    setMassMatrixRegularization)."""
+    ns = 2_001
+    n = ns * cps
+    st = syn.make_states(n, seed=85 + cps, heterogeneous=het)
+    rng = np.random.default_rng(cps * 100 + ncols)
+    J = rng.uniform(-1.0, 1.0, (n, 6, ncols))
+    bias = rng.uniform(-50.0, 50.0, (ns, ncols))
+    M, _, tau, reg = _case(ncols, ns, 60 + ncols, spread=spread, with_reg=with_reg)
+    want, wref = ref.floating_base_dynamics(cps, st["twists"], st["poses"], st["null_poses"], J, bias, M,
+                                            tau, reg, params=st["params"] if het else None,
+                                            uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True,
+                                            nthreads=NTHREADS)
+    planes = _dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+    acc, wr = dyn.acceleration(cps, planes, _dev(torch, J), _dev(torch, bias), _dev(torch, M),
+                               _dev(torch, tau), _dev(torch, reg),
+                               param_planes=_dev(torch, st["params"].T) if het else None, want_wrench=True)
+    assert_parity(wr.cpu().numpy().T, wref, "wrench")
+    mag = np.abs(bias) + np.einsum("scrq,scr->sq", np.abs(J.reshape(ns, cps, 6, ncols)),
+                                   np.abs(wref.reshape(ns, cps, 6)))
+    if tau is not None:
+        mag[:, 6:] += np.abs(tau)
+    Meff = M if reg is None else M + reg
+    tol = _acc_tolerance(Meff, want, mag.max(axis=1))
+    err = np.abs(acc.cpu().numpy() - want).max(axis=1)
+    assert (err <= tol).all(), (int(np.argmax(err / tol)), (err / tol).max())
+
+
+def test_floating_base_acceleration_equals_its_two_steps(torch, batch, dyn):
+    """One call = blf_ccm_generalized_force_soa on the negated bias + blf_sys_mass_matrix_solve,
+    bit for bit; the bias array is left untouched."""
+    from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
+    cps, ncols, ns = 2, 29, 30_001
+    st = syn.make_states(ns * cps, seed=3)
+    rng = np.random.default_rng(8)
+    J = _dev(torch, rng.uniform(-1, 1, (ns * cps, 6, ncols)))
+    bias = _dev(torch, rng.uniform(-50, 50, (ns, ncols)))
+    bias0 = bias.clone()
+    M, _, tau, _ = _case(ncols, ns, 4)
+    dM, dt = _dev(torch, M), _dev(torch, tau)
+    planes = _dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+    acc = dyn.acceleration(cps, planes, J, bias, dM, dt)
+    known = GeneralizedForceBatch(batch).run(cps, ncols, planes, J, -bias)
+    assert torch.equal(acc, dyn.solve(dM, known, dt)) and torch.equal(bias, bias0)
+
+
+def test_floating_base_acceleration_large_batch_residual(torch, batch, dyn):
+    """409 600 systems (an MPC batch of 4096 samples x 100 steps), 2 contacts, 6 + 23 DoF: the
+    size-independent property M acc = -bias + sum J^T wrench + torques, checked on the device."""
+    cps, ncols, ns = 2, 29, 409_600
+    planes = syn.make_planes_torch(ns * cps, batch.device, seed=12)[0]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    J = torch.rand((ns * cps, 6, ncols), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    bias = (torch.rand((ns, ncols), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 100
+    tau = (torch.rand((ns, ncols - 6), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 10
+    A = torch.rand((ns, ncols, ncols), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    M = torch.bmm(A, A.transpose(1, 2)) / ncols
+    del A
+    M.diagonal(dim1=1, dim2=2).add_(0.5)
+    M = torch.tril(M) + torch.tril(M, -1).transpose(1, 2)
+    acc, wr = dyn.acceleration(cps, planes, J, bias, M, tau, want_wrench=True)
+    assert bool(torch.isfinite(acc).all())
+    W = wr.T.reshape(ns, cps, 6)
+    rhs = -bias + torch.einsum("scrq,scr->sq", J.reshape(ns, cps, 6, ncols), W)
+    rhs[:, 6:] += tau
+    res = (torch.bmm(M, acc.unsqueeze(2)).squeeze(2) - rhs).abs().amax(dim=1)
+    mag = bias.abs().amax(dim=1) + (J.reshape(ns, cps, 6, ncols).abs() * W.abs().unsqueeze(3)).sum(dim=(1, 2)).amax(dim=1)
+    assert bool((res <= 1e-12 * (mag + M.abs().sum(dim=2).amax(dim=1) * acc.abs().amax(dim=1))).all())

@@ -280,6 +280,41 @@ def test_generalized_force_oracle_vs_reference_build(sys_oracle, ref, cps, ncols
     assert np.array_equal(o, r) and np.array_equal(wo.T, wr)
 
 
+# --- the whole of dynamics(): -bias + J^T wrench + torques, (M + reg).llt().solve -------------------
+
+@pytest.mark.parametrize("cps,ncols,het,with_tau,with_reg,spread", [
+    (2, 29, False, True, False, 0.0), (2, 29, True, True, True, 1.0), (1, 6, False, False, False, 0.5),
+    (4, 38, True, True, True, 0.5), (3, 12, False, True, False, 1.5), (2, 7, True, True, True, 0.0)])
+def test_floating_base_dynamics_oracle_vs_reference_build(sys_oracle, ref, cps, ncols, het, with_tau,
+                                                          with_reg, spread):
+    """FloatingBaseSystemDynamics.cpp compiled unmodified, run over the KinDynComputations test double
+    loaded with random symmetric positive definite mass matrices, bias forces, joint torques and
+    (through setMassMatrixRegularization) a regularisation term.  Bit for bit: the stand-in Eigen
+    evaluates LLT in the order the C oracle restates."""
+    rng = np.random.default_rng(77 * cps + ncols)
+    ns = 300
+    n = ns * cps
+    st = syn.make_states(n, seed=90 + cps, heterogeneous=het)
+    J = rng.normal(size=(n, 6, ncols))
+    bias = rng.normal(size=(ns, ncols)) * 20.0
+    tau = rng.normal(size=(ns, ncols - 6)) * 5.0 if with_tau and ncols > 6 else None
+    reg = None
+    if with_reg:
+        reg = np.diag(10.0 ** rng.uniform(-4, -2, ncols))
+        reg[ncols - 1, 0] = reg[0, ncols - 1] = 1e-3
+    M = syn.make_mass_matrices(ns, ncols, seed=11 + ncols, spread=spread)
+    planes = syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])
+    o, wo = sys_oracle.floating_base_acceleration(cps, planes, J, bias, M, tau, reg,
+                                                  param_planes=st["params"].T if het else None,
+                                                  uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True,
+                                                  nthreads=2)
+    r, wr = ref.floating_base_dynamics(cps, st["twists"], st["poses"], st["null_poses"], J, bias, M, tau, reg,
+                                       params=st["params"] if het else None,
+                                       uniform=syn.REFERENCE_TEST_PARAMS, want_wrench=True, nthreads=4)
+    assert np.isfinite(r).all()
+    assert np.array_equal(o, r) and np.array_equal(wo.T, wr)
+
+
 # --- integrate -> contact model rollout ------------------------------------------------------------
 
 @pytest.mark.parametrize("rho", [0.0, 2.0])

@@ -175,3 +175,71 @@ def test_generalized_force_matches_exact(g, tag):
     # base = NULL means zeros
     out0 = so.generalized_force(cps, ncols, planes, g[tag + "_J"], None, param_planes=prm)
     assert np.allclose(out0 + g[tag + "_base"], g[tag + "_out"], rtol=0, atol=1e-9 * mag.max())
+
+
+# --- (M + reg).llt().solve(known + torques): the end of FloatingBaseDynamicalSystem::dynamics -------
+
+EPS = 2.0 ** -52
+
+
+def llt_tolerance(nc, cond):
+    """Forward-error bound of a floating-point Cholesky solve: relative error <= c n eps cond(A)
+    (Higham, Accuracy and Stability of Numerical Algorithms, thm 10.4 + 7.2); flat 1e-12 (north_star)
+    where the conditioning allows it."""
+    return np.maximum(TOL, 4.0 * nc * EPS * cond)
+
+
+@pytest.fixture(scope="module")
+def gd():
+    from oracle import ccm_oracle
+    ccm_oracle.build()
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "dyn_exact_golden.npz")))
+
+
+def test_mass_matrix_solve_matches_exact_rationals(gd):
+    """oracle/exact_golden_dyn.py: the solution is rational in the inputs, evaluated exactly."""
+    for tag in gd["tags"]:
+        M, known, acc, cond = (gd[f"{tag}_{k}"] for k in ("M", "known", "acc", "cond"))
+        tau, reg = gd.get(f"{tag}_tau"), gd.get(f"{tag}_reg")
+        nc = known.shape[1]
+        for nthreads in (1, 3):
+            x = so.mass_matrix_solve(M, known, tau, reg, nthreads=nthreads)
+            assert (rel(x, acc) <= llt_tolerance(nc, cond)).all(), tag
+        # well conditioned systems meet the flat tolerance
+        easy = cond < 100
+        if easy.any():
+            assert rel(x[easy], acc[easy]).max() <= TOL
+
+
+def test_mass_matrix_solve_reads_only_the_lower_triangle(gd):
+    """Eigen's LLT<Lower>: the strict upper triangle never enters."""
+    M, known = gd["c_M"].copy(), gd["c_known"]
+    x0 = so.mass_matrix_solve(M, known)
+    iu = np.triu_indices(M.shape[1], 1)
+    M[:, iu[0], iu[1]] = np.nan
+    assert np.array_equal(so.mass_matrix_solve(M, known), x0)
+
+
+def test_mass_matrix_solve_not_positive_definite_is_nan():
+    M = np.array([[[1.0, 2.0], [2.0, 1.0]]])
+    assert np.isnan(so.mass_matrix_solve(M, np.ones((1, 2)))).any()
+
+
+def test_floating_base_acceleration_composes_force_and_solve(g):
+    from bipedal_locomotion_framework_b200 import synthetic as syn
+    tag = "gfa"
+    ns, cps, ncols = (int(x) for x in g[tag + "_shape"])
+    planes = syn.aos_to_planes(g[tag + "_twists"], g[tag + "_poses"], g[tag + "_null_poses"])
+    prm = np.ascontiguousarray(g[tag + "_params"].T)
+    rng = np.random.default_rng(5)
+    bias = rng.normal(size=(ns, ncols))
+    tau = rng.normal(size=(ns, ncols - 6))
+    M = syn.make_mass_matrices(ns, ncols, seed=2)
+    acc = so.floating_base_acceleration(cps, planes, g[tag + "_J"], bias, M, tau, param_planes=prm)
+    known = so.generalized_force(cps, ncols, planes, g[tag + "_J"], -bias, param_planes=prm)
+    assert np.array_equal(acc, so.mass_matrix_solve(M, known, tau))
+    # residual of the linear system, the property that does not depend on any factorisation
+    rhs = known.copy()
+    rhs[:, 6:] += tau
+    res = np.einsum("sij,sj->si", M, acc) - rhs
+    assert np.abs(res).max() <= 1e-12 * np.abs(rhs).max()

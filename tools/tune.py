@@ -192,9 +192,75 @@ def gf_only():
     os.environ.pop("BLF_CCM_TUNE_GF_STAGES", None)
 
 
+def dyn_only():
+    """Mass-matrix solve (the end of FloatingBaseDynamicalSystem::dynamics) and the whole step.
+    Bytes per system: the lower triangle LLT reads (nc(nc+1)/2) + known in + acc out (+ torques);
+    the dense matrix the caller hands over is nc*nc -- both fractions are printed."""
+    from bipedal_locomotion_framework_b200.system import FloatingBaseDynamicsBatch
+    b = make_batch()
+    dyn = FloatingBaseDynamicsBatch(b)
+    rnd = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda") * 2 - 1
+    shapes = ((409600, 29), (1 << 20, 29), (1 << 20, 18), (1 << 21, 12), (1 << 22, 6), (1 << 19, 31),
+              (1 << 20, 24), (1 << 21, 7), (1 << 21, 15), (1 << 17, 38), (1 << 15, 64))
+    only = [int(x) for x in os.environ.get("DYN_NC", "").split(",") if x]
+    for ns, nc in shapes:
+        if only and nc not in only:
+            continue
+        nb = 3
+        Ms = []
+        for _ in range(nb):
+            A = rnd(ns, nc, nc)
+            M = torch.bmm(A, A.transpose(1, 2)) / nc
+            del A
+            M.diagonal(dim1=1, dim2=2).add_(0.5)
+            Ms.append(M)
+        known = rnd(ns, nc)
+        tau = rnd(ns, nc - 6) if nc > 6 else None
+        outs = [torch.empty_like(known) for _ in range(nb)]
+        cls = [dyn.prepare_solve(Ms[j], known, tau, out=outs[j])[0] for j in range(nb)]
+        ms = timeit(lambda i: cls[i % nb](), iters=30, warm=5)
+        tri = 8 * (nc * (nc + 1) // 2 + 2 * nc + max(nc - 6, 0))
+        dense = 8 * (nc * nc + 2 * nc + max(nc - 6, 0))
+        gbs_t, gbs_d = ns * tri / (ms * 1e-3) / 1e9, ns * dense / (ms * 1e-3) / 1e9
+        flops = ns * (nc ** 3 / 3 + 2 * nc * nc) / (ms * 1e-3) / 1e12
+        print(f"mass-matrix solve systems={ns:8d} nc={nc:3d}  {ms*1e3:9.1f} us  {ns/ms/1e3:8.1f} M systems/s  "
+              f"lower-triangle {gbs_t:7.1f} GB/s {gbs_t/PEAK*100:5.1f} %   dense {gbs_d:7.1f} GB/s {gbs_d/PEAK*100:5.1f} %   "
+              f"{flops:5.2f} TFLOP/s", flush=True)
+        del Ms, outs, cls
+        torch.cuda.empty_cache()
+    # the whole step at the MPC batch size: 409600 systems x 2 contacts, 6 + 23 DoF
+    for ns, cps, nc in ((409600, 2, 29), (409600, 2, 12)):
+        n = ns * cps
+        st = syn.make_states(min(n, 1 << 18), seed=49)
+        reps = (n + st["n"] - 1) // st["n"]
+        pl = torch.from_numpy(np.ascontiguousarray(np.tile(
+            syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]), (1, reps))[:, :n])).cuda()
+        nb = 3
+        Js = [rnd(n, 6, nc) for _ in range(nb)]
+        Ms = []
+        for _ in range(nb):
+            A = rnd(ns, nc, nc)
+            M = torch.bmm(A, A.transpose(1, 2)) / nc
+            del A
+            M.diagonal(dim1=1, dim2=2).add_(0.5)
+            Ms.append(M)
+        bias, tau = rnd(ns, nc), rnd(ns, nc - 6)
+        outs = [torch.empty_like(bias) for _ in range(nb)]
+        cls = [dyn.prepare_acceleration(cps, pl, Js[j], bias, Ms[j], tau, out=outs[j])[0] for j in range(nb)]
+        ms = timeit(lambda i: cls[i % nb](), iters=30, warm=5)
+        per_sys = cps * (200 + 48 * nc) + 8 * (nc * (nc + 1) // 2 + 2 * nc + (nc - 6))
+        gbs = ns * per_sys / (ms * 1e-3) / 1e9
+        print(f"floating-base acceleration systems={ns} contacts/system={cps} nc={nc}  {ms*1e3:9.1f} us  "
+              f"{ns/ms/1e3:8.1f} M systems/s  {gbs:7.1f} GB/s {gbs/PEAK*100:5.1f} % (lower-triangle bytes)", flush=True)
+        del Js, Ms, outs, cls, pl
+        torch.cuda.empty_cache()
+
+
 def main():
     if "--rls-only" in sys.argv:
         return rls_only()
+    if "--dyn-only" in sys.argv:
+        return dyn_only()
     if "--sys-only" in sys.argv:
         return sys_only()
     if "--gf-only" in sys.argv:
