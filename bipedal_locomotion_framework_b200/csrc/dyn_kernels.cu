@@ -7,143 +7,322 @@
 // in the reference tree) is the lower Cholesky factorisation A = L L^T read from the LOWER triangle of
 // A, followed by the two triangular solves; restated here, not ported.
 //
-// Warp-level kernel (nc <= 31).  A system is owned by a group of G = 8, 16 or 32 lanes (4, 2, 1
-// systems per warp); lane r of the group owns ROW r of A / L in registers and one extra lane owns
-// the right-hand side as row nc of the augmented matrix [A b; b^T .], so that the forward
-// substitution L y = b comes out of the factorisation itself (y = the last row of the augmented
-// factor).  Right-looking, column by column:
-//     d = A[j][j] (one shuffle);  rs = 1/sqrt(d);  L[r][j] = A[r][j] * rs;
-//     the column goes to shared memory (as row j of L^T, in the tile's unused upper triangle) and
-//     every lane updates the rest of its row:  A[r][k] -= L[r][j] * L[k][j],  k > j,
-//     L[k][j] read back as a broadcast (one 16-byte shared load per two multiply-adds).
-// Lanes never test k <= r: the entries right of a row's diagonal are never read by anybody, so
-// they are allowed to hold garbage and the inner loop is a pure LDS + DFMA stream.
-// The back substitution L^T x = y walks k = nc-1 .. 0 with x_k broadcast by shuffle and lane r
-// reading ITS row of L^T (what the column writes left in the tile).
-// Tile rows have an odd pitch (G + 1 doubles), so "lane r reads element k of row r" is free of
-// bank conflicts; the global reads are row-wise (lanes = columns <= row): coalesced, and only the
-// sectors of the lower triangle are touched.
-// Arithmetic deviates from a textbook LLT in one rounding: L[r][j] = s * rsqrt(d) instead of
-// s / sqrt(d) (<= 2 ulp per entry; parity tests bound the effect on the solution).  A matrix that is
-// not positive definite gives NaN (the reference's Eigen stops the factorisation and solves with the
-// partial factor: garbage either way; include/blf_ccm.h states it).
+// Warp-level kernel (nc <= 47).  A system is owned by a group of H = 4, 8 or 16 lanes (8, 4 or 2 systems
+// per warp); lane r of the group owns the ROWS r, r + H, r + 2H, ... of A / L in registers ("slots"),
+// and the right-hand side rides along as the last row of the augmented matrix [A b; b^T .], so
+// that the forward substitution L y = b comes out of the factorisation itself (y = the last row of
+// the augmented factor).  Right-looking, column by column:
+//     d = A[j][j] (one shuffle);  rs = 1/sqrt(d);  L[i][j] = A[i][j] * rs  for the lane's rows i > j;
+//     the column goes through a small shared-memory buffer and every lane updates the rest of its
+//     rows:  A[i][k] -= L[i][j] * L[k][j],  k > j,  L[k][j] read back as a broadcast.
+// What bounds this kernel is the shared-memory data pipe (one wavefront per broadcast double per
+// warp; ncu of the first one-row-per-lane form: 86 % busy at 20 % of HBM) and, with few warps, the
+// latency of the column-to-column dependency -- not FP64 issue and not HBM.  A broadcast value read
+// once is used for every row the lane owns and for every system of the warp, so several rows per
+// lane and several systems per warp divide that traffic.
+// Lanes never test k <= i: the entries right of a row's diagonal are never read by anybody, so they
+// may hold garbage and the inner loop is a pure LDS + DFMA stream.  The size class N (rows incl. the
+// right-hand side) is a template parameter; a smaller system is padded with identity rows (exact
+// no-ops: the real entries see the same operations in the same order).
+// The back substitution L^T x = y needs COLUMN k of L for x_k -- which is exactly what the lanes of
+// a group hold between them (each its rows' entries): per k every lane multiplies its rows' entries
+// by its rows' x (the right-hand side row counts as x = -1), a butterfly of shuffles sums over the
+// group, and the lane that owns row k keeps -sum / L[k][k].  So L never goes back to shared memory,
+// the tile of a system is only its input triangle, and that tile is refilled for the warp's NEXT
+// group of systems (per-thread async copies, LDGSTS: no registers, no waiting) as soon as the rows
+// are in registers -- the loads of the next group overlap the whole factorisation of this one.  (A
+// first form that loaded, then computed, spent 77 % of its time waiting for its loads; a second
+// that kept L^T in shared memory for the back substitution had room for only 6 warps per SM.)
+// Shared memory per system: the packed lower triangle of A, N(N+1)/2 doubles (row i at i(i+1)/2;
+// rows H apart x 8-byte accesses are free of bank conflicts), the joint torques and two column
+// buffers.  The global reads are row-wise (lanes = columns <= row): coalesced, and only the sectors
+// of the lower triangle are touched.
+// Arithmetic deviates from a textbook LLT in two places: L[i][j] = s * rsqrt(d) instead of
+// s / sqrt(d) (<= 2 ulp per entry), and the back substitution's sums are taken in butterfly order;
+// parity tests bound the effect on the solution.  A matrix that is not positive definite gives NaN
+// (the reference's Eigen stops the factorisation and solves with the partial factor: garbage either
+// way; include/blf_ccm.h states it).
 //
-// Block-level kernel (32 <= nc <= 128 or forced): one CTA per system, thread r owns row r in
-// shared memory, same operations in the same order -- bit-identical to the warp-level kernel where
-// both apply (tested) -- three barriers per column; correctness path, not tuned.
+// Block-level kernel (48 <= nc <= 128 or forced): one CTA per system, thread r owns row r in
+// shared memory, the same factorisation in the same order (the back substitution sums sequentially),
+// three barriers per column; correctness path, not tuned.
 #include "dyn_kernels.h"
 
+#include <algorithm>
 #include <cstdint>
+#include <type_traits>
 
 #include "ccm_ptx.cuh"
 
 namespace blfccm {
 namespace {
 
-constexpr int kLltThreads = 128;
+// compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>)
+template <int N, int I = 0, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
+}
+
+constexpr int kLltThreads = 64;   // two warps share the regularisation triangle; CTAs per SM from the occupancy API
 constexpr unsigned kFullMask = 0xffffffffu;
 
-template <int G> struct LltTile {
-    static constexpr int P = G + 1;          // pitch in doubles, odd
-    static constexpr int DOUBLES = G * P;    // G rows (rows >= nc + 1 are only ever touched as garbage)
+// shared memory of one system
+template <int H, int N> struct LltTile {
+    static constexpr int TRI = N * (N + 1) / 2;                        // packed lower triangle + right-hand side row
+    static constexpr int TAU = (N - 1 > 6) ? N - 1 - 6 : 0;           // joint torques
+    static constexpr int TAU_AT = (TRI + 1) / 2 * 2;
+    static constexpr int NP = (N + 1) / 2 * 2;                         // one column buffer
+    static constexpr int COL_AT = (TAU_AT + TAU + 1) / 2 * 2;
+    static constexpr int STRIDE = (COL_AT + 2 * NP + 15) / 16 * 16 + (H == 8 ? 8 : 4);   // + bank spreading of the groups
+    static constexpr int PER_WARP = (32 / H) * STRIDE;
+    static constexpr size_t bytes(bool reg)
+    {
+        return sizeof(double) * (size_t(kLltThreads / 32) * PER_WARP + (reg ? TAU_AT : 0));
+    }
 };
 
-template <int G, int NCMAX, bool REG>
-__global__ void __launch_bounds__(kLltThreads)
-ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
+// One piece of a system's input into its tile, per-thread async copies (lanes = columns: coalesced
+// rows, only the sectors of the lower triangle are touched).  PIECE i < N-1: row i of the lower
+// triangle; PIECE N-1: the right-hand side row and the joint torques.  Padding rows and the missing
+// systems of the last group are written as identity / zeros with plain stores.
+struct LltSource {
+    const double* M;      // mass + s * nc * nc + r
+    const double* known;  // known + s * nc + r
+    const double* tau;    // tau + s * (nc - 6) + r, or nullptr
+    double* t;            // the tile, + r
+    uint32_t ts;          // its shared-window address
+    int nc, r;
+    bool valid;
+};
+
+template <int H, int N>
+__device__ __forceinline__ LltSource llt_source(const LltArgs& a, long long s, double* tile, int r)
 {
-    static_assert(NCMAX + 1 <= G && (G == 8 || G == 16 || G == 32), "size class");
-    constexpr int SPW = 32 / G;
-    constexpr int P = LltTile<G>::P;
-    extern __shared__ __align__(16) double llt_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / G, r = lane % G;
-    const int nc = a.nc;
-    const long long s0 = (static_cast<long long>(blockIdx.x) * (kLltThreads / 32) + warp) * SPW;
-    if (s0 >= a.n) return;   // whole warp
-    const long long s = s0 + g;
-    const bool valid = s < a.n;
-    double* tile = llt_smem + (warp * SPW + g) * LltTile<G>::DOUBLES;
+    LltSource q;
+    q.nc = a.nc;
+    q.r = r;
+    q.valid = s < a.n;
+    q.M = a.mass + s * q.nc * q.nc + r;
+    q.known = a.known + s * q.nc + r;
+    q.tau = a.tau ? a.tau + s * (q.nc - 6) + r : nullptr;
+    q.t = tile + r;
+    q.ts = ptx::smem_addr(tile) + r * 8;
+    return q;
+}
 
-    ptx::grid_dep_wait();
-
-    // ---- lower triangle + right-hand side into the tile (coalesced rows) ------------------------
-    {
-        const double* M = a.mass + s * nc * nc + r;
+template <int H, int N, int PIECE>
+__device__ __forceinline__ void llt_issue_piece(const LltSource& q)
+{
+    using T = LltTile<H, N>;
+    constexpr int NM = N - 1;
+    if constexpr (PIECE < NM) {
+        constexpr int i = PIECE;
 #pragma unroll
-        for (int i = 0; i < NCMAX; ++i) {
-            if (i < nc) {
-                if (r <= i) {
-                    double v = 1.0;
-                    if (valid) {
-                        v = __ldcs(M + i * nc);
-                        if constexpr (REG) v += __ldg(a.reg + i * nc + r);
-                    } else if (r != i) v = 0.0;   // identity for the missing systems of the last warp
-                    tile[i * P + r] = v;
+        for (int qq = 0; qq * H <= i; ++qq) {
+            if (q.r + qq * H <= i) {
+                if (q.valid && i < q.nc) ptx::cp_async8(q.ts + (i * (i + 1) / 2 + qq * H) * 8, q.M + i * q.nc + qq * H);
+                else q.t[i * (i + 1) / 2 + qq * H] = (q.r + qq * H == i) ? 1.0 : 0.0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int qq = 0; qq * H < NM; ++qq) {
+            const int c = q.r + qq * H;
+            if (c < NM) {
+                if (q.valid && c < q.nc) ptx::cp_async8(q.ts + (NM * (NM + 1) / 2 + qq * H) * 8, q.known + qq * H);
+                else q.t[NM * (NM + 1) / 2 + qq * H] = 0.0;
+            }
+        }
+        if constexpr (T::TAU > 0) {
+            if (q.tau) {
+#pragma unroll
+                for (int qq = 0; qq * H < NM - 6; ++qq) {
+                    const int c = q.r + qq * H;
+                    if (c < NM - 6) {
+                        if (q.valid && c < q.nc - 6) ptx::cp_async8(q.ts + (T::TAU_AT + qq * H) * 8, q.tau + qq * H);
+                        else q.t[T::TAU_AT + qq * H] = 0.0;
+                    }
                 }
             }
         }
-        if (r < nc) {
-            double v = 0.0;
-            if (valid) {
-                v = __ldcs(a.known + s * nc + r);
-                if (a.tau && r >= 6) v += __ldcs(a.tau + s * (nc - 6) + (r - 6));
-            }
-            tile[nc * P + r] = v;
-        }
     }
-    __syncwarp();
+}
 
-    // ---- row r into registers (entries right of the diagonal: whatever the tile holds) ----------
-    double row[NCMAX];
-#pragma unroll
-    for (int k = 0; k < NCMAX; ++k) row[k] = tile[r * P + k];
-    __syncwarp();   // the tile's rows are overwritten by columns from here on
+template <int H, int N, int PIECE = 0>
+__device__ __forceinline__ void llt_issue_all(const LltSource& q)
+{
+    llt_issue_piece<H, N, PIECE>(q);
+    if constexpr (PIECE + 1 < N) llt_issue_all<H, N, PIECE + 1>(q);
+}
 
-    // ---- factorisation, forward substitution riding along in lane nc -----------------------------
-    double rdiag = 0.0;   // 1 / L[r][r]
+// Persistent warps: a warp takes groups of 32 / H systems with a grid stride.
+// The whole input of the next group through a real call: made with the lane's rows live in registers,
+// where the ~80 inlined address computations would push the kernel over 255 registers.
+template <int H, int N>
+__device__ __noinline__ void llt_issue_all_call(const LltArgs& a, long long s, double* tile, int r)
+{
+    llt_issue_all<H, N>(llt_source<H, N>(a, s, tile, r));
+    ptx::cp_async_commit();
+}
+
+template <int H, int N, bool REG>
+__global__ void __launch_bounds__(kLltThreads)
+ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
+{
+    static_assert((H == 4 || H == 8 || H == 16) && N >= 2 && N <= (H == 16 ? 48 : 4 * H), "size class");
+    using T = LltTile<H, N>;
+    constexpr int R = (N + H - 1) / H;        // rows (slots) per lane
+    constexpr int SPW = 32 / H;               // systems per warp
+    constexpr int NM = N - 1;                 // order of the (identity-padded) matrix; row NM = right-hand side
+    constexpr bool SHORT = H * R > N;         // the last slot has lanes without a row
+    constexpr int WPB = kLltThreads / 32;
+    // start 1/sqrt of the next diagonal entry as soon as it is final: pays with few warps per SM
+    // (tools/micro/llt_bench.cu: +17 % at 29 unknowns, -4 % at 18 and 23)
+    constexpr bool LOOK = N >= 28;
+    extern __shared__ __align__(16) double llt_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / H, r = lane % H;
+    const int nc = a.nc;
+    const long long ngroups = (a.n + SPW - 1) / SPW;
+    const long long gstride = static_cast<long long>(gridDim.x) * WPB;
+    long long grp = static_cast<long long>(blockIdx.x) * WPB + warp;
+    double* const tile = llt_smem + warp * T::PER_WARP + g * T::STRIDE;
+    double* const col = tile + T::COL_AT;
+    const double* regt = llt_smem + WPB * T::PER_WARP;
+
+    ptx::grid_dep_wait();
+
+    if constexpr (REG) {   // lower triangle of the regularisation term, packed like the tiles, once per CTA
+        double* w = llt_smem + WPB * T::PER_WARP;
+        for (int i = 0; i < N; ++i)   // rows >= nc (identity padding, the right-hand side row): + 0.0
+            for (int c = threadIdx.x; c <= i; c += kLltThreads)
+                w[i * (i + 1) / 2 + c] = (i < nc) ? __ldg(a.reg + i * nc + c) : 0.0;
+        __syncthreads();
+    }
+    if (grp >= ngroups) return;
+
+    llt_issue_all<H, N>(llt_source<H, N>(a, grp * SPW + g, tile, r));
+    ptx::cp_async_commit();
+    for (; grp < ngroups; grp += gstride) {
+        const long long s = grp * SPW + g;
+        const bool valid = s < a.n;
+        ptx::cp_async_wait<0>();
+        __syncwarp();
+
+        // ---- the lane's rows into registers (entries right of a diagonal: whatever the tile holds:
+        //      entries of the same system's later rows) ------------------------------------------------
+        double row[R][NM];
+        bool rowok[R];
 #pragma unroll
-    for (int j = 0; j < NCMAX; ++j) {
-        if (j < nc) {
-            const double d = __shfl_sync(kFullMask, row[j], j, G);
-            const double rs = rsqrt(d);
-            if (r == j) rdiag = rs;
-            const double l = row[j] * rs;
-            row[j] = l;
-            tile[j * P + r] = l;   // column j = row j of L^T (r > j), y_j at r == nc
+        for (int m = 0; m < R; ++m) {
+            const int i = r + m * H;
+            rowok[m] = !SHORT || m < R - 1 || i < N;
+            const int ic = (SHORT && m == R - 1) ? min(i, N - 1) : i;
+            const double* src = tile + ic * (ic + 1) / 2;
+#pragma unroll
+            for (int k = 0; k < NM; ++k)
+                if (k < H * (m + 1)) {
+                    row[m][k] = src[k];
+                    if constexpr (REG) row[m][k] += regt[ic * (ic + 1) / 2 + k];   // M + reg, one rounding (:236-239)
+                }
+        }
+        if constexpr (T::TAU > 0) {
+            // the right-hand side row: known.tail += jointTorques (:226-227)
+            if (a.tau && r == NM % H) {
+#pragma unroll
+                for (int k = 6; k < NM; ++k) row[R - 1][k] += tile[T::TAU_AT + k - 6];
+            }
+        }
+        __syncwarp();
+        // The tile is free: the next group's triangle lands in it while this one is factorised.
+        // How the copies are issued is a measured choice per class (tools/micro/llt_bench.cu,
+        // profiles/r02_llt_variants.log): groups of 4 lanes -- one piece per column step, inlined;
+        // groups of 8 lanes -- all at once through a real call (spread over the steps they cost
+        // 13-23 % there, inlined at once they spill).
+        constexpr bool SPREAD = H == 4;
+        const bool more = grp + gstride < ngroups;
+        const LltSource next = llt_source<H, N>(a, (grp + gstride) * SPW + g, tile, r);
+        if constexpr (SPREAD) {
+            if (more) llt_issue_piece<H, N, NM>(next);
+        } else {
+            if (more) llt_issue_all_call<H, N>(a, (grp + gstride) * SPW + g, tile, r);
+        }
+
+        // ---- factorisation; the forward substitution rides along in the last row -----------------
+        double rdiag[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) rdiag[m] = 0.0;
+        double rs = LOOK ? rsqrt(__shfl_sync(kFullMask, row[0][0], 0, H)) : 0.0;
+        static_for<NM>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr int mj = j / H, rj = j % H;
+            if constexpr (SPREAD) {
+                if (more) llt_issue_piece<H, N, j>(next);
+            }
+            if constexpr (!LOOK) rs = rsqrt(__shfl_sync(kFullMask, row[mj][j], rj, H));
+            if (r == rj) rdiag[mj] = rs;
+            double* cb = col + (j & 1) * T::NP;   // cb[i] = L[i][j]; two buffers: one __syncwarp per column
+            double nl[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                if (m >= mj) {
+                    const double l = row[m][j] * rs;
+                    row[m][j] = l;   // L stays in the registers of its row's lane (back substitution)
+                    nl[m] = -l;
+                    const int i = r + m * H;
+                    if (i > j && rowok[m]) cb[i] = l;
+                }
+            }
             __syncwarp();
-            const double nl = -l;
-            const double* trow = tile + j * P;
-            constexpr int k0c = 0;
-            (void)k0c;
             const int k0 = j + 1;
-            const int odd = (j * P + k0) & 1;   // 16-byte alignment of the pairs (tile base is aligned)
-            if (odd && k0 < NCMAX) row[k0] = fma(nl, trow[k0], row[k0]);
+            const int odd = k0 & 1;   // 16-byte alignment of the pairs
+            auto upd = [&](int k, double t) {
 #pragma unroll
-            for (int k = k0 + odd; k + 1 < NCMAX; k += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(trow + k);
-                row[k] = fma(nl, v.x, row[k]);
-                row[k + 1] = fma(nl, v.y, row[k + 1]);
+                for (int m = 0; m < R; ++m)
+                    if (m >= k / H) row[m][k] = fma(nl[m], t, row[m][k]);
+                if (LOOK && k == j + 1)   // the next diagonal entry is final
+                    rs = rsqrt(__shfl_sync(kFullMask, row[(j + 1) / H][j + 1], (j + 1) % H, H));
+            };
+            if (odd && k0 < NM) upd(k0, cb[k0]);
+#pragma unroll
+            for (int k = k0 + odd; k + 1 < NM; k += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(cb + k);
+                upd(k, v.x);
+                upd(k + 1, v.y);
             }
-            if (((NCMAX - (k0 + odd)) & 1) && k0 + odd < NCMAX)
-                row[NCMAX - 1] = fma(nl, trow[NCMAX - 1], row[NCMAX - 1]);
+            if (((NM - (k0 + odd)) & 1) && k0 + odd < NM) upd(NM - 1, cb[NM - 1]);
+        });
+        if constexpr (SPREAD) {
+            if (more) ptx::cp_async_commit();
         }
-    }
 
-    // ---- back substitution: lane r reads its row of L^T, x_k arrives by shuffle -----------------
-    double acc = tile[r * P + nc];   // y_r
+        // ---- back substitution: x_k = -(sum over rows i > k of L[i][k] x_i) / L[k][k], the
+        //      right-hand side row (i = NM) entering with x = -1; the sum runs over the group's lanes
+        double x[R];
 #pragma unroll
-    for (int k = 1; k < NCMAX; ++k) row[k] = tile[r * P + k];
-    double x = 0.0;
+        for (int m = 0; m < R; ++m) x[m] = 0.0;
+        if (r == NM % H) x[R - 1] = -1.0;
 #pragma unroll
-    for (int k = NCMAX - 1; k >= 0; --k) {
-        if (k < nc) {
-            const double xk = __shfl_sync(kFullMask, acc * rdiag, k, G);
-            if (r == k) x = xk;
-            if (k > 0) acc = fma(-row[k], xk, acc);
+        for (int k = NM - 1; k >= 0; --k) {
+            const int mk = k / H, rk = k % H;
+            double p = (r > rk) ? row[mk][k] * x[mk] : 0.0;   // rows of slot mk above k (the others: x not yet known)
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                if (m > mk) p = fma(row[m][k], x[m], p);
+#pragma unroll
+            for (int w = 1; w < H; w <<= 1) p += __shfl_xor_sync(kFullMask, p, w, H);
+            if (r == rk) x[mk] = -p * rdiag[mk];
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = r + m * H;
+            if (valid && i < nc) a.acc[s * nc + i] = x[m];
         }
     }
-    if (valid && r < nc) a.acc[s * nc + r] = x;
 }
 
 // One CTA per system, thread r = row r (r == nc: the right-hand side), everything in shared memory.
@@ -210,9 +389,9 @@ ccm_llt_solve_general_kernel(const __grid_constant__ LltArgs a)
 
 template <typename K>
 cudaError_t launch(K kernel, long long grid, int threads, size_t smem, cudaStream_t st, bool pdl,
-                   const LltArgs& a)
+                   const LltArgs& a, bool set_attr = true)
 {
-    if (smem > 48 * 1024) {
+    if (set_attr && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return e;
@@ -230,37 +409,67 @@ cudaError_t launch(K kernel, long long grid, int threads, size_t smem, cudaStrea
     return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-template <int G, int NCMAX>
+template <int H, int N, bool REG>
+cudaError_t launch_fast_k(const LltArgs& a, cudaStream_t st, bool pdl)
+{
+    auto kernel = ccm_llt_solve_kernel<H, N, REG>;
+    const size_t smem = LltTile<H, N>::bytes(REG);
+    static int per_sm[64] = {};   // CTAs per SM of this instantiation, per device
+    static int sms[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (per_sm[dev] == 0) {
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return e;
+        }
+        int v = 0, n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kLltThreads, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (v < 1) return cudaErrorLaunchOutOfResources;
+        sms[dev] = n;
+        per_sm[dev] = v;
+    }
+    constexpr int SPW = 32 / H;
+    const long long groups = (a.n + SPW - 1) / SPW;
+    const long long want = (groups + kLltThreads / 32 - 1) / (kLltThreads / 32);
+    const long long grid = std::min<long long>(want, static_cast<long long>(per_sm[dev]) * sms[dev]);
+    return launch(kernel, grid, kLltThreads, smem, st, pdl, a, false);
+}
+
+template <int H, int N>
 cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
 {
-    constexpr int SPW = 32 / G;
-    const long long per_block = static_cast<long long>(kLltThreads / 32) * SPW;
-    const long long grid = (a.n + per_block - 1) / per_block;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const size_t smem = size_t(kLltThreads / 32) * SPW * LltTile<G>::DOUBLES * sizeof(double);
-    return a.reg ? launch(ccm_llt_solve_kernel<G, NCMAX, true>, grid, kLltThreads, smem, st, pdl, a)
-                 : launch(ccm_llt_solve_kernel<G, NCMAX, false>, grid, kLltThreads, smem, st, pdl, a);
+    return a.reg ? launch_fast_k<H, N, true>(a, st, pdl) : launch_fast_k<H, N, false>(a, st, pdl);
 }
 
 }  // namespace
 
-// size classes of the warp-level kernel: the inner loops are unrolled to NCMAX, so a system of nc
-// unknowns pays for the next class up -- classes are at most two apart
-#define BLF_LLT_CLASSES(X)                                                                     \
-    X(8, 3) X(8, 4) X(8, 5) X(8, 6) X(8, 7)                                                       \
-    X(16, 8) X(16, 9) X(16, 10) X(16, 12) X(16, 14) X(16, 15)                                     \
-    X(32, 16) X(32, 18) X(32, 20) X(32, 22) X(32, 24) X(32, 26) X(32, 28) X(32, 29) X(32, 30) X(32, 31)
+// size classes of the warp-level kernel, X(lanes per system, rows incl. the right-hand side): a
+// system of nc unknowns runs in the first class with N >= nc + 1, padded with identity rows
+#ifdef BLF_LLT_BENCH_CLASSES
+#define BLF_LLT_CLASSES(X) X(4, 7) X(4, 13) X(8, 19) X(8, 24) X(8, 30) X(16, 39)
+#else
+#define BLF_LLT_CLASSES(X)                                                      \
+    X(4, 4) X(4, 7) X(4, 8) X(4, 10) X(4, 13) X(4, 14) X(4, 16)                   \
+    X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 25) X(8, 26) X(8, 28) X(8, 30) X(8, 31) X(8, 32)           \
+    X(16, 34) X(16, 36) X(16, 37) X(16, 39) X(16, 40) X(16, 42) X(16, 45) X(16, 48)
+#endif
 
 cudaError_t llt_solve_launch(const LltArgs& a, cudaStream_t st, bool pdl, int force_general,
                              int* path_out, int* ncmax_out)
 {
     if (a.n <= 0) return cudaSuccess;
     if (!force_general && a.nc <= kLltMaxFast) {
-#define BLF_LLT_TRY(G, NCMAX)                         \
-    if (a.nc <= NCMAX) {                              \
-        if (path_out) *path_out = G;                  \
-        if (ncmax_out) *ncmax_out = NCMAX;            \
-        return launch_fast<G, NCMAX>(a, st, pdl);     \
+#define BLF_LLT_TRY(H, N)                          \
+    if (a.nc < N) {                                \
+        if (path_out) *path_out = H;               \
+        if (ncmax_out) *ncmax_out = N - 1;         \
+        return launch_fast<H, N>(a, st, pdl);      \
     }
         BLF_LLT_CLASSES(BLF_LLT_TRY)
 #undef BLF_LLT_TRY

@@ -102,23 +102,25 @@ def test_mass_matrix_solve_matches_exact_rationals(torch, dyn, gd):
             assert err[easy].max() <= TOL, (tag, err[easy].max())
 
 
-@pytest.mark.parametrize("nc", list(range(1, 41)) + [64, 100, 128])
+@pytest.mark.parametrize("nc", list(range(1, 50)) + [64, 100, 128])
 def test_mass_matrix_solve_vs_oracle_every_size(torch, batch, dyn, so, nc):
-    """Every size class of the warp-level kernel (nc <= 31) and the block-level kernel above, a
+    """Every size class of the warp-level kernel (nc <= 47) and the block-level kernel above, a
     system count that fills no warp or CTA evenly; benign conditioning (cond < 4): flat 1e-12."""
-    ns = 1003 if nc <= 40 else 37
+    ns = 1003 if nc <= 49 else 37
     M, known, tau, reg = _case(nc, ns, 500 + nc, with_reg=bool(nc % 2))
     want = so.mass_matrix_solve(M, known, tau, reg, nthreads=NTHREADS)
     x = dyn.solve(_dev(torch, M), _dev(torch, known), _dev(torch, tau), _dev(torch, reg)).cpu().numpy()
-    assert _last_path(batch) == (PATH_LLT_WARP if nc <= 31 else PATH_LLT_BLOCK)
+    assert _last_path(batch) == (PATH_LLT_WARP if nc <= 47 else PATH_LLT_BLOCK)
     assert np.isfinite(x).all()
     err = rel(x, want)
     assert err.max() <= TOL, (int(np.argmax(err)), err.max())
 
 
-def test_warp_and_block_kernels_agree_bit_for_bit(torch, dyn):
-    """Same operations in the same order: the block-level kernel (forced on a second handle through
-    BLF_CCM_TUNE_LLT_GENERAL, read when a handle is created) reproduces the warp-level one."""
+def test_warp_and_block_kernels_agree(torch, dyn, so):
+    """The block-level kernel (forced on a second handle through BLF_CCM_TUNE_LLT_GENERAL, read when
+    a handle is created) runs the same factorisation in the same order as the warp-level one; the
+    back substitutions sum in different orders (butterfly over the lanes / sequential), so the two
+    agree to rounding -- both within the tolerance against the oracle."""
     from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
     from bipedal_locomotion_framework_b200.system import FloatingBaseDynamicsBatch
     os.environ["BLF_CCM_TUNE_LLT_GENERAL"] = "1"
@@ -127,14 +129,17 @@ def test_warp_and_block_kernels_agree_bit_for_bit(torch, dyn):
     finally:
         os.environ.pop("BLF_CCM_TUNE_LLT_GENERAL", None)
     gen = FloatingBaseDynamicsBatch(b2)
-    for nc in (1, 3, 6, 7, 8, 12, 15, 16, 23, 29, 31):
-        M, known, tau, reg = _case(nc, 301, 900 + nc, spread=1.0, with_reg=nc in (7, 29))
+    for nc in (1, 3, 6, 7, 8, 12, 15, 16, 23, 29, 31, 38, 47):
+        M, known, tau, reg = _case(nc, 301, 900 + nc, spread=1.0, with_reg=nc in (7, 29, 38))
         args = [_dev(torch, a) for a in (M, known, tau, reg)]
         fast = dyn.solve(*args).cpu().numpy()
         assert _last_path(dyn._b) == PATH_LLT_WARP
         slow = gen.solve(*args).cpu().numpy()
         assert _last_path(b2) == PATH_LLT_BLOCK
-        assert np.array_equal(fast, slow), nc
+        want = so.mass_matrix_solve(M, known, tau, reg, nthreads=NTHREADS)
+        tol = llt_tolerance(nc, np.linalg.cond(M if reg is None else M + reg, np.inf))
+        assert (rel(fast, want) <= tol).all() and (rel(slow, want) <= tol).all(), nc
+        assert (rel(fast, slow) <= tol).all(), nc
 
 
 def test_mass_matrix_solve_in_place_and_stream(torch, dyn):
