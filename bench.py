@@ -670,7 +670,7 @@ def fused_rollout_leg(cx: Ctx, planes_np, K: int, W: int, no_cpu: bool) -> dict:
     return res
 
 
-def next_rows_leg(cx: Ctx, planes_np) -> dict:
+def next_rows_leg(cx: Ctx, planes_np, no_cpu: bool = False) -> dict:
     """The rows next to the path, one GPU, briefly (fractions of the measured HBM peak)."""
     from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch, KinematicsBatch
     torch, batch, dev = cx.torch, cx.batch, cx.dev
@@ -704,6 +704,54 @@ def next_rows_leg(cx: Ctx, planes_np) -> dict:
             "ms": g_ms, "contacts_per_s": n / (g_ms * 1e-3), "algorithmic_gbs": g_bytes / (g_ms * 1e-3) / 1e9,
             "hbm_frac_of_measured": g_bytes / (g_ms * 1e-3) / 1e9 / cx.peak}
         del Js, base, gouts, gcalls
+    # the end of FloatingBaseDynamicalSystem::dynamics: (M).llt().solve(-h + sum J^T wrench + torques)
+    from bipedal_locomotion_framework_b200.system import FloatingBaseDynamicsBatch
+    dyn = FloatingBaseDynamicsBatch(batch)
+    for ncols in (29, 12):
+        cps, ns = FEET, n // FEET
+        Ms = []
+        for _ in range(2):
+            A = torch.rand((ns, ncols, ncols), dtype=torch.float64, device=dev) * 2 - 1
+            M = torch.bmm(A, A.transpose(1, 2)) / ncols
+            del A
+            M.diagonal(dim1=1, dim2=2).add_(0.5)
+            Ms.append(M)
+        Js = [torch.rand((n, 6, ncols), dtype=torch.float64, device=dev) for _ in range(2)]
+        bias = torch.rand((ns, ncols), dtype=torch.float64, device=dev)
+        tau = torch.rand((ns, ncols - 6), dtype=torch.float64, device=dev)
+        outs = [torch.empty_like(bias) for _ in range(2)]
+        scalls = [dyn.prepare_solve(Ms[j], bias, tau, out=outs[j])[0] for j in range(2)]
+        s_ms = timed(lambda i: scalls[i % 2](), iters=20)
+        acalls = [dyn.prepare_acceleration(cps, planes[j], Js[j], bias, Ms[j], tau, out=outs[j])[0] for j in range(2)]
+        a_ms = timed(lambda i: acalls[i % 2](), iters=20)
+        tri = 8 * (ncols * (ncols + 1) // 2 + 2 * ncols + (ncols - 6))       # what LLT reads + rhs in + acc out + torques
+        dense = 8 * (ncols * ncols + 2 * ncols + (ncols - 6))                 # the dense matrix the caller hands over
+        a_bytes = cps * (200 + 48 * ncols) + tri
+        row = {"what": f"blf_sys_mass_matrix_solve / blf_sys_floating_base_acceleration: {ns} systems x {cps} contacts, "
+                       f"{ncols} unknowns (6 + {ncols - 6} joints), random symmetric positive definite mass matrices",
+               "solve_ms": s_ms, "solve_systems_per_s": ns / (s_ms * 1e-3),
+               "solve_hbm_frac_lower_triangle_bytes": ns * tri / (s_ms * 1e-3) / 1e9 / cx.peak,
+               "solve_hbm_frac_dense_bytes": ns * dense / (s_ms * 1e-3) / 1e9 / cx.peak,
+               "whole_step_ms": a_ms, "whole_step_systems_per_s": ns / (a_ms * 1e-3),
+               "hbm_frac_of_measured": ns * a_bytes / (a_ms * 1e-3) / 1e9 / cx.peak,
+               "bound": "shared-memory data pipe and column-to-column latency, not HBM (DESIGN section 10 row 5)"}
+        if cx.rank == 0 and not no_cpu:
+            from oracle import sys_oracle          # cpu_baseline leg: the C restatement, all host cores
+            cores = os.cpu_count() or 1
+            sample = 20000
+            Mh, kh, th = (x[:sample].cpu().numpy() for x in (Ms[0], bias, tau))
+            best_s = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                sys_oracle.mass_matrix_solve(Mh, kh, th, nthreads=cores)
+                dt_ = time.perf_counter() - t0
+                best_s = dt_ if best_s is None else min(best_s, dt_)
+            row["cpu_baseline"] = {"value": sample / best_s, "unit": "systems/s", "cores": cores, "kind": "port",
+                                   "sample": f"best of 3 passes of oracle/sys_oracle.c syso_mass_matrix_solve over "
+                                             f"the first {sample} systems"}
+        rows[f"floating_base_dynamics_{ncols}"] = row
+        del Ms, Js, bias, tau, outs, scalls, acalls
+        torch.cuda.empty_cache()
     kb = KinematicsBatch(cx.local, batch.handle)
     kp = [planes[j][6:18].clone() for j in range(3)]
     kcalls = [kb.prepare_euler_step(0.01, 1e-4, planes[j][0:6], kp[j][0:3], kp[j][3:12]) for j in range(3)]
@@ -860,7 +908,7 @@ def run_ours(args):
         c2["mpc_fused"]["speedup_vs_unfused_mpc"] = c2["mpc"]["ms_per_step"] / c2["mpc_fused"]["ms_per_step"]
         line["configs2"] = c2
         if cx.world == 1:
-            line["next_rows"] = next_rows_leg(cx, planes_np)
+            line["next_rows"] = next_rows_leg(cx, planes_np, args.no_cpu)
         line["e2e"] = e2e_leg(cx, K)
         line["cpu_baseline"] = None
         if cx.world == 1 and cx.rank == 0 and not args.no_cpu:

@@ -2,8 +2,8 @@
  * @file ContactRolloutBatch.h
  * Batched forms of the steps either side of the contact model (no reference equivalent as a
  * class; the per-system semantics are those of FloatingBaseSystemKinematics + ForwardEuler and of
- * the contact loop of FloatingBaseDynamicalSystem::dynamics,
- * src/System/src/FloatingBaseSystemDynamics.cpp:199-226).  Host code is C++17 and reaches the GPU
+ * FloatingBaseDynamicalSystem::dynamics from the bias forces on,
+ * src/System/src/FloatingBaseSystemDynamics.cpp:188-248).  Host code is C++17 and reaches the GPU
  * only through the C ABI (include/blf_ccm.h).
  */
 #ifndef BIPEDAL_LOCOMOTION_SYSTEM_CONTACT_ROLLOUT_BATCH_H
@@ -89,6 +89,32 @@ public:
                           const GenericContainer::DeviceSoA* parameters, const double* jacobians,
                           const double* base, double* out, GenericContainer::DeviceSoA* wrench = nullptr,
                           void* stream = nullptr);
+
+    /**
+     * Last step of FloatingBaseDynamicalSystem::dynamics (FloatingBaseSystemDynamics.cpp:226-243):
+     * acceleration[s] = (massMatrices[s] + regularization).llt().solve(known[s] (+ jointTorques[s] on
+     * the tail)).  Device arrays: massMatrices nSystems x columns x columns row-major (the lower
+     * triangle is read), regularization columns x columns or nullptr (what
+     * setMassMatrixRegularization stores), known / acceleration nSystems x columns (may alias),
+     * jointTorques nSystems x (columns - 6) or nullptr.
+     */
+    bool massMatrixSolve(std::size_t nSystems, int columns, const double* massMatrices,
+                         const double* regularization, const double* known, const double* jointTorques,
+                         double* acceleration, void* stream = nullptr);
+
+    /**
+     * dynamics() from the bias forces on (:188-248), the rigid-body quantities supplied by the caller:
+     * acceleration = (M + regularization).llt().solve(-biasForces + sum_c J_c^T wrench_c + [0; jointTorques]).
+     * states / parameters / jacobians / wrench as generalizedForce; biasForces nSystems x columns
+     * = [base wrench; joint torques] of generalizedBiasForces.
+     */
+    bool floatingBaseAcceleration(std::size_t nSystems, int contactsPerSystem, int columns,
+                                  const GenericContainer::DeviceSoA& states,
+                                  const GenericContainer::DeviceSoA* parameters, const double* jacobians,
+                                  const double* biasForces, const double* jointTorques,
+                                  const double* massMatrices, const double* regularization,
+                                  double* acceleration, GenericContainer::DeviceSoA* wrench = nullptr,
+                                  void* stream = nullptr);
 
 private:
     std::shared_ptr<ContactModels::CudaDevice> m_device;

@@ -157,3 +157,34 @@ bool ContactRolloutBatch::generalizedForce(std::size_t nSystems, int contactsPer
                                                 wrench ? wrench->planePointers() : nullptr, stream),
                   "generalizedForce");
 }
+
+bool ContactRolloutBatch::massMatrixSolve(std::size_t nSystems, int columns, const double* massMatrices,
+                                          const double* regularization, const double* known,
+                                          const double* jointTorques, double* acceleration, void* stream)
+{
+    if (m_device == nullptr) return report(BLF_CCM_ERR_INVALID_HANDLE, "massMatrixSolve");
+    return report(blf_sys_mass_matrix_solve(raw(m_device), static_cast<std::int64_t>(nSystems), columns,
+                                            massMatrices, regularization, known, jointTorques, acceleration,
+                                            stream),
+                  "massMatrixSolve");
+}
+
+bool ContactRolloutBatch::floatingBaseAcceleration(std::size_t nSystems, int contactsPerSystem, int columns,
+                                                   const DeviceSoA& states, const DeviceSoA* parameters,
+                                                   const double* jacobians, const double* biasForces,
+                                                   const double* jointTorques, const double* massMatrices,
+                                                   const double* regularization, double* acceleration,
+                                                   DeviceSoA* wrench, void* stream)
+{
+    if (m_device == nullptr) return report(BLF_CCM_ERR_INVALID_HANDLE, "floatingBaseAcceleration");
+    if (contactsPerSystem < 1
+        || !planes(states, 30, nSystems * static_cast<std::size_t>(contactsPerSystem), "states",
+                   "floatingBaseAcceleration"))
+        return false;
+    return report(blf_sys_floating_base_acceleration(
+                      raw(m_device), static_cast<std::int64_t>(nSystems), contactsPerSystem, columns,
+                      states.planePointers(), parameters ? parameters->planePointers() : nullptr, jacobians,
+                      biasForces, jointTorques, massMatrices, regularization, acceleration,
+                      wrench ? wrench->planePointers() : nullptr, stream),
+                  "floatingBaseAcceleration");
+}

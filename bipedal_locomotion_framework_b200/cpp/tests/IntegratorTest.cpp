@@ -434,5 +434,86 @@ TEST_CASE("Batched steps either side of the contact model")
             for (int q = 0; q < cols; ++q) worst = std::max(worst, std::fabs(out[s * cols + q] - ref[q]) / m);
         }
         REQUIRE(worst <= 1e-12);
+
+        // the whole of dynamics() from the bias forces on: acc = M^-1 (-h + sum J^T wrench + [0; tau]),
+        // checked through its defining property M acc = rhs with rhs rebuilt from per-instance wrenches
+        std::vector<double> mass(nSystems * cols * cols), tau(nSystems * (cols - 6)), acc(nSystems * cols);
+        for (std::size_t s = 0; s < nSystems; ++s)
+        {
+            double* M = &mass[s * cols * cols];
+            std::vector<double> A(cols * cols);
+            for (double& x : A) x = u(gen);
+            for (int i = 0; i < cols; ++i)
+                for (int k = 0; k <= i; ++k)
+                {
+                    double v = (i == k) ? 0.5 : 0.0;
+                    for (int q = 0; q < cols; ++q) v += A[i * cols + q] * A[k * cols + q] / cols;
+                    M[i * cols + k] = M[k * cols + i] = v;
+                }
+        }
+        for (double& x : tau) x = u(gen);
+        DeviceSoA massd(dev, 1, mass.size()), taud(dev, 1, tau.size()), accd(dev, 1, acc.size());
+        REQUIRE(massd.upload(0, mass.data()));
+        REQUIRE(taud.upload(0, tau.data()));
+        REQUIRE(rollouts.floatingBaseAcceleration(nSystems, cps, cols, states, nullptr, Jd.plane(0), based.plane(0),
+                                                  taud.plane(0), massd.plane(0), nullptr, accd.plane(0)));
+        REQUIRE(accd.download(0, acc.data()));
+        double worstResidual = 0;
+        for (std::size_t s = 0; s < nSystems; s += 7)
+        {
+            std::vector<double> rhs(cols), mag(cols);
+            for (int q = 0; q < cols; ++q)
+            {
+                rhs[q] = -base[s * cols + q];
+                mag[q] = std::fabs(rhs[q]);
+            }
+            for (int c = 0; c < cps; ++c)
+            {
+                const std::size_t i = s * cps + c;
+                model.setState(tws[i], pose[i]);
+                model.setNullForceTransform(nullPose[i]);
+                const iDynTree::Wrench& w = model.getContactWrench();
+                for (int q = 0; q < cols; ++q)
+                    for (int rr = 0; rr < 6; ++rr)
+                    {
+                        rhs[q] += J[(i * 6 + rr) * cols + q] * w(rr);
+                        mag[q] += std::fabs(J[(i * 6 + rr) * cols + q] * w(rr));
+                    }
+            }
+            for (int q = 6; q < cols; ++q) rhs[q] += tau[s * (cols - 6) + (q - 6)];
+            double m = 0, xm = 0, mm = 0;
+            for (int q = 0; q < cols; ++q) m = std::max(m, mag[q]);
+            for (int q = 0; q < cols; ++q) xm = std::max(xm, std::fabs(acc[s * cols + q]));
+            for (int i = 0; i < cols; ++i)
+            {
+                double rowSum = 0, res = -rhs[i];
+                for (int k = 0; k < cols; ++k)
+                {
+                    res += mass[(s * cols + i) * cols + k] * acc[s * cols + k];
+                    rowSum += std::fabs(mass[(s * cols + i) * cols + k]);
+                }
+                mm = std::max(mm, rowSum);
+                worstResidual = std::max(worstResidual, std::fabs(res) / (m + mm * xm));
+            }
+        }
+        REQUIRE(worstResidual <= 1e-12);
+        // the solve on its own, in place: known = M * (1, 2, ..., cols) comes back as (1, 2, ..., cols)
+        std::vector<double> known(nSystems * cols);
+        for (std::size_t s = 0; s < nSystems; ++s)
+            for (int i = 0; i < cols; ++i)
+            {
+                double v = 0;
+                for (int k = 0; k < cols; ++k) v += mass[(s * cols + i) * cols + k] * (k + 1);
+                known[s * cols + i] = v;
+            }
+        REQUIRE(outd.upload(0, known.data()));
+        REQUIRE(rollouts.massMatrixSolve(nSystems, cols, massd.plane(0), nullptr, outd.plane(0), nullptr,
+                                         outd.plane(0)));
+        REQUIRE(outd.download(0, known.data()));
+        double worstSolve = 0;
+        for (std::size_t s = 0; s < nSystems; ++s)
+            for (int i = 0; i < cols; ++i)
+                worstSolve = std::max(worstSolve, std::fabs(known[s * cols + i] - (i + 1)) / cols);
+        REQUIRE(worstSolve <= 1e-12);
     }
 }
