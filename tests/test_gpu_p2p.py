@@ -116,3 +116,69 @@ def test_p2p_argmin_exchange_two_gpus():
         assert ok, f"rank {rank}: wrong global arg-min"
         print(f"rank {rank}: {us:.2f} us per peer-memory exchange")
         assert us < 100.0
+
+
+def _missing_peer_worker(rank, world, port, q):
+    import time
+
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bipedal_locomotion_framework_b200 import sharding
+        from bipedal_locomotion_framework_b200.contact_models import ContinuousContactModelBatch
+        batch = ContinuousContactModelBatch(rank)
+        peer = sharding.PeerArgmin(batch, world, rank, dist)
+        mine = torch.tensor(list(sharding.pack_pair(1.0 + rank, 10 + rank)), dtype=torch.int64,
+                            device=batch.device)
+        ok = batch.decode_best(peer.exchange(mine)) == (1.0, 10)
+        dist.barrier()
+        # rank 1 never shows up for this exchange: rank 0's kernel gives up after its bounded spin
+        # (~2 s) and reports (NaN, -2) instead of hanging the GPU
+        waited = 0.0
+        if rank == 0:
+            t0 = time.perf_counter()
+            got = batch.decode_best(peer.exchange(mine))     # decode synchronises
+            waited = time.perf_counter() - t0
+            ok = ok and got[1] == -2 and got[0] != got[0] and 0.5 < waited < 20.0
+        dist.barrier()
+        # the epochs of the two ranks differ now: the mailbox is re-created (documented recovery) ...
+        peer.close()
+        peer = sharding.PeerArgmin(batch, world, rank, dist)     # includes its own self-check exchange
+        for r in range(50):                                      # ... and exchanges work again
+            pair = torch.tensor(list(sharding.pack_pair(float((r * 7 + rank * 3) % 5), r * world + rank)),
+                                dtype=torch.int64, device=batch.device)
+            got = batch.decode_best(peer.exchange(pair))
+            want = min((float((r * 7 + k * 3) % 5), r * world + k) for k in range(world))
+            ok = ok and got == want
+        peer.close()
+        q.put((rank, ok, waited))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_p2p_missing_peer_times_out_and_recovers():
+    """Liveness of the mailbox spin: a peer that never arrives costs a bounded wait and an error
+    value (index -2), not a hung GPU; after re-creating the mailbox the exchange works again."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one box")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_missing_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, waited in results:
+        assert ok, f"rank {rank}: missing-peer behaviour wrong (waited {waited:.2f} s)"
+        if rank == 0:
+            print(f"rank 0 gave up after {waited:.2f} s")
