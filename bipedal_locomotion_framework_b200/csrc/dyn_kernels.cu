@@ -184,7 +184,10 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
     // (tools/micro/llt_bench.cu: +17 % at 29 unknowns, -4 % at 18 and 23)
     constexpr bool LOOK = N >= 28;
     extern __shared__ __align__(16) double llt_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index through a broadcast: the compiler then knows it -- and the loop over the warp's
+    // groups below -- to be warp-uniform; without it every shuffle in the loop is wrapped in a
+    // WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair (a quarter of the instructions of the 29-unknown kernel)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(kFullMask, threadIdx.x >> 5, 0);
     const int g = lane / H, r = lane % H;
     const int nc = a.nc;
     const long long ngroups = (a.n + SPW - 1) / SPW;
