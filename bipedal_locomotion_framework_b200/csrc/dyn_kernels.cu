@@ -169,6 +169,8 @@ __device__ __noinline__ void llt_issue_all_call(const LltArgs& a, long long s, d
     ptx::cp_async_commit();
 }
 
+// No register cap: asked for 5 CTAs per SM (or __maxnreg__ 184 / 200) the four-rows-per-lane classes
+// spill ~0.5-1 KB per thread and lose 16-60 % (profiles/r02_llt_variants.log).
 template <int H, int N, bool REG>
 __global__ void __launch_bounds__(kLltThreads)
 ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
