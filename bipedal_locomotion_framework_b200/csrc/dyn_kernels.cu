@@ -9,9 +9,9 @@
 //
 // Warp-level kernel (nc <= 47).  A system is owned by a group of H = 4, 8 or 16 lanes (8, 4 or 2 systems
 // per warp); lane r of the group owns the ROWS r, r + H, r + 2H, ... of A / L in registers ("slots"),
-// and the right-hand side rides along as the last row of the augmented matrix [A b; b^T .], so
-// that the forward substitution L y = b comes out of the factorisation itself (y = the last row of
-// the augmented factor).  Right-looking, column by column:
+// and the right-hand side rides along as the last row of the augmented matrix [A b; b^T .] (or,
+// where that row would open a slot of its own, as one more column), so that the forward substitution
+// L y = b comes out of the factorisation itself (y = the last row of the augmented factor).  Right-looking, column by column:
 //     d = A[j][j] (one shuffle);  rs = 1/sqrt(d);  L[i][j] = A[i][j] * rs  for the lane's rows i > j;
 //     the column goes through a small shared-memory buffer and every lane updates the rest of its
 //     rows:  A[i][k] -= L[i][j] * L[k][j],  k > j,  L[k][j] read back as a broadcast.
@@ -177,10 +177,16 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
 {
     static_assert((H == 4 || H == 8 || H == 16) && N >= 2 && N <= (H == 16 ? 48 : 4 * H), "size class");
     using T = LltTile<H, N>;
-    constexpr int R = (N + H - 1) / H;        // rows (slots) per lane
+    constexpr int NM = N - 1;                 // order of the (identity-padded) matrix
+    // Where the right-hand side rides: as row NM of the augmented matrix -- free when the last slot
+    // has room for it -- or, when the order is a multiple of H and a row more would open a slot of
+    // its own (12 unknowns on 4 lanes, 24 on 8: a third more multiply-adds and registers), as one
+    // more COLUMN: every row carries its right-hand side entry b_i, updated like any other entry.
+    constexpr bool RHSCOL = NM % H == 0;
+    constexpr int ROWS = RHSCOL ? NM : N;     // rows held in slots
+    constexpr int R = (ROWS + H - 1) / H;     // rows (slots) per lane
     constexpr int SPW = 32 / H;               // systems per warp
-    constexpr int NM = N - 1;                 // order of the (identity-padded) matrix; row NM = right-hand side
-    constexpr bool SHORT = H * R > N;         // the last slot has lanes without a row
+    constexpr bool SHORT = H * R > ROWS;      // the last slot has lanes without a row
     constexpr int WPB = kLltThreads / 32;
     // start 1/sqrt of the next diagonal entry as soon as it is final: pays with few warps per SM
     // (tools/micro/llt_bench.cu: +17 % at 29 unknowns, -4 % at 18 and 23)
@@ -225,8 +231,8 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
 #pragma unroll
         for (int m = 0; m < R; ++m) {
             const int i = r + m * H;
-            rowok[m] = !SHORT || m < R - 1 || i < N;
-            const int ic = (SHORT && m == R - 1) ? min(i, N - 1) : i;
+            rowok[m] = !SHORT || m < R - 1 || i < ROWS;
+            const int ic = (SHORT && m == R - 1) ? min(i, ROWS - 1) : i;
             const double* src = tile + ic * (ic + 1) / 2;
 #pragma unroll
             for (int k = 0; k < NM; ++k)
@@ -235,7 +241,18 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                     if constexpr (REG) row[m][k] += regt[ic * (ic + 1) / 2 + k];   // M + reg, one rounding (:236-239)
                 }
         }
-        if constexpr (T::TAU > 0) {
+        double b[R], ysave[R];   // RHSCOL: the rows' right-hand side entries, y_i once row i is the pivot
+        if constexpr (RHSCOL) {
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const int i = r + m * H;      // SHORT cannot happen here: ROWS is a multiple of H
+                b[m] = tile[NM * (NM + 1) / 2 + i];
+                ysave[m] = 0.0;
+                if constexpr (T::TAU > 0) {   // known.tail += jointTorques (:226-227)
+                    if (a.tau && i >= 6) b[m] += tile[T::TAU_AT + i - 6];
+                }
+            }
+        } else if constexpr (T::TAU > 0) {
             // the right-hand side row: known.tail += jointTorques (:226-227)
             if (a.tau && r == NM % H) {
 #pragma unroll
@@ -282,6 +299,13 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                     if (i > j && rowok[m]) cb[i] = l;
                 }
             }
+            if constexpr (RHSCOL) {   // y_j = b_j / L_jj, broadcast like the column
+                const double yj = b[mj] * rs;
+                if (r == rj) {
+                    ysave[mj] = yj;
+                    cb[NM] = yj;
+                }
+            }
             __syncwarp();
             const int k0 = j + 1;
             const int odd = k0 & 1;   // 16-byte alignment of the pairs
@@ -300,17 +324,26 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                 upd(k + 1, v.y);
             }
             if (((NM - (k0 + odd)) & 1) && k0 + odd < NM) upd(NM - 1, cb[NM - 1]);
+            if constexpr (RHSCOL) {   // b_i -= L_ij y_j for the rows below the pivot
+                const double t = cb[NM];
+#pragma unroll
+                for (int m = 0; m < R; ++m)
+                    if (m >= mj) b[m] = fma(nl[m], t, b[m]);
+            }
         });
         if constexpr (SPREAD) {
             if (more) ptx::cp_async_commit();
         }
 
-        // ---- back substitution: x_k = -(sum over rows i > k of L[i][k] x_i) / L[k][k], the
-        //      right-hand side row (i = NM) entering with x = -1; the sum runs over the group's lanes
+        // ---- back substitution: x_k = (y_k - sum over rows i > k of L[i][k] x_i) / L[k][k]; with the
+        //      right-hand side as a row, that row (i = NM) enters the sum with x = -1 and y_k is inside
+        //      it; the sum runs over the group's lanes
         double x[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) x[m] = 0.0;
-        if (r == NM % H) x[R - 1] = -1.0;
+        if constexpr (!RHSCOL) {
+            if (r == NM % H) x[R - 1] = -1.0;
+        }
 #pragma unroll
         for (int k = NM - 1; k >= 0; --k) {
             const int mk = k / H, rk = k % H;
@@ -320,7 +353,11 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                 if (m > mk) p = fma(row[m][k], x[m], p);
 #pragma unroll
             for (int w = 1; w < H; w <<= 1) p += __shfl_xor_sync(kFullMask, p, w, H);
-            if (r == rk) x[mk] = -p * rdiag[mk];
+            if constexpr (RHSCOL) {
+                if (r == rk) x[mk] = (ysave[mk] - p) * rdiag[mk];
+            } else {
+                if (r == rk) x[mk] = -p * rdiag[mk];
+            }
         }
 #pragma unroll
         for (int m = 0; m < R; ++m) {
@@ -457,12 +494,12 @@ cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
 // size classes of the warp-level kernel, X(lanes per system, rows incl. the right-hand side): a
 // system of nc unknowns runs in the first class with N >= nc + 1, padded with identity rows
 #ifdef BLF_LLT_BENCH_CLASSES
-#define BLF_LLT_CLASSES(X) X(4, 7) X(4, 13) X(8, 19) X(8, 24) X(8, 30) X(16, 39)
+#define BLF_LLT_CLASSES(X) X(4, 7) X(4, 13) X(8, 19) X(8, 24) X(8, 25) X(8, 30) X(16, 39)
 #else
 #define BLF_LLT_CLASSES(X)                                                      \
-    X(4, 4) X(4, 7) X(4, 8) X(4, 10) X(4, 13) X(4, 14) X(4, 16)                   \
-    X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 25) X(8, 26) X(8, 28) X(8, 30) X(8, 31) X(8, 32)           \
-    X(16, 34) X(16, 36) X(16, 37) X(16, 39) X(16, 40) X(16, 42) X(16, 45) X(16, 48)
+    X(4, 4) X(4, 5) X(4, 7) X(4, 8) X(4, 9) X(4, 10) X(4, 13) X(4, 14) X(4, 16)   \
+    X(8, 17) X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 25) X(8, 26) X(8, 28) X(8, 30) X(8, 31) X(8, 32)  \
+    X(16, 33) X(16, 34) X(16, 36) X(16, 37) X(16, 39) X(16, 40) X(16, 42) X(16, 45) X(16, 48)
 #endif
 
 cudaError_t llt_solve_launch(const LltArgs& a, cudaStream_t st, bool pdl, int force_general,

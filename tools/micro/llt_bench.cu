@@ -36,7 +36,7 @@ __global__ void fill_kernel(double* M, double* known, long long n, int nc)
 
 int main(int argc, char** argv)
 {
-    const int sizes[][2] = {{6, 1 << 22}, {12, 1 << 21}, {18, 1 << 20}, {23, 1 << 20}, {29, 1 << 20}};
+    const int sizes[][2] = {{6, 1 << 22}, {12, 1 << 21}, {18, 1 << 20}, {23, 1 << 20}, {24, 1 << 20}, {29, 1 << 20}};
     for (auto& sz : sizes) {
         const int nc = sz[0];
         const long long n = sz[1];
