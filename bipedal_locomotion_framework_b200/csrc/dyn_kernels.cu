@@ -49,6 +49,7 @@
 #include "dyn_kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <type_traits>
 
@@ -456,13 +457,15 @@ cudaError_t launch_fast_k(const LltArgs& a, cudaStream_t st, bool pdl)
 {
     auto kernel = ccm_llt_solve_kernel<H, N, REG>;
     const size_t smem = LltTile<H, N>::bytes(REG);
-    static int per_sm[64] = {};   // CTAs per SM of this instantiation, per device
-    static int sms[64] = {};
+    // resident CTAs of this instantiation per device (CTAs per SM x SMs), filled on first use; an
+    // atomic because distinct handles may make their first call from different host threads
+    static std::atomic<int> resident[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (per_sm[dev] == 0) {
+    int cap = resident[dev].load(std::memory_order_acquire);
+    if (cap == 0) {
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) return e;
@@ -473,13 +476,13 @@ cudaError_t launch_fast_k(const LltArgs& a, cudaStream_t st, bool pdl)
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         if (v < 1) return cudaErrorLaunchOutOfResources;
-        sms[dev] = n;
-        per_sm[dev] = v;
+        cap = v * n;
+        resident[dev].store(cap, std::memory_order_release);
     }
     constexpr int SPW = 32 / H;
     const long long groups = (a.n + SPW - 1) / SPW;
     const long long want = (groups + kLltThreads / 32 - 1) / (kLltThreads / 32);
-    const long long grid = std::min<long long>(want, static_cast<long long>(per_sm[dev]) * sms[dev]);
+    const long long grid = std::min<long long>(want, cap);
     return launch(kernel, grid, kLltThreads, smem, st, pdl, a, false);
 }
 
