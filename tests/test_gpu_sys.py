@@ -325,6 +325,10 @@ def test_generalized_force_matches_exact(torch, batch, g, tag):
     (1, 9, 33_333, False, True, False),     # ... one contact per system
     (7, 8, 4_001, True, True, True),        # four contacts per iteration, 32 % 7 != 0
     (32, 5, 100, False, True, True),        # a whole warp is one system
+    (8, 6, 4_001, False, True, True),       # 8 corner contacts of a rigid body: one 9 KB stage per warp
+    (8, 8, 1_000, True, True, True),        # ... 12 KB, the largest single stage
+    (16, 4, 999, False, True, False),       # two systems per warp on 4-lane groups
+    (5, 6, 2_222, True, True, True),        # 6 systems per warp > 4 lane groups: two-stage ring
 ])
 def test_generalized_force_vs_oracle(torch, batch, so, cps, ncols, ns, het, aligned, with_base):
     from bipedal_locomotion_framework_b200.system import GeneralizedForceBatch
