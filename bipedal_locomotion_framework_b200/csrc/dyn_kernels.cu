@@ -43,9 +43,9 @@
 // (the reference's Eigen stops the factorisation and solves with the partial factor: garbage either
 // way; include/blf_ccm.h states it).
 //
-// Block-level kernel (48 <= nc <= 128 or forced): one CTA per system, thread r owns row r in
-// shared memory, the same factorisation in the same order (the back substitution sums sequentially),
-// three barriers per column; correctness path, not tuned.
+// Block-level kernel (48 <= nc <= 128 or forced): one CTA per system, the matrix in shared memory, the
+// same factorisation in the same column order with the trailing update spread over the CTA (a warp
+// per row), two barriers per column; the path for sizes the register-resident form cannot hold.
 #include "dyn_kernels.h"
 
 #include <algorithm>
@@ -368,66 +368,71 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
     }
 }
 
-// One CTA per system, thread r = row r (r == nc: the right-hand side), everything in shared memory.
-constexpr int kLltGenThreads = 160;
+// One CTA per system, everything in shared memory: the augmented matrix (rows 0..nc, row nc = the
+// right-hand side) with an odd pitch, the scaled pivot column, 1/L_jj and y.  Per column: every thread
+// scales entries of the column (L[i][j], kept in place for the back substitution), then the trailing
+// update is spread over the CTA -- a warp per row, lanes over the row's entries -- so no thread walks
+// a whole row on its own (the first version did: one dependent load-multiply-store chain per thread,
+// 7.7 M systems/s at 64 unknowns).  Same operations on the same operands in the same column order as
+// the warp-level kernel; the back substitution subtracts x_k L[k][i] in descending k.
+constexpr int kLltGenThreads = 256;
 
 __global__ void __launch_bounds__(kLltGenThreads)
 ccm_llt_solve_general_kernel(const __grid_constant__ LltArgs a)
 {
     extern __shared__ __align__(16) double llt_smem[];
     const int nc = a.nc;
-    const int P = (nc + 1) | 1;   // odd pitch >= nc + 1
-    double* tile = llt_smem;
-    const int r = threadIdx.x;
+    const int P = (nc + 1) | 1;            // odd pitch >= nc + 1
+    double* tile = llt_smem;               // (nc + 1) x P
+    double* colb = tile + (nc + 1) * P;    // nc + 1: L[i][j] of the current column (i == nc: y_j)
+    double* rd = colb + (nc + 2);          // nc: 1 / L_jj
+    double* ys = rd + (nc + 1);            // nc: y, then x
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int W = kLltGenThreads / 32;
     const long long s = blockIdx.x;
     ptx::grid_dep_wait();
     {
         const double* M = a.mass + s * nc * nc;
-        for (int e = r; e < nc * nc; e += kLltGenThreads) {
-            const int i = e / nc, c = e - i * nc;
-            if (c <= i) {
-                double v = __ldcs(M + e);
-                if (a.reg) v += __ldg(a.reg + e);
+        for (int i = warp; i < nc; i += W)          // rows of the lower triangle, lanes = columns
+            for (int c = lane; c <= i; c += 32) {
+                double v = __ldcs(M + i * nc + c);
+                if (a.reg) v += __ldg(a.reg + i * nc + c);
                 tile[i * P + c] = v;
             }
-        }
-        if (r < nc) {
-            double v = __ldcs(a.known + s * nc + r);
-            if (a.tau && r >= 6) v += __ldcs(a.tau + s * (nc - 6) + (r - 6));
-            tile[nc * P + r] = v;
+        for (int c = t; c < nc; c += kLltGenThreads) {
+            double v = __ldcs(a.known + s * nc + c);
+            if (a.tau && c >= 6) v += __ldcs(a.tau + s * (nc - 6) + (c - 6));
+            tile[nc * P + c] = v;
         }
     }
     __syncthreads();
-    double rdiag = 0.0;
-    const bool mine = r <= nc;
     for (int j = 0; j < nc; ++j) {
-        const double d = tile[j * P + j];
-        const double rs = rsqrt(d);
-        if (r == j) rdiag = rs;
-        double l = 0.0;
-        if (mine && r >= j) l = tile[r * P + j] * rs;
-        __syncthreads();   // everybody has read the diagonal and its own entry of column j
-        if (mine && r > j) tile[j * P + r] = l;
+        const double rs = rsqrt(tile[j * P + j]);   // untouched by the updates of earlier columns' barriers
+        if (t == 0) rd[j] = rs;
+        for (int i = j + 1 + t; i <= nc; i += kLltGenThreads) {
+            const double l = tile[i * P + j] * rs;
+            tile[i * P + j] = l;
+            colb[i] = l;
+        }
         __syncthreads();
-        if (mine && r > j) {
-            const double nl = -l;
-            const int kend = r < nc ? r : nc - 1;   // the right-hand side row has no diagonal
-            for (int k = j + 1; k <= kend; ++k) tile[r * P + k] = fma(nl, tile[j * P + k], tile[r * P + k]);
+        for (int i = j + 1 + warp; i <= nc; i += W) {
+            const double nl = -colb[i];
+            const int kend = i < nc ? i : nc - 1;   // the right-hand side row has no diagonal
+            double* ri = tile + i * P;
+            for (int k = j + 1 + lane; k <= kend; k += 32) ri[k] = fma(nl, colb[k], ri[k]);
         }
         __syncthreads();
     }
-    double acc = (r < nc) ? tile[r * P + nc] : 0.0;
-    double x = 0.0;
-    double* xs = tile + nc * P;   // the right-hand side row is free now
+    for (int i = t; i < nc; i += kLltGenThreads) ys[i] = tile[nc * P + i];   // y
+    __syncthreads();
     for (int k = nc - 1; k >= 0; --k) {
-        if (r == k) {
-            x = acc * rdiag;
-            xs[k] = x;
-        }
+        if (t == 0) ys[k] = ys[k] * rd[k];          // x_k
         __syncthreads();
-        if (r < k) acc = fma(-tile[r * P + k], xs[k], acc);
+        const double xk = ys[k];
+        for (int i = t; i < k; i += kLltGenThreads) ys[i] = fma(-tile[k * P + i], xk, ys[i]);
+        __syncthreads();
     }
-    if (r < nc) a.acc[s * nc + r] = x;
+    for (int i = t; i < nc; i += kLltGenThreads) a.acc[s * nc + i] = ys[i];
 }
 
 template <typename K>
@@ -524,7 +529,7 @@ cudaError_t llt_solve_launch(const LltArgs& a, cudaStream_t st, bool pdl, int fo
     if (path_out) *path_out = 0;
     if (ncmax_out) *ncmax_out = a.nc;
     const int P = (a.nc + 1) | 1;
-    const size_t smem = size_t(a.nc + 1) * P * sizeof(double);
+    const size_t smem = (size_t(a.nc + 1) * P + 3 * size_t(a.nc) + 4) * sizeof(double);
     return launch(ccm_llt_solve_general_kernel, a.n, kLltGenThreads, smem, st, pdl, a);
 }
 
