@@ -45,14 +45,14 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     if not force and _newer(CUDA_LIB, cuda_sources()):
         return CUDA_LIB
-    # two CUDA translation units compiled side by side (ccm_capi.cu: C ABI + contact / estimator /
-    # system kernels; dyn_kernels.cu: the unrolled mass-matrix solves) + the host-only expansion
+    # three CUDA translation units compiled side by side (ccm_capi.cu: C ABI + contact / estimator /
+    # system kernels; dyn_kernels.cu + dyn_kernels_wide.cu: the unrolled mass-matrix solves) + the host-only expansion
     # helper (plain C++, passed through to g++); one device link-free shared library
     from concurrent.futures import ThreadPoolExecutor
 
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
-    units = ["ccm_capi.cu", "dyn_kernels.cu", "host_expand.cpp"]
+    units = ["ccm_capi.cu", "dyn_kernels.cu", "dyn_kernels_wide.cu", "host_expand.cpp"]
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
 
     def compile_one(name: str) -> tuple[str, str]:

@@ -7,8 +7,8 @@
 // in the reference tree) is the lower Cholesky factorisation A = L L^T read from the LOWER triangle of
 // A, followed by the two triangular solves; restated here, not ported.
 //
-// Warp-level kernel (nc <= 47).  A system is owned by a group of H = 4, 8 or 16 lanes (8, 4 or 2 systems
-// per warp); lane r of the group owns the ROWS r, r + H, r + 2H, ... of A / L in registers ("slots"),
+// Warp-level kernel (nc <= 64).  A system is owned by a group of H = 4, 8, 16 or 32 lanes (8, 4, 2 or 1
+// systems per warp); lane r of the group owns the ROWS r, r + H, r + 2H, ... of A / L in registers ("slots"),
 // and the right-hand side rides along as the last row of the augmented matrix [A b; b^T .] (or,
 // where that row would open a slot of its own, as one more column), so that the forward substitution
 // L y = b comes out of the factorisation itself (y = the last row of the augmented factor).  Right-looking, column by column:
@@ -43,7 +43,7 @@
 // (the reference's Eigen stops the factorisation and solves with the partial factor: garbage either
 // way; include/blf_ccm.h states it).
 //
-// Block-level kernel (48 <= nc <= 128 or forced): one CTA per system, the matrix in shared memory, the
+// Block-level kernel (65 <= nc <= 128 or forced): one CTA per system, the matrix in shared memory, the
 // same factorisation in the same column order with the trailing update spread over the CTA (a warp
 // per row), two barriers per column; the path for sizes the register-resident form cannot hold.
 #include "dyn_kernels.h"
@@ -176,7 +176,7 @@ template <int H, int N, bool REG>
 __global__ void __launch_bounds__(kLltThreads)
 ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
 {
-    static_assert((H == 4 || H == 8 || H == 16) && N >= 2 && N <= (H == 16 ? 48 : 4 * H), "size class");
+    static_assert((H == 4 || H == 8 || H == 16 || H == 32) && N >= 2 && N <= (H == 32 ? 65 : (H == 16 ? 48 : 4 * H)), "size class");
     using T = LltTile<H, N>;
     constexpr int NM = N - 1;                 // order of the (identity-padded) matrix
     // Where the right-hand side rides: as row NM of the augmented matrix -- free when the last slot
@@ -499,30 +499,57 @@ cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
 
 }  // namespace
 
-// size classes of the warp-level kernel, X(lanes per system, rows incl. the right-hand side): a
-// system of nc unknowns runs in the first class with N >= nc + 1, padded with identity rows
-#ifdef BLF_LLT_BENCH_CLASSES
+// Size classes of the warp-level kernel, X(lanes per system, rows incl. the right-hand side): a
+// system of nc unknowns runs in the first class with N >= nc + 1, padded with identity rows.  The
+// classes are compiled in two translation units side by side (this file, and this file again
+// included by dyn_kernels_wide.cu with BLF_LLT_TU_WIDE defined: the 16- and 32-lane classes), which
+// halves the build's wall time; tools/micro/llt_bench.cu includes this file once with a short list.
+#if defined(BLF_LLT_BENCH_CLASSES)
+#ifdef BLF_LLT_ONLY_WIDE
+#define BLF_LLT_CLASSES(X) X(32, 64)
+#else
 #define BLF_LLT_CLASSES(X) X(4, 7) X(4, 13) X(8, 19) X(8, 24) X(8, 25) X(8, 30) X(16, 39)
+#endif
+#define BLF_LLT_NARROW_MAX kLltMaxFast
+#elif defined(BLF_LLT_TU_WIDE)
+#define BLF_LLT_CLASSES(X)                                                                               \
+    X(16, 33) X(16, 34) X(16, 36) X(16, 37) X(16, 39) X(16, 40) X(16, 42) X(16, 45) X(16, 48)          \
+    X(32, 52) X(32, 56) X(32, 60) X(32, 64) X(32, 65)
 #else
 #define BLF_LLT_CLASSES(X)                                                      \
     X(4, 4) X(4, 5) X(4, 7) X(4, 8) X(4, 9) X(4, 10) X(4, 13) X(4, 14) X(4, 16)   \
-    X(8, 17) X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 25) X(8, 26) X(8, 28) X(8, 30) X(8, 31) X(8, 32)  \
-    X(16, 33) X(16, 34) X(16, 36) X(16, 37) X(16, 39) X(16, 40) X(16, 42) X(16, 45) X(16, 48)
+    X(8, 17) X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 25) X(8, 26) X(8, 28) X(8, 30) X(8, 31) X(8, 32)
+#define BLF_LLT_NARROW_MAX 31
 #endif
 
-cudaError_t llt_solve_launch(const LltArgs& a, cudaStream_t st, bool pdl, int force_general,
-                             int* path_out, int* ncmax_out)
-{
-    if (a.n <= 0) return cudaSuccess;
-    if (!force_general && a.nc <= kLltMaxFast) {
 #define BLF_LLT_TRY(H, N)                          \
     if (a.nc < N) {                                \
         if (path_out) *path_out = H;               \
         if (ncmax_out) *ncmax_out = N - 1;         \
         return launch_fast<H, N>(a, st, pdl);      \
     }
-        BLF_LLT_CLASSES(BLF_LLT_TRY)
-#undef BLF_LLT_TRY
+
+#ifdef BLF_LLT_TU_WIDE
+// the 16- and 32-lane classes (32 .. 64 unknowns); called by llt_solve_launch of the other unit
+cudaError_t llt_solve_launch_wide(const LltArgs& a, cudaStream_t st, bool pdl, int* path_out, int* ncmax_out)
+{
+    BLF_LLT_CLASSES(BLF_LLT_TRY)
+    return cudaErrorInvalidValue;
+}
+#else
+cudaError_t llt_solve_launch_wide(const LltArgs& a, cudaStream_t st, bool pdl, int* path_out, int* ncmax_out);
+
+cudaError_t llt_solve_launch(const LltArgs& a, cudaStream_t st, bool pdl, int force_general,
+                             int* path_out, int* ncmax_out)
+{
+    if (a.n <= 0) return cudaSuccess;
+    if (!force_general && a.nc <= kLltMaxFast) {
+        if (a.nc <= BLF_LLT_NARROW_MAX) {
+            BLF_LLT_CLASSES(BLF_LLT_TRY)
+        }
+#ifndef BLF_LLT_BENCH_CLASSES
+        return llt_solve_launch_wide(a, st, pdl, path_out, ncmax_out);
+#endif
     }
     if (a.nc > kLltMaxCols) return cudaErrorInvalidValue;
     if (a.n > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
@@ -532,5 +559,7 @@ cudaError_t llt_solve_launch(const LltArgs& a, cudaStream_t st, bool pdl, int fo
     const size_t smem = (size_t(a.nc + 1) * P + 3 * size_t(a.nc) + 4) * sizeof(double);
     return launch(ccm_llt_solve_general_kernel, a.n, kLltGenThreads, smem, st, pdl, a);
 }
+#endif
+#undef BLF_LLT_TRY
 
 }  // namespace blfccm

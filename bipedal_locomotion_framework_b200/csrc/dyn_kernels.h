@@ -20,10 +20,10 @@ struct LltArgs {
     int nc;
 };
 
-constexpr int kLltMaxFast = 47;    // warp-level kernel: nc + 1 rows (the right-hand side rides along) <= 48 = 3 rows x 16 lanes
+constexpr int kLltMaxFast = 64;    // warp-level kernel: up to 2 rows x 32 lanes (64 unknowns with the right-hand side as a column)
 constexpr int kLltMaxCols = 128;   // block-level kernel
 
-// path_out: lanes per system of the warp-level kernel (4, 8, 16) or 0 for the block-level kernel;
+// path_out: lanes per system of the warp-level kernel (4, 8, 16, 32) or 0 for the block-level kernel;
 // ncmax_out: the compile-time size class the call ran in.  force_general != 0: block-level kernel
 // whatever the size (tests compare the two bit for bit).
 cudaError_t llt_solve_launch(const LltArgs& a, cudaStream_t st, bool pdl, int force_general,

@@ -102,8 +102,8 @@ enum {
     BLF_CCM_PATH_NONE = 0,
     BLF_CCM_PATH_BULK = 1,    /* bulk-copy (TMA) staging in use: every staged buffer 16-byte aligned */
     BLF_CCM_PATH_DIRECT64 = 2,/* a staged buffer is only 8-byte aligned: direct 64-bit accesses     */
-    BLF_CCM_PATH_LLT_WARP = 3,/* mass-matrix solve: warp-level kernel (ncols <= 47)                 */
-    BLF_CCM_PATH_LLT_BLOCK = 4/* mass-matrix solve: block-level kernel (ncols 48..128)              */
+    BLF_CCM_PATH_LLT_WARP = 3,/* mass-matrix solve: warp-level kernel (ncols <= 64)                 */
+    BLF_CCM_PATH_LLT_BLOCK = 4/* mass-matrix solve: block-level kernel (ncols 65..128)              */
 };
 
 BLF_CCM_API const char* blf_ccm_version(void);
@@ -378,7 +378,7 @@ BLF_CCM_API int blf_ccm_generalized_force_soa(blf_ccm_handle* h, int64_t n_syste
  * getFreeFloatingMassMatrix fills it); like Eigen's LLT only the LOWER triangle is read.
  * regularization: ncols*ncols row-major DEVICE array shared by all systems (what
  * setMassMatrixRegularization stores, :72-95) or NULL.  known, acc: n_systems*ncols (acc may alias
- * known); joint_torques: n_systems*(ncols-6) or NULL.  ncols 1..128: up to 47 a warp-level kernel
+ * known); joint_torques: n_systems*(ncols-6) or NULL.  ncols 1..128: up to 64 a warp-level kernel
  * (rows in registers), above a block-level one (blf_ccm_last_path tells which).  A matrix that is
  * not positive definite yields NaN for that system (the reference's Eigen stops factorising and
  * solves with the partial factor: meaningless numbers, no error there either).

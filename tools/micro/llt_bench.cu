@@ -36,7 +36,11 @@ __global__ void fill_kernel(double* M, double* known, long long n, int nc)
 
 int main(int argc, char** argv)
 {
+#ifdef BLF_LLT_ONLY_WIDE
+    const int sizes[][2] = {{63, 1 << 17}, {56, 1 << 17}};
+#else
     const int sizes[][2] = {{6, 1 << 22}, {12, 1 << 21}, {18, 1 << 20}, {23, 1 << 20}, {24, 1 << 20}, {29, 1 << 20}};
+#endif
     for (auto& sz : sizes) {
         const int nc = sz[0];
         const long long n = sz[1];

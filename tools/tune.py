@@ -201,7 +201,7 @@ def dyn_only():
     dyn = FloatingBaseDynamicsBatch(b)
     rnd = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda") * 2 - 1
     shapes = ((409600, 29), (1 << 20, 29), (1 << 20, 18), (1 << 21, 12), (1 << 22, 6), (1 << 19, 31),
-              (1 << 20, 23), (1 << 20, 24), (1 << 21, 7), (1 << 21, 15), (1 << 18, 38), (1 << 18, 44), (1 << 15, 64))
+              (1 << 20, 23), (1 << 20, 24), (1 << 21, 7), (1 << 21, 15), (1 << 18, 38), (1 << 18, 44), (1 << 17, 59), (1 << 17, 64), (1 << 15, 80))
     only = [int(x) for x in os.environ.get("DYN_NC", "").split(",") if x]
     for ns, nc in shapes:
         if only and nc not in only:
