@@ -116,6 +116,21 @@ def test_mass_matrix_solve_vs_oracle_every_size(torch, batch, dyn, so, nc):
     assert err.max() <= TOL, (int(np.argmax(err)), err.max())
 
 
+@pytest.mark.parametrize("nc", [6, 12, 24, 29, 38, 59])
+def test_mass_matrix_solve_tiny_batches(torch, dyn, so, nc):
+    """1 .. 9 systems: partly filled groups of every lane layout (8, 4, 2, 1 systems per warp); the
+    missing systems of a group are identity-padded inside the kernel and never written."""
+    M, known, tau, reg = _case(nc, 9, 70 + nc, with_reg=True)
+    want = so.mass_matrix_solve(M, known, tau, reg)
+    dM, dk, dt, dr = (_dev(torch, a) for a in (M, known, tau, reg))
+    for ns in range(1, 10):
+        guard = torch.full((ns + 2, nc), 123.0, dtype=torch.float64, device="cuda")
+        out = guard[1:ns + 1]
+        dyn.solve(dM[:ns].contiguous(), dk[:ns].contiguous(), None if dt is None else dt[:ns].contiguous(), dr, out=out)
+        assert rel(out.cpu().numpy(), want[:ns]).max() <= TOL, (nc, ns)
+        assert bool((guard[0] == 123.0).all()) and bool((guard[ns + 1] == 123.0).all())   # nothing written outside
+
+
 def test_warp_and_block_kernels_agree(torch, dyn, so):
     """The block-level kernel (forced on a second handle through BLF_CCM_TUNE_LLT_GENERAL, read when
     a handle is created) runs the same factorisation in the same order as the warp-level one; the
