@@ -243,3 +243,25 @@ def test_floating_base_acceleration_composes_force_and_solve(g):
     rhs[:, 6:] += tau
     res = np.einsum("sij,sj->si", M, acc) - rhs
     assert np.abs(res).max() <= 1e-12 * np.abs(rhs).max()
+
+
+@pytest.mark.parametrize("nc", [1, 2, 6, 13, 29, 40])
+def test_mass_matrix_solve_properties(nc):
+    """Size-independent properties of the solve: M * solve(M, b) = b to rounding; a zero regularisation
+    and zero torques change nothing, bit for bit; systems are independent (any order, any threads)."""
+    from bipedal_locomotion_framework_b200 import synthetic as syn
+    rng = np.random.default_rng(nc)
+    ns = 64
+    M = syn.make_mass_matrices(ns, nc, seed=nc, spread=0.5)
+    xs = rng.normal(size=(ns, nc))
+    b = np.einsum("sij,sj->si", M, xs)
+    x = so.mass_matrix_solve(M, b)
+    cond = np.linalg.cond(M, np.inf)
+    assert (rel(x, xs) <= llt_tolerance(nc, cond)).all()
+    tau0 = np.zeros((ns, nc - 6)) if nc > 6 else None
+    assert np.array_equal(so.mass_matrix_solve(M, b, tau0, np.zeros((nc, nc))), x)
+    perm = rng.permutation(ns)
+    assert np.array_equal(so.mass_matrix_solve(M[perm], b[perm], nthreads=3), x[perm])
+    # the regularisation enters as M + reg, evaluated once in double
+    reg = np.diag(rng.uniform(1e-4, 1e-2, nc))
+    assert np.array_equal(so.mass_matrix_solve(M, b, None, reg), so.mass_matrix_solve(M + reg, b))
