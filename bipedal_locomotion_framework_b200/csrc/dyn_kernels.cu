@@ -78,7 +78,19 @@ template <int H, int N> struct LltTile {
     static constexpr int TAU_AT = (TRI + 1) / 2 * 2;
     static constexpr int NP = (N + 1) / 2 * 2;                         // one column buffer
     static constexpr int COL_AT = (TAU_AT + TAU + 1) / 2 * 2;
-    static constexpr int STRIDE = (COL_AT + 2 * NP + 15) / 16 * 16 + (H == 8 ? 8 : 4);   // + bank spreading of the groups
+    // groups of 8 and 16 lanes: the strictly lower part of every H x H diagonal block of L, column by
+    // column (H (H - 1) / 2 doubles a block), for the blocked back substitution
+    // (measured per class, profiles/r02_llt_variants.log: +6 .. +15 % everywhere except the 24-row class
+    // of 8-lane groups, -9 %, which keeps the unblocked form)
+#ifdef BLF_LLT_UNBLOCKED
+    static constexpr bool BLOCKED = false;
+#else
+    static constexpr bool BLOCKED = (H == 8 && N != 24) || H == 16;
+#endif
+    static constexpr int DB = H * (H - 1) / 2;
+    static constexpr int DIAG_AT = COL_AT + 2 * NP;
+    static constexpr int DIAG = BLOCKED ? DB * ((N + H - 1) / H) : 0;
+    static constexpr int STRIDE = (DIAG_AT + DIAG + 15) / 16 * 16 + (H == 8 ? 8 : 4);   // + bank spreading of the groups
     static constexpr int PER_WARP = (32 / H) * STRIDE;
     static constexpr size_t bytes(bool reg)
     {
@@ -298,6 +310,10 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                     nl[m] = -l;
                     const int i = r + m * H;
                     if (i > j && rowok[m]) cb[i] = l;
+                    if constexpr (T::BLOCKED) {   // column j of its H x H diagonal block, rows below the diagonal
+                        if (m == mj && r > rj && rowok[m])
+                            tile[T::DIAG_AT + T::DB * mj + ((H - 1) * rj - rj * (rj - 1) / 2) - rj - 1 + r] = l;
+                    }
                 }
             }
             if constexpr (RHSCOL) {   // y_j = b_j / L_jj, broadcast like the column
@@ -337,27 +353,79 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
         }
 
         // ---- back substitution: x_k = (y_k - sum over rows i > k of L[i][k] x_i) / L[k][k]; with the
-        //      right-hand side as a row, that row (i = NM) enters the sum with x = -1 and y_k is inside
-        //      it; the sum runs over the group's lanes
+        //      right-hand side as a row, that row (i = NM) enters the sum with x = -1 and y_k is inside it
         double x[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) x[m] = 0.0;
         if constexpr (!RHSCOL) {
             if (r == NM % H) x[R - 1] = -1.0;
         }
+        if constexpr (T::BLOCKED) {
+            // Blocked, H unknowns (one slot) at a time, last slot first.  (a) The part of the sums that
+            // comes from the slots already solved is one multiply-add per slot and unknown, summed over
+            // the group by a reduce-scatter (H - 1 shuffles for H sums: lane r ends up with the sum of
+            // ITS unknown); (b) inside the block the unknowns follow one another with a single
+            // broadcast each, lane r reading column r of the block from shared memory (left there
+            // during the factorisation).  The unblocked form below spends log2(H) dependent shuffle
+            // rounds per unknown: at 29 unknowns 29 x ~150 cycles of latency against 4 x ~500 here.
+            __syncwarp();
+            // ld[DB mb + kk] = L[H mb + kk][H mb + r]
+            const double* ld = tile + T::DIAG_AT + ((H - 2) * r - r * (r - 1) / 2) - 1;
+            static_for<R>([&](auto mc) {
+                constexpr int mb = R - 1 - decltype(mc)::value;
+                double acc = 0.0;
+                if constexpr (RHSCOL) acc = ysave[mb];
+                if constexpr (mb < R - 1) {
+                    double p[H];
 #pragma unroll
-        for (int k = NM - 1; k >= 0; --k) {
-            const int mk = k / H, rk = k % H;
-            double p = (r > rk) ? row[mk][k] * x[mk] : 0.0;   // rows of slot mk above k (the others: x not yet known)
+                    for (int kk = 0; kk < H; ++kk) {
+                        p[kk] = 0.0;
 #pragma unroll
-            for (int m = 0; m < R; ++m)
-                if (m > mk) p = fma(row[m][k], x[m], p);
+                        for (int m = mb + 1; m < R; ++m) p[kk] = fma(row[m][H * mb + kk], x[m], p[kk]);
+                    }
 #pragma unroll
-            for (int w = 1; w < H; w <<= 1) p += __shfl_xor_sync(kFullMask, p, w, H);
-            if constexpr (RHSCOL) {
-                if (r == rk) x[mk] = (ysave[mk] - p) * rdiag[mk];
-            } else {
-                if (r == rk) x[mk] = -p * rdiag[mk];
+                    for (int bit = H / 2; bit >= 1; bit >>= 1) {
+#pragma unroll
+                        for (int t = 0; t < bit; ++t) {
+                            const double keep = (r & bit) ? p[t + bit] : p[t], send = (r & bit) ? p[t] : p[t + bit];
+                            p[t] = keep + __shfl_xor_sync(kFullMask, send, bit, H);
+                        }
+                    }
+                    acc -= p[0];
+                }
+                double lcol[H];
+#pragma unroll
+                for (int kk = 1; kk < H; ++kk)
+                    if (H * mb + kk < ROWS) lcol[kk] = ld[T::DB * mb + kk];
+#pragma unroll
+                for (int kk = H - 1; kk >= 0; --kk) {
+                    const int i = H * mb + kk;
+                    if (i < ROWS) {
+                        if (!RHSCOL && i == NM) {   // the right-hand side row: x = -1, nothing to solve
+                            if (kk > 0) acc += lcol[kk];
+                        } else {
+                            const double xk = __shfl_sync(kFullMask, acc * rdiag[mb], kk, H);
+                            if (r == kk) x[mb] = xk;
+                            if (kk > 0) acc = fma(-lcol[kk], xk, acc);
+                        }
+                    }
+                }
+            });
+        } else {
+#pragma unroll
+            for (int k = NM - 1; k >= 0; --k) {
+                const int mk = k / H, rk = k % H;
+                double p = (r > rk) ? row[mk][k] * x[mk] : 0.0;   // rows of slot mk above k (the others: x not yet known)
+#pragma unroll
+                for (int m = 0; m < R; ++m)
+                    if (m > mk) p = fma(row[m][k], x[m], p);
+#pragma unroll
+                for (int w = 1; w < H; w <<= 1) p += __shfl_xor_sync(kFullMask, p, w, H);
+                if constexpr (RHSCOL) {
+                    if (r == rk) x[mk] = (ysave[mk] - p) * rdiag[mk];
+                } else {
+                    if (r == rk) x[mk] = -p * rdiag[mk];
+                }
             }
         }
 #pragma unroll
@@ -505,8 +573,10 @@ cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
 // included by dyn_kernels_wide.cu with BLF_LLT_TU_WIDE defined: the 16- and 32-lane classes), which
 // halves the build's wall time; tools/micro/llt_bench.cu includes this file once with a short list.
 #if defined(BLF_LLT_BENCH_CLASSES)
-#ifdef BLF_LLT_ONLY_WIDE
+#if defined(BLF_LLT_ONLY_WIDE)
 #define BLF_LLT_CLASSES(X) X(32, 64)
+#elif defined(BLF_LLT_ONLY_MID)
+#define BLF_LLT_CLASSES(X) X(8, 17) X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 26) X(8, 28)
 #else
 #define BLF_LLT_CLASSES(X) X(4, 7) X(4, 13) X(8, 19) X(8, 24) X(8, 25) X(8, 30) X(16, 39)
 #endif

@@ -36,7 +36,9 @@ __global__ void fill_kernel(double* M, double* known, long long n, int nc)
 
 int main(int argc, char** argv)
 {
-#ifdef BLF_LLT_ONLY_WIDE
+#if defined(BLF_LLT_ONLY_MID)
+    const int sizes[][2] = {{16, 1 << 20}, {18, 1 << 20}, {19, 1 << 20}, {21, 1 << 20}, {23, 1 << 20}, {25, 1 << 20}, {27, 1 << 20}};
+#elif defined(BLF_LLT_ONLY_WIDE)
     const int sizes[][2] = {{63, 1 << 17}, {56, 1 << 17}};
 #else
     const int sizes[][2] = {{6, 1 << 22}, {12, 1 << 21}, {18, 1 << 20}, {23, 1 << 20}, {24, 1 << 20}, {29, 1 << 20}};
