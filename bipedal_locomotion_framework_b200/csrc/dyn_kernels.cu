@@ -201,9 +201,6 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
     constexpr int SPW = 32 / H;               // systems per warp
     constexpr bool SHORT = H * R > ROWS;      // the last slot has lanes without a row
     constexpr int WPB = kLltThreads / 32;
-    // start 1/sqrt of the next diagonal entry as soon as it is final: pays with few warps per SM
-    // (tools/micro/llt_bench.cu: +17 % at 29 unknowns, -4 % at 18 and 23)
-    constexpr bool LOOK = N >= 28;
     extern __shared__ __align__(16) double llt_smem[];
     // the warp index through a broadcast: the compiler then knows it -- and the loop over the warp's
     // groups below -- to be warp-uniform; without it every shuffle in the loop is wrapped in a
@@ -291,14 +288,13 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
         double rdiag[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) rdiag[m] = 0.0;
-        double rs = LOOK ? rsqrt(__shfl_sync(kFullMask, row[0][0], 0, H)) : 0.0;
         static_for<NM>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             constexpr int mj = j / H, rj = j % H;
             if constexpr (SPREAD) {
                 if (more) llt_issue_piece<H, N, j>(next);
             }
-            if constexpr (!LOOK) rs = rsqrt(__shfl_sync(kFullMask, row[mj][j], rj, H));
+            const double rs = rsqrt(__shfl_sync(kFullMask, row[mj][j], rj, H));
             if (r == rj) rdiag[mj] = rs;
             double* cb = col + (j & 1) * T::NP;   // cb[i] = L[i][j]; two buffers: one __syncwarp per column
             double nl[R];
@@ -330,8 +326,6 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
 #pragma unroll
                 for (int m = 0; m < R; ++m)
                     if (m >= k / H) row[m][k] = fma(nl[m], t, row[m][k]);
-                if (LOOK && k == j + 1)   // the next diagonal entry is final
-                    rs = rsqrt(__shfl_sync(kFullMask, row[(j + 1) / H][j + 1], (j + 1) % H, H));
             };
             if (odd && k0 < NM) upd(k0, cb[k0]);
 #pragma unroll
