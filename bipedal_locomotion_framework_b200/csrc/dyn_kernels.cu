@@ -78,14 +78,14 @@ template <int H, int N> struct LltTile {
     static constexpr int TAU_AT = (TRI + 1) / 2 * 2;
     static constexpr int NP = (N + 1) / 2 * 2;                         // one column buffer
     static constexpr int COL_AT = (TAU_AT + TAU + 1) / 2 * 2;
-    // groups of 8 and 16 lanes: the strictly lower part of every H x H diagonal block of L, column by
+    // groups of 8, 16 and 32 lanes: the strictly lower part of every H x H diagonal block of L, column by
     // column (H (H - 1) / 2 doubles a block), for the blocked back substitution
     // (measured per class, profiles/r02_llt_variants.log: +6 .. +15 % everywhere except the 24-row class
     // of 8-lane groups, -9 %, which keeps the unblocked form)
 #ifdef BLF_LLT_UNBLOCKED
     static constexpr bool BLOCKED = false;
 #else
-    static constexpr bool BLOCKED = (H == 8 && N != 24) || H == 16;
+    static constexpr bool BLOCKED = (H == 8 && N != 24) || H == 16 || H == 32;
 #endif
     static constexpr int DB = H * (H - 1) / 2;
     static constexpr int DIAG_AT = COL_AT + 2 * NP;
@@ -370,15 +370,21 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                 double acc = 0.0;
                 if constexpr (RHSCOL) acc = ysave[mb];
                 if constexpr (mb < R - 1) {
-                    double p[H];
+                    auto part = [&](int kk) {   // this lane's share of the sum of unknown H mb + kk
+                        double q = 0.0;
 #pragma unroll
-                    for (int kk = 0; kk < H; ++kk) {
-                        p[kk] = 0.0;
+                        for (int m = mb + 1; m < R; ++m) q = fma(row[m][H * mb + kk], x[m], q);
+                        return q;
+                    };
+                    double p[H / 2];   // the first exchange takes the shares as they are computed
 #pragma unroll
-                        for (int m = mb + 1; m < R; ++m) p[kk] = fma(row[m][H * mb + kk], x[m], p[kk]);
+                    for (int t = 0; t < H / 2; ++t) {
+                        const double lo = part(t), hi = part(t + H / 2);
+                        const double keep = (r & (H / 2)) ? hi : lo, send = (r & (H / 2)) ? lo : hi;
+                        p[t] = keep + __shfl_xor_sync(kFullMask, send, H / 2, H);
                     }
 #pragma unroll
-                    for (int bit = H / 2; bit >= 1; bit >>= 1) {
+                    for (int bit = H / 4; bit >= 1; bit >>= 1) {
 #pragma unroll
                         for (int t = 0; t < bit; ++t) {
                             const double keep = (r & bit) ? p[t + bit] : p[t], send = (r & bit) ? p[t] : p[t + bit];
@@ -387,20 +393,16 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                     }
                     acc -= p[0];
                 }
-                double lcol[H];
-#pragma unroll
-                for (int kk = 1; kk < H; ++kk)
-                    if (H * mb + kk < ROWS) lcol[kk] = ld[T::DB * mb + kk];
 #pragma unroll
                 for (int kk = H - 1; kk >= 0; --kk) {
                     const int i = H * mb + kk;
                     if (i < ROWS) {
                         if (!RHSCOL && i == NM) {   // the right-hand side row: x = -1, nothing to solve
-                            if (kk > 0) acc += lcol[kk];
+                            if (kk > 0) acc += ld[T::DB * mb + kk];
                         } else {
                             const double xk = __shfl_sync(kFullMask, acc * rdiag[mb], kk, H);
                             if (r == kk) x[mb] = xk;
-                            if (kk > 0) acc = fma(-lcol[kk], xk, acc);
+                            if (kk > 0) acc = fma(-ld[T::DB * mb + kk], xk, acc);
                         }
                     }
                 }
