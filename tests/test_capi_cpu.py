@@ -37,6 +37,12 @@ def test_invalid_handle_is_rejected(lib):
     assert lib.blf_ccm_set_uniform_params(None, 0.1, 0.1, 1.0, 1.0) == _capi.ERR_INVALID_HANDLE
     assert lib.blf_ccm_launch_count(None) == -1
     assert b"invalid handle" in lib.blf_ccm_last_error()
+    # the entry points of the System rows check the handle before anything else (no CUDA call is made)
+    assert lib.blf_sys_mass_matrix_solve(None, 1, 6, None, None, None, None, None, None) == _capi.ERR_INVALID_HANDLE
+    assert lib.blf_sys_floating_base_acceleration(None, 1, 1, 6, None, None, None, None, None, None, None, None,
+                                                  None, None) == _capi.ERR_INVALID_HANDLE
+    assert lib.blf_ccm_generalized_force_soa(None, 1, 1, 6, None, None, None, None, None, None,
+                                             None) == _capi.ERR_INVALID_HANDLE
 
 
 def test_create_fails_loudly_without_a_device(lib):
