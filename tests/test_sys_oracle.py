@@ -265,3 +265,25 @@ def test_mass_matrix_solve_properties(nc):
     # the regularisation enters as M + reg, evaluated once in double
     reg = np.diag(rng.uniform(1e-4, 1e-2, nc))
     assert np.array_equal(so.mass_matrix_solve(M, b, None, reg), so.mass_matrix_solve(M + reg, b))
+
+
+@pytest.mark.parametrize("nc,spread", [(6, 0.0), (12, 1.0), (29, 0.5), (29, 1.5), (38, 1.0), (64, 0.5)])
+def test_mass_matrix_solve_against_lapack(nc, spread):
+    """An implementation nobody here wrote: numpy's LAPACK solve (dgesv, partial pivoting) on the same
+    systems.  Eigen's LLT is absent from this image; LAPACK stands for 'any correct solver in IEEE
+    double' and bounds what a real-Eigen build could differ by: rounding x cond(M)."""
+    from bipedal_locomotion_framework_b200 import synthetic as syn
+    rng = np.random.default_rng(100 + nc)
+    ns = 500
+    M = syn.make_mass_matrices(ns, nc, seed=9 + nc, spread=spread)
+    b = rng.normal(size=(ns, nc)) * 40.0
+    tau = rng.normal(size=(ns, nc - 6)) if nc > 6 else None
+    rhs = b.copy()
+    if tau is not None:
+        rhs[:, 6:] += tau
+    want = np.linalg.solve(M, rhs[:, :, None])[:, :, 0]
+    x = so.mass_matrix_solve(M, b, tau, nthreads=2)
+    cond = np.linalg.cond(M, np.inf)
+    assert (rel(x, want) <= 2 * llt_tolerance(nc, cond)).all()
+    if spread == 0.0:
+        assert rel(x, want).max() <= TOL
