@@ -26,8 +26,10 @@
 // no-ops: the real entries see the same operations in the same order).
 // The back substitution L^T x = y needs COLUMN k of L for x_k -- which is exactly what the lanes of
 // a group hold between them (each its rows' entries): per k every lane multiplies its rows' entries
-// by its rows' x (the right-hand side row counts as x = -1), a butterfly of shuffles sums over the
-// group, and the lane that owns row k keeps -sum / L[k][k].  So L never goes back to shared memory,
+// by its rows' x (the right-hand side row counts as x = -1), shuffles sum over the group (a butterfly
+// per unknown on 4-lane groups; on wider ones one reduce-scatter per slot of H unknowns, and inside a
+// slot one broadcast per unknown off the slot's diagonal block, kept in shared memory), and the lane
+// that owns row k keeps -sum / L[k][k].  So the rows of L never go back to shared memory,
 // the tile of a system is only its input triangle, and that tile is refilled for the warp's NEXT
 // group of systems (per-thread async copies, LDGSTS: no registers, no waiting) as soon as the rows
 // are in registers -- the loads of the next group overlap the whole factorisation of this one.  (A
@@ -38,7 +40,7 @@
 // buffers.  The global reads are row-wise (lanes = columns <= row): coalesced, and only the sectors
 // of the lower triangle are touched.
 // Arithmetic deviates from a textbook LLT in two places: L[i][j] = s * rsqrt(d) instead of
-// s / sqrt(d) (<= 2 ulp per entry), and the back substitution's sums are taken in butterfly order;
+// s / sqrt(d) (<= 2 ulp per entry), and the back substitution's sums are taken in tree order;
 // parity tests bound the effect on the solution.  A matrix that is not positive definite gives NaN
 // (the reference's Eigen stops the factorisation and solves with the partial factor: garbage either
 // way; include/blf_ccm.h states it).
