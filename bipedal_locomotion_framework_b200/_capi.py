@@ -29,7 +29,7 @@ SYMBOLS = [
     "blf_sys_kinematics_euler_step_soa", "blf_sys_kinematics_dynamics_host",
     "blf_sys_kinematics_integrate_host", "blf_ccm_rollout_integrate_cost",
     "blf_ccm_generalized_force_soa", "blf_ccm_rollout_integrate_cost_host",
-    "blf_sys_mass_matrix_solve", "blf_sys_floating_base_acceleration",
+    "blf_sys_mass_matrix_solve", "blf_sys_floating_base_acceleration", "blf_sys_floating_base_euler_step",
     "blf_ccm_p2p_mailbox_create", "blf_ccm_p2p_mailbox_connect", "blf_ccm_argmin_exchange_p2p",
     "blf_ccm_p2p_mailbox_destroy", "blf_ccm_rollout_set_exchange",
 ]
@@ -92,6 +92,7 @@ def lib():
     L.blf_sys_mass_matrix_solve.argtypes = [vp, i64, ci, vp, vp, vp, vp, vp, vp]
     L.blf_sys_floating_base_acceleration.argtypes = [vp, i64, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp,
                                                      vp, vp]
+    L.blf_sys_floating_base_euler_step.argtypes = [vp, i64, ci, dbl, dbl, vp, vp, vp, vp, vp, vp]
     L.blf_ccm_p2p_mailbox_create.argtypes = [vp, ci, ci, vp]
     L.blf_ccm_p2p_mailbox_connect.argtypes = [vp, vp]
     L.blf_ccm_argmin_exchange_p2p.argtypes = [vp, vp, vp, vp]

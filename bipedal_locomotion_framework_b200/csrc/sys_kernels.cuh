@@ -1881,4 +1881,96 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One ForwardEuler step of System::FloatingBaseDynamicalSystem (ForwardEuler.tpp:19-49: x = x0 + dx * dT
+// over the state tuple of FloatingBaseSystemDynamics.h:33-52), every derivative at the state BEFORE the
+// step: base position += nu.head<3>() dT, base rotation += (rotation rate of
+// FloatingBaseSystemDynamics.cpp:139-145 = the kinematics' formula) dT, joint positions += nu.tail dT,
+// nu += acc dT.  Array-of-structures state as the reference holds it (per system: nu[nc], jointPos[nc-6],
+// basePos[3], baseRot[9] row-major).  A system is a group of P2 = 8, 16 or 32 lanes (one lane per entry of
+// nu: coalesced), its first lane also does the pose; above 32 entries one warp walks the system in chunks.
+// Every lane reads its old velocity before anybody writes, and the pose lane gets the base twist by
+// shuffle -- no ordering between threads is needed.  HBM-bound: (5 nc + 12) doubles per system.
+// ------------------------------------------------------------------------------------------------
+struct FbdEulerArgs {
+    const double* acc;   // [n][nc]
+    double* nu;          // [n][nc]   in/out
+    double* jp;          // [n][nc-6] in/out (nullptr when nc == 6)
+    double* pos;         // [n][3]    in/out
+    double* rot;         // [n][9]    in/out, row-major
+    double half_rho, dT;
+    long long n;
+    int nc;
+    int p2;              // lanes per system: 8, 16, 32 (nc <= 32), or 0: one warp per system, chunks of 32
+};
+
+template <bool BAUM>
+__device__ __forceinline__ void fbd_pose_step(const FbdEulerArgs& a, long long s, const double (&tw)[6])
+{
+    double* P = a.pos + 3 * s;
+    double* R = a.rot + 9 * s;
+    Pose q{V3{P[0], P[1], P[2]}, V3{R[0], R[3], R[6]}, V3{R[1], R[4], R[7]}, V3{R[2], R[5], R[8]}};
+    kin_euler_step<BAUM>(q, V3{tw[0], tw[1], tw[2]}, V3{tw[3], tw[4], tw[5]}, a.half_rho, a.dT);
+    P[0] = q.p.x; P[1] = q.p.y; P[2] = q.p.z;
+    R[0] = q.c0.x; R[1] = q.c1.x; R[2] = q.c2.x;
+    R[3] = q.c0.y; R[4] = q.c1.y; R[5] = q.c2.y;
+    R[6] = q.c0.z; R[7] = q.c1.z; R[8] = q.c2.z;
+}
+
+template <bool BAUM>
+__global__ void __launch_bounds__(128)
+sys_fbd_euler_kernel(const __grid_constant__ FbdEulerArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nc = a.nc, nj = nc - 6;
+    ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
+    ptx::grid_dep_wait();
+    if (a.p2 > 0) {
+        const int p2 = a.p2, spw = 32 / p2;
+        const int g = lane / p2, q = lane - g * p2;
+        const long long s = wid * spw + g;
+        if (wid * spw >= a.n) return;   // whole warp
+        const bool sys = s < a.n, mine = sys && q < nc;
+        const double old = mine ? __ldcs(a.nu + s * nc + q) : 0.0;
+        const double ac = mine ? __ldcs(a.acc + s * nc + q) : 0.0;
+        double tw[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tw[k] = __shfl_sync(0xffffffffu, old, g * p2 + k);
+        if (mine) {
+            __stcs(a.nu + s * nc + q, fma(ac, a.dT, old));
+            if (q >= 6) {
+                double* j = a.jp + s * nj + (q - 6);
+                __stcs(j, fma(old, a.dT, __ldcs(j)));
+            }
+        }
+        if (sys && q == 0) fbd_pose_step<BAUM>(a, s, tw);
+    } else {
+        const long long s = wid;
+        if (s >= a.n) return;
+        double old[4], ac[4];   // nc <= 128
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int q = c * 32 + lane;
+            old[c] = q < nc ? __ldcs(a.nu + s * nc + q) : 0.0;
+            ac[c] = q < nc ? __ldcs(a.acc + s * nc + q) : 0.0;
+        }
+        double tw[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tw[k] = __shfl_sync(0xffffffffu, old[0], k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int q = c * 32 + lane;
+            if (q < nc) {
+                __stcs(a.nu + s * nc + q, fma(ac[c], a.dT, old[c]));
+                if (q >= 6) {
+                    double* j = a.jp + s * nj + (q - 6);
+                    __stcs(j, fma(old[c], a.dT, __ldcs(j)));
+                }
+            }
+        }
+        if (lane == 0) fbd_pose_step<BAUM>(a, s, tw);
+    }
+}
+
 }  // namespace blfccm

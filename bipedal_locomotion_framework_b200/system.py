@@ -360,3 +360,24 @@ class FloatingBaseDynamicsBatch:
         call, out, wrench = self.prepare_acceleration(*args, **kw)
         call()
         return (out, wrench) if wrench is not None else out
+
+    def prepare_euler_step(self, rho, dT, acc, nu, joint_pos, base_pos, base_rot):
+        """One ForwardEuler step of FloatingBaseDynamicalSystem in place (blf_sys_floating_base_euler_step):
+        acc, nu (n,nc); joint_pos (n,nc-6) or None; base_pos (n,3); base_rot (n,3,3) or (n,9)."""
+        ns, nc = int(nu.shape[0]), int(nu.shape[1])
+        for x in (acc, nu, joint_pos, base_pos, base_rot):
+            assert x is None or x.is_contiguous()
+        dp = lambda x: x.data_ptr() if x is not None else None
+        args = (self._b.handle.ptr, ns, nc, float(rho), float(dT), dp(acc), dp(nu), dp(joint_pos), dp(base_pos),
+                dp(base_rot), self._b._stream())
+        fn = _capi.lib().blf_sys_floating_base_euler_step
+        keep = (acc, nu, joint_pos, base_pos, base_rot)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                _capi.check(rc)
+        return call
+
+    def euler_step(self, *args, **kw):
+        self.prepare_euler_step(*args, **kw)()

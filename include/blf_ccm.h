@@ -406,6 +406,22 @@ BLF_CCM_API int blf_sys_floating_base_acceleration(
     const double* regularization, double* acc, double* const* wrench_planes, void* stream);
 
 /*
+ * One ForwardEuler step of FloatingBaseDynamicalSystem
+ * (src/System/include/BipedalLocomotion/System/ForwardEuler.tpp:19-49, x = x0 + dx * dT over the state
+ * tuple of FloatingBaseSystemDynamics.h:33-52), every derivative taken at the state BEFORE the step:
+ *   base_pos += nu[0..2] * dT;  base_rot += (rotation rate of FloatingBaseSystemDynamics.cpp:139-145,
+ *   rho = the Baumgarte parameter of initalize, :17-37) * dT;  joint_pos += nu[6..] * dT;  nu += acc * dT
+ * acc = what blf_sys_floating_base_acceleration returned for that state.  Per-system arrays as the
+ * reference holds them: acc, nu n_systems*ncols ([base (6); joints]); joint_pos n_systems*(ncols-6)
+ * (NULL when ncols == 6); base_pos n_systems*3; base_rot n_systems*9 row-major; all but acc updated
+ * in place.  ncols 6..128.  With rho == 0 the Baumgarte term is skipped (as blf_sys_kinematics_*).
+ */
+BLF_CCM_API int blf_sys_floating_base_euler_step(blf_ccm_handle* h, int64_t n_systems, int ncols,
+                                                 double rho, double dT, const double* acc, double* nu,
+                                                 double* joint_pos, double* base_pos, double* base_rot,
+                                                 void* stream);
+
+/*
  * Device / pinned-host memory and stream helpers, so that host code above this ABI (the C++17
  * facade, the device-side SoA container) needs no CUDA headers.  Device allocations are 256-byte
  * aligned.  Copies are asynchronous on `stream` when the host side is pinned.

@@ -92,6 +92,7 @@ def lib():
         L.blf_ref_rollout.argtypes = [sz, i, d, d, vp, vp, vp, vp, vp, C.c_uint, vp, vp, vp, i]
         L.blf_ref_generalized_force.argtypes = [sz, i, i] + [vp] * 9 + [i]
         L.blf_ref_floating_base_dynamics.argtypes = [sz, i, i] + [vp] * 12 + [i]
+        L.blf_ref_floating_base_euler_step.argtypes = [sz, i, i] + [vp] * 10 + [d, d] + [vp] * 9 + [i]
         _lib = L
     return _lib
 
@@ -318,6 +319,35 @@ def floating_base_dynamics(contacts_per_system, twists, poses, null_poses, jacob
     if rc != 0:
         raise RuntimeError(f"reference FloatingBaseDynamicalSystem failed (rc={rc})")
     return (out, wr) if want_wrench else out
+
+
+def floating_base_euler_step(contacts_per_system, twists, poses, null_poses, jacobians, bias, mass, rho, dT, nu,
+                             joint_pos, base_pos, base_rot, joint_torques=None, reg=None, params=None,
+                             uniform=None, nthreads=1):
+    """ForwardEuler<FloatingBaseDynamicalSystem>(dT).integrate(0, dT) per system from the reference's own
+    sources over the KinDynComputations test double.  Returns (acc, nu, joint_pos, base_pos, base_rot)."""
+    twists, poses, null_poses = _f64(twists), _f64(poses), _f64(null_poses)
+    n = twists.shape[0]
+    ns = n // contacts_per_system
+    b = _f64(bias)
+    ncols = b.shape[1]
+    J, M = _f64(jacobians), _f64(mass)
+    tau = None if joint_torques is None else _f64(joint_torques).reshape(ns, ncols - 6)
+    rg = None if reg is None else _f64(reg).reshape(ncols, ncols)
+    pr = None if params is None else _f64(params).reshape(n, 4)
+    uni = np.asarray(uniform if uniform is not None else (0, 0, 0, 0), dtype=np.float64)
+    v, p, r = _f64(nu).reshape(ns, ncols), _f64(base_pos).reshape(ns, 3), _f64(base_rot).reshape(ns, 9)
+    jp = np.zeros((ns, max(ncols - 6, 0))) if joint_pos is None else _f64(joint_pos).reshape(ns, ncols - 6)
+    acc, vo, jo = np.empty((ns, ncols)), np.empty((ns, ncols)), np.empty((ns, max(ncols - 6, 0)))
+    po, ro = np.empty((ns, 3)), np.empty((ns, 9))
+    rc = lib().blf_ref_floating_base_euler_step(ns, int(contacts_per_system), int(ncols), _ptr(twists), _ptr(poses),
+                                                _ptr(null_poses), _ptr(pr), _ptr(uni), _ptr(J), _ptr(b), _ptr(tau),
+                                                _ptr(M), _ptr(rg), float(rho), float(dT), _ptr(v), _ptr(jp), _ptr(p),
+                                                _ptr(r), _ptr(acc), _ptr(vo), _ptr(jo), _ptr(po), _ptr(ro),
+                                                int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"reference ForwardEuler<FloatingBaseDynamicalSystem> failed (rc={rc})")
+    return acc, vo, jo, po, ro.reshape(ns, 3, 3)
 
 
 def run_reference_test(name: str, timeout: float = 600.0) -> subprocess.CompletedProcess:

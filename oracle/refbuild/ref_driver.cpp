@@ -430,6 +430,21 @@ int blf_ref_rollout(std::size_t chains, int horizon, double dT, double rho, cons
     });
 }
 
+// State in / out of one ForwardEuler<FloatingBaseDynamicalSystem> step (all arrays per system, row-major):
+// nu = [base velocity (6); joint velocity], joint positions, base position (3), base rotation (9).
+struct EulerStepIO
+{
+    double rho, dT;
+    const double* nu;
+    const double* jointPos;
+    const double* basePos;
+    const double* baseRot;
+    double* nuOut;
+    double* jointPosOut;
+    double* basePosOut;
+    double* baseRotOut;
+};
+
 // FloatingBaseDynamicalSystem::dynamics, contact part (FloatingBaseSystemDynamics.cpp:188-229), run
 // from the reference's own source: per system the KinDynComputations test double is loaded with
 //   mass matrix = identity (so the final llt().solve() returns m_knownCoefficent unchanged),
@@ -445,7 +460,8 @@ static int dynamicsOverTestDouble(std::size_t n_systems, int contacts_per_system
                                   const double* poses, const double* null_poses, const double* params,
                                   const double uniform[4], const double* jacobians, const double* base,
                                   bool base_is_bias, const double* joint_torques, const double* mass_matrices,
-                                  const double* regularization, double* out, double* wrench, int nthreads)
+                                  const double* regularization, double* out, double* wrench, int nthreads,
+                                  const EulerStepIO* step = nullptr)
 {
     if (ncols < 6 || contacts_per_system < 1) return -3;
     return runPartitioned(n_systems, nthreads, [=](std::size_t b, std::size_t e, int* status) {
@@ -492,11 +508,22 @@ static int dynamicsOverTestDouble(std::size_t n_systems, int contacts_per_system
                 contacts.emplace_back(static_cast<iDynTree::FrameIndex>(c), model);
             }
 
-            FloatingBaseDynamicalSystem system;
+            auto systemPtr = std::make_shared<FloatingBaseDynamicalSystem>();
+            FloatingBaseDynamicalSystem& system = *systemPtr;
             if (!system.setKinDyn(kinDyn))
             {
                 *status = -1;
                 return;
+            }
+            if (step)
+            {
+                std::shared_ptr<IParametersHandler> handler = std::make_shared<StdImplementation>();
+                handler->setParameter("rho", step->rho);
+                if (!system.initalize(handler))
+                {
+                    *status = -1;
+                    return;
+                }
             }
             const Eigen::Index nd = Eigen::Index(dofs);
             Eigen::Matrix<double, 6, 1> baseVelocity;
@@ -525,7 +552,24 @@ static int dynamicsOverTestDouble(std::size_t n_systems, int contacts_per_system
                     return;
                 }
             }
-            if (!system.setState({baseVelocity, zeros, basePosition, baseOrientation, zeros})
+            Eigen::VectorXd jointVelocity = zeros, jointPosition = zeros;
+            if (step)
+            {
+                for (Eigen::Index q = 0; q < 6; ++q)
+                    baseVelocity(q) = step->nu[s * nc + std::size_t(q)];
+                for (Eigen::Index q = 0; q < nd; ++q)
+                {
+                    jointVelocity(q) = step->nu[s * nc + 6 + std::size_t(q)];
+                    jointPosition(q) = step->jointPos[s * dofs + std::size_t(q)];
+                }
+                for (Eigen::Index i = 0; i < 3; ++i)
+                {
+                    basePosition(i) = step->basePos[s * 3 + std::size_t(i)];
+                    for (Eigen::Index k = 0; k < 3; ++k)
+                        baseOrientation(i, k) = step->baseRot[s * 9 + std::size_t(3 * i + k)];
+                }
+            }
+            if (!system.setState({baseVelocity, jointVelocity, basePosition, baseOrientation, jointPosition})
                 || !system.setControlInput({torques, contacts}))
             {
                 *status = -1;
@@ -536,6 +580,29 @@ static int dynamicsOverTestDouble(std::size_t n_systems, int contacts_per_system
             {
                 *status = -2;
                 return;
+            }
+            if (step)
+            {   // x <- x + dx * dT through the reference's own integrator (ForwardEuler.tpp:19-49)
+                ForwardEuler<FloatingBaseDynamicalSystem> integrator(step->dT);
+                if (!integrator.setDynamicalSystem(systemPtr) || !integrator.integrate(0.0, step->dT))
+                {
+                    *status = -2;
+                    return;
+                }
+                const auto& [v6, jv, p3, R3, jp] = integrator.getSolution();
+                for (Eigen::Index q = 0; q < 6; ++q)
+                    step->nuOut[s * nc + std::size_t(q)] = v6(q);
+                for (Eigen::Index q = 0; q < nd; ++q)
+                {
+                    step->nuOut[s * nc + 6 + std::size_t(q)] = jv(q);
+                    step->jointPosOut[s * dofs + std::size_t(q)] = jp(q);
+                }
+                for (Eigen::Index i = 0; i < 3; ++i)
+                {
+                    step->basePosOut[s * 3 + std::size_t(i)] = p3(i);
+                    for (Eigen::Index k = 0; k < 3; ++k)
+                        step->baseRotOut[s * 9 + std::size_t(3 * i + k)] = R3(i, k);
+                }
             }
             for (std::size_t q = 0; q < 6; ++q)
                 out[s * nc + q] = std::get<0>(dx)(Eigen::Index(q));
@@ -575,6 +642,26 @@ int blf_ref_floating_base_dynamics(std::size_t n_systems, int contacts_per_syste
     return dynamicsOverTestDouble(n_systems, contacts_per_system, ncols, twists, poses, null_poses, params,
                                   uniform, jacobians, bias_forces, true, joint_torques, mass_matrices,
                                   regularization, out, wrench, nthreads);
+}
+
+// One ForwardEuler<FloatingBaseDynamicalSystem>(dT).integrate(0, dT) per system, from the reference's own
+// sources: dynamics() as blf_ref_floating_base_dynamics (out = the acceleration at the state before the
+// step), then x += dx * dT over the whole state tuple.  nu / nu_out n*ncols, joint_pos n*(ncols-6),
+// base_pos n*3, base_rot n*9 row-major.
+int blf_ref_floating_base_euler_step(std::size_t n_systems, int contacts_per_system, int ncols, const double* twists,
+                                     const double* poses, const double* null_poses, const double* params,
+                                     const double uniform[4], const double* jacobians, const double* bias_forces,
+                                     const double* joint_torques, const double* mass_matrices,
+                                     const double* regularization, double rho, double dT, const double* nu,
+                                     const double* joint_pos, const double* base_pos, const double* base_rot,
+                                     double* acc, double* nu_out, double* joint_pos_out, double* base_pos_out,
+                                     double* base_rot_out, int nthreads)
+{
+    if (!bias_forces || !mass_matrices || !nu || !base_pos || !base_rot) return -3;
+    const EulerStepIO io{rho, dT, nu, joint_pos, base_pos, base_rot, nu_out, joint_pos_out, base_pos_out, base_rot_out};
+    return dynamicsOverTestDouble(n_systems, contacts_per_system, ncols, twists, poses, null_poses, params,
+                                  uniform, jacobians, bias_forces, true, joint_torques, mass_matrices,
+                                  regularization, acc, nullptr, nthreads, &io);
 }
 
 } // extern "C"

@@ -177,6 +177,11 @@ struct job {
     const double* base;
     double* out;
     int base_negate;
+    /* floating-base Euler step */
+    double* nu;
+    double* joint_pos;
+    double* base_pos;
+    double* base_rot;
     /* mass-matrix solve */
     const double* mass;
     const double* reg;
@@ -490,4 +495,38 @@ void syso_floating_base_acceleration(size_t n_systems, int contacts_per_system, 
     j.wrench_planes = wrench_planes;
     parallel_for(&j, n_systems, nthreads);
     syso_mass_matrix_solve(n_systems, ncols, mass, reg, acc, joint_torques, acc, nthreads);
+}
+
+/* ---- ForwardEuler<FloatingBaseDynamicalSystem>: x += dx * dT over the state tuple ---------------- */
+
+static void fbd_euler_range(const job_t* j, size_t begin, size_t end)
+{
+    const int nc = j->ncols, nj = nc - 6;
+    for (size_t s = begin; s < end; ++s) {
+        double* nu = j->nu + s * (size_t)nc;
+        /* base position, base rotation, joint positions: derivatives at the state before the step
+         * (baseLinearVelocity = nu.head<3>(), the rotation rate of :139-145, jointVelocity) */
+        syso_forward_euler_step(j->rho, j->dT, nu, j->base_pos + 3 * s, j->base_rot + 9 * s, nj > 0 ? nj : 0,
+                                nj > 0 ? nu + 6 : NULL, nj > 0 ? j->joint_pos + s * (size_t)nj : NULL);
+        /* base and joint velocity += acceleration * dT */
+        for (int q = 0; q < nc; ++q) nu[q] = nu[q] + j->acc[s * (size_t)nc + (size_t)q] * j->dT;
+    }
+}
+
+void syso_floating_base_euler_step(size_t n_systems, int ncols, double rho, double dT, const double* acc,
+                                   double* nu, double* joint_pos, double* base_pos, double* base_rot,
+                                   int nthreads)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.fn = fbd_euler_range;
+    j.ncols = ncols;
+    j.rho = rho;
+    j.dT = dT;
+    j.acc = (double*)acc;
+    j.nu = nu;
+    j.joint_pos = joint_pos;
+    j.base_pos = base_pos;
+    j.base_rot = base_rot;
+    parallel_for(&j, n_systems, nthreads);
 }

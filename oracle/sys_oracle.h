@@ -142,6 +142,19 @@ void syso_floating_base_acceleration(size_t n_systems, int contacts_per_system, 
                                      const double* reg, double* acc, double* const* wrench_planes,
                                      int nthreads);
 
+/*
+ * One ForwardEuler step of FloatingBaseDynamicalSystem (ForwardEuler.tpp:19-49: x = x0 + dx * dT over the
+ * state tuple of FloatingBaseSystemDynamics.h:33-52), every derivative taken at the state BEFORE the
+ * step: base position += nu.head<3>() * dT; base rotation += (rotation rate of
+ * FloatingBaseSystemDynamics.cpp:139-145, the formula of FloatingBaseSystemKinematics) * dT;
+ * joint positions += nu.tail * dT; nu += acc * dT.  acc as syso_floating_base_acceleration returns it.
+ * nu n*ncols in/out, joint_pos n*(ncols-6) in/out (NULL when ncols == 6), base_pos n*3, base_rot n*9
+ * row-major in/out.
+ */
+void syso_floating_base_euler_step(size_t n_systems, int ncols, double rho, double dT, const double* acc,
+                                   double* nu, double* joint_pos, double* base_pos, double* base_rot,
+                                   int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ def lib():
                                    vp, vp, vp, vp, vp, ci]
         L.syso_generalized_force.argtypes = [sz, ci, ci, vp, vp, vp, vp, vp, vp, vp, ci]
         L.syso_mass_matrix_solve.argtypes = [sz, ci, vp, vp, vp, vp, vp, ci]
+        L.syso_floating_base_euler_step.argtypes = [sz, ci, dbl, dbl, vp, vp, vp, vp, vp, ci]
         L.syso_floating_base_acceleration.argtypes = [sz, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                       vp, ci]
         _configured = True
@@ -195,3 +196,17 @@ def floating_base_acceleration(contacts_per_system, in_planes, jacobians, bias, 
                                           _planes(pr), _ptr(uni), _ptr(J), _ptr(b), _ptr(tau), _ptr(M),
                                           _ptr(rg), _ptr(acc), _planes(wr), int(nthreads))
     return (acc, wr) if want_wrench else acc
+
+
+def floating_base_euler_step(rho, dT, acc, nu, joint_pos, base_pos, base_rot, nthreads=1):
+    """One ForwardEuler step of FloatingBaseDynamicalSystem on copies of the state arrays:
+    nu (n, nc), joint_pos (n, nc-6) or None, base_pos (n, 3), base_rot (n, 3, 3) -> the new four."""
+    a = np.ascontiguousarray(acc, dtype=np.float64)
+    v = np.array(nu, dtype=np.float64).copy()
+    ns, nc = v.shape
+    jp = None if joint_pos is None else np.array(joint_pos, dtype=np.float64).copy()
+    p = np.array(base_pos, dtype=np.float64).copy()
+    r = np.array(base_rot, dtype=np.float64).reshape(ns, 9).copy()
+    lib().syso_floating_base_euler_step(ns, int(nc), float(rho), float(dT), _ptr(a), _ptr(v), _ptr(jp), _ptr(p),
+                                        _ptr(r), int(nthreads))
+    return v, jp, p, r.reshape(ns, 3, 3)

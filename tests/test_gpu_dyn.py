@@ -314,3 +314,82 @@ def test_floating_base_acceleration_large_batch_residual(torch, batch, dyn):
     res = (torch.bmm(M, acc.unsqueeze(2)).squeeze(2) - rhs).abs().amax(dim=1)
     mag = bias.abs().amax(dim=1) + (J.reshape(ns, cps, 6, ncols).abs() * W.abs().unsqueeze(3)).sum(dim=(1, 2)).amax(dim=1)
     assert bool((res <= 1e-12 * (mag + M.abs().sum(dim=2).amax(dim=1) * acc.abs().amax(dim=1))).all())
+
+
+# --- one ForwardEuler step of FloatingBaseDynamicalSystem ---------------------------------------------
+
+def _rot(rng, scaled):
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    return q * (1.0 + (0.02 * rng.normal() if scaled else 0.0))   # off the manifold: the Baumgarte term acts
+
+
+@pytest.mark.parametrize("ncols,ns,rho", [(29, 5_003, 0.7), (29, 1_000, 0.0), (6, 4_099, 0.3), (12, 3_001, 2.0),
+                                          (16, 777, 0.01), (38, 1_025, 0.5), (64, 131, 0.1), (128, 33, 0.0)])
+def test_floating_base_euler_step_vs_oracle(torch, dyn, so, ncols, ns, rho):
+    """blf_sys_floating_base_euler_step against the C oracle (itself bit-identical to the reference's
+    ForwardEuler<FloatingBaseDynamicalSystem>): every lane layout (8, 16, 32 lanes per system, chunks),
+    ragged counts, guard rows."""
+    rng = np.random.default_rng(ncols + ns)
+    dT = 0.01
+    acc = rng.normal(size=(ns, ncols)) * 30.0
+    nu = rng.normal(size=(ns, ncols))
+    jp = rng.normal(size=(ns, ncols - 6)) if ncols > 6 else None
+    p = rng.normal(size=(ns, 3))
+    R = np.stack([_rot(rng, i % 2 == 0) for i in range(ns)])
+    wv, wq, wp, wR = so.floating_base_euler_step(rho, dT, acc, nu, jp, p, R, nthreads=NTHREADS)
+    pad = lambda x: None if x is None else torch.from_numpy(np.concatenate([np.full((1,) + x.shape[1:], 7.5), x,
+                                                                           np.full((1,) + x.shape[1:], 7.5)])).cuda()
+    dv, dq, dp_, dR = pad(nu), pad(jp), pad(p), pad(R.reshape(ns, 9))
+    view = lambda x: None if x is None else x[1:ns + 1]
+    dyn.euler_step(rho, dT, _dev(torch, acc), view(dv), view(dq), view(dp_), view(dR))
+    for got, want in ((dv, wv), (dq, wq), (dp_, wp), (dR, wR.reshape(ns, 9))):
+        if got is None:
+            continue
+        g = got.cpu().numpy()
+        assert (g[0] == 7.5).all() and (g[-1] == 7.5).all()                  # nothing written outside
+        assert rel(g[1:-1], want).max() <= TOL
+    assert rel(dR.cpu().numpy()[1:-1].reshape(ns, 3, 3), wR).max() <= TOL    # row by row
+
+
+def test_floating_base_whole_step_vs_reference_build(torch, batch, dyn, ref):
+    """Acceleration + Euler step through the C ABI against ForwardEuler<FloatingBaseDynamicalSystem>
+    run from the reference's own sources over the test double."""
+    cps, ncols, ns, rho, dT = 2, 29, 1_501, 0.7, 0.01
+    st = syn.make_states(ns * cps, seed=17)
+    rng = np.random.default_rng(99)
+    J = rng.uniform(-1.0, 1.0, (ns * cps, 6, ncols))
+    bias = rng.uniform(-50.0, 50.0, (ns, ncols))
+    M, _, tau, _ = _case(ncols, ns, 21)
+    nu = rng.normal(size=(ns, ncols))
+    jp = rng.normal(size=(ns, ncols - 6))
+    p = rng.normal(size=(ns, 3))
+    R = np.stack([_rot(rng, True) for _ in range(ns)])
+    racc, rv, rq, rp, rR = ref.floating_base_euler_step(cps, st["twists"], st["poses"], st["null_poses"], J, bias, M,
+                                                        rho, dT, nu, jp, p, R, joint_torques=tau,
+                                                        uniform=syn.REFERENCE_TEST_PARAMS, nthreads=NTHREADS)
+    planes = _dev(torch, syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"]))
+    acc = dyn.acceleration(cps, planes, _dev(torch, J), _dev(torch, bias), _dev(torch, M), _dev(torch, tau))
+    dv, dq, dp_, dR = (_dev(torch, x) for x in (nu, jp, p, R.reshape(ns, 9)))
+    dyn.euler_step(rho, dT, acc, dv, dq, dp_, dR)
+    # the velocity inherits the acceleration's tolerance scaled by dT; the rest is elementwise
+    mag = np.abs(bias).max(axis=1) + np.abs(J.reshape(ns, cps, 6, ncols)).sum(axis=(1, 2)).max(axis=1) * 1e3
+    tol_acc = _acc_tolerance(M, racc, mag)
+    assert (np.abs(acc.cpu().numpy() - racc).max(axis=1) <= tol_acc).all()
+    assert (np.abs(dv.cpu().numpy() - rv).max(axis=1) <= tol_acc * dT + TOL * np.abs(rv).max(axis=1)).all()
+    assert rel(dq.cpu().numpy(), rq).max() <= TOL and rel(dp_.cpu().numpy(), rp).max() <= TOL
+    assert rel(dR.cpu().numpy().reshape(ns, 3, 3), rR).max() <= TOL
+
+
+def test_floating_base_euler_step_rejects_bad_arguments(torch, batch):
+    from bipedal_locomotion_framework_b200 import _capi
+    L, h = _capi.lib(), batch.handle.ptr
+    z = lambda *s: torch.zeros(s, dtype=torch.float64, device="cuda")
+    acc, nu, jp, p, R = z(4, 8), z(4, 8), z(4, 2), z(4, 3), z(4, 9)
+    R[:, 0] = R[:, 4] = R[:, 8] = 1.0
+    f = lambda *a: L.blf_sys_floating_base_euler_step(h, *a)
+    assert f(4, 8, 0.1, 0.01, acc.data_ptr(), nu.data_ptr(), jp.data_ptr(), p.data_ptr(), R.data_ptr(), None) == 0
+    assert f(0, 8, 0.1, 0.01, None, None, None, None, None, None) == 0
+    assert f(4, 5, 0.1, 0.01, acc.data_ptr(), nu.data_ptr(), jp.data_ptr(), p.data_ptr(), R.data_ptr(), None) != 0
+    assert f(4, 8, 0.1, 0.01, acc.data_ptr(), nu.data_ptr(), None, p.data_ptr(), R.data_ptr(), None) != 0
+    assert f(4, 8, 0.1, 0.01, nu.data_ptr(), nu.data_ptr(), jp.data_ptr(), p.data_ptr(), R.data_ptr(), None) != 0
+    assert f(4, 6, 0.1, 0.01, acc.data_ptr(), nu.data_ptr(), None, p.data_ptr(), R.data_ptr(), None) == 0

@@ -315,6 +315,39 @@ def test_floating_base_dynamics_oracle_vs_reference_build(sys_oracle, ref, cps, 
     assert np.array_equal(o, r) and np.array_equal(wo.T, wr)
 
 
+@pytest.mark.parametrize("cps,ncols,rho,het", [(2, 29, 0.0, False), (2, 29, 0.7, True), (1, 6, 0.3, False),
+                                               (3, 12, 2.0, False), (4, 38, 0.01, True)])
+def test_floating_base_euler_step_oracle_vs_reference_build(sys_oracle, ref, cps, ncols, rho, het):
+    """ForwardEuler<FloatingBaseDynamicalSystem>(dT).integrate(0, dT) from the reference's own sources
+    (ForwardEuler.tpp + FloatingBaseSystemDynamics.cpp over the test double): the acceleration at the old
+    state, then x += dx * dT over the whole state tuple.  Bit for bit."""
+    rng = np.random.default_rng(5 * cps + ncols)
+    ns, dT = 200, 0.01
+    st = syn.make_states(ns * cps, seed=33 + cps, heterogeneous=het)
+    J = rng.normal(size=(ns * cps, 6, ncols))
+    bias = rng.normal(size=(ns, ncols)) * 20.0
+    tau = rng.normal(size=(ns, ncols - 6)) if ncols > 6 else None
+    M = syn.make_mass_matrices(ns, ncols, seed=3 + ncols, spread=0.5)
+    nu = rng.normal(size=(ns, ncols))
+    jp = rng.normal(size=(ns, ncols - 6)) if ncols > 6 else None
+    p = rng.normal(size=(ns, 3))
+    R = np.stack([_rand_rot(rng, i % 3 == 0) for i in range(ns)])
+    planes = syn.aos_to_planes(st["twists"], st["poses"], st["null_poses"])
+    acc = sys_oracle.floating_base_acceleration(cps, planes, J, bias, M, tau,
+                                                param_planes=st["params"].T if het else None,
+                                                uniform=syn.REFERENCE_TEST_PARAMS, nthreads=2)
+    v, q, pp, RR = sys_oracle.floating_base_euler_step(rho, dT, acc, nu, jp, p, R, nthreads=2)
+    racc, rv, rq, rp, rR = ref.floating_base_euler_step(cps, st["twists"], st["poses"], st["null_poses"], J, bias, M,
+                                                        rho, dT, nu, jp, p, R, joint_torques=tau,
+                                                        params=st["params"] if het else None,
+                                                        uniform=syn.REFERENCE_TEST_PARAMS, nthreads=4)
+    assert np.array_equal(acc, racc) and np.array_equal(v, rv) and np.array_equal(pp, rp) and np.array_equal(RR, rR)
+    if jp is not None:
+        assert np.array_equal(q, rq)
+    # the step really moved the state, and positions used the OLD velocities
+    assert np.array_equal(pp, p + nu[:, :3] * dT)
+
+
 # --- integrate -> contact model rollout ------------------------------------------------------------
 
 @pytest.mark.parametrize("rho", [0.0, 2.0])
