@@ -724,6 +724,13 @@ def next_rows_leg(cx: Ctx, planes_np, no_cpu: bool = False) -> dict:
         s_ms = timed(lambda i: scalls[i % 2](), iters=20)
         acalls = [dyn.prepare_acceleration(cps, planes[j], Js[j], bias, Ms[j], tau, out=outs[j])[0] for j in range(2)]
         a_ms = timed(lambda i: acalls[i % 2](), iters=20)
+        # one ForwardEuler step of the whole state with that acceleration (blf_sys_floating_base_euler_step)
+        nu, jp = torch.rand_like(bias), torch.rand_like(tau)
+        bp = torch.rand((ns, 3), dtype=torch.float64, device=dev)
+        br = torch.eye(3, dtype=torch.float64, device=dev).reshape(1, 9).repeat(ns, 1)
+        ecall = dyn.prepare_euler_step(0.01, 1e-5, outs[0], nu, jp, bp, br)
+        e_ms = timed(lambda i: ecall(), iters=20)
+        e_bytes = 8 * (5 * ncols + 12)       # acc in, nu / joints / base pose in and out
         tri = 8 * (ncols * (ncols + 1) // 2 + 2 * ncols + (ncols - 6))       # what LLT reads + rhs in + acc out + torques
         dense = 8 * (ncols * ncols + 2 * ncols + (ncols - 6))                 # the dense matrix the caller hands over
         a_bytes = cps * (200 + 48 * ncols) + tri
@@ -734,6 +741,8 @@ def next_rows_leg(cx: Ctx, planes_np, no_cpu: bool = False) -> dict:
                "solve_hbm_frac_dense_bytes": ns * dense / (s_ms * 1e-3) / 1e9 / cx.peak,
                "whole_step_ms": a_ms, "whole_step_systems_per_s": ns / (a_ms * 1e-3),
                "hbm_frac_of_measured": ns * a_bytes / (a_ms * 1e-3) / 1e9 / cx.peak,
+               "euler_step_ms": e_ms, "euler_step_systems_per_s": ns / (e_ms * 1e-3),
+               "euler_step_hbm_frac": ns * e_bytes / (e_ms * 1e-3) / 1e9 / cx.peak,
                "bound": "shared-memory data pipe and column-to-column latency, not HBM (DESIGN section 10 row 5)"}
         if cx.rank == 0 and not no_cpu:
             from oracle import sys_oracle          # cpu_baseline leg: the C restatement, all host cores
@@ -750,7 +759,7 @@ def next_rows_leg(cx: Ctx, planes_np, no_cpu: bool = False) -> dict:
                                    "sample": f"best of 3 passes of oracle/sys_oracle.c syso_mass_matrix_solve over "
                                              f"the first {sample} systems"}
         rows[f"floating_base_dynamics_{ncols}"] = row
-        del Ms, Js, bias, tau, outs, scalls, acalls
+        del Ms, Js, bias, tau, outs, scalls, acalls, ecall, nu, jp, bp, br
         torch.cuda.empty_cache()
     kb = KinematicsBatch(cx.local, batch.handle)
     kp = [planes[j][6:18].clone() for j in range(3)]

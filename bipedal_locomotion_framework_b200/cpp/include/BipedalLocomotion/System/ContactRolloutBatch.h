@@ -116,6 +116,19 @@ public:
                                   double* acceleration, GenericContainer::DeviceSoA* wrench = nullptr,
                                   void* stream = nullptr);
 
+    /**
+     * One ForwardEuler step of FloatingBaseDynamicalSystem (ForwardEuler.tpp:19-49 over the state tuple
+     * of FloatingBaseSystemDynamics.h:33-52), in place, every derivative at the state before the step:
+     * basePosition += velocity.head<3>() dT, baseRotation += (rotation rate of
+     * FloatingBaseSystemDynamics.cpp:139-145 with the Baumgarte parameter rho) dT, jointPositions +=
+     * velocity.tail dT, velocity += acceleration dT.  Device arrays: acceleration / velocity nSystems x
+     * columns ([base (6); joints]), jointPositions nSystems x (columns - 6) (nullptr when columns == 6),
+     * basePositions nSystems x 3, baseRotations nSystems x 9 row-major.
+     */
+    bool floatingBaseEulerStep(std::size_t nSystems, int columns, double rho, double dT,
+                               const double* acceleration, double* velocity, double* jointPositions,
+                               double* basePositions, double* baseRotations, void* stream = nullptr);
+
 private:
     std::shared_ptr<ContactModels::CudaDevice> m_device;
     void* m_best{nullptr};

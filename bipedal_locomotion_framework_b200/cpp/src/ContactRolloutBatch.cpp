@@ -188,3 +188,15 @@ bool ContactRolloutBatch::floatingBaseAcceleration(std::size_t nSystems, int con
                       wrench ? wrench->planePointers() : nullptr, stream),
                   "floatingBaseAcceleration");
 }
+
+bool ContactRolloutBatch::floatingBaseEulerStep(std::size_t nSystems, int columns, double rho, double dT,
+                                                const double* acceleration, double* velocity,
+                                                double* jointPositions, double* basePositions,
+                                                double* baseRotations, void* stream)
+{
+    if (m_device == nullptr) return report(BLF_CCM_ERR_INVALID_HANDLE, "floatingBaseEulerStep");
+    return report(blf_sys_floating_base_euler_step(raw(m_device), static_cast<std::int64_t>(nSystems), columns,
+                                                   rho, dT, acceleration, velocity, jointPositions,
+                                                   basePositions, baseRotations, stream),
+                  "floatingBaseEulerStep");
+}

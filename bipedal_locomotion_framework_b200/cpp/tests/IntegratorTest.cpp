@@ -515,5 +515,60 @@ TEST_CASE("Batched steps either side of the contact model")
             for (int i = 0; i < cols; ++i)
                 worstSolve = std::max(worstSolve, std::fabs(known[s * cols + i] - (i + 1)) / cols);
         REQUIRE(worstSolve <= 1e-12);
+
+        // one ForwardEuler step of the whole floating-base state with that acceleration, against the
+        // per-instance FloatingBaseSystemKinematics + ForwardEuler facade (pose, joints) and x + dx dT (velocity)
+        const int nj = cols - 6;
+        std::vector<double> nu(nSystems * cols), jp(nSystems * nj), bp(nSystems * 3), br(nSystems * 9);
+        for (double& x : nu) x = u(gen);
+        for (double& x : jp) x = u(gen);
+        for (double& x : bp) x = u(gen);
+        for (std::size_t s = 0; s < nSystems; ++s)
+        {
+            const double scale = 1.0 + 0.02 * u(gen);   // off the manifold: the Baumgarte term acts
+            for (int k = 0; k < 9; ++k) br[s * 9 + k] = scale * pose[s].getRotation().data()[k];
+        }
+        const std::vector<double> nu0 = nu, jp0 = jp, bp0 = bp, br0 = br;
+        DeviceSoA nud(dev, 1, nu.size()), jpd(dev, 1, jp.size()), bpd(dev, 1, bp.size()), brd(dev, 1, br.size());
+        REQUIRE(nud.upload(0, nu.data()));
+        REQUIRE(jpd.upload(0, jp.data()));
+        REQUIRE(bpd.upload(0, bp.data()));
+        REQUIRE(brd.upload(0, br.data()));
+        REQUIRE(rollouts.floatingBaseEulerStep(nSystems, cols, rho, dT, accd.plane(0), nud.plane(0), jpd.plane(0),
+                                               bpd.plane(0), brd.plane(0)));
+        REQUIRE_FALSE(rollouts.floatingBaseEulerStep(nSystems, 5, rho, dT, accd.plane(0), nud.plane(0),
+                                                     jpd.plane(0), bpd.plane(0), brd.plane(0)));
+        REQUIRE(nud.download(0, nu.data()));
+        REQUIRE(jpd.download(0, jp.data()));
+        REQUIRE(bpd.download(0, bp.data()));
+        REQUIRE(brd.download(0, br.data()));
+        double worstStep = 0;
+        for (std::size_t s = 0; s < nSystems; s += 11)
+        {
+            auto system = std::make_shared<FloatingBaseSystemKinematics>(dev);
+            REQUIRE(system->initalize(kinHandler));
+            Vector3d p0;
+            Matrix3d r0;
+            VectorXd s0(nj), sd(nj);
+            Vector6d twist;
+            for (int k = 0; k < 3; ++k) p0[k] = bp0[s * 3 + k];
+            for (int k = 0; k < 9; ++k) r0[k] = br0[s * 9 + k];
+            for (int k = 0; k < nj; ++k) s0[k] = jp0[s * nj + k];
+            for (int k = 0; k < nj; ++k) sd[k] = nu0[s * cols + 6 + k];
+            for (int k = 0; k < 6; ++k) twist[k] = nu0[s * cols + k];
+            REQUIRE(system->setState({p0, r0, s0}));
+            REQUIRE(system->setControlInput({twist, sd}));
+            ForwardEuler<FloatingBaseSystemKinematics> integrator(dT);
+            REQUIRE(integrator.setDynamicalSystem(system));
+            REQUIRE(integrator.integrate(0, dT));
+            const auto& [p, R, q] = integrator.getSolution();
+            worstStep = std::max(worstStep, relErr(&bp[s * 3], p.data(), 3));
+            worstStep = std::max(worstStep, relErr(&br[s * 9], R.data(), 9));
+            worstStep = std::max(worstStep, relErr(&jp[s * nj], q.data(), nj));
+            std::vector<double> v(cols);
+            for (int k = 0; k < cols; ++k) v[k] = nu0[s * cols + k] + acc[s * cols + k] * dT;
+            worstStep = std::max(worstStep, relErr(&nu[s * cols], v.data(), cols));
+        }
+        REQUIRE(worstStep <= 1e-12);
     }
 }

@@ -126,6 +126,8 @@ struct blf_ccm_handle {
     int tune_host_ramp = 1;      // BLF_CCM_TUNE_HOST_RAMP=0: equal chunks instead of the ramped schedule
     int tune_host_noexpand = 0;  // BLF_CCM_TUNE_HOST_NOEXPAND=1: measurement aid, the workers skip the expansion (results WRONG)
     int tune_llt_general = 0;    // BLF_CCM_TUNE_LLT_GENERAL=1: mass-matrix solve with the block-level kernel whatever the size
+    int tune_fbd_tile_kb = 0;    // BLF_CCM_TUNE_FBD_TILE_KB: shared-memory target per CTA of the floating-base Euler step (default 24)
+    int tune_fbd_no_bulk = 0;    // BLF_CCM_TUNE_FBD_NO_BULK=1: floating-base Euler step with per-thread copies even when 16-byte aligned
     int tune_rls_pipe = 0;       // BLF_CCM_TUNE_RLS_PIPE=1: the plain one-estimator-per-thread RLS kernel instead of the pipelined one
     // peer-memory arg-min exchange
     int p2p_nranks = 0, p2p_rank = -1;
@@ -224,6 +226,8 @@ extern "C" int blf_ccm_create(int device, blf_ccm_handle** out)
     h->sm_count = prop.multiProcessorCount;
     h->mem_pitch = prop.memPitch;
     h->tune_cpt = env_int("BLF_CCM_TUNE_CPT");
+    h->tune_fbd_tile_kb = env_int("BLF_CCM_TUNE_FBD_TILE_KB");
+    h->tune_fbd_no_bulk = env_int("BLF_CCM_TUNE_FBD_NO_BULK");
     h->tune_blocks_per_sm = env_int("BLF_CCM_TUNE_BLOCKS_PER_SM");
     h->tune_rollout_split = env_int("BLF_CCM_TUNE_ROLLOUT_SPLIT");
     h->tune_no_pdl = env_int("BLF_CCM_TUNE_NO_PDL");

@@ -1887,10 +1887,16 @@ ccm_genforce_packed_kernel(const __grid_constant__ GenForceArgs a)
 // step: base position += nu.head<3>() dT, base rotation += (rotation rate of
 // FloatingBaseSystemDynamics.cpp:139-145 = the kinematics' formula) dT, joint positions += nu.tail dT,
 // nu += acc dT.  Array-of-structures state as the reference holds it (per system: nu[nc], jointPos[nc-6],
-// basePos[3], baseRot[9] row-major).  A system is a group of P2 = 8, 16 or 32 lanes (one lane per entry of
-// nu: coalesced), its first lane also does the pose; above 32 entries one warp walks the system in chunks.
-// Every lane reads its old velocity before anybody writes, and the pose lane gets the base twist by
-// shuffle -- no ordering between threads is needed.  HBM-bound: (5 nc + 12) doubles per system.
+// basePos[3], baseRot[9] row-major).
+//
+// HBM-bound: (5 nc + 12) doubles per system.  A CTA owns a tile of `tile` consecutive systems; in each of
+// the five arrays that tile is ONE contiguous run of bytes, so it is brought into shared memory by five 1-D
+// bulk copies (TMA engine) signalled on one mbarrier, updated there, and written back by four bulk stores.
+// No per-thread global access at all on that path; bytes in flight = tile bytes x resident CTAs.  A tile
+// with an odd count (the last one) or arrays that are only 8-byte aligned take the same route with
+// per-thread 8-byte async copies (LDGSTS) and plain streaming stores.  The new velocity is built in the
+// acceleration's buffer, so nothing reads a value another thread has replaced.  One thread per system
+// does the pose (warp 0 mostly; the other warps go on with the elementwise part).
 // ------------------------------------------------------------------------------------------------
 struct FbdEulerArgs {
     const double* acc;   // [n][nc]
@@ -1901,75 +1907,103 @@ struct FbdEulerArgs {
     double half_rho, dT;
     long long n;
     int nc;
-    int p2;              // lanes per system: 8, 16, 32 (nc <= 32), or 0: one warp per system, chunks of 32
+    int tile;            // systems per CTA, even
+    int bulk;            // all five arrays 16-byte aligned
+    unsigned magic;      // ceil(2^32 / nc): e / nc == __umulhi(e, magic) for e < tile * nc
 };
-
-template <bool BAUM>
-__device__ __forceinline__ void fbd_pose_step(const FbdEulerArgs& a, long long s, const double (&tw)[6])
-{
-    double* P = a.pos + 3 * s;
-    double* R = a.rot + 9 * s;
-    Pose q{V3{P[0], P[1], P[2]}, V3{R[0], R[3], R[6]}, V3{R[1], R[4], R[7]}, V3{R[2], R[5], R[8]}};
-    kin_euler_step<BAUM>(q, V3{tw[0], tw[1], tw[2]}, V3{tw[3], tw[4], tw[5]}, a.half_rho, a.dT);
-    P[0] = q.p.x; P[1] = q.p.y; P[2] = q.p.z;
-    R[0] = q.c0.x; R[1] = q.c1.x; R[2] = q.c2.x;
-    R[3] = q.c0.y; R[4] = q.c1.y; R[5] = q.c2.y;
-    R[6] = q.c0.z; R[7] = q.c1.z; R[8] = q.c2.z;
-}
 
 template <bool BAUM>
 __global__ void __launch_bounds__(128)
 sys_fbd_euler_kernel(const __grid_constant__ FbdEulerArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int nc = a.nc, nj = nc - 6;
+    extern __shared__ __align__(16) double fbd_sm[];
+    __shared__ __align__(8) unsigned long long fbd_bar;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nc = a.nc, nj = nc - 6, S = a.tile;
+    const long long s0 = static_cast<long long>(blockIdx.x) * S;
+    const int cnt = static_cast<int>(a.n - s0 < S ? a.n - s0 : S);
+    double* s_acc = fbd_sm;              // becomes the new velocity
+    double* s_nu = s_acc + S * nc;
+    double* s_jp = s_nu + S * nc;
+    double* s_pos = s_jp + S * nj;
+    double* s_rot = s_pos + S * 3;
+    const double* g_acc = a.acc + s0 * nc;
+    double* g_nu = a.nu + s0 * nc;
+    double* g_jp = a.jp + s0 * nj;
+    double* g_pos = a.pos + s0 * 3;
+    double* g_rot = a.rot + s0 * 9;
+    const bool bulk = a.bulk && !(cnt & 1);   // every run a multiple of 16 bytes
+    const int n_nu = cnt * nc, n_jp = cnt * nj;
+    if (bulk && tid == 0) {
+        ptx::mbar_init(ptx::smem_addr(&fbd_bar), 1);
+        ptx::fence_mbar_init();
+    }
     ptx::grid_dep_launch_dependents();   // PDL: see ccm_soa_kernel
     ptx::grid_dep_wait();
-    if (a.p2 > 0) {
-        const int p2 = a.p2, spw = 32 / p2;
-        const int g = lane / p2, q = lane - g * p2;
-        const long long s = wid * spw + g;
-        if (wid * spw >= a.n) return;   // whole warp
-        const bool sys = s < a.n, mine = sys && q < nc;
-        const double old = mine ? __ldcs(a.nu + s * nc + q) : 0.0;
-        const double ac = mine ? __ldcs(a.acc + s * nc + q) : 0.0;
-        double tw[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) tw[k] = __shfl_sync(0xffffffffu, old, g * p2 + k);
-        if (mine) {
-            __stcs(a.nu + s * nc + q, fma(ac, a.dT, old));
-            if (q >= 6) {
-                double* j = a.jp + s * nj + (q - 6);
-                __stcs(j, fma(old, a.dT, __ldcs(j)));
-            }
+    if (bulk) {
+        __syncthreads();
+        const uint32_t bar = ptx::smem_addr(&fbd_bar);
+        if (tid == 0) {
+            ptx::mbar_arrive_expect_tx(bar, static_cast<uint32_t>((2 * n_nu + n_jp + 12 * cnt) * 8));
+            ptx::bulk_g2s(ptx::smem_addr(s_nu), g_nu, n_nu * 8, bar);
+            ptx::bulk_g2s(ptx::smem_addr(s_rot), g_rot, cnt * 72, bar);
+            ptx::bulk_g2s(ptx::smem_addr(s_pos), g_pos, cnt * 24, bar);
+            if (nj > 0) ptx::bulk_g2s(ptx::smem_addr(s_jp), g_jp, n_jp * 8, bar);
+            ptx::bulk_g2s(ptx::smem_addr(s_acc), g_acc, n_nu * 8, bar);
         }
-        if (sys && q == 0) fbd_pose_step<BAUM>(a, s, tw);
+        ptx::mbar_wait(bar, 0);
     } else {
-        const long long s = wid;
-        if (s >= a.n) return;
-        double old[4], ac[4];   // nc <= 128
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int q = c * 32 + lane;
-            old[c] = q < nc ? __ldcs(a.nu + s * nc + q) : 0.0;
-            ac[c] = q < nc ? __ldcs(a.acc + s * nc + q) : 0.0;
+        for (int e = tid; e < n_nu; e += nth) {
+            ptx::cp_async8(ptx::smem_addr(s_nu + e), g_nu + e);
+            ptx::cp_async8(ptx::smem_addr(s_acc + e), g_acc + e);
         }
-        double tw[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) tw[k] = __shfl_sync(0xffffffffu, old[0], k);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int q = c * 32 + lane;
-            if (q < nc) {
-                __stcs(a.nu + s * nc + q, fma(ac[c], a.dT, old[c]));
-                if (q >= 6) {
-                    double* j = a.jp + s * nj + (q - 6);
-                    __stcs(j, fma(old[c], a.dT, __ldcs(j)));
-                }
-            }
+        for (int e = tid; e < n_jp; e += nth) ptx::cp_async8(ptx::smem_addr(s_jp + e), g_jp + e);
+        for (int e = tid; e < cnt * 9; e += nth) ptx::cp_async8(ptx::smem_addr(s_rot + e), g_rot + e);
+        for (int e = tid; e < cnt * 3; e += nth) ptx::cp_async8(ptx::smem_addr(s_pos + e), g_pos + e);
+        ptx::cp_async_commit();
+        ptx::cp_async_wait<0>();
+        __syncthreads();
+    }
+    // pose of system tid (reads the old base twist; nobody writes s_nu)
+    for (int s = tid; s < cnt; s += nth) {
+        const double* t = s_nu + s * nc;
+        double* P = s_pos + 3 * s;
+        double* R = s_rot + 9 * s;
+        Pose q{V3{P[0], P[1], P[2]}, V3{R[0], R[3], R[6]}, V3{R[1], R[4], R[7]}, V3{R[2], R[5], R[8]}};
+        kin_euler_step<BAUM>(q, V3{t[0], t[1], t[2]}, V3{t[3], t[4], t[5]}, a.half_rho, a.dT);
+        P[0] = q.p.x; P[1] = q.p.y; P[2] = q.p.z;
+        R[0] = q.c0.x; R[1] = q.c1.x; R[2] = q.c2.x;
+        R[3] = q.c0.y; R[4] = q.c1.y; R[5] = q.c2.y;
+        R[6] = q.c0.z; R[7] = q.c1.z; R[8] = q.c2.z;
+    }
+    // joint positions += old joint velocity * dT; velocity += acceleration * dT (into the acceleration's buffer)
+    for (int e = tid; e < n_nu; e += nth) {
+        const int s = static_cast<int>(__umulhi(static_cast<unsigned>(e), a.magic));
+        const int q = e - s * nc;
+        const double old = s_nu[e];
+        if (q >= 6) {
+            double* j = s_jp + s * nj + (q - 6);
+            *j = fma(old, a.dT, *j);
         }
-        if (lane == 0) fbd_pose_step<BAUM>(a, s, tw);
+        s_acc[e] = fma(s_acc[e], a.dT, old);
+    }
+    if (bulk) {
+        ptx::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            ptx::bulk_s2g(g_nu, ptx::smem_addr(s_acc), n_nu * 8);
+            if (nj > 0) ptx::bulk_s2g(g_jp, ptx::smem_addr(s_jp), n_jp * 8);
+            ptx::bulk_s2g(g_pos, ptx::smem_addr(s_pos), cnt * 24);
+            ptx::bulk_s2g(g_rot, ptx::smem_addr(s_rot), cnt * 72);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read_all();
+        }
+    } else {
+        __syncthreads();
+        for (int e = tid; e < n_nu; e += nth) __stcs(g_nu + e, s_acc[e]);
+        for (int e = tid; e < n_jp; e += nth) __stcs(g_jp + e, s_jp[e]);
+        for (int e = tid; e < cnt * 9; e += nth) __stcs(g_rot + e, s_rot[e]);
+        for (int e = tid; e < cnt * 3; e += nth) __stcs(g_pos + e, s_pos[e]);
     }
 }
 

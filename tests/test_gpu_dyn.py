@@ -324,11 +324,13 @@ def _rot(rng, scaled):
 
 
 @pytest.mark.parametrize("ncols,ns,rho", [(29, 5_003, 0.7), (29, 1_000, 0.0), (6, 4_099, 0.3), (12, 3_001, 2.0),
-                                          (16, 777, 0.01), (38, 1_025, 0.5), (64, 131, 0.1), (128, 33, 0.0)])
-def test_floating_base_euler_step_vs_oracle(torch, dyn, so, ncols, ns, rho):
+                                          (16, 777, 0.01), (38, 1_025, 0.5), (64, 131, 0.1), (128, 33, 0.0), (29, 4_096, 0.7), (7, 1, 0.2), (29, 2, 0.2), (23, 3, 0.0)])
+@pytest.mark.parametrize("guard", [2, 1])
+def test_floating_base_euler_step_vs_oracle(torch, dyn, so, ncols, ns, rho, guard):
     """blf_sys_floating_base_euler_step against the C oracle (itself bit-identical to the reference's
-    ForwardEuler<FloatingBaseDynamicalSystem>): every lane layout (8, 16, 32 lanes per system, chunks),
-    ragged counts, guard rows."""
+    ForwardEuler<FloatingBaseDynamicalSystem>): tiles of every size class, ragged and odd counts (last tile
+    on the per-thread copy route), guard rows either side; two guard rows keep the arrays 16-byte aligned
+    (bulk-copy route), one row leaves them 8-byte aligned (per-thread route)."""
     rng = np.random.default_rng(ncols + ns)
     dT = 0.01
     acc = rng.normal(size=(ns, ncols)) * 30.0
@@ -337,18 +339,18 @@ def test_floating_base_euler_step_vs_oracle(torch, dyn, so, ncols, ns, rho):
     p = rng.normal(size=(ns, 3))
     R = np.stack([_rot(rng, i % 2 == 0) for i in range(ns)])
     wv, wq, wp, wR = so.floating_base_euler_step(rho, dT, acc, nu, jp, p, R, nthreads=NTHREADS)
-    pad = lambda x: None if x is None else torch.from_numpy(np.concatenate([np.full((1,) + x.shape[1:], 7.5), x,
-                                                                           np.full((1,) + x.shape[1:], 7.5)])).cuda()
+    pad = lambda x: None if x is None else torch.from_numpy(np.concatenate([np.full((guard,) + x.shape[1:], 7.5), x,
+                                                                           np.full((guard,) + x.shape[1:], 7.5)])).cuda()
     dv, dq, dp_, dR = pad(nu), pad(jp), pad(p), pad(R.reshape(ns, 9))
-    view = lambda x: None if x is None else x[1:ns + 1]
+    view = lambda x: None if x is None else x[guard:ns + guard]
     dyn.euler_step(rho, dT, _dev(torch, acc), view(dv), view(dq), view(dp_), view(dR))
     for got, want in ((dv, wv), (dq, wq), (dp_, wp), (dR, wR.reshape(ns, 9))):
         if got is None:
             continue
         g = got.cpu().numpy()
-        assert (g[0] == 7.5).all() and (g[-1] == 7.5).all()                  # nothing written outside
-        assert rel(g[1:-1], want).max() <= TOL
-    assert rel(dR.cpu().numpy()[1:-1].reshape(ns, 3, 3), wR).max() <= TOL    # row by row
+        assert (g[:guard] == 7.5).all() and (g[-guard:] == 7.5).all()        # nothing written outside
+        assert rel(g[guard:-guard], want).max() <= TOL
+    assert rel(dR.cpu().numpy()[guard:-guard].reshape(ns, 3, 3), wR).max() <= TOL    # row by row
 
 
 def test_floating_base_whole_step_vs_reference_build(torch, batch, dyn, ref):

@@ -202,7 +202,8 @@ def dyn_only():
     rnd = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda") * 2 - 1
     shapes = ((409600, 29), (1 << 20, 29), (1 << 20, 18), (1 << 21, 12), (1 << 22, 6), (1 << 19, 31),
               (1 << 20, 23), (1 << 20, 24), (1 << 21, 7), (1 << 21, 15), (1 << 18, 38), (1 << 18, 44), (1 << 17, 59), (1 << 17, 64), (1 << 15, 80))
-    only = [int(x) for x in os.environ.get("DYN_NC", "").split(",") if x]
+    only = [int(x) if x != "none" else -1 for x in os.environ.get("DYN_NC", "").split(",") if x]
+    euler_only = os.environ.get("DYN_EULER_ONLY") == "1"
     for ns, nc in shapes:
         if only and nc not in only:
             continue
@@ -229,7 +230,7 @@ def dyn_only():
         del Ms, outs, cls
         torch.cuda.empty_cache()
     # the whole step at the MPC batch size: 409600 systems x 2 contacts, 6 + 23 DoF
-    for ns, cps, nc in ((409600, 2, 29), (409600, 2, 12)):
+    for ns, cps, nc in ((409600, 2, 29), (409600, 2, 12), (1 << 21, 2, 29), (1 << 22, 1, 6)):
         n = ns * cps
         st = syn.make_states(min(n, 1 << 18), seed=49)
         reps = (n + st["n"] - 1) // st["n"]
@@ -244,14 +245,24 @@ def dyn_only():
             del A
             M.diagonal(dim1=1, dim2=2).add_(0.5)
             Ms.append(M)
-        bias, tau = rnd(ns, nc), rnd(ns, nc - 6)
+        bias, tau = rnd(ns, nc), (rnd(ns, nc - 6) if nc > 6 else None)
         outs = [torch.empty_like(bias) for _ in range(nb)]
         cls = [dyn.prepare_acceleration(cps, pl, Js[j], bias, Ms[j], tau, out=outs[j])[0] for j in range(nb)]
-        ms = timeit(lambda i: cls[i % nb](), iters=30, warm=5)
+        ms = timeit(lambda i: cls[i % nb](), iters=(3 if euler_only else 30), warm=(1 if euler_only else 5))
         per_sys = cps * (200 + 48 * nc) + 8 * (nc * (nc + 1) // 2 + 2 * nc + (nc - 6))
         gbs = ns * per_sys / (ms * 1e-3) / 1e9
-        print(f"floating-base acceleration systems={ns} contacts/system={cps} nc={nc}  {ms*1e3:9.1f} us  "
+        if not euler_only:
+            print(f"floating-base acceleration systems={ns} contacts/system={cps} nc={nc}  {ms*1e3:9.1f} us  "
               f"{ns/ms/1e3:8.1f} M systems/s  {gbs:7.1f} GB/s {gbs/PEAK*100:5.1f} % (lower-triangle bytes)", flush=True)
+        # one ForwardEuler step of the whole floating-base state: (5 nc + 12) doubles per system
+        nu, jp, bp = rnd(ns, nc), (rnd(ns, nc - 6) if nc > 6 else None), rnd(ns, 3)
+        br = torch.eye(3, dtype=torch.float64, device="cuda").reshape(1, 9).repeat(ns, 1)
+        for rho in (0.01, 0.0):
+            ec = dyn.prepare_euler_step(rho, 1e-5, outs[0], nu, jp, bp, br)
+            ems = timeit(lambda i: ec(), iters=30, warm=5)
+            eb = 8 * (5 * nc + 12)
+            print(f"floating-base Euler step systems={ns} nc={nc} rho={rho}  {ems*1e3:9.1f} us  {ns/ems/1e3:8.1f} M systems/s  "
+                  f"{ns*eb/(ems*1e-3)/1e9:7.1f} GB/s {ns*eb/(ems*1e-3)/1e9/PEAK*100:5.1f} %", flush=True)
         del Js, Ms, outs, cls, pl
         torch.cuda.empty_cache()
 
