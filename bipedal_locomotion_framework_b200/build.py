@@ -85,6 +85,7 @@ CPP_TESTS = {
     "RecursiveLeastSquareUnitTests": "RecursiveLeastSquareTest.cpp",       # needs a GPU
     "IntegratorUnitTests": "IntegratorTest.cpp",                           # host section + GPU
     "ContactWrenchUnitTests": "ContactWrenchTest.cpp",                     # host only
+    "FloatingBaseSystemDynamicsUnitTests": "FloatingBaseSystemDynamicsTest.cpp",   # needs a GPU
     "ApiConformanceUnitTests": "ApiConformanceTest.cpp",                   # compile-time signature checks
 }
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra"]

@@ -223,3 +223,15 @@ const double& ContinuousContactModel::springCoeff() const { return m_springCoeff
 double& ContinuousContactModel::springCoeff() { return m_springCoeff; }
 const double& ContinuousContactModel::damperCoeff() const { return m_damperCoeff; }
 double& ContinuousContactModel::damperCoeff() { return m_damperCoeff; }
+
+void ContinuousContactModel::batchInputs(double state[30], double parameters[4]) const
+{
+    static_assert(sizeof(iDynTree::Twist) == 48 && sizeof(iDynTree::Transform) == 96, "C-ABI row layout");
+    std::memcpy(state, &m_twist, 48);
+    std::memcpy(state + 6, &m_frameTransform, 96);
+    std::memcpy(state + 18, &m_nullForceTransform, 96);
+    parameters[0] = m_length;
+    parameters[1] = m_width;
+    parameters[2] = m_springCoeff;
+    parameters[3] = m_damperCoeff;
+}

@@ -6,7 +6,7 @@
  *   ContactModel.h:110-144, ContinuousContactModel.h:105-142,
  *   IParametersHandler.h:88-242, RecursiveLeastSquare.h:79-110,
  *   DynamicalSystem.h:63-98, Integrator.h:50-71, FixedStepIntegrator.h:59, ForwardEuler.h:58-65,
- *   FloatingBaseSystemKinematics.h:59-69, ContactWrench.h:36-54.
+ *   FloatingBaseSystemKinematics.h:59-69, FloatingBaseSystemDynamics.h:91-143, ContactWrench.h:36-54.
  */
 #ifdef BLF_HAVE_CATCH2
 #include <catch2/catch.hpp>
@@ -23,6 +23,7 @@
 #include <BipedalLocomotion/Estimators/RecursiveLeastSquare.h>
 #include <BipedalLocomotion/ParametersHandler/StdImplementation.h>
 #include <BipedalLocomotion/System/ContactWrench.h>
+#include <BipedalLocomotion/System/FloatingBaseSystemDynamics.h>
 #include <BipedalLocomotion/System/FloatingBaseSystemKinematics.h>
 #include <BipedalLocomotion/System/ForwardEuler.h>
 
@@ -93,6 +94,22 @@ static_assert(same<decltype(std::declval<Euler&>().integrate(0.0, 1.0)), bool>, 
 static_assert(same<decltype(std::declval<Euler&>().setDynamicalSystem(std::shared_ptr<Kin>())), bool>, "setDynamicalSystem");
 static_assert(same<decltype(std::declval<const Euler&>().getSolution()), const Kin::StateType&>, "getSolution");
 static_assert(same<decltype(std::declval<const Euler&>().dynamicalSystem()), const std::weak_ptr<Kin>>, "dynamicalSystem");
+
+// ---- FloatingBaseDynamicalSystem (FloatingBaseSystemDynamics.h:91-143) ----
+// setGravityVector / setMassMatrixRegularization take Eigen::Ref upstream; without Eigen here they take
+// the facade's Vector3d and a row-major block (or an iDynTree::MatrixDynSize)
+using Dyn = System::FloatingBaseDynamicalSystem;
+static_assert(std::is_default_constructible<Dyn>::value, "FloatingBaseDynamicalSystem()");
+static_assert(same<bool (Dyn::*)(HandlerWeak), decltype(&Dyn::initalize)>, "initalize [sic]");
+static_assert(same<bool (Dyn::*)(std::shared_ptr<iDynTree::KinDynComputations>), decltype(&Dyn::setKinDyn)>, "setKinDyn");
+static_assert(same<bool (Dyn::*)(const double&, Dyn::StateDerivativeType&), decltype(&Dyn::dynamics)>, "dynamics");
+static_assert(same<decltype(std::declval<Dyn&>().setGravityVector(std::declval<const System::Vector3d&>())), void>, "setGravityVector");
+static_assert(std::tuple_size<Dyn::StateType>::value == 5 && std::tuple_size<Dyn::StateDerivativeType>::value == 5
+                  && std::tuple_size<Dyn::InputType>::value == 2, "state / derivative / input tuples");
+static_assert(same<std::tuple_element<1, Dyn::InputType>::type, std::vector<ContactWrench>>, "input: contact wrenches");
+static_assert(same<std::tuple_element<0, Dyn::StateType>::type, System::Vector6d>
+                  && same<std::tuple_element<3, Dyn::StateType>::type, System::Matrix3d>, "state: base velocity ... base rotation");
+static_assert(same<decltype(std::declval<ForwardEuler<Dyn>&>().integrate(0.0, 1.0)), bool>, "ForwardEuler<FloatingBaseDynamicalSystem>");
 
 // ---- ContactWrench (ContactWrench.h:36-54) ----
 static_assert(std::is_constructible<ContactWrench, const iDynTree::FrameIndex&, std::shared_ptr<ContactModel>>::value, "ContactWrench ctor");

@@ -98,3 +98,13 @@ def test_reference_integrator_test_and_batched_system_steps(cpp):
     r = _run("IntegratorUnitTests")
     assert r.returncode == 0, r.stdout + r.stderr
     assert "3 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
+
+
+@pytest.mark.gpu
+def test_floating_base_dynamical_system_facade(cpp):
+    """System::FloatingBaseDynamicalSystem (src/System/src/FloatingBaseSystemDynamics.cpp:17-251) over an
+    injected KinDynComputations: every failure return of the reference, M acc = -h + sum J^T wrench + tau
+    against the per-instance contact models, regularisation, no contacts / no joints, one ForwardEuler step."""
+    r = _run("FloatingBaseSystemDynamicsUnitTests")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "2 test case(s)" in r.stdout and "0 failure(s)" in r.stdout
