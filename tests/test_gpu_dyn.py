@@ -395,3 +395,29 @@ def test_floating_base_euler_step_rejects_bad_arguments(torch, batch):
     assert f(4, 8, 0.1, 0.01, acc.data_ptr(), nu.data_ptr(), None, p.data_ptr(), R.data_ptr(), None) != 0
     assert f(4, 8, 0.1, 0.01, nu.data_ptr(), nu.data_ptr(), jp.data_ptr(), p.data_ptr(), R.data_ptr(), None) != 0
     assert f(4, 6, 0.1, 0.01, acc.data_ptr(), nu.data_ptr(), None, p.data_ptr(), R.data_ptr(), None) == 0
+
+
+def test_floating_base_euler_step_large_batch_properties(torch, batch, dyn):
+    """2^21 systems x 29 unknowns (2.6 GB of state, well past L2), checked on the device: the velocity, joint
+    and position updates against the same multiply-add in torch (two roundings there, one here: 1e-15), the
+    rotations bit for bit against the kinematics' own batched Euler step (blf_sys_kinematics_euler_step_soa,
+    another kernel around the same device function), and the step is a pure function of its inputs."""
+    from bipedal_locomotion_framework_b200.system import KinematicsBatch
+    ns, nc, rho, dT = 1 << 21, 29, 0.7, 0.01
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rnd = lambda *s: torch.rand(s, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    acc, nu, jp, p = rnd(ns, nc) * 30, rnd(ns, nc), rnd(ns, nc - 6), rnd(ns, 3)
+    q, _ = torch.linalg.qr(rnd(ns, 3, 3))
+    R = (q * (1.0 + 0.02 * rnd(ns, 1, 1))).reshape(ns, 9).contiguous()
+    v1, j1, p1, R1 = nu.clone(), jp.clone(), p.clone(), R.clone()
+    dyn.euler_step(rho, dT, acc, v1, j1, p1, R1)
+    close = lambda a, b: bool(((a - b).abs() <= 1e-15 * b.abs().clamp_min(1e-3)).all())
+    assert close(v1, nu + acc * dT) and close(j1, jp + nu[:, 6:] * dT) and close(p1, p + nu[:, :3] * dT)
+    kb = KinematicsBatch(0, batch.handle)
+    tw = nu[:, :6].t().contiguous()
+    kp, kR = p.t().contiguous(), R.t().contiguous()
+    kb.prepare_euler_step(rho, dT, tw, kp, kR)()
+    assert torch.equal(kp.t(), p1) and bool(((kR.t() - R1).abs() <= 1e-14).all())
+    v2, j2, p2, R2 = nu.clone(), jp.clone(), p.clone(), R.clone()
+    dyn.euler_step(rho, dT, acc, v2, j2, p2, R2)
+    assert torch.equal(v1, v2) and torch.equal(j1, j2) and torch.equal(p1, p2) and torch.equal(R1, R2)
