@@ -90,8 +90,8 @@ template <int H, int N> struct LltTile {
     static constexpr bool BLOCKED = (H == 8 && N != 24) || H == 16 || H == 32;
 #endif
     static constexpr int DB = H * (H - 1) / 2;
-    static constexpr int DIAG_AT = COL_AT + 2 * NP;
     static constexpr int DIAG = BLOCKED ? DB * ((N + H - 1) / H) : 0;
+    static constexpr int DIAG_AT = COL_AT + 2 * NP;
     static constexpr int STRIDE = (DIAG_AT + DIAG + 15) / 16 * 16 + (H == 8 ? 8 : 4);   // + bank spreading of the groups
     static constexpr int PER_WARP = (32 / H) * STRIDE;
     static constexpr size_t bytes(bool reg)
@@ -573,6 +573,10 @@ cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
 #if defined(BLF_LLT_BENCH_CLASSES)
 #if defined(BLF_LLT_ONLY_WIDE)
 #define BLF_LLT_CLASSES(X) X(32, 64)
+#elif defined(BLF_LLT_ONLY_29_H16)
+#define BLF_LLT_CLASSES(X) X(16, 30)
+#elif defined(BLF_LLT_ONLY_29_H32)
+#define BLF_LLT_CLASSES(X) X(32, 30)
 #elif defined(BLF_LLT_ONLY_MID)
 #define BLF_LLT_CLASSES(X) X(8, 17) X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 26) X(8, 28)
 #else

@@ -40,6 +40,8 @@ int main(int argc, char** argv)
     const int sizes[][2] = {{16, 1 << 20}, {18, 1 << 20}, {19, 1 << 20}, {21, 1 << 20}, {23, 1 << 20}, {25, 1 << 20}, {27, 1 << 20}};
 #elif defined(BLF_LLT_ONLY_WIDE)
     const int sizes[][2] = {{63, 1 << 17}, {56, 1 << 17}};
+#elif defined(BLF_LLT_ONLY_29) || defined(BLF_LLT_ONLY_29_H16) || defined(BLF_LLT_ONLY_29_H32)
+    const int sizes[][2] = {{29, 1 << 20}, {29, 409600}};
 #else
     const int sizes[][2] = {{6, 1 << 22}, {12, 1 << 21}, {18, 1 << 20}, {23, 1 << 20}, {24, 1 << 20}, {29, 1 << 20}};
 #endif
