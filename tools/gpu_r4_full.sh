@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, fourth session: full single-GPU validation -- all GPU tests (with skip reasons), smoke, both bench arms, C++ tests.
-TAG=${1:-r4full}
+TAG=${1:-r4full}; export TAG
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit,memory.total --format=csv > $O/gpu.csv 2>&1
@@ -24,3 +24,17 @@ for k in ("floating_base_dynamics_29", "floating_base_dynamics_12"):
 PY
 for t in ContinuousContactModelUnitTests IntegratorUnitTests RecursiveLeastSquareUnitTests FloatingBaseSystemDynamicsUnitTests; do ./bipedal_locomotion_framework_b200/lib/$t > $O/cpp_$t.log 2>&1; echo "$t exit $?"; tail -1 $O/cpp_$t.log; done
 ls $O
+# launch list of the dynamics rows (solve, J^T wrench, Euler step) under ncu: per-launch durations, cold and serialised
+DYN_NC=29 timeout 300 python tools/tune.py --dyn-only > $O/tune_dyn29.log 2>&1 && \
+DYN_NC=29 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_dyn29.csv python tools/tune.py --dyn-only > $O/ncu_dyn29.log 2>&1
+grep -E "acceleration|Euler|solve" $O/tune_dyn29.log | cut -c1-170
+python - <<'PY'
+import csv, os, collections
+O = "gpurun_out/%s" % os.environ.get("TAG", "r4full")
+rows = [r for r in csv.reader(open(O + "/launches_dyn29.csv")) if len(r) > 10 and r[0].isdigit()]
+agg = collections.defaultdict(list)
+for r in rows:
+    agg[r[4].split("(")[0][:70]].append(float(r[-1]))
+for k, v in agg.items():
+    print("%-72s launches %4d  mean %10.1f us" % (k, len(v), sum(v) / len(v) / 1e3))
+PY
