@@ -26,7 +26,7 @@ SYMBOLS = [
     "blf_ccm_device_alloc", "blf_ccm_device_free", "blf_ccm_host_alloc", "blf_ccm_host_free",
     "blf_ccm_copy_h2d", "blf_ccm_copy_d2h", "blf_ccm_stream_synchronize",
     "blf_rls_advance_batch", "blf_rls_advance_host", "blf_ccm_rls_advance_contacts",
-    "blf_sys_kinematics_euler_step_soa", "blf_sys_kinematics_dynamics_host",
+    "blf_sys_kinematics_euler_step_soa", "blf_sys_kinematics_dynamics_host", "blf_sys_kinematics_dynamics",
     "blf_sys_kinematics_integrate_host", "blf_ccm_rollout_integrate_cost",
     "blf_ccm_generalized_force_soa", "blf_ccm_rollout_integrate_cost_host",
     "blf_sys_mass_matrix_solve", "blf_sys_floating_base_acceleration", "blf_sys_floating_base_euler_step",
@@ -82,6 +82,7 @@ def lib():
     L.blf_ccm_rls_advance_contacts.argtypes = [vp, i64, vp, vp, vp, vp, dbl, vp, vp, vp]
     L.blf_sys_kinematics_euler_step_soa.argtypes = [vp, i64, dbl, dbl, vp, vp, vp, vp]
     L.blf_sys_kinematics_dynamics_host.argtypes = [vp, i64, dbl, vp, vp, vp, vp]
+    L.blf_sys_kinematics_dynamics.argtypes = [vp, i64, dbl, vp, vp, vp, vp, vp]
     L.blf_sys_kinematics_integrate_host.argtypes = [vp, i64, dbl, dbl, dbl, ci, vp, vp, vp, i64,
                                                     vp, vp]
     L.blf_ccm_rollout_integrate_cost.argtypes = [vp, i64, ci, ci, dbl, dbl, vp, vp, vp, vp, vp, u32,

@@ -1,7 +1,7 @@
 /**
  * @file FloatingBaseSystemDynamics.cpp
  * Facade over blf_sys_floating_base_acceleration / blf_sys_mass_matrix_solve /
- * blf_sys_kinematics_dynamics_host with one system (reference:
+ * blf_sys_kinematics_dynamics with one system (reference:
  * src/System/src/FloatingBaseSystemDynamics.cpp:17-251).  The order of the checks, their messages and
  * the calls made on the KinDynComputations object and on the contact models follow the reference; the
  * arithmetic is the device's.
@@ -148,17 +148,11 @@ bool FloatingBaseDynamicalSystem::dynamics(const double& /*time*/, StateDerivati
     if (!ensureDevice("dynamics")) return false;
     blf_ccm_handle* h = static_cast<blf_ccm_handle*>(m_device->handle());
 
-    // base linear velocity and rotation rate (:134-140) -- the kinematics' formula, on the device
-    double twist[6], rotation[9], rotationRate[9], linearVelocity[3];
+    // base twist and rotation as they cross the C ABI; linear velocity and rotation rate (:134-140) come
+    // back from the device with the acceleration
+    double twist[6], rotation[9];
     for (int i = 0; i < 6; ++i) twist[i] = baseVelocity[i];
     toRowMajor(baseOrientation, rotation);
-    if (blf_sys_kinematics_dynamics_host(h, 1, m_rho, twist, rotation, linearVelocity, rotationRate) != BLF_CCM_OK)
-    {
-        std::cerr << "[FloatingBaseDynamicalSystem::dynamics] " << blf_ccm_last_error() << std::endl;
-        return false;
-    }
-    for (int i = 0; i < 3; ++i) baseLinearVelocity[i] = linearVelocity[i];
-    fromRowMajor(rotationRate, baseRotationRate);
     jointVelocityOutput = jointVelocity;
 
     // update the kinDynComputations object (:144-170)
@@ -203,7 +197,9 @@ bool FloatingBaseDynamicalSystem::dynamics(const double& /*time*/, StateDerivati
                       atReg = atMass + even(n * n),
                       atStates = atReg + (m_useMassMatrixRegularizationTerm ? even(n * n) : 0),
                       atParams = atStates + even(30 * contacts), atJac = atParams + even(4 * contacts),
-                      atAcc = atJac + even(contacts * 6 * n), total = atAcc + even(n);
+                      atTwist = atJac + even(contacts * 6 * n), atRot = atTwist + 6,
+                      atAcc = atRot + 10,   // results, one run: acceleration | linear velocity (3) | rotation rate (9)
+                      atLin = atAcc + even(n), atRate = atLin + 4, total = atRate + 10;
     m_staging.assign(total, 0.0);
     double* s = m_staging.data();
     std::memcpy(s + atBias, m_generalizedBiasForces.baseWrench().data(), 6 * sizeof(double));
@@ -213,6 +209,8 @@ bool FloatingBaseDynamicalSystem::dynamics(const double& /*time*/, StateDerivati
         s[atTau + i] = jointTorques[i];
     }
     std::memcpy(s + atMass, m_massMatrix.data(), n * n * sizeof(double));
+    std::memcpy(s + atTwist, twist, sizeof(twist));
+    std::memcpy(s + atRot, rotation, sizeof(rotation));
     if (m_useMassMatrixRegularizationTerm)
         std::memcpy(s + atReg, m_massMatrixReglarizationTerm.data(), n * n * sizeof(double));
 
@@ -263,8 +261,10 @@ bool FloatingBaseDynamicalSystem::dynamics(const double& /*time*/, StateDerivati
     if (contacts == 0)   // known = -h: the sign change is exact
         for (std::size_t i = 0; i < n; ++i) s[atBias + i] = -s[atBias + i];
 
+    // one upload (everything up to the results), the launches, one download, one synchronisation
     if (!m_deviceBlock.valid() || m_deviceBlock.size() != total) m_deviceBlock = DeviceSoA(m_device, 1, total);
-    if (!m_deviceBlock.valid() || !m_deviceBlock.upload(0, s))
+    if (!m_deviceBlock.valid()
+        || blf_ccm_copy_h2d(h, m_deviceBlock.plane(0), s, atAcc * sizeof(double), nullptr) != BLF_CCM_OK)
     {
         std::cerr << "[FloatingBaseDynamicalSystem::dynamics] " << blf_ccm_last_error() << std::endl;
         return false;
@@ -286,14 +286,20 @@ bool FloatingBaseDynamicalSystem::dynamics(const double& /*time*/, StateDerivati
     {
         rc = blf_sys_mass_matrix_solve(h, 1, static_cast<int>(n), d + atMass, reg, d + atBias, tau, d + atAcc, nullptr);
     }
-    m_acceleration.resize(n);
-    if (rc == BLF_CCM_OK) rc = blf_ccm_copy_d2h(h, m_acceleration.data(), d + atAcc, n * sizeof(double), nullptr);
+    if (rc == BLF_CCM_OK)
+        rc = blf_sys_kinematics_dynamics(h, 1, m_rho, d + atTwist, d + atRot, d + atLin, d + atRate, nullptr);
+    m_acceleration.resize(total - atAcc);
+    if (rc == BLF_CCM_OK)
+        rc = blf_ccm_copy_d2h(h, m_acceleration.data(), d + atAcc, (total - atAcc) * sizeof(double), nullptr);
     if (rc == BLF_CCM_OK) rc = blf_ccm_stream_synchronize(h, nullptr);
     if (rc != BLF_CCM_OK)
     {
         std::cerr << "[FloatingBaseDynamicalSystem::dynamics] " << blf_ccm_last_error() << std::endl;
         return false;
     }
+
+    for (int i = 0; i < 3; ++i) baseLinearVelocity[i] = m_acceleration[atLin - atAcc + i];
+    fromRowMajor(m_acceleration.data() + (atRate - atAcc), baseRotationRate);
 
     // split the acceleration in base and joint acceleration (:245-248)
     for (std::size_t i = 0; i < m_baseDoFs; ++i) baseAcceleration[i] = m_acceleration[i];

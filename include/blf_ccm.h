@@ -296,6 +296,13 @@ BLF_CCM_API int blf_sys_kinematics_dynamics_host(blf_ccm_handle* h, int64_t n, d
                                                  const double* twists, const double* rotations,
                                                  double* pos_dot, double* rot_dot);
 
+/* The same for arrays already on the device (n*6, n*9 -> n*3, n*9), asynchronous on `stream`: what
+ * FloatingBaseDynamicalSystem::dynamics needs beside the acceleration
+ * (src/System/src/FloatingBaseSystemDynamics.cpp:134-140, the same formula). */
+BLF_CCM_API int blf_sys_kinematics_dynamics(blf_ccm_handle* h, int64_t n, double rho,
+                                            const double* twists, const double* rotations,
+                                            double* pos_dot, double* rot_dot, void* stream);
+
 /* FixedStepIntegrator::integrate on HOST arrays with a constant control input: n_steps Euler
  * steps, the first n_steps-1 of size step_dT and the last of size last_dT (the caller computes
  * the reference's schedule, FixedStepIntegrator.tpp:48-64).  positions n*3, rotations n*9 in/out;

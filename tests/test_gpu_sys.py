@@ -756,3 +756,34 @@ def test_rollout_warp_specialised_variant_vs_oracle(torch, so, variant, het, rho
                                _dev(torch, rot0), _dev(torch, null), ref_w, wts,
                                param_planes=_dev(torch, prm), mask=0, index_base=1000, want_cost=False)
     assert b.decode_best(out3["best"]) == (c, idx + 1000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rho", [0.0, 0.7])
+def test_kinematics_dynamics_device_arrays_vs_oracle_and_host_call(torch, batch, so, rho):
+    """blf_sys_kinematics_dynamics (device arrays, asynchronous) against the C oracle system by system
+    and bit for bit against blf_sys_kinematics_dynamics_host (same kernel behind both)."""
+    from bipedal_locomotion_framework_b200 import _capi
+    L, h = _capi.lib(), batch.handle.ptr
+    n = 1_003
+    rng = np.random.default_rng(12)
+    tw = rng.normal(size=(n, 6))
+    R = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] * (1.0 + 0.02 * rng.normal()) for _ in range(n)])
+    d_tw, d_R = _dev(torch, tw), _dev(torch, R.reshape(n, 9))
+    d_pd = torch.full((n + 2, 3), 7.5, dtype=torch.float64, device="cuda")
+    d_rd = torch.full((n + 2, 9), 7.5, dtype=torch.float64, device="cuda")
+    assert L.blf_sys_kinematics_dynamics(h, n, rho, d_tw.data_ptr(), d_R.data_ptr(), d_pd[1:].data_ptr(),
+                                         d_rd[1:].data_ptr(), None) == 0
+    pd, rd = d_pd.cpu().numpy(), d_rd.cpu().numpy()
+    assert (pd[0] == 7.5).all() and (pd[-1] == 7.5).all() and (rd[0] == 7.5).all() and (rd[-1] == 7.5).all()
+    hp, hr = np.empty((n, 3)), np.empty((n, 9))
+    ptr = lambda a: a.ctypes.data
+    assert L.blf_sys_kinematics_dynamics_host(h, n, rho, ptr(tw), ptr(np.ascontiguousarray(R.reshape(n, 9))),
+                                              ptr(hp), ptr(hr)) == 0
+    assert np.array_equal(pd[1:-1], hp) and np.array_equal(rd[1:-1], hr)
+    for i in range(0, n, 17):
+        wp, wr = so.kinematics_dynamics(rho, tw[i], R[i])
+        assert np.array_equal(hp[i], wp)
+        assert rel(hr[i].reshape(3, 3), np.asarray(wr).reshape(3, 3)).max() <= TOL
+    assert L.blf_sys_kinematics_dynamics(h, 1, rho, None, d_R.data_ptr(), d_pd.data_ptr(), d_rd.data_ptr(), None) != 0
+    assert L.blf_sys_kinematics_dynamics(h, 0, rho, None, None, None, None, None) == 0
