@@ -117,6 +117,15 @@ public:
                                   void* stream = nullptr);
 
     /**
+     * The base part of FloatingBaseSystemKinematics::dynamics / FloatingBaseDynamicalSystem::dynamics
+     * (FloatingBaseSystemKinematics.cpp:60-70, FloatingBaseSystemDynamics.cpp:134-140) for device arrays:
+     * twists nSystems x 6, rotations nSystems x 9 row-major -> linearVelocities nSystems x 3,
+     * rotationRates nSystems x 9.
+     */
+    bool kinematicsDynamics(std::size_t nSystems, double rho, const double* twists, const double* rotations,
+                            double* linearVelocities, double* rotationRates, void* stream = nullptr);
+
+    /**
      * One ForwardEuler step of FloatingBaseDynamicalSystem (ForwardEuler.tpp:19-49 over the state tuple
      * of FloatingBaseSystemDynamics.h:33-52), in place, every derivative at the state before the step:
      * basePosition += velocity.head<3>() dT, baseRotation += (rotation rate of

@@ -189,6 +189,16 @@ bool ContactRolloutBatch::floatingBaseAcceleration(std::size_t nSystems, int con
                   "floatingBaseAcceleration");
 }
 
+bool ContactRolloutBatch::kinematicsDynamics(std::size_t nSystems, double rho, const double* twists,
+                                             const double* rotations, double* linearVelocities,
+                                             double* rotationRates, void* stream)
+{
+    if (m_device == nullptr) return report(BLF_CCM_ERR_INVALID_HANDLE, "kinematicsDynamics");
+    return report(blf_sys_kinematics_dynamics(raw(m_device), static_cast<std::int64_t>(nSystems), rho, twists,
+                                              rotations, linearVelocities, rotationRates, stream),
+                  "kinematicsDynamics");
+}
+
 bool ContactRolloutBatch::floatingBaseEulerStep(std::size_t nSystems, int columns, double rho, double dT,
                                                 const double* acceleration, double* velocity,
                                                 double* jointPositions, double* basePositions,
