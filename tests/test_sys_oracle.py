@@ -287,3 +287,31 @@ def test_mass_matrix_solve_against_lapack(nc, spread):
     assert (rel(x, want) <= 2 * llt_tolerance(nc, cond)).all()
     if spread == 0.0:
         assert rel(x, want).max() <= TOL
+
+
+@pytest.mark.parametrize("nc,rho", [(6, 0.0), (12, 0.3), (29, 0.7)])
+def test_floating_base_euler_step_properties(nc, rho):
+    """syso_floating_base_euler_step (ForwardEuler.tpp:19-49 over the floating-base state): the pose and
+    joint part IS the kinematics' forward Euler step with the OLD velocity as control input, the velocity
+    part is nu + acc dT with one rounding each, dT = 0 changes nothing, and the inputs are not written."""
+    rng = np.random.default_rng(40 + nc)
+    ns, dT = 37, 0.01
+    acc, nu = rng.normal(size=(ns, nc)) * 20.0, rng.normal(size=(ns, nc))
+    jp = rng.normal(size=(ns, nc - 6)) if nc > 6 else None
+    p = rng.normal(size=(ns, 3))
+    R = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] * (1.0 + 0.03 * rng.normal()) for _ in range(ns)])
+    keep = [x.copy() if x is not None else None for x in (acc, nu, jp, p, R)]
+    v, q, pp, RR = so.floating_base_euler_step(rho, dT, acc, nu, jp, p, R, nthreads=2)
+    for a, b in zip((acc, nu, jp, p, R), keep):
+        assert a is None or np.array_equal(a, b)
+    assert np.array_equal(v, nu + acc * dT)
+    for s in range(ns):
+        out = so.forward_euler_step(rho, dT, nu[s, :6], p[s], R[s], nu[s, 6:] if nc > 6 else None,
+                                    jp[s] if nc > 6 else None)
+        kp, kR, kq = out if nc > 6 else (*out, None)
+        assert np.array_equal(pp[s], kp) and np.array_equal(RR[s], np.asarray(kR).reshape(3, 3))
+        if nc > 6:
+            assert np.array_equal(q[s], kq)
+    v0, q0, p0, R0 = so.floating_base_euler_step(rho, 0.0, acc, nu, jp, p, R)
+    assert np.array_equal(v0, nu) and np.array_equal(p0, p) and np.array_equal(R0, R)
+    assert nc == 6 or np.array_equal(q0, jp)
