@@ -350,6 +350,48 @@ def floating_base_euler_step(contacts_per_system, twists, poses, null_poses, jac
     return acc, vo, jo, po, ro.reshape(ns, 3, 3)
 
 
+FACADE_FBD_DRIVER = "libblf_facade_fbd_driver.so"   # facade_glue/facade_fbd_driver.cpp; needs a CUDA device to run
+_facade_fbd = None
+
+
+def facade_floating_base_euler_step(contacts_per_system, twists, poses, null_poses, jacobians, bias, mass, rho, dT,
+                                    nu, joint_pos, base_pos, base_rot, joint_torques=None, reg=None, params=None,
+                                    uniform=None):
+    """The same call as floating_base_euler_step, answered by the PRODUCT's C++ facade classes
+    (System::FloatingBaseDynamicalSystem + ForwardEuler on the GPU) through facade_fbd_driver.cpp."""
+    global _facade_fbd
+    if _facade_fbd is None:
+        path = os.path.join(REF_DIR, FACADE_FBD_DRIVER)
+        if not os.path.exists(path):
+            build()
+        _facade_fbd = C.CDLL(path)
+        vp, dbl = C.c_void_p, C.c_double
+        _facade_fbd.blf_facade_floating_base_euler_step.argtypes = [C.c_size_t, C.c_int, C.c_int] + [vp] * 10 + \
+            [dbl, dbl] + [vp] * 9
+        _facade_fbd.blf_facade_floating_base_euler_step.restype = C.c_int
+    twists, poses, null_poses = _f64(twists), _f64(poses), _f64(null_poses)
+    n = twists.shape[0]
+    ns = n // contacts_per_system
+    b = _f64(bias)
+    ncols = b.shape[1]
+    J, M = _f64(jacobians), _f64(mass)
+    tau = None if joint_torques is None else _f64(joint_torques).reshape(ns, ncols - 6)
+    rg = None if reg is None else _f64(reg).reshape(ncols, ncols)
+    pr = None if params is None else _f64(params).reshape(n, 4)
+    uni = np.asarray(uniform if uniform is not None else (0, 0, 0, 0), dtype=np.float64)
+    v, p, r = _f64(nu).reshape(ns, ncols), _f64(base_pos).reshape(ns, 3), _f64(base_rot).reshape(ns, 9)
+    jp = np.zeros((ns, max(ncols - 6, 0))) if joint_pos is None else _f64(joint_pos).reshape(ns, ncols - 6)
+    acc, vo, jo = np.empty((ns, ncols)), np.empty((ns, ncols)), np.empty((ns, max(ncols - 6, 0)))
+    po, ro = np.empty((ns, 3)), np.empty((ns, 9))
+    rc = _facade_fbd.blf_facade_floating_base_euler_step(
+        ns, int(contacts_per_system), int(ncols), _ptr(twists), _ptr(poses), _ptr(null_poses), _ptr(pr), _ptr(uni),
+        _ptr(J), _ptr(b), _ptr(tau), _ptr(M), _ptr(rg), float(rho), float(dT), _ptr(v), _ptr(jp), _ptr(p), _ptr(r),
+        _ptr(acc), _ptr(vo), _ptr(jo), _ptr(po), _ptr(ro))
+    if rc != 0:
+        raise RuntimeError(f"facade ForwardEuler<FloatingBaseDynamicalSystem> failed (rc={rc})")
+    return acc, vo, jo, po, ro.reshape(ns, 3, 3)
+
+
 def run_reference_test(name: str, timeout: float = 600.0) -> subprocess.CompletedProcess:
     """Run one of the reference's own (unmodified) Catch2 test executables built into oracle/_ref."""
     exe = os.path.join(REF_DIR, name)

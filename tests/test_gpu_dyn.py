@@ -426,3 +426,35 @@ def test_floating_base_euler_step_large_batch_properties(torch, batch, dyn):
     v2, j2, p2, R2 = nu.clone(), jp.clone(), p.clone(), R.clone()
     dyn.euler_step(rho, dT, acc, v2, j2, p2, R2)
     assert torch.equal(v1, v2) and torch.equal(j1, j2) and torch.equal(p1, p2) and torch.equal(R1, R2)
+
+
+@pytest.mark.parametrize("cps,ncols,het,with_reg", [(2, 29, False, False), (2, 29, True, True), (1, 6, False, False),
+                                                    (3, 12, True, False)])
+def test_facade_class_vs_reference_class(torch, ref, cps, ncols, het, with_reg):
+    """The PRODUCT's C++ class System::FloatingBaseDynamicalSystem + ForwardEuler (GPU; through
+    oracle/refbuild/facade_glue/facade_fbd_driver.cpp) against the REFERENCE'S own class compiled from its
+    sources (CPU; ref_driver.cpp), both driven through their public methods on the same arrays:
+    dynamics() and one integrate(0, dT) per system."""
+    ns, rho, dT = 40, 0.7, 0.01
+    st = syn.make_states(ns * cps, seed=60 + ncols, heterogeneous=het)
+    rng = np.random.default_rng(61 + ncols)
+    J = rng.uniform(-1.0, 1.0, (ns * cps, 6, ncols))
+    bias = rng.uniform(-50.0, 50.0, (ns, ncols))
+    M = syn.make_mass_matrices(ns, ncols, seed=5 + ncols, spread=0.5)
+    tau = rng.uniform(-5.0, 5.0, (ns, ncols - 6)) if ncols > 6 else None
+    reg = np.diag(rng.uniform(0.01, 0.2, ncols)) if with_reg else None
+    nu = rng.normal(size=(ns, ncols))
+    jp = rng.normal(size=(ns, ncols - 6)) if ncols > 6 else None
+    p = rng.normal(size=(ns, 3))
+    R = np.stack([_rot(rng, True) for _ in range(ns)])
+    kw = dict(joint_torques=tau, reg=reg, params=st["params"] if het else None, uniform=syn.REFERENCE_TEST_PARAMS)
+    args = (cps, st["twists"], st["poses"], st["null_poses"], J, bias, M, rho, dT, nu, jp, p, R)
+    racc, rv, rq, rp, rR = ref.floating_base_euler_step(*args, nthreads=NTHREADS, **kw)
+    facc, fv, fq, fp, fR = ref.facade_floating_base_euler_step(*args, **kw)
+    mag = np.abs(bias).max(axis=1) + np.abs(J.reshape(ns, cps, 6, ncols)).sum(axis=(1, 2)).max(axis=1) * 1e3
+    tol_acc = _acc_tolerance(M if reg is None else M + reg, racc, mag)
+    assert (np.abs(facc - racc).max(axis=1) <= tol_acc).all()
+    assert (np.abs(fv - rv).max(axis=1) <= tol_acc * dT + TOL * np.abs(rv).max(axis=1)).all()
+    assert rel(fp, rp).max() <= TOL and rel(fR, rR).max() <= TOL
+    if ncols > 6:
+        assert rel(fq, rq).max() <= TOL
