@@ -422,6 +422,8 @@ BLF_CCM_API int blf_sys_floating_base_acceleration(
  * reference holds them: acc, nu n_systems*ncols ([base (6); joints]); joint_pos n_systems*(ncols-6)
  * (NULL when ncols == 6); base_pos n_systems*3; base_rot n_systems*9 row-major; all but acc updated
  * in place.  ncols 6..128.  With rho == 0 the Baumgarte term is skipped (as blf_sys_kinematics_*).
+ * 8-byte alignment is enough; when all five arrays are 16-byte aligned (any cudaMalloc'ed array is) the
+ * tiles move by bulk copies, the fast route.  acc must not alias nu.  One launch on `stream`.
  */
 BLF_CCM_API int blf_sys_floating_base_euler_step(blf_ccm_handle* h, int64_t n_systems, int ncols,
                                                  double rho, double dT, const double* acc, double* nu,
