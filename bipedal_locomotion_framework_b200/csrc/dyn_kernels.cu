@@ -278,7 +278,13 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
         // groups of 8 lanes -- all at once through a real call (spread over the steps they cost
         // 13-23 % there, inlined at once they spill).
         constexpr bool SPREAD = H == 4;
+#ifdef BLF_LLT_BENCH_NOFILL
+        // measurement aid of tools/micro/llt_bench.cu only: every pass factorises the first group's tile again --
+        // the kernel without its refills (no LDGSTS, no HBM traffic but the results): the most a cheaper fill could give
+        const bool more = false;
+#else
         const bool more = grp + gstride < ngroups;
+#endif
         const LltSource next = llt_source<H, N>(a, (grp + gstride) * SPW + g, tile, r);
         if constexpr (SPREAD) {
             if (more) llt_issue_piece<H, N, NM>(next);
