@@ -53,6 +53,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "ccm_ptx.cuh"
@@ -98,7 +99,44 @@ template <int H, int N> struct LltTile {
     {
         return sizeof(double) * (size_t(kLltThreads / 32) * PER_WARP + (reg ? TAU_AT : 0));
     }
+    // Bulk-copy route (4-lane classes, exact fit, even order: see ccm_llt_solve_kernel): the tile holds the
+    // system's DENSE block, row i at i * (N - 1), then the right-hand side (= row N - 1 of the augmented
+    // matrix), the joint torques and the two column buffers; every piece starts on a 16-byte boundary.
+    static constexpr int B_RHS_AT = (N - 1) * (N - 1);
+    static constexpr int B_TAU_AT = B_RHS_AT + (N - 1);
+    static constexpr int B_COL_AT = (B_TAU_AT + TAU + 1) / 2 * 2;
+    static constexpr int B_STRIDE = (B_COL_AT + 2 * NP + 15) / 16 * 16 + 4;
+    static constexpr int B_PER_WARP = (32 / H) * B_STRIDE;
+    static constexpr size_t bytes_bulk(bool reg)
+    {
+        return sizeof(double) * (size_t(kLltThreads / 32) * B_PER_WARP + (reg ? TAU_AT : 0));
+    }
 };
+
+// Bulk-copy fill of one system's tile (issued by ONE lane of its group): the dense block, the right-hand
+// side and the joint torques are three contiguous runs of global memory, 16-byte aligned when the order is
+// even and the arrays are -- three bulk copies (TMA engine) signalled on the warp's mbarrier instead of ~25
+// per-thread async copies per lane.  A system past the end of the batch gets the identity with plain stores.
+template <int H, int N>
+__device__ __forceinline__ void llt_bulk_fill(const LltArgs& a, long long s, double* tile, uint32_t bar)
+{
+    using T = LltTile<H, N>;
+    constexpr int NM = N - 1;
+    if (s < a.n) {
+        const bool tq = T::TAU > 0 && a.tau != nullptr;
+        ptx::mbar_arrive_expect_tx(bar, static_cast<uint32_t>((NM * NM + NM + (tq ? T::TAU : 0)) * 8));
+        ptx::bulk_g2s(ptx::smem_addr(tile), a.mass + s * (NM * NM), NM * NM * 8, bar);
+        ptx::bulk_g2s(ptx::smem_addr(tile + T::B_RHS_AT), a.known + s * NM, NM * 8, bar);
+        if constexpr (T::TAU > 0) {
+            if (tq) ptx::bulk_g2s(ptx::smem_addr(tile + T::B_TAU_AT), a.tau + s * T::TAU, T::TAU * 8, bar);
+        }
+    } else {
+        for (int i = 0; i < NM; ++i)
+            for (int k = 0; k < NM; ++k) tile[i * NM + k] = (i == k) ? 1.0 : 0.0;
+        for (int k = 0; k < NM + T::TAU; ++k) tile[T::B_RHS_AT + k] = 0.0;
+        ptx::mbar_arrive(bar);
+    }
+}
 
 // One piece of a system's input into its tile, per-thread async copies (lanes = columns: coalesced
 // rows, only the sectors of the lower triangle are touched).  PIECE i < N-1: row i of the lower
@@ -186,13 +224,24 @@ __device__ __noinline__ void llt_issue_all_call(const LltArgs& a, long long s, d
 
 // No register cap: asked for 5 CTAs per SM (or __maxnreg__ 184 / 200) the four-rows-per-lane classes
 // spill ~0.5-1 KB per thread and lose 16-60 % (profiles/r02_llt_variants.log).
-template <int H, int N, bool REG>
+// BULK (4-lane classes only, chosen by the launcher when the order fills the class exactly (nc == N - 1), is
+// even, and mass / known / tau are 16-byte aligned): the tiles are dense and refilled by bulk copies
+// (llt_bulk_fill) -- with the per-thread copies the refills cost 35-45 % of the kernel's time, a warp's 32 lanes
+// touching 8 systems = 8 cache lines per LDGSTS (7 wavefronts of the shared-memory pipe each).
+template <int H, int N, bool REG, bool BULK = false>
 __global__ void __launch_bounds__(kLltThreads)
 ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
 {
     static_assert((H == 4 || H == 8 || H == 16 || H == 32) && N >= 2 && N <= (H == 32 ? 65 : (H == 16 ? 48 : 4 * H)), "size class");
+    static_assert(!BULK || (H == 4 && (N - 1) % 2 == 0), "bulk route: 4-lane classes of even order");
     using T = LltTile<H, N>;
     constexpr int NM = N - 1;                 // order of the (identity-padded) matrix
+    constexpr int kPerWarp = BULK ? T::B_PER_WARP : T::PER_WARP;
+    constexpr int kStride = BULK ? T::B_STRIDE : T::STRIDE;
+    constexpr int kRhsAt = BULK ? T::B_RHS_AT : NM * (NM + 1) / 2;
+    constexpr int kTauAt = BULK ? T::B_TAU_AT : T::TAU_AT;
+    constexpr int kColAt = BULK ? T::B_COL_AT : T::COL_AT;
+    auto rowoff = [](int ic) { return BULK ? ic * NM : ic * (ic + 1) / 2; };
     // Where the right-hand side rides: as row NM of the augmented matrix -- free when the last slot
     // has room for it -- or, when the order is a multiple of H and a row more would open a slot of
     // its own (12 unknowns on 4 lanes, 24 on 8: a third more multiply-adds and registers), as one
@@ -213,14 +262,24 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
     const long long ngroups = (a.n + SPW - 1) / SPW;
     const long long gstride = static_cast<long long>(gridDim.x) * WPB;
     long long grp = static_cast<long long>(blockIdx.x) * WPB + warp;
-    double* const tile = llt_smem + warp * T::PER_WARP + g * T::STRIDE;
-    double* const col = tile + T::COL_AT;
-    const double* regt = llt_smem + WPB * T::PER_WARP;
+    double* const tile = llt_smem + warp * kPerWarp + g * kStride;
+    double* const col = tile + kColAt;
+    const double* regt = llt_smem + WPB * kPerWarp;
+    __shared__ __align__(8) unsigned long long llt_bars[WPB];   // BULK: one mbarrier per warp, one arrival per system
+    const uint32_t bar = ptx::smem_addr(&llt_bars[warp]);
+    uint32_t phase = 0;
+    if constexpr (BULK) {
+        if (lane == 0) {
+            ptx::mbar_init(bar, SPW);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+    }
 
     ptx::grid_dep_wait();
 
     if constexpr (REG) {   // lower triangle of the regularisation term, packed like the tiles, once per CTA
-        double* w = llt_smem + WPB * T::PER_WARP;
+        double* w = llt_smem + WPB * kPerWarp;
         for (int i = 0; i < N; ++i)   // rows >= nc (identity padding, the right-hand side row): + 0.0
             for (int c = threadIdx.x; c <= i; c += kLltThreads)
                 w[i * (i + 1) / 2 + c] = (i < nc) ? __ldg(a.reg + i * nc + c) : 0.0;
@@ -228,13 +287,22 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
     }
     if (grp >= ngroups) return;
 
-    llt_issue_all<H, N>(llt_source<H, N>(a, grp * SPW + g, tile, r));
-    ptx::cp_async_commit();
+    if constexpr (BULK) {
+        if (r == 0) llt_bulk_fill<H, N>(a, grp * SPW + g, tile, bar);
+    } else {
+        llt_issue_all<H, N>(llt_source<H, N>(a, grp * SPW + g, tile, r));
+        ptx::cp_async_commit();
+    }
     for (; grp < ngroups; grp += gstride) {
         const long long s = grp * SPW + g;
         const bool valid = s < a.n;
-        ptx::cp_async_wait<0>();
-        __syncwarp();
+        if constexpr (BULK) {
+            ptx::mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            ptx::cp_async_wait<0>();
+            __syncwarp();
+        }
 
         // ---- the lane's rows into registers (entries right of a diagonal: whatever the tile holds:
         //      entries of the same system's later rows) ------------------------------------------------
@@ -245,7 +313,7 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
             const int i = r + m * H;
             rowok[m] = !SHORT || m < R - 1 || i < ROWS;
             const int ic = (SHORT && m == R - 1) ? min(i, ROWS - 1) : i;
-            const double* src = tile + ic * (ic + 1) / 2;
+            const double* src = tile + rowoff(ic);
 #pragma unroll
             for (int k = 0; k < NM; ++k)
                 if (k < H * (m + 1)) {
@@ -258,17 +326,17 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
 #pragma unroll
             for (int m = 0; m < R; ++m) {
                 const int i = r + m * H;      // SHORT cannot happen here: ROWS is a multiple of H
-                b[m] = tile[NM * (NM + 1) / 2 + i];
+                b[m] = tile[kRhsAt + i];
                 ysave[m] = 0.0;
                 if constexpr (T::TAU > 0) {   // known.tail += jointTorques (:226-227)
-                    if (a.tau && i >= 6) b[m] += tile[T::TAU_AT + i - 6];
+                    if (a.tau && i >= 6) b[m] += tile[kTauAt + i - 6];
                 }
             }
         } else if constexpr (T::TAU > 0) {
             // the right-hand side row: known.tail += jointTorques (:226-227)
             if (a.tau && r == NM % H) {
 #pragma unroll
-                for (int k = 6; k < NM; ++k) row[R - 1][k] += tile[T::TAU_AT + k - 6];
+                for (int k = 6; k < NM; ++k) row[R - 1][k] += tile[kTauAt + k - 6];
             }
         }
         __syncwarp();
@@ -286,7 +354,9 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
         const bool more = grp + gstride < ngroups;
 #endif
         const LltSource next = llt_source<H, N>(a, (grp + gstride) * SPW + g, tile, r);
-        if constexpr (SPREAD) {
+        if constexpr (BULK) {
+            if (more && r == 0) llt_bulk_fill<H, N>(a, (grp + gstride) * SPW + g, tile, bar);
+        } else if constexpr (SPREAD) {
             if (more) llt_issue_piece<H, N, NM>(next);
         } else {
             if (more) llt_issue_all_call<H, N>(a, (grp + gstride) * SPW + g, tile, r);
@@ -299,7 +369,7 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
         static_for<NM>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             constexpr int mj = j / H, rj = j % H;
-            if constexpr (SPREAD) {
+            if constexpr (SPREAD && !BULK) {
                 if (more) llt_issue_piece<H, N, j>(next);
             }
             const double rs = rsqrt(__shfl_sync(kFullMask, row[mj][j], rj, H));
@@ -350,7 +420,7 @@ ccm_llt_solve_kernel(const __grid_constant__ LltArgs a)
                     if (m >= mj) b[m] = fma(nl[m], t, b[m]);
             }
         });
-        if constexpr (SPREAD) {
+        if constexpr (SPREAD && !BULK) {
             if (more) ptx::cp_async_commit();
         }
 
@@ -529,11 +599,11 @@ cudaError_t launch(K kernel, long long grid, int threads, size_t smem, cudaStrea
     return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-template <int H, int N, bool REG>
+template <int H, int N, bool REG, bool BULK = false>
 cudaError_t launch_fast_k(const LltArgs& a, cudaStream_t st, bool pdl)
 {
-    auto kernel = ccm_llt_solve_kernel<H, N, REG>;
-    const size_t smem = LltTile<H, N>::bytes(REG);
+    auto kernel = ccm_llt_solve_kernel<H, N, REG, BULK>;
+    const size_t smem = BULK ? LltTile<H, N>::bytes_bulk(REG) : LltTile<H, N>::bytes(REG);
     // resident CTAs of this instantiation per device (CTAs per SM x SMs), filled on first use; an
     // atomic because distinct handles may make their first call from different host threads
     static std::atomic<int> resident[64] = {};
@@ -566,6 +636,17 @@ cudaError_t launch_fast_k(const LltArgs& a, cudaStream_t st, bool pdl)
 template <int H, int N>
 cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
 {
+    // the bulk-copy route: 6, 8 and 12 unknowns (the 4-lane classes an even order fills exactly), arrays on
+    // 16-byte boundaries; BLF_CCM_TUNE_LLT_NO_BULK=1 keeps the per-thread copies (A/B, tests of both routes)
+    if constexpr (H == 4 && (N == 7 || N == 9 || N == 13)) {
+        static const bool no_bulk = [] {
+            const char* e = std::getenv("BLF_CCM_TUNE_LLT_NO_BULK");
+            return e && e[0] == '1';
+        }();
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+        if (!no_bulk && a.nc == N - 1 && al16(a.mass) && al16(a.known) && al16(a.tau))
+            return a.reg ? launch_fast_k<H, N, true, true>(a, st, pdl) : launch_fast_k<H, N, false, true>(a, st, pdl);
+    }
     return a.reg ? launch_fast_k<H, N, true>(a, st, pdl) : launch_fast_k<H, N, false>(a, st, pdl);
 }
 

@@ -458,3 +458,32 @@ def test_facade_class_vs_reference_class(torch, ref, cps, ncols, het, with_reg):
     assert rel(fp, rp).max() <= TOL and rel(fR, rR).max() <= TOL
     if ncols > 6:
         assert rel(fq, rq).max() <= TOL
+
+
+@pytest.mark.parametrize("nc,ns,with_reg", [(6, 4_099, False), (8, 2_051, True), (12, 4_099, False), (12, 1_003, True),
+                                            (12, 5, False), (6, 1, False)])
+def test_mass_matrix_solve_bulk_and_per_thread_fill_agree(torch, dyn, so, nc, ns, with_reg):
+    """6, 8 and 12 unknowns on 16-byte aligned arrays take the bulk-copy fill (dense tiles, three bulk copies per
+    system); the same arrays 8 bytes off take the per-thread copies (packed tiles).  Same arithmetic on the same
+    operands: bit-identical results, both within 1e-12 of the oracle; ragged last groups; in place."""
+    M, known, tau, reg = _case(nc, ns, 900 + nc + ns, with_reg=with_reg)
+    want = so.mass_matrix_solve(M, known, tau, reg, nthreads=NTHREADS)
+
+    def run(shift):
+        def place(a):   # the array `shift` doubles into a fresh buffer: 16-byte aligned (0) or 8 bytes off (1)
+            if a is None:
+                return None
+            buf = torch.empty(a.size + 2, dtype=torch.float64, device="cuda")
+            v = buf[shift:shift + a.size].view(a.shape)
+            v.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            assert v.data_ptr() % 16 == 8 * shift
+            return v
+        dM, dk, dt = place(M), place(known), place(tau)
+        x = dyn.solve(dM, dk, dt, _dev(torch, reg)).cpu().numpy()
+        dyn.solve(dM, dk, dt, _dev(torch, reg), out=dk)          # in place: acc may alias known
+        assert np.array_equal(dk.cpu().numpy(), x)
+        return x
+
+    bulk, per_thread = run(0), run(1)
+    assert np.array_equal(bulk, per_thread)
+    assert rel(bulk, want).max() <= TOL
