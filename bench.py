@@ -743,7 +743,9 @@ def next_rows_leg(cx: Ctx, planes_np, no_cpu: bool = False) -> dict:
                "hbm_frac_of_measured": ns * a_bytes / (a_ms * 1e-3) / 1e9 / cx.peak,
                "euler_step_ms": e_ms, "euler_step_systems_per_s": ns / (e_ms * 1e-3),
                "euler_step_hbm_frac": ns * e_bytes / (e_ms * 1e-3) / 1e9 / cx.peak,
-               "bound": "shared-memory data pipe and column-to-column latency, not HBM (DESIGN section 10 row 5)"}
+               "bound": ("HBM on dense bytes (tiles refilled by bulk copies)" if ncols in (6, 8, 12) else
+                         "shared-memory data pipe (a third of it the per-thread tile refills) and column-to-column "
+                         "latency, not HBM") + " (DESIGN section 10 row 5)"}
         if cx.rank == 0 and not no_cpu:
             from oracle import sys_oracle          # cpu_baseline leg: the C restatement, all host cores
             cores = os.cpu_count() or 1
