@@ -636,9 +636,9 @@ cudaError_t launch_fast_k(const LltArgs& a, cudaStream_t st, bool pdl)
 template <int H, int N>
 cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
 {
-    // the bulk-copy route: 6, 8 and 12 unknowns (the 4-lane classes an even order fills exactly), arrays on
+    // the bulk-copy route: 6, 8, 10, 12 and 14 unknowns (the 4-lane classes an even order fills exactly), arrays on
     // 16-byte boundaries; BLF_CCM_TUNE_LLT_NO_BULK=1 keeps the per-thread copies (A/B, tests of both routes)
-    if constexpr (H == 4 && (N == 7 || N == 9 || N == 13)) {
+    if constexpr (H == 4 && (N == 7 || N == 9 || N == 11 || N == 13 || N == 15)) {
         static const bool no_bulk = [] {
             const char* e = std::getenv("BLF_CCM_TUNE_LLT_NO_BULK");
             return e && e[0] == '1';
@@ -676,7 +676,7 @@ cudaError_t launch_fast(const LltArgs& a, cudaStream_t st, bool pdl)
     X(32, 52) X(32, 56) X(32, 60) X(32, 64) X(32, 65)
 #else
 #define BLF_LLT_CLASSES(X)                                                      \
-    X(4, 4) X(4, 5) X(4, 7) X(4, 8) X(4, 9) X(4, 10) X(4, 13) X(4, 14) X(4, 16)   \
+    X(4, 4) X(4, 5) X(4, 7) X(4, 8) X(4, 9) X(4, 10) X(4, 11) X(4, 13) X(4, 14) X(4, 15) X(4, 16)   \
     X(8, 17) X(8, 19) X(8, 20) X(8, 22) X(8, 24) X(8, 25) X(8, 26) X(8, 28) X(8, 30) X(8, 31) X(8, 32)
 #define BLF_LLT_NARROW_MAX 31
 #endif

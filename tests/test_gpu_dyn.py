@@ -461,9 +461,9 @@ def test_facade_class_vs_reference_class(torch, ref, cps, ncols, het, with_reg):
 
 
 @pytest.mark.parametrize("nc,ns,with_reg", [(6, 4_099, False), (8, 2_051, True), (12, 4_099, False), (12, 1_003, True),
-                                            (12, 5, False), (6, 1, False)])
+                                            (12, 5, False), (6, 1, False), (10, 3_001, True), (14, 2_003, False)])
 def test_mass_matrix_solve_bulk_and_per_thread_fill_agree(torch, dyn, so, nc, ns, with_reg):
-    """6, 8 and 12 unknowns on 16-byte aligned arrays take the bulk-copy fill (dense tiles, three bulk copies per
+    """6, 8, 10, 12 and 14 unknowns on 16-byte aligned arrays take the bulk-copy fill (dense tiles, three bulk copies per
     system); the same arrays 8 bytes off take the per-thread copies (packed tiles).  Same arithmetic on the same
     operands: bit-identical results, both within 1e-12 of the oracle; ragged last groups; in place."""
     M, known, tau, reg = _case(nc, ns, 900 + nc + ns, with_reg=with_reg)
